@@ -1,0 +1,155 @@
+/*
+ * slate_b200.h -- C ABI of libslate_b200.so: the B200 (sm_100a) implementation of slate_quantum's
+ * Bloch build -> batched Hermitian eigh -> eigenbasis evolution hot path.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers owned by the caller (the Python layer owns them through
+ *    torch tensors) unless the parameter name ends in `_host`.
+ *  - complex128 is interleaved (re, im) doubles: `sqb_c128`.
+ *  - Every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream) and returns immediately; nothing is allocated behind the caller's back - scratch space is
+ *    passed in as `workspace` with the size reported by the matching *_workspace_bytes function.
+ *  - Return value: 0 = OK, < 0 = bad argument (SQB_E_*), > 0 = a cudaError_t from a launch.
+ *    Numerical failures of the eigensolver are reported per matrix in `info[]`, not in the return value.
+ *  - Re-entrant / thread-safe: no global mutable state.
+ *
+ * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
+ * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency
+ * slate_core@4aa5106 and is reached through the cited call sites.
+ */
+#ifndef SLATE_B200_H
+#define SLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqb_c128 {
+  double re, im;
+} sqb_c128;
+
+#define SQB_MAX_DIMS 4
+
+enum {
+  SQB_OK = 0,
+  SQB_E_BADARG = -1,     /* null pointer / non-positive size / nd out of range            */
+  SQB_E_UNSUPPORTED = -2, /* size outside what the kernels implement (documented per call) */
+  SQB_E_WORKSPACE = -3,  /* workspace too small                                           */
+};
+
+/* ABI version (bumped on any signature change) and a human-readable description of an error code. */
+int sqb_abi_version(void);
+const char* sqb_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  Bloch block builder.
+ * Replaces: slate_quantum/bloch/build.py:146-167 `kinetic_hamiltonian` (python loop over k-points
+ * at :156-161 + densification `with_operator_basis(transformed...)` at :123-128), using
+ * slate_quantum/operator/_build/_hamiltonian.py:32-48,72-94,121-146 for the kinetic diagonal.
+ *
+ *   H[b, k, k'] = E_b[k] * delta(k,k') + vtable[(k' - k) mod shape] / sqrt(N)
+ *
+ * nd        number of axes (1..SQB_MAX_DIMS); N = prod(shape), n_k = prod(repeat)
+ * dk_host   [nd*nd] row i = reciprocal vector dk_i (Cartesian components), host memory
+ * vtable    [N] device: potential Fourier components zero-padded to `shape`, FFT order per axis,
+ *           C order over axes, NOT yet divided by sqrt(N)
+ * blocks    [block_begin, block_begin + block_count) in meshgrid(indexing="ij") C order of the
+ *           FFT-ordered fractions (bloch/build.py:40-42,138-143)
+ * H_out     [block_count, N, N] row = ket k, col = bra k'
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_bloch_build(int nd, const int* shape_host, const int* repeat_host, const double* dk_host,
+                    const sqb_c128* vtable, double mass, double hbar, int64_t block_begin,
+                    int64_t block_count, sqb_c128* H_out, void* stream);
+
+/* Kinetic diagonals only: E_out[block_count, N] complex128 (imag 0), same block order.
+ * Replaces operator/_build/_hamiltonian.py:149-158 `kinetic_energy` over a list of fractions. */
+int sqb_bloch_kinetic(int nd, const int* shape_host, const int* repeat_host, const double* dk_host,
+                      double mass, double hbar, int64_t block_begin, int64_t block_count,
+                      sqb_c128* E_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  Bloch index permutation (BlochShiftedBasis per axis + BlochTransposedBasis).
+ * Replaces: bloch/_shifted_basis.py:62-84 / 87-111 and bloch/_transposed_basis.py:102-133 / 136-167.
+ * Vectors are [lead, M] with M = prod(shape)*prod(repeat).
+ *   direction 0 (= __from_inner__):  supercell-momentum order -> Bloch [(blk...),(in...)] order
+ *   direction 1 (= __into_inner__):  Bloch order -> supercell-momentum order
+ * in != out.
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_bloch_permute(int nd, const int* shape_host, const int* repeat_host, int direction,
+                      int64_t lead, const sqb_c128* in, sqb_c128* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  complex128 FFT, norm="ortho", over the trailing `nd` axes of a [batch, dims...] C-order array.
+ * Replaces: slate_core TransformedBasis conversions (np.fft.fft / ifft(norm="ortho") per axis;
+ * convention pinned by tests/test_operator.py:197-204) reached from Array.with_basis
+ * (operator/_operator.py:70-74, state/_state.py:37-43).
+ *   sign = -1 : forward  (np.fft.fftn,  position -> momentum on a ket index)
+ *   sign = +1 : backward (np.fft.ifftn, momentum -> position on a ket index)
+ * Every axis length must factor into primes <= 31.  in == out allowed.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sqb_fft_workspace_bytes(int nd, const int* dims_host, int64_t batch);
+int sqb_fft_c2c(int nd, const int* dims_host, int64_t batch, int sign, const sqb_c128* in,
+                sqb_c128* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Same transform along ONE axis of a [outer, len, inner] array (used for operator indices). */
+int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, const sqb_c128* in, sqb_c128* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  Batched Hermitian eigensolver, complex128, one problem per k-block.
+ * Replaces: slate_core.linalg.into_diagonal_hermitian (np.linalg.eigh / LAPACK zheevd per block),
+ * call site operator/_linalg.py:56 (`into_diagonal_hermitian`), bloch/_linalg.py:72-84.
+ *
+ * A_inout  [batch, n, n] in:  H_b (row-major, Hermitian; both triangles are read)
+ *                        out: transform_b[e, k] = component k of eigenvector e (ROWS = eigenvectors,
+ *                             i.e. np.linalg.eigh(H_b)[1].T - the layout of the reference's
+ *                             EigenstateBasis transform, bloch/_linalg.py:35-57)
+ * w        [batch, n] eigenvalues, ascending within each matrix (quirk Q3: not globally sorted)
+ * info     [batch] 0 = converged; k > 0 = the implicit-QL iteration failed on k eigenvalues or ran
+ *          out of rotation storage (results for that matrix are undefined)
+ * n <= 1024.  Algorithm: Householder tridiagonalisation, implicit-shift QL on the real tridiagonal
+ * with recorded Givens rotations, rotation replay on shared-memory strips, Householder
+ * back-transformation.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sqb_eigh_workspace_bytes(int n, int64_t batch);
+int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* info, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  Eigenbasis projection, phase evolution, back-transformation.
+ * Replaces: dynamics/schrodinger.py:31-56 `_solve_schrodinger_equation_diagonal`
+ *   (:45-47 projection via State.with_basis -> ExplicitUnitaryBasis, :51-53 np.exp broadcast) and the
+ *   caller-side StateList.with_state_basis back-transform (state/_state.py:153-165).
+ *
+ * transform [batch, n, n] rows = eigenvectors (output layout of sqb_eigh_batched)
+ * sqb_project:       c[b, e]      = sum_k conj(transform[b,e,k]) * psi[b,k]
+ * sqb_evolve_eigen:  a[t, b, e]   = c[b,e] * exp(-1j * w[b,e] * times[t] / hbar)     (the reference's
+ *                    returned StateList raw data, [T, batch*n])
+ * sqb_evolve_bloch:  out[t, b, k] = sum_e a[t,b,e] * transform[b,e,k]  with a[] generated on the fly
+ *                    (never materialised): FP64 tensor-core (DMMA) complex GEMM per block.
+ *                    Rows t in [t_begin, t_begin+t_count) of `times` are produced; `out` points at
+ *                    row t_begin's storage, row stride = out_row_stride elements (>= batch*n).
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
+                void* stream);
+int sqb_evolve_eigen(int64_t m, const double* w, const sqb_c128* c, const double* times,
+                     int64_t n_times, double hbar, sqb_c128* out, void* stream);
+int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w,
+                     const sqb_c128* c, const double* times, int64_t t_count, double hbar,
+                     sqb_c128* out, int64_t out_row_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measured-peak micro-benchmarks (used by bench.py for the roofline denominators; not on the path).
+ *   sqb_peak_dmma : runs `iters` dependent-free DMMA.8x8x4 chains on every SM; returns 0 and the
+ *                   number of real FP64 flops executed in *flops_host.  Time it with CUDA events.
+ *   sqb_peak_dfma : same with plain DFMA.
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_peak_dmma(int64_t iters, double* sink, double* flops_host, void* stream);
+int sqb_peak_dfma(int64_t iters, double* sink, double* flops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLATE_B200_H */

@@ -1,0 +1,539 @@
+"""CPU ORACLE (test infrastructure, NOT product code) for the Bloch build -> eigh -> evolve hot path.
+
+This file is a plain numpy (float64 / complex128) restatement of what the reference
+``Matt-Ord/slate_quantum`` computes on the path named by ``BASELINE.json:north_star``.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it; the shipped package ``slate_quantum_b200`` never does.
+
+Why a restatement and not the reference itself
+----------------------------------------------
+* the reference needs CPython >= 3.14 (``/root/reference/pyproject.toml:7``) and fails to *parse* on
+  the 3.12 interpreter of this image (PEP 696 type-parameter defaults), and
+* every floating point operation of the path runs inside the un-vendored dependency
+  ``slate_core @ git+https://github.com/Matt-Ord/slate.git@4aa5106`` (version 0.0.2,
+  ``pyproject.toml:11``, ``uv.lock:931-933``) whose source is absent from ``/root/reference``.
+
+The arithmetic slate_core reaches on this path is numpy's own (``np.linalg.eigh`` = LAPACK zheevd,
+``np.fft`` = pocketfft, ``np.matmul``), so the restatement below calls exactly those.
+
+Parity pinning status (see tests/test_oracle_golden.py, tests/golden/README.md)
+-------------------------------------------------------------------------------
+PINNED by the reference's own known-answer tests / invariants, re-expressed against this oracle:
+  * kinetic literal ``[0, .5, 2, 2, .5]``                        (tests/test_operator.py:22-28)
+  * split raw layout ``[0,0,0, 0,.5,2,2,.5]`` and dense diagonal  (tests/test_operator.py:31-59)
+  * eigenvalue multiset equality through eigh                    (tests/test_operator.py:62-75)
+  * FFT-order literal ``[0,1,2,-2,-1]`` and FFT directions        (tests/test_operator.py:184-210)
+  * cos / fcc potential == analytic functions                    (tests/test_operator.py:305-353)
+  * Bloch blocks == supercell Hamiltonian on the (shape, repeat) grid of
+    tests/test_bloch.py:16-47, 50-86, 89-126 (orthogonal 2*pi lattice, atol 1e-14 / 1e-15)
+PARITY UNPINNED by the reference (it has no test): eigenvectors of Bloch blocks, the whole of
+``dynamics/schrodinger.py``, non-orthogonal lattices through ``bloch.*``.  For those this oracle is
+cross-checked by independent identities (dense supercell ``scipy.linalg.expm`` evolution, residuals,
+``eigvalsh`` of the dense supercell matrix) in tests/test_oracle_golden.py.
+
+Every function cites the reference file:line it follows.
+"""
+
+from __future__ import annotations
+
+import itertools
+from typing import Sequence
+
+import numpy as np
+
+HBAR_SI = 1.054571817e-34  # scipy.constants.hbar (CODATA 2018), the reference's default
+
+
+# --------------------------------------------------------------------------------------
+# index conventions
+# --------------------------------------------------------------------------------------
+def nk_points(n: int) -> np.ndarray:
+    """FFT-ordered integer frequencies, e.g. n=5 -> [0,1,2,-2,-1].
+
+    slate_core ``fundamental_nk_points``; literal pinned at tests/test_operator.py:195.
+    """
+    return np.fft.ifftshift(np.arange((-n + 1) // 2, (n + 1) // 2))
+
+
+def stacked_nk(shape: Sequence[int]) -> np.ndarray:
+    """(nd, N) integer mesh, ``indexing="ij"`` C-order ravel.
+
+    operator/_build/_hamiltonian.py:61-69 (_fundamental_stacked_n_kinetic).
+    """
+    mesh = np.meshgrid(*(nk_points(n) for n in shape), indexing="ij")
+    return np.array([m.ravel() for m in mesh])
+
+
+def stacked_dk(delta_x: np.ndarray) -> np.ndarray:
+    """Reciprocal vectors, row i = dk_i with dk_i . a_j = 2 pi delta_ij (a_j = full cell vectors).
+
+    slate_core ``fundamental_stacked_dk``; pinned 1-D (L=2pi => dk=1) at tests/test_operator.py:22-28
+    and on the hexagonal cell at tests/test_operator.py:323-353.
+    """
+    delta_x = np.asarray(delta_x, dtype=np.float64)
+    return 2 * np.pi * np.linalg.inv(delta_x).T
+
+
+def sample_fractions(repeat: Sequence[int]) -> np.ndarray:
+    """(nd, n_k) Bloch fractions, block order = meshgrid(indexing="ij") C-order ravel.
+
+    bloch/build.py:40-42 (values = nk/R) and :138-143 (get_sample_fractions).
+    """
+    mesh = np.meshgrid(*(nk_points(r) / r for r in repeat), indexing="ij")
+    return np.array([m.ravel() for m in mesh])
+
+
+# --------------------------------------------------------------------------------------
+# a-1 kinetic energy
+# --------------------------------------------------------------------------------------
+def wrap_k_points(k_points: np.ndarray, delta_k: Sequence[float]) -> np.ndarray:
+    """operator/_build/_hamiltonian.py:32-37 -- half-open [-d/2, d/2) via np.mod (quirk Q2)."""
+    shift = np.array(delta_k).reshape(-1, 1) / 2
+    return np.mod(k_points + shift, 2 * shift) - shift
+
+
+def kinetic_energy(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    mass: float,
+    fraction: np.ndarray | None = None,
+    *,
+    hbar: float = HBAR_SI,
+) -> np.ndarray:
+    """Kinetic diagonal E[N] (complex128, imag 0) for one Bloch fraction.
+
+    operator/_build/_hamiltonian.py:40-48 (_get_bloch_phase), :72-94
+    (_fundamental_stacked_kinetic_points, incl. the Cartesian-row wrap with lattice-vector norms,
+    quirk Q1), :121-146 (energy = sum (hbar k)^2 / 2m as complex128).
+    All axes periodic ("Fourier").
+    """
+    nd = len(shape)
+    dk = stacked_dk(delta_x)  # fundamental_stacked_dk
+    fraction = np.zeros(nd) if fraction is None else np.asarray(fraction, dtype=np.float64)
+    bloch_phase = np.tensordot(dk, fraction, axes=(0, 0))
+    points = np.einsum("ij,ik->jk", dk, stacked_nk(shape).astype(np.float64))
+    points = points + bloch_phase[:, np.newaxis]
+    delta_k = dk * np.asarray(shape, dtype=np.float64)[:, np.newaxis]  # fundamental_stacked_delta_k
+    points = wrap_k_points(points, tuple(np.linalg.norm(delta_k, axis=1)))
+    return np.sum(np.square(hbar * points) / (2 * mass), axis=0, dtype=np.complex128)
+
+
+# --------------------------------------------------------------------------------------
+# a-2 potentials (raw data = Fourier components in a cropped transformed basis)
+# --------------------------------------------------------------------------------------
+def outer_product(*arrays: np.ndarray) -> np.ndarray:
+    """_util/_prod.py:6-10."""
+    grids = np.meshgrid(*arrays, indexing="ij")
+    return np.prod(grids, axis=0)
+
+
+def cos_potential_components(shape: Sequence[int], height: float, offset: float = 0.0) -> np.ndarray:
+    """(3,)*nd components at frequencies [0,+1,-1] per axis. operator/_build/_potential.py:86-108."""
+    nd = len(shape)
+    size = int(np.prod(shape))
+    data = outer_product(*(np.array([2 * (1 + offset), 1, 1], dtype=np.complex128),) * nd)
+    return 0.25**nd * height * data * np.sqrt(size)
+
+
+def sin_potential_components(shape: Sequence[int], height: float, offset: float = 0.0) -> np.ndarray:
+    """operator/_build/_potential.py:111-131."""
+    nd = len(shape)
+    size = int(np.prod(shape))
+    data = outer_product(*(np.array([2 * (1 + offset), 1j, -1j]),) * nd)
+    return 0.25**nd * height * data * np.sqrt(size)
+
+
+def fcc_potential_components(shape: Sequence[int], height: float) -> np.ndarray:
+    """operator/_build/_potential.py:167-190 (2-D only, as in the reference)."""
+    assert len(shape) == 2  # noqa: PLR2004
+    size = int(np.prod(shape))
+    data = np.array([[3, 1, 1], [1, 1, 0], [1, 0, 1]]).astype(np.complex128)
+    return (1 / 3) ** 2 * data * height * np.sqrt(size)
+
+
+def pad_components(shape: Sequence[int], components: np.ndarray) -> np.ndarray:
+    """Zero-pad cropped Fourier components to ``shape`` in FFT order (CroppedBasis semantics).
+
+    CroppedBasis(n, transformed) keeps the n lowest |frequency| entries in FFT order, i.e.
+    cropped index j <-> frequency nk_points(n)[j] (assumption U4, pinned by
+    tests/test_operator.py:305-320 and tests/test_bloch.py:89-126).
+    """
+    components = np.asarray(components, dtype=np.complex128)
+    full = np.zeros(tuple(shape), dtype=np.complex128)
+    idx = [nk_points(c) % n for c, n in zip(components.shape, shape, strict=True)]
+    full[np.ix_(*idx)] = components
+    return full
+
+
+def potential_position_values(shape: Sequence[int], components: np.ndarray) -> np.ndarray:
+    """V(x) on the grid.
+
+    The diagonal of a position operator is stored on the *dual* outer basis
+    (operator/_diagonal.py:64-73: ``RecastBasis(inner, inner_recast.dual_basis(),
+    outer_recast.dual_basis())``), and a dual index goes transformed -> fundamental with
+    fft(norm="ortho") (tests/test_operator.py:197-204).  Pinned by ``sin_potential(meta, 2) ==
+    1 + sin x`` (tests/test_operator.py:316-320), which distinguishes fft from ifft.
+    """
+    return np.fft.fftn(pad_components(shape, components), norm="ortho")
+
+
+def repeat_components(shape: Sequence[int], components: np.ndarray, repeat: Sequence[int]) -> np.ndarray:
+    """Supercell Fourier table of the repeated potential, zero padded, FFT order.
+
+    operator/_build/_potential.py:56-83: unit-cell component j goes to supercell index j*R
+    (TruncatedBasis(Truncation(n=N_a, step=R_a, offset=0))), data * sqrt(prod R).
+    """
+    full = pad_components(shape, components)
+    big = np.zeros(tuple(n * r for n, r in zip(shape, repeat, strict=True)), dtype=np.complex128)
+    big[tuple(slice(None, None, r) for r in repeat)] = full * np.sqrt(np.prod(repeat))
+    return big
+
+
+def convolution_matrix(full_table: np.ndarray) -> np.ndarray:
+    """Momentum-basis matrix of a position-diagonal operator: V[k,k'] = Vt[(k'-k) mod shape]/sqrt(N).
+
+    With v(x) = fft_ortho(Vt) (see :func:`potential_position_values`) and the ket index going
+    position -> momentum by fft(ortho), bra by ifft(ortho):
+    V[k,k'] = (1/N) sum_x v(x) e^{-2 pi i (k-k') x/N} = Vt[(k'-k) mod N] / sqrt(N).
+    (Symmetric tables such as cos/fcc cannot tell k-k' from k'-k; sin_potential can.)
+    """
+    shape = full_table.shape
+    size = int(np.prod(shape))
+    idx = np.array(np.unravel_index(np.arange(size), shape))  # (nd, N) array indices
+    diff = (idx[:, None, :] - idx[:, :, None]) % np.array(shape)[:, None, None]
+    flat = np.ravel_multi_index(tuple(diff), shape)
+    return full_table.ravel()[flat] / np.sqrt(size)
+
+
+def convolution_matrix_via_fft(full_table: np.ndarray) -> np.ndarray:
+    """The reference's own densification route (slate_core): values -> diag in x -> 2-sided FFT.
+
+    Ket index: position -> momentum is fft(ortho); bra (dual) index the opposite direction
+    (tests/test_operator.py:197-204).  Independent check of :func:`convolution_matrix`.
+    """
+    shape = full_table.shape
+    nd = len(shape)
+    size = int(np.prod(shape))
+    v_x = np.fft.fftn(full_table, norm="ortho").ravel()
+    dense = np.diag(v_x).reshape(*shape, *shape)
+    dense = np.fft.fftn(dense, axes=tuple(range(nd)), norm="ortho")
+    dense = np.fft.ifftn(dense, axes=tuple(range(nd, 2 * nd)), norm="ortho")
+    return dense.reshape(size, size)
+
+
+# --------------------------------------------------------------------------------------
+# a-3 / a-4 Hamiltonians
+# --------------------------------------------------------------------------------------
+def split_raw_data(components: np.ndarray, kinetic: np.ndarray) -> np.ndarray:
+    """operator/_build/_hamiltonian.py:177-182: raw = concatenate([potential.raw, kinetic.raw])."""
+    return np.concatenate([np.asarray(components, dtype=np.complex128), kinetic], axis=None)
+
+
+def dense_hamiltonian(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    full_table: np.ndarray,
+    mass: float,
+    fraction: np.ndarray | None = None,
+    *,
+    hbar: float = HBAR_SI,
+) -> np.ndarray:
+    """One cell's H in its transformed (momentum) basis = diag(E) + convolution matrix."""
+    energy = kinetic_energy(delta_x, shape, mass, fraction, hbar=hbar)
+    return np.diag(energy) + convolution_matrix(full_table)
+
+
+def bloch_blocks(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    components: np.ndarray,
+    mass: float,
+    repeat: Sequence[int],
+    *,
+    hbar: float = HBAR_SI,
+    block_begin: int = 0,
+    block_count: int | None = None,
+) -> np.ndarray:
+    """K1: raw data [n_k, N, N] of ``bloch.build.kinetic_hamiltonian`` (bloch/build.py:146-167).
+
+    Row index = ket k, column = bra k', block order per :func:`sample_fractions`.
+    """
+    fractions = sample_fractions(repeat)
+    n_k = fractions.shape[1]
+    block_count = n_k - block_begin if block_count is None else block_count
+    conv = convolution_matrix(pad_components(shape, components))
+    out = np.empty((block_count, conv.shape[0], conv.shape[0]), dtype=np.complex128)
+    for i in range(block_count):
+        energy = kinetic_energy(delta_x, shape, mass, fractions[:, block_begin + i], hbar=hbar)
+        out[i] = conv
+        out[i][np.diag_indices(conv.shape[0])] += energy
+    return out
+
+
+def supercell_hamiltonian(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    components: np.ndarray,
+    mass: float,
+    repeat: Sequence[int],
+    *,
+    hbar: float = HBAR_SI,
+) -> np.ndarray:
+    """Dense H of the repeated cell in the supercell momentum basis (tests/test_bloch.py:32-45).
+
+    repeat_potential + operator.build.kinetic_hamiltonian on the RepeatedMetadata volume
+    (metadata/_repeat.py:9-25: size N*R, delta = R*delta).
+    """
+    big_shape = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    big_delta_x = np.asarray(delta_x, dtype=np.float64) * np.asarray(repeat, dtype=np.float64)[:, None]
+    table = repeat_components(shape, components, repeat)
+    return dense_hamiltonian(big_delta_x, big_shape, table, mass, None, hbar=hbar)
+
+
+# --------------------------------------------------------------------------------------
+# a-5 K5 permutations, literal numpy restatements
+# --------------------------------------------------------------------------------------
+def shifted_from_inner(vectors: np.ndarray, n_states: int, n_repeats: int, axis: int = -1) -> np.ndarray:
+    """bloch/_shifted_basis.py:87-111."""
+    axis %= vectors.ndim
+    shift = n_repeats // 2 + (n_repeats * (n_states // 2))
+    shifted = np.roll(vectors, shift, axis=axis)
+    stacked = shifted.reshape(*vectors.shape[:axis], n_states, n_repeats, *vectors.shape[axis + 1 :])
+    return np.fft.ifftshift(stacked, axes=(axis, axis + 1)).reshape(vectors.shape)
+
+
+def shifted_into_inner(vectors: np.ndarray, n_states: int, n_repeats: int, axis: int = -1) -> np.ndarray:
+    """bloch/_shifted_basis.py:62-84."""
+    axis %= vectors.ndim
+    stacked = vectors.reshape(*vectors.shape[:axis], n_states, n_repeats, *vectors.shape[axis + 1 :])
+    shifted = np.fft.fftshift(stacked, axes=(axis, axis + 1))
+    shift = n_repeats // 2 + (n_repeats * (n_states // 2))
+    return np.roll(shifted.reshape(vectors.shape), -shift, axis=axis)
+
+
+def transposed_from_inner(
+    vectors: np.ndarray, n_states: Sequence[int], n_repeats: Sequence[int], axis: int = -1
+) -> np.ndarray:
+    """bloch/_transposed_basis.py:136-167: [(in,blk),...] -> [(blk...),(in...)]."""
+    axis %= vectors.ndim
+    n_dim = len(n_repeats)
+    stacked = vectors.reshape(
+        *vectors.shape[:axis],
+        *itertools.chain(*zip(n_states, n_repeats, strict=True)),
+        *vectors.shape[axis + 1 :],
+    )
+    flipped = stacked.transpose(
+        *range(axis),
+        *range(axis + 1, axis + 2 * n_dim, 2),
+        *range(axis, axis + 2 * n_dim, 2),
+        *range(axis + 2 * n_dim, stacked.ndim),
+    )
+    return flipped.reshape(vectors.shape)
+
+
+def transposed_into_inner(
+    vectors: np.ndarray, n_states: Sequence[int], n_repeats: Sequence[int], axis: int = -1
+) -> np.ndarray:
+    """bloch/_transposed_basis.py:102-133: [(blk...),(in...)] -> [(in,blk),...]."""
+    axis %= vectors.ndim
+    n_dim = len(n_repeats)
+    stacked = vectors.reshape(*vectors.shape[:axis], *n_repeats, *n_states, *vectors.shape[axis + 1 :])
+    flipped = stacked.transpose(
+        *range(axis),
+        *itertools.chain(*((axis + i + n_dim, axis + i) for i in range(n_dim))),
+        *range(axis + 2 * n_dim, stacked.ndim),
+    )
+    return flipped.reshape(vectors.shape)
+
+
+def bloch_from_supercell(
+    vectors: np.ndarray, shape: Sequence[int], repeat: Sequence[int], axis: int = -1
+) -> np.ndarray:
+    """Supercell-momentum (TupleBasis of TransformedBasis, C order) -> Bloch [(blk...),(in...)] order.
+
+    = per-axis BlochShiftedBasis.__from_inner__ then BlochTransposedBasis.__from_inner__
+    (basis nesting at bloch/build.py:79-88).
+    """
+    axis %= vectors.ndim
+    nd = len(shape)
+    big = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    stacked = vectors.reshape(*vectors.shape[:axis], *big, *vectors.shape[axis + 1 :])
+    for a in range(nd):
+        stacked = shifted_from_inner(stacked, shape[a], repeat[a], axis=axis + a)
+    flat = stacked.reshape(vectors.shape)
+    return transposed_from_inner(flat, shape, repeat, axis=axis)
+
+
+def bloch_into_supercell(
+    vectors: np.ndarray, shape: Sequence[int], repeat: Sequence[int], axis: int = -1
+) -> np.ndarray:
+    """Inverse of :func:`bloch_from_supercell` (the two ``__into_inner__``)."""
+    axis %= vectors.ndim
+    nd = len(shape)
+    big = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    flat = transposed_into_inner(vectors, shape, repeat, axis=axis)
+    stacked = flat.reshape(*vectors.shape[:axis], *big, *vectors.shape[axis + 1 :])
+    for a in range(nd):
+        stacked = shifted_into_inner(stacked, shape[a], repeat[a], axis=axis + a)
+    return stacked.reshape(vectors.shape)
+
+
+def bloch_permutation(shape: Sequence[int], repeat: Sequence[int]) -> np.ndarray:
+    """perm with bloch[i] = supercell[perm[i]] -- closed form used by the CUDA kernel.
+
+    Element (block b, inner p) with signed FFT-order integers (q_a, k_a) per axis sits at supercell
+    index (k_a * R_a + q_a) mod (N_a R_a) per axis (C order over axes).
+    """
+    nd = len(shape)
+    n_k = int(np.prod(repeat))
+    size = int(np.prod(shape))
+    b_idx = np.array(np.unravel_index(np.arange(n_k), repeat))  # (nd, n_k)
+    p_idx = np.array(np.unravel_index(np.arange(size), shape))  # (nd, N)
+    perm = np.zeros((n_k, size), dtype=np.int64)
+    for a in range(nd):
+        n, r = shape[a], repeat[a]
+        q = nk_points(r)[b_idx[a]][:, None]
+        k = nk_points(n)[p_idx[a]][None, :]
+        perm = perm * (n * r) + (k * r + q) % (n * r)
+    return perm.ravel()
+
+
+def embed_blocks(blocks: np.ndarray, shape: Sequence[int], repeat: Sequence[int]) -> np.ndarray:
+    """Block-diagonal [n_k,N,N] -> dense supercell momentum matrix [M,M] (BlockDiagonalBasis + K5)."""
+    n_k, size, _ = blocks.shape
+    m = n_k * size
+    dense = np.zeros((m, m), dtype=blocks.dtype)
+    for b in range(n_k):
+        dense[b * size : (b + 1) * size, b * size : (b + 1) * size] = blocks[b]
+    dense = bloch_into_supercell(dense, shape, repeat, axis=0)
+    return bloch_into_supercell(dense, shape, repeat, axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# a-8 K4 FFT basis change
+# --------------------------------------------------------------------------------------
+def position_to_momentum(vectors: np.ndarray, big_shape: Sequence[int], axis: int = -1) -> np.ndarray:
+    """Ket index: fundamental -> transformed = fft(norm="ortho") per axis (tests/test_operator.py:197-204)."""
+    axis %= vectors.ndim
+    nd = len(big_shape)
+    stacked = vectors.reshape(*vectors.shape[:axis], *big_shape, *vectors.shape[axis + 1 :])
+    out = np.fft.fftn(stacked, axes=tuple(range(axis, axis + nd)), norm="ortho")
+    return out.reshape(vectors.shape)
+
+
+def momentum_to_position(vectors: np.ndarray, big_shape: Sequence[int], axis: int = -1) -> np.ndarray:
+    """Ket index: transformed -> fundamental = ifft(norm="ortho") per axis."""
+    axis %= vectors.ndim
+    nd = len(big_shape)
+    stacked = vectors.reshape(*vectors.shape[:axis], *big_shape, *vectors.shape[axis + 1 :])
+    out = np.fft.ifftn(stacked, axes=tuple(range(axis, axis + nd)), norm="ortho")
+    return out.reshape(vectors.shape)
+
+
+# --------------------------------------------------------------------------------------
+# a-6 K2 eigh, a-7 K3 evolve
+# --------------------------------------------------------------------------------------
+def eigh_blocks(blocks: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """K2: per-block ``np.linalg.eigh`` (slate_core.linalg.into_diagonal_hermitian on a
+    BlockDiagonalBasis operator; call site operator/_linalg.py:56).
+
+    Returns (E [n_k, N] float64 ascending within a block (quirk Q3),
+             transform [n_k, N(eigen index), N(component)] = eigh(...)[1]^T, rows = eigenvectors).
+    """
+    w, v = np.linalg.eigh(blocks)
+    return w, np.ascontiguousarray(np.swapaxes(v, -1, -2))
+
+
+def project(transform: np.ndarray, psi_bloch: np.ndarray) -> np.ndarray:
+    """K3a: c[b,n] = sum_p conj(V_b[p,n]) psi[b,p]  (ExplicitUnitaryBasis inner -> explicit, U6)."""
+    return np.einsum("bnp,bp->bn", transform.conj(), psi_bloch)
+
+
+def evolve_eigenbasis(coefficients: np.ndarray, eigenvalues: np.ndarray, times: np.ndarray, hbar: float) -> np.ndarray:
+    """K3b, literally dynamics/schrodinger.py:48-53 (operation order -1j * E * t / hbar, E complex128)."""
+    coefficients = np.asarray(coefficients).ravel()
+    eig = np.asarray(eigenvalues).ravel().astype(np.complex128)
+    time_values = np.asarray(times, dtype=np.float64)
+    return coefficients[np.newaxis, :] * np.exp(-1j * eig * time_values[:, np.newaxis] / hbar)
+
+
+def back_transform(transform: np.ndarray, amplitudes: np.ndarray) -> np.ndarray:
+    """K3c: psi[t,b,p] = sum_n a[t,b,n] V_b[p,n] (explicit -> inner)."""
+    n_k, size, _ = transform.shape
+    a = amplitudes.reshape(-1, n_k, size)
+    return np.einsum("tbn,bnp->tbp", a, transform)
+
+
+def evolve_pipeline(
+    psi0_position: np.ndarray,
+    shape: Sequence[int],
+    repeat: Sequence[int],
+    eigenvalues: np.ndarray,
+    transform: np.ndarray,
+    times: np.ndarray,
+    hbar: float,
+) -> dict[str, np.ndarray]:
+    """Full K4 -> K5 -> K3a -> K3b -> K3c -> K5 -> K4 chain."""
+    big = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    n_k = int(np.prod(repeat))
+    size = int(np.prod(shape))
+    psi_k = position_to_momentum(psi0_position, big)
+    psi_b = bloch_from_supercell(psi_k, shape, repeat).reshape(n_k, size)
+    c = project(transform, psi_b)
+    a = evolve_eigenbasis(c, eigenvalues, times, hbar)  # [T, M] eigenbasis
+    psi_bt = back_transform(transform, a).reshape(len(times), n_k * size)  # bloch momentum
+    psi_kt = bloch_into_supercell(psi_bt, shape, repeat, axis=-1)
+    psi_xt = momentum_to_position(psi_kt, big, axis=-1)
+    return {
+        "coefficients": c,
+        "eigen": a,
+        "bloch": psi_bt,
+        "momentum": psi_kt,
+        "position": psi_xt,
+    }
+
+
+def momentum_matrix_to_position(dense: np.ndarray, big_shape: Sequence[int]) -> np.ndarray:
+    """Operator.as_array(): ket index ifft(ortho), bra index fft(ortho) (tests/test_operator.py:197-204)."""
+    nd = len(big_shape)
+    m = dense.shape[0]
+    stacked = dense.reshape(*big_shape, *big_shape)
+    stacked = np.fft.ifftn(stacked, axes=tuple(range(nd)), norm="ortho")
+    stacked = np.fft.fftn(stacked, axes=tuple(range(nd, 2 * nd)), norm="ortho")
+    return stacked.reshape(m, m)
+
+
+# --------------------------------------------------------------------------------------
+# parity metrics shared by the tests (SURVEY §8d tolerances)
+# --------------------------------------------------------------------------------------
+def eigh_residuals(blocks: np.ndarray, eigenvalues: np.ndarray, transform: np.ndarray) -> tuple[float, float]:
+    """max_b ||H V - V L||_F / ||H||_F and max_b ||V^H V - I||_F."""
+    v = np.swapaxes(transform, -1, -2)  # columns = eigenvectors
+    hv = blocks @ v
+    res = np.linalg.norm(hv - v * eigenvalues[:, None, :], axis=(1, 2)) / np.maximum(
+        np.linalg.norm(blocks, axis=(1, 2)), 1e-300
+    )
+    eye = np.eye(blocks.shape[-1])
+    orth = np.linalg.norm(np.swapaxes(v.conj(), -1, -2) @ v - eye, axis=(1, 2))
+    return float(res.max()), float(orth.max())
+
+
+def subspace_projector_error(
+    eigenvalues: np.ndarray, transform_a: np.ndarray, transform_b: np.ndarray, norm_h: float, tol: float = 1e-8
+) -> float:
+    """Compare eigenvectors through projectors onto (near-)degenerate clusters, one block.
+
+    Clusters = runs with gaps < tol * ||H||; returns max_cluster ||P_a - P_b||_F.
+    """
+    n = len(eigenvalues)
+    worst = 0.0
+    start = 0
+    for i in range(1, n + 1):
+        if i == n or abs(eigenvalues[i] - eigenvalues[i - 1]) > tol * norm_h:
+            va = transform_a[start:i]
+            vb = transform_b[start:i]
+            pa = va.T @ va.conj()
+            pb = vb.T @ vb.conj()
+            worst = max(worst, float(np.linalg.norm(pa - pb)))
+            start = i
+    return worst

@@ -1,0 +1,110 @@
+"""ctypes binding of libslate_b200.so (the C ABI declared in include/slate_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is present the calls
+raise.  PyTorch is used only to own device buffers and to provide the current stream.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = Path(os.environ.get("SLATE_B200_LIB", _HERE / "libslate_b200.so"))
+
+EXPORTED_SYMBOLS = (
+    "sqb_abi_version",
+    "sqb_error_string",
+    "sqb_bloch_build",
+    "sqb_bloch_kinetic",
+    "sqb_bloch_permute",
+    "sqb_fft_workspace_bytes",
+    "sqb_fft_c2c",
+    "sqb_fft_axis",
+    "sqb_eigh_workspace_bytes",
+    "sqb_eigh_batched",
+    "sqb_project",
+    "sqb_evolve_eigen",
+    "sqb_evolve_bloch",
+    "sqb_peak_dmma",
+    "sqb_peak_dfma",
+)
+
+
+class SlateB200Error(RuntimeError):
+    """Raised when the native library is missing or a C-ABI call returns a non-zero status."""
+
+
+_lib: ctypes.CDLL | None = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises SlateB200Error when it is not built."""
+    global _lib  # noqa: PLW0603
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        msg = (
+            f"{_LIB_PATH} not found: build it with `python -m slate_quantum_b200.build` "
+            "(nvcc, sm_100a). slate_quantum_b200 has no CPU fallback."
+        )
+        raise SlateB200Error(msg)
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    ip = POINTER(c_int)
+    dp = POINTER(c_double)
+    lib.sqb_abi_version.restype = c_int
+    lib.sqb_abi_version.argtypes = []
+    lib.sqb_error_string.restype = c_char_p
+    lib.sqb_error_string.argtypes = [c_int]
+    lib.sqb_bloch_build.restype = c_int
+    lib.sqb_bloch_build.argtypes = [c_int, ip, ip, dp, c_void_p, c_double, c_double, c_int64, c_int64, c_void_p, c_void_p]
+    lib.sqb_bloch_kinetic.restype = c_int
+    lib.sqb_bloch_kinetic.argtypes = [c_int, ip, ip, dp, c_double, c_double, c_int64, c_int64, c_void_p, c_void_p]
+    lib.sqb_bloch_permute.restype = c_int
+    lib.sqb_bloch_permute.argtypes = [c_int, ip, ip, c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.sqb_fft_workspace_bytes.restype = c_size_t
+    lib.sqb_fft_workspace_bytes.argtypes = [c_int, ip, c_int64]
+    lib.sqb_fft_c2c.restype = c_int
+    lib.sqb_fft_c2c.argtypes = [c_int, ip, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_fft_axis.restype = c_int
+    lib.sqb_fft_axis.argtypes = [c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_eigh_workspace_bytes.restype = c_size_t
+    lib.sqb_eigh_workspace_bytes.argtypes = [c_int, c_int64]
+    lib.sqb_eigh_batched.restype = c_int
+    lib.sqb_eigh_batched.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_project.restype = c_int
+    lib.sqb_project.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sqb_evolve_eigen.restype = c_int
+    lib.sqb_evolve_eigen.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]
+    lib.sqb_evolve_bloch.restype = c_int
+    lib.sqb_evolve_bloch.argtypes = [
+        c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_int64, c_void_p,
+    ]
+    lib.sqb_peak_dmma.restype = c_int
+    lib.sqb_peak_dmma.argtypes = [c_int64, c_void_p, dp, c_void_p]
+    lib.sqb_peak_dfma.restype = c_int
+    lib.sqb_peak_dfma.argtypes = [c_int64, c_void_p, dp, c_void_p]
+    _lib = lib
+    return lib
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().sqb_error_string(code).decode()
+        raise SlateB200Error(f"{what} failed with status {code}: {msg}")
+
+
+def int_array(values) -> ctypes.Array:
+    vals = [int(v) for v in values]
+    return (c_int * len(vals))(*vals)
+
+
+def double_array(values) -> ctypes.Array:
+    vals = [float(v) for v in values]
+    return (c_double * len(vals))(*vals)

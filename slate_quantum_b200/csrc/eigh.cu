@@ -1,0 +1,595 @@
+// K2: batched complex128 Hermitian eigensolver for the Bloch k-blocks.
+//
+// Replaces np.linalg.eigh per block (slate_core.linalg.into_diagonal_hermitian, call site
+// slate_quantum/operator/_linalg.py:56).  Four kernels per chunk of matrices:
+//
+//   (1) tridiag_kernel     one CTA per matrix.  Householder reduction H -> real symmetric tridiagonal T
+//                          (LAPACK zhetd2 recurrences, lower/column form) carried out in the column-major
+//                          view of the row-major input, i.e. on conj(H).  The rank-2 update of step i-1 is
+//                          deferred and fused with the matrix-vector product of step i, so every step
+//                          streams the trailing block exactly once (16 B read + 16 B write per element);
+//                          the block lives in L2.  Reflectors go to workspace Y, so A is dead afterwards.
+//   (2) ql_kernel          one warp per matrix.  Implicit-shift QL (EISPACK imtql2 recurrences) on (d, e):
+//                          latency-bound scalar chain run by lane 0 for thousands of matrices at once; the
+//                          Givens rotations are RECORDED (c, s) instead of applied.  Also ranks eigenvalues.
+//   (3) replay_kernel      one warp per (matrix, 32-row strip).  Replays the recorded rotations on a strip of
+//                          the identity held in shared memory (rows are independent) -> real eigenvectors
+//                          Q_T of T, written with columns in ascending-eigenvalue order.
+//   (4) backtransform_kernel  one warp per 2 eigenvectors, vector in registers.  Applies the n-1 Householder
+//                          reflectors, conjugates (undoing the conj(H) view) and writes rows = eigenvectors
+//                          into A.
+//
+// The algorithm is modelled step by step in tests/eigh_model.py (numpy).
+#include <math.h>
+
+#include "sqb_common.cuh"
+
+namespace {
+
+constexpr int kMaxN = 512;
+constexpr int kQlMaxIter = 60;
+
+__host__ __device__ inline int64_t rot_capacity(int n) { return (int64_t)5 * n * n / 2 + 64 * (int64_t)n + 64; }
+__host__ __device__ inline int sweep_capacity(int n) { return 8 * n + 64; }
+
+struct EighWs {  // per-chunk workspace pointers (each array is [chunk, ...])
+  double* d;      // [chunk, n]
+  double* e;      // [chunk, n]
+  c128* tau;      // [chunk, n]
+  int* rank;      // [chunk, n]
+  int* nsweeps;   // [chunk]
+  int4* sweeps;   // [chunk, sweep_capacity]  {l, m, count, offset}
+  double2* rot;   // [chunk, rot_capacity]    {c, s}
+  c128* y;        // [chunk, n, n]  reflector i at y[i*n + r]
+  double* qt;     // [chunk, n, n]  qt[e*n + k]
+};
+
+// ------------------------------------------------------------------------------------------------
+// block-wide sum of a double over `nthreads` (multiple of 32) threads; result broadcast to all.
+// scratch: >= 33 doubles of shared memory.  Contains two __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double* scratch, int nwarps) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nwarps ? scratch[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1) Householder tridiagonalisation.  Threads = 256*RG; warp w: row group rg = w % RG, column group
+// cg = w / RG (8 column groups).  Lane rows: r = (c*RG + rg)*32 + lane, c < NR.
+template <int NR, int RG>
+__global__ void __launch_bounds__(256 * RG)
+tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
+  constexpr int kThreads = 256 * RG;
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ double smem_d[];
+  c128* vo = reinterpret_cast<c128*>(smem_d);  // pending update vectors (rows >= i)
+  c128* wo = vo + n;
+  c128* vn = wo + n;                            // new reflector
+  c128* red = vn + n;                           // [8][n] partial A22*v sums per column group
+  double* scratch = reinterpret_cast<double*>(red + 8 * n);  // [40]
+  // scalars: scratch[34..39]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp % RG, cg = warp / RG;
+  const int64_t b = blockIdx.x;
+  c128* A = A_all + b * (int64_t)n * n;
+  c128* Y = ws.y + b * (int64_t)n * n;
+  double* dd = ws.d + b * n;
+  double* ee = ws.e + b * n;
+  c128* tt = ws.tau + b * n;
+
+  for (int r = tid; r < n; r += kThreads) {
+    vo[r] = make_double2(0.0, 0.0);
+    wo[r] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+
+  for (int i = 0; i < n - 1; ++i) {
+    // ---- phase A: materialise column i (rows >= i); one row per thread (kThreads >= n)
+    const int r = tid;
+    c128 colv = make_double2(0.0, 0.0);
+    double part = 0.0;
+    if (r >= i && r < n) {
+      const c128 cw = cconj(wo[i]), cv = cconj(vo[i]);
+      c128 a = A[(int64_t)i * n + r];
+      a = csub(a, cmul(vo[r], cw));
+      a = csub(a, cmul(wo[r], cv));
+      colv = a;
+      if (r >= i + 2) part = a.x * a.x + a.y * a.y;
+      if (r == i) dd[i] = a.x;
+      if (r == i + 1) {
+        scratch[34] = a.x;
+        scratch[35] = a.y;
+      }
+    }
+    const double xnorm2 = block_sum(part, scratch, kWarps);  // also publishes scratch[34..35]
+    const double ar = scratch[34], ai = scratch[35];
+    // every thread computes the same scalars (cheaper than another broadcast round)
+    double beta, tau_r, tau_i;
+    c128 scal;
+    if (xnorm2 == 0.0 && ai == 0.0) {
+      beta = ar;
+      tau_r = 0.0;
+      tau_i = 0.0;
+      scal = make_double2(0.0, 0.0);
+    } else {
+      beta = -copysign(sqrt(ar * ar + ai * ai + xnorm2), ar);
+      tau_r = (beta - ar) / beta;
+      tau_i = -ai / beta;
+      // scal = 1 / (alpha - beta)
+      const double pr = ar - beta, pi = ai;
+      const double den = pr * pr + pi * pi;
+      scal = make_double2(pr / den, -pi / den);
+    }
+    const c128 tau = make_double2(tau_r, tau_i);
+    if (r < n) {
+      c128 v = make_double2(0.0, 0.0);
+      if (r == i + 1) v = make_double2(1.0, 0.0);
+      else if (r >= i + 2) v = cmul(colv, scal);
+      vn[r] = v;
+      if (r >= i + 1) Y[(int64_t)i * n + r] = v;
+    }
+    if (tid == 0) {
+      ee[i] = beta;
+      tt[i] = tau;
+    }
+    __syncthreads();
+
+    // ---- phase B: apply pending update to trailing block, accumulate A22 * vn
+    c128 acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = make_double2(0.0, 0.0);
+    {
+      const int lo = i + 1;
+      int j = lo + cg;
+      c128 cur[NR], nxt[NR];
+      int rows[NR];
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        rows[c] = (c * RG + rg) * 32 + lane;
+        cur[c] = make_double2(0.0, 0.0);
+        if (j < n && rows[c] >= lo && rows[c] < n) cur[c] = A[(int64_t)j * n + rows[c]];
+      }
+      for (; j < n; j += 8) {
+        const int jn = j + 8;
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          nxt[c] = make_double2(0.0, 0.0);
+          if (jn < n && rows[c] >= lo && rows[c] < n) nxt[c] = A[(int64_t)jn * n + rows[c]];
+        }
+        const c128 cw = cconj(wo[j]), cv = cconj(vo[j]), vj = vn[j];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          if (rows[c] >= lo && rows[c] < n) {
+            c128 a = cur[c];
+            a = csub(a, cmul(vo[rows[c]], cw));
+            a = csub(a, cmul(wo[rows[c]], cv));
+            A[(int64_t)j * n + rows[c]] = a;
+            cfma(acc[c], a, vj);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NR; ++c) cur[c] = nxt[c];
+      }
+#pragma unroll
+      for (int c = 0; c < NR; ++c)
+        if (rows[c] < n) red[cg * n + rows[c]] = acc[c];
+    }
+    __syncthreads();
+
+    // ---- p = tau * A22 vn ; w = p - (tau/2)(p^H vn) vn
+    c128 p = make_double2(0.0, 0.0);
+    double dr = 0.0, di = 0.0;
+    if (r >= i + 1 && r < n) {
+      c128 s = red[r];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) s = cadd(s, red[g * n + r]);
+      p = cmul(tau, s);
+      const c128 v = vn[r];
+      // conj(p) * v
+      dr = p.x * v.x + p.y * v.y;
+      di = p.x * v.y - p.y * v.x;
+    }
+    const double dot_r = block_sum(dr, scratch, kWarps);
+    const double dot_i = block_sum(di, scratch, kWarps);
+    if (r < n) {
+      // alpha2 = -0.5 * tau * dot
+      const c128 al = cscale(cmul(tau, make_double2(dot_r, dot_i)), -0.5);
+      c128 w = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+      if (r >= i + 1) {
+        v = vn[r];
+        w = cadd(p, cmul(al, v));
+      }
+      vo[r] = v;
+      wo[r] = w;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int l = n - 1;
+    c128 a = A[(int64_t)l * n + l];
+    a = csub(a, cmul(vo[l], cconj(wo[l])));
+    a = csub(a, cmul(wo[l], cconj(vo[l])));
+    dd[l] = a.x;
+    ee[l] = 0.0;
+    tt[l] = make_double2(0.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2) implicit QL with recorded rotations; one warp per matrix.
+__global__ void __launch_bounds__(32)
+ql_kernel(int n, int64_t count, EighWs ws, double* __restrict__ w_out, int* __restrict__ info) {
+  extern __shared__ double smem_d[];
+  double* d = smem_d;            // [n]
+  double* e = d + n;             // [n]
+  double2* rbuf = reinterpret_cast<double2*>(e + n + (n & 1));  // [n]
+  const int lane = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  if (b >= count) return;
+  const double* dg = ws.d + b * n;
+  const double* eg = ws.e + b * n;
+  for (int i = lane; i < n; i += 32) {
+    d[i] = dg[i];
+    e[i] = eg[i];
+  }
+  __syncwarp();
+  if (lane == 0) e[n - 1] = 0.0;
+  __syncwarp();
+
+  double2* rot = ws.rot + b * rot_capacity(n);
+  int4* sweeps = ws.sweeps + b * (int64_t)sweep_capacity(n);
+  const int64_t rcap = rot_capacity(n);
+  const int scap = sweep_capacity(n);
+  int64_t nrot = 0;
+  int nsw = 0;
+  int fails = 0;
+  const double eps = 2.220446049250313e-16;
+
+  for (int l = 0; l < n; ++l) {
+    int iter = 0;
+    while (true) {
+      // warp-parallel search for the first negligible off-diagonal at or after l
+      int m = n - 1;
+      for (int base = l; base < n - 1; base += 32) {
+        const int idx = base + lane;
+        bool small = false;
+        if (idx < n - 1) {
+          const double ddv = fabs(d[idx]) + fabs(d[idx + 1]);
+          small = fabs(e[idx]) <= eps * ddv;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, small);
+        if (mask) {
+          m = base + __ffs(mask) - 1;
+          break;
+        }
+      }
+      if (m == l) break;
+      if (iter == kQlMaxIter) {
+        ++fails;
+        break;
+      }
+      ++iter;
+      int cnt = 0;
+      if (lane == 0) {
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i = m - 1;
+        bool underflow = false;
+        for (; i >= l; --i) {
+          const double ei = e[i];
+          const double f = s * ei;
+          const double bb = c * ei;
+          r = sqrt(f * f + g * g);
+          e[i + 1] = r;
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            underflow = true;
+            break;
+          }
+          const double rinv = 1.0 / r;
+          s = f * rinv;
+          c = g * rinv;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * bb;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - bb;
+          rbuf[cnt++] = make_double2(c, s);
+        }
+        if (!underflow) {
+          d[l] -= p;
+          e[l] = g;
+          e[m] = 0.0;
+        }
+      }
+      cnt = __shfl_sync(0xffffffffu, cnt, 0);
+      __syncwarp();
+      // flush this sweep's rotations (coalesced) and its header
+      if (nsw < scap && nrot + cnt <= rcap) {
+        for (int k = lane; k < cnt; k += 32) rot[nrot + k] = rbuf[k];
+        if (lane == 0) sweeps[nsw] = make_int4(l, m, cnt, (int)nrot);
+        nrot += cnt;
+        ++nsw;
+      } else {
+        fails = n + 1;  // out of rotation storage
+      }
+      __syncwarp();
+    }
+  }
+  // rank eigenvalues (ascending, stable) and emit sorted
+  int* rank = ws.rank + b * n;
+  double* wo = w_out + b * n;
+  bool bad = false;
+  for (int j = lane; j < n; j += 32) {
+    const double dj = d[j];
+    if (!(dj == dj)) bad = true;
+    int rk = 0;
+    for (int k = 0; k < n; ++k) {
+      const double dk = d[k];
+      rk += (dk < dj) || (dk == dj && k < j);
+    }
+    rank[j] = rk;
+    wo[rk] = dj;
+  }
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    ws.nsweeps[b] = nsw;
+    info[b] = anybad ? n + 2 : fails;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (3) rotation replay on a 32-row strip of the identity; one warp per (strip, matrix).
+constexpr int kRotWindow = 64;
+
+__global__ void __launch_bounds__(32)
+replay_kernel(int n, EighWs ws) {
+  extern __shared__ double smem_d[];
+  double* zs = smem_d;  // [n][32]  zs[col*32 + lane]
+  __shared__ double2 win[2][kRotWindow];
+  const int lane = threadIdx.x;
+  const int r0 = blockIdx.x * 32;
+  const int64_t b = blockIdx.y;
+  const double2* rot = ws.rot + b * rot_capacity(n);
+  const int4* sweeps = ws.sweeps + b * (int64_t)sweep_capacity(n);
+  const int nsw = ws.nsweeps[b];
+  const int* rank = ws.rank + b * n;
+  double* qt = ws.qt + b * (int64_t)n * n;
+
+  for (int col = 0; col < n; ++col) zs[col * 32 + lane] = (col == r0 + lane) ? 1.0 : 0.0;
+  __syncwarp();
+
+  // total rotations
+  int64_t total = 0;
+  if (nsw > 0) {
+    const int4 last = sweeps[nsw - 1];
+    total = (int64_t)last.w + last.z;
+  }
+  // window prefetch: win[buf] holds rotations [wbase, wbase + kRotWindow)
+  int64_t wbase = 0;
+  int buf = 0;
+  for (int k = lane; k < kRotWindow; k += 32) win[0][k] = (k < total) ? rot[k] : make_double2(1.0, 0.0);
+  double2 pre[kRotWindow / 32];
+#pragma unroll
+  for (int q = 0; q < kRotWindow / 32; ++q) {
+    const int64_t idx = kRotWindow + q * 32 + lane;
+    pre[q] = idx < total ? rot[idx] : make_double2(1.0, 0.0);
+  }
+  __syncwarp();
+
+  for (int sw = 0; sw < nsw; ++sw) {
+    const int4 h = sweeps[sw];
+    const int m = h.y, cnt = h.z;
+    const int64_t off = h.w;
+    double carry = zs[m * 32 + lane];
+    int i = m - 1;
+    for (int k = 0; k < cnt; ++k, --i) {
+      const int64_t idx = off + k;
+      if (idx >= wbase + kRotWindow) {
+        // rotate windows: publish prefetched, fetch the one after
+        buf ^= 1;
+        wbase += kRotWindow;
+#pragma unroll
+        for (int q = 0; q < kRotWindow / 32; ++q) win[buf][q * 32 + lane] = pre[q];
+#pragma unroll
+        for (int q = 0; q < kRotWindow / 32; ++q) {
+          const int64_t nidx = wbase + kRotWindow + q * 32 + lane;
+          pre[q] = nidx < total ? rot[nidx] : make_double2(1.0, 0.0);
+        }
+        __syncwarp();
+      }
+      const double2 cs = win[buf][idx - wbase];
+      const double zi = zs[i * 32 + lane];
+      zs[(i + 1) * 32 + lane] = fma(cs.y, zi, cs.x * carry);
+      carry = fma(-cs.y, carry, cs.x * zi);
+    }
+    zs[(i + 1) * 32 + lane] = carry;
+  }
+  __syncwarp();
+  if (r0 + lane < n) {
+    for (int col = 0; col < n; ++col) qt[(int64_t)rank[col] * n + r0 + lane] = zs[col * 32 + lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (4) Householder back-transformation.  Warp = 2 eigenvectors; lane: kg = lane & 15 owns components
+// k = kk*LPE + kg (kk < KPT) of eigenvector e, all in registers (LPE = 16 lanes per eigenvector, 32 for n > 256).
+template <int KPT, int LPE>
+__global__ void __launch_bounds__(256)
+backtransform_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kg = lane % LPE;
+  const int e = (blockIdx.x * 8 + warp) * (32 / LPE) + (lane / LPE);
+  const int64_t b = blockIdx.y;
+  const c128* Y = ws.y + b * (int64_t)n * n;
+  const c128* tau = ws.tau + b * n;
+  const double* qt = ws.qt + b * (int64_t)n * n;
+  c128* out = A_all + b * (int64_t)n * n;
+  const bool valid = e < n;
+
+  c128 z[KPT];
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk) {
+    const int k = kk * LPE + kg;
+    z[kk] = make_double2((valid && k < n) ? qt[(int64_t)e * n + k] : 0.0, 0.0);
+  }
+  // reflectors n-2 .. 0 ; reflector i touches rows >= i+1.  Group by q = (i+1)/16 so that the chunk loop
+  // [q, KPT) has compile-time bounds (registers stay statically indexed).
+#pragma unroll
+  for (int q = KPT - 1; q >= 0; --q) {
+    int i_hi = min(n - 2, q * LPE + LPE - 2);  // i+1 <= q*LPE + LPE-1
+    int i_lo = max(0, q * LPE - 1);            // i+1 >= q*LPE
+    for (int i = i_hi; i >= i_lo; --i) {
+      const c128 t = tau[i];
+      if (t.x == 0.0 && t.y == 0.0) continue;
+      const c128* yi = Y + (int64_t)i * n;
+      c128 v[KPT];
+      c128 dot = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int kk = q; kk < KPT; ++kk) {
+        const int k = kk * LPE + kg;
+        v[kk] = (k >= i + 1 && k < n) ? yi[k] : make_double2(0.0, 0.0);
+        cfmac(dot, v[kk], z[kk]);
+      }
+#pragma unroll
+      for (int o = LPE / 2; o > 0; o >>= 1) {
+        dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o);
+        dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
+      }
+      const c128 s = cmul(t, dot);
+      const c128 ms = make_double2(-s.x, -s.y);
+#pragma unroll
+      for (int kk = q; kk < KPT; ++kk) cfma(z[kk], v[kk], ms);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk) {
+      const int k = kk * LPE + kg;
+      if (k < n) out[(int64_t)e * n + k] = cconj(z[kk]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t per_matrix_bytes(int n) {
+  size_t s = 0;
+  s += align_up((size_t)n * 8, 256) * 2;                       // d, e
+  s += align_up((size_t)n * 16, 256);                          // tau
+  s += align_up((size_t)n * 4, 256);                           // rank
+  s += 256;                                                    // nsweeps (amortised)
+  s += align_up((size_t)sweep_capacity(n) * 16, 256);          // sweeps
+  s += align_up((size_t)rot_capacity(n) * 16, 256);            // rot
+  s += align_up((size_t)n * n * 16, 256);                      // y
+  s += align_up((size_t)n * n * 8, 256);                       // qt
+  return s;
+}
+
+void carve(EighWs& ws, void* base, int n, int64_t chunk) {
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t bytes_per, int64_t cnt) {
+    char* r = p;
+    p += align_up(bytes_per * (size_t)cnt, 256);
+    return r;
+  };
+  ws.d = reinterpret_cast<double*>(take((size_t)n * 8, chunk));
+  ws.e = reinterpret_cast<double*>(take((size_t)n * 8, chunk));
+  ws.tau = reinterpret_cast<c128*>(take((size_t)n * 16, chunk));
+  ws.rank = reinterpret_cast<int*>(take((size_t)n * 4, chunk));
+  ws.nsweeps = reinterpret_cast<int*>(take(4, chunk));
+  ws.sweeps = reinterpret_cast<int4*>(take((size_t)sweep_capacity(n) * 16, chunk));
+  ws.rot = reinterpret_cast<double2*>(take((size_t)rot_capacity(n) * 16, chunk));
+  ws.y = reinterpret_cast<c128*>(take((size_t)n * n * 16, chunk));
+  ws.qt = reinterpret_cast<double*>(take((size_t)n * n * 8, chunk));
+}
+
+template <int NR, int RG>
+int launch_tridiag(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st) {
+  const size_t smem = (size_t)(3 + 8) * n * sizeof(c128) + 40 * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(tridiag_kernel<NR, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  tridiag_kernel<NR, RG><<<(unsigned)count, 256 * RG, smem, st>>>(n, A, ws);
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+template <int KPT, int LPE>
+int launch_back(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st) {
+  const int per_cta = 8 * (32 / LPE);
+  dim3 grid((unsigned)((n + per_cta - 1) / per_cta), (unsigned)count);
+  backtransform_kernel<KPT, LPE><<<grid, 256, 0, st>>>(n, A, ws);
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t sqb_eigh_workspace_bytes(int n, int64_t batch) {
+  if (n < 1 || n > kMaxN || batch < 0) return 0;
+  // recommended: whole batch in one chunk up to 8192 matrices (the QL stage is latency bound, so it wants
+  // thousands of matrices in flight); sqb_eigh_batched accepts anything >= one matrix' worth.
+  const int64_t chunk = batch < 8192 ? (batch < 1 ? 1 : batch) : 8192;
+  return per_matrix_bytes(n) * (size_t)chunk + 4096;
+}
+
+extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* info, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (n < 1 || batch < 0 || !A_inout || !w || !info) return SQB_E_BADARG;
+  if (n > kMaxN) return SQB_E_UNSUPPORTED;
+  if (batch == 0) return SQB_OK;
+  const size_t per = per_matrix_bytes(n);
+  if (!workspace || workspace_bytes < per + 4096) return SQB_E_WORKSPACE;
+  int64_t chunk = (int64_t)((workspace_bytes - 4096) / per);
+  if (chunk > batch) chunk = batch;
+  if (chunk > 65535) chunk = 65535;  // grid.y limit of the strip kernels
+  cudaStream_t st = sqb_stream(stream);
+  c128* A = reinterpret_cast<c128*>(A_inout);
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+
+  {
+    cudaError_t e = cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 32 * 8);
+    if (e != cudaSuccess) return (int)e;
+  }
+  for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+    const int64_t cnt = sqb_min64(chunk, batch - b0);
+    EighWs ws;
+    carve(ws, base, n, chunk);
+    c128* Ab = A + b0 * (int64_t)n * n;
+    int rc;
+    if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, st);
+    else if (n <= 64) rc = launch_tridiag<2, 1>(n, cnt, Ab, ws, st);
+    else if (n <= 128) rc = launch_tridiag<4, 1>(n, cnt, Ab, ws, st);
+    else if (n <= 256) rc = launch_tridiag<8, 1>(n, cnt, Ab, ws, st);
+    else rc = launch_tridiag<8, 2>(n, cnt, Ab, ws, st);
+    if (rc) return rc;
+
+    const size_t ql_smem = (size_t)(2 * n + 2) * 8 + (size_t)n * 16;
+    ql_kernel<<<(unsigned)cnt, 32, ql_smem, st>>>(n, cnt, ws, w + b0 * n, info + b0);
+    SQB_LAUNCH_CHECK();
+
+    dim3 rgrid((unsigned)((n + 31) / 32), (unsigned)cnt);
+    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8, st>>>(n, ws);
+    SQB_LAUNCH_CHECK();
+
+    if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, st);
+    else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, st);
+    else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, st);
+    else if (n <= 384) rc = launch_back<12, 32>(n, cnt, Ab, ws, st);
+    else rc = launch_back<16, 32>(n, cnt, Ab, ws, st);
+    if (rc) return rc;
+  }
+  return SQB_OK;
+}

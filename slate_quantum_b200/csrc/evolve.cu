@@ -1,0 +1,280 @@
+// K3: eigenbasis projection, phase evolution and back-transformation.
+//
+//   sqb_project       c[b,e] = sum_k conj(V_b[e,k]) psi[b,k]                  (HBM bound: reads V once)
+//   sqb_evolve_eigen  a[t,i] = c[i] exp(-1j * w[i] * t / hbar)                (materialises the reference's
+//                                                                              return value, schrodinger.py:51-53)
+//   sqb_evolve_bloch  out[t,b,k] = sum_e (c[b,e] exp(-1j w[b,e] t/hbar)) V_b[e,k]
+//                     batched complex GEMM [T x n] x [n x n] per k-block on the FP64 tensor cores
+//                     (DMMA.8x8x4 through mma.sync.m8n8k4.f64; 4 real MMAs per complex MAC tile).
+//                     The A operand (phases) is GENERATED in shared memory by the CTA - the [T, M]
+//                     eigenbasis array is never written or read - and the B operand (eigenvectors) is
+//                     staged by 1-D bulk TMA copies (cp.async.bulk + mbarrier), double buffered.
+//
+// Reference: slate_quantum/dynamics/schrodinger.py:31-56; ExplicitUnitaryBasis conversions reached from
+// state/_state.py:37-43 (projection) and :153-165 (back-transform).
+#include <math.h>
+
+#include "sqb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// projection: one warp per (b, e) row
+__global__ void __launch_bounds__(256)
+project_kernel(int n, int64_t rows, const c128* __restrict__ V, const c128* __restrict__ psi, c128* __restrict__ c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t b = row / n;
+  const c128* v = V + row * n;
+  const c128* p = psi + b * n;
+  c128 acc = make_double2(0.0, 0.0);
+  for (int k = lane; k < n; k += 32) cfmac(acc, v[k], p[k]);
+  acc.x = warp_sum(acc.x);
+  acc.y = warp_sum(acc.y);
+  if (lane == 0) c[row] = acc;
+}
+
+// literal phase of dynamics/schrodinger.py:51-53: exp(-1j * E * t / hbar) with E real-valued complex128
+__device__ __forceinline__ c128 phase_factor(double w, double t, double hbar) {
+  const double theta = -((w * t) / hbar);
+  double s, c;
+  sincos(theta, &s, &c);
+  return make_double2(c, s);
+}
+
+__global__ void __launch_bounds__(256)
+evolve_eigen_kernel(int64_t m, const double* __restrict__ w, const c128* __restrict__ c, const double* __restrict__ times,
+                    int64_t n_times, double hbar, c128* __restrict__ out) {
+  const int64_t total = m * n_times;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = g / m, i = g - t * m;
+    out[g] = cmul(c[i], phase_factor(w[i], times[t], hbar));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused phase x eigenvector GEMM
+constexpr int TM = 64;    // times per CTA tile
+constexpr int TN = 128;   // components per CTA tile
+constexpr int KC = 16;    // eigen-index chunk
+constexpr int LDA = KC + 4;   // complex elements; == 4 (mod 8) -> conflict-free 16 B fragment loads
+constexpr int LDB = TN + 2;   // == 2 (mod 8)
+constexpr int kGemmThreads = 256;
+constexpr size_t kGemmSmem = (size_t)2 * (TM * LDA + KC * LDB) * sizeof(c128) + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+evolve_bloch_kernel(int n, const c128* __restrict__ V, const double* __restrict__ w, const c128* __restrict__ coef,
+                    const double* __restrict__ times, int64_t t_count, double hbar, c128* __restrict__ out,
+                    int64_t out_row_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c128* As = reinterpret_cast<c128*>(smem_raw);        // [2][TM][LDA]
+  c128* Bs = As + 2 * TM * LDA;                         // [2][KC][LDB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 2 * KC * LDB);  // [2]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = blockIdx.x * TN;
+  const int64_t t0 = (int64_t)blockIdx.y * TM;
+  const int64_t b = blockIdx.z;
+  const c128* Vb = V + b * (int64_t)n * n;
+  const double* wb = w + b * n;
+  const c128* cb = coef + b * n;
+  const int ncols = min(TN, n - p0);
+  const int nchunks = (n + KC - 1) / KC;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // A generation mapping: thread -> (e_local = tid % KC, rows j = tid / KC + 16*q, q < TM/16)
+  const int ge = tid % KC;
+  const int gj = tid / KC;  // 0..15
+  double tj[TM / 16];
+#pragma unroll
+  for (int q = 0; q < TM / 16; ++q) {
+    const int64_t t = t0 + gj + 16 * q;
+    tj[q] = t < t_count ? times[t] : 0.0;
+  }
+
+  auto issue_b = [&](int kc, int s) {
+    // thread 0: bulk copies of the rows e in [kc*KC, kc*KC+KC) that exist; others are zero-filled by all
+    const int e0 = kc * KC;
+    const int nrows = min(KC, n - e0);
+    if (tid == 0) {
+      mbar_expect_tx(&bars[s], (uint32_t)(nrows * ncols * sizeof(c128)));
+      for (int r = 0; r < nrows; ++r)
+        bulk_g2s(Bs + (s * KC + r) * LDB, Vb + (int64_t)(e0 + r) * n + p0, (uint32_t)(ncols * sizeof(c128)), &bars[s]);
+    }
+    if (nrows < KC) {
+      for (int idx = tid; idx < (KC - nrows) * LDB; idx += kGemmThreads)
+        Bs[(s * KC + nrows) * LDB + idx] = make_double2(0.0, 0.0);
+    }
+  };
+  auto gen_a = [&](int kc, int s) {
+    const int e = kc * KC + ge;
+    double we = 0.0;
+    c128 ce = make_double2(0.0, 0.0);
+    if (e < n) {
+      we = wb[e];
+      ce = cb[e];
+    }
+#pragma unroll
+    for (int q = 0; q < TM / 16; ++q) {
+      const int j = gj + 16 * q;
+      c128 v = make_double2(0.0, 0.0);
+      if (e < n && t0 + j < t_count) v = cmul(ce, phase_factor(we, tj[q], hbar));
+      As[(s * TM + j) * LDA + ge] = v;
+    }
+  };
+
+  // warp tile: 32 (t) x 32 (k);  8 warps = 2 (t) x 4 (k)
+  const int wm = (warp & 1) * 32;
+  const int wn = (warp >> 1) * 32;
+  double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      cr[a][c][0] = cr[a][c][1] = 0.0;
+      ci[a][c][0] = ci[a][c][1] = 0.0;
+    }
+
+  issue_b(0, 0);
+  gen_a(0, 0);
+  __syncthreads();
+
+  const int frow = lane >> 2, fcol = lane & 3;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int s = kc & 1;
+    if (kc + 1 < nchunks) {
+      issue_b(kc + 1, s ^ 1);
+      gen_a(kc + 1, s ^ 1);
+    }
+    mbar_wait(&bars[s], (uint32_t)((kc >> 1) & 1));
+    const c128* Asb = As + s * TM * LDA;
+    const c128* Bsb = Bs + s * KC * LDB;
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      c128 af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = Asb[(wm + a * 8 + frow) * LDA + k4 + fcol];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bf[c] = Bsb[(k4 + fcol) * LDB + wn + c * 8 + frow];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double nai = -af[a].y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          dmma(cr[a][c][0], cr[a][c][1], af[a].x, bf[c].x);
+          dmma(ci[a][c][0], ci[a][c][1], af[a].x, bf[c].y);
+          dmma(cr[a][c][0], cr[a][c][1], nai, bf[c].y);
+          dmma(ci[a][c][0], ci[a][c][1], af[a].y, bf[c].x);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: lane holds C[row = frow][cols 2*fcol, 2*fcol+1] of each 8x8 tile
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t t = t0 + wm + a * 8 + frow;
+    if (t >= t_count) continue;
+    c128* orow = out + t * out_row_stride + b * (int64_t)n;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int p = p0 + wn + c * 8 + fcol * 2;
+      if (p < n) orow[p] = make_double2(cr[a][c][0], ci[a][c][0]);
+      if (p + 1 < n) orow[p + 1] = make_double2(cr[a][c][1], ci[a][c][1]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
+                           void* stream) {
+  if (n < 1 || batch < 0 || !transform || !psi || !c) return SQB_E_BADARG;
+  if (batch == 0) return SQB_OK;
+  const int64_t rows = batch * n;
+  const int64_t grid = (rows + 7) / 8;
+  if (grid > 2147483647LL) return SQB_E_UNSUPPORTED;
+  project_kernel<<<(unsigned)grid, 256, 0, sqb_stream(stream)>>>(n, rows, reinterpret_cast<const c128*>(transform),
+                                                                reinterpret_cast<const c128*>(psi),
+                                                                reinterpret_cast<c128*>(c));
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+extern "C" int sqb_evolve_eigen(int64_t m, const double* w, const sqb_c128* c, const double* times, int64_t n_times,
+                                double hbar, sqb_c128* out, void* stream) {
+  if (m < 0 || n_times < 0 || !w || !c || !times || !out || hbar == 0.0) return SQB_E_BADARG;
+  if (m == 0 || n_times == 0) return SQB_OK;
+  const int64_t total = m * n_times;
+  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 32);
+  evolve_eigen_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, reinterpret_cast<const c128*>(c), times, n_times,
+                                                            hbar, reinterpret_cast<c128*>(out));
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
+                                const double* times, int64_t t_count, double hbar, sqb_c128* out,
+                                int64_t out_row_stride, void* stream) {
+  if (n < 1 || batch < 0 || t_count < 0 || !transform || !w || !c || !times || !out || hbar == 0.0 ||
+      out_row_stride < batch * n)
+    return SQB_E_BADARG;
+  if (batch == 0 || t_count == 0) return SQB_OK;
+  cudaError_t e = cudaFuncSetAttribute(evolve_bloch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t t_tiles = (t_count + TM - 1) / TM;
+  if (t_tiles > 65535) return SQB_E_UNSUPPORTED;
+  const unsigned p_tiles = (unsigned)((n + TN - 1) / TN);
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t cnt = sqb_min64(65535, batch - b0);
+    dim3 grid(p_tiles, (unsigned)t_tiles, (unsigned)cnt);
+    evolve_bloch_kernel<<<grid, kGemmThreads, kGemmSmem, sqb_stream(stream)>>>(
+        n, reinterpret_cast<const c128*>(transform) + b0 * (int64_t)n * n, w + b0 * n,
+        reinterpret_cast<const c128*>(c) + b0 * n, times, t_count, hbar, reinterpret_cast<c128*>(out) + b0 * n,
+        out_row_stride);
+    SQB_LAUNCH_CHECK();
+  }
+  return SQB_OK;
+}

@@ -1,0 +1,223 @@
+"""Functional wrappers over the C ABI taking torch CUDA tensors (device-buffer ownership only).
+
+Every function enqueues on torch's current CUDA stream and returns device tensors; nothing here
+computes on the CPU.  Calling without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from slate_quantum_b200 import _lib
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        msg = "slate_quantum_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback."
+        raise _lib.SlateB200Error(msg)
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _c128(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+        msg = f"{name} must be a contiguous CUDA complex128 tensor"
+        raise TypeError(msg)
+    return t
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        msg = f"{name} must be a contiguous CUDA float64 tensor"
+        raise TypeError(msg)
+    return t
+
+
+def to_device(a: np.ndarray | torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device="cuda", dtype=dtype)
+
+
+def bloch_build(
+    shape: Sequence[int],
+    repeat: Sequence[int],
+    dk: np.ndarray,
+    vtable: torch.Tensor,
+    mass: float,
+    hbar: float,
+    block_begin: int = 0,
+    block_count: int | None = None,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """K1: H[b,k,k'] for blocks [block_begin, block_begin+block_count). See include/slate_b200.h."""
+    _require_cuda()
+    lib = _lib.load()
+    nd = len(shape)
+    n = int(np.prod(shape))
+    n_k = int(np.prod(repeat))
+    block_count = n_k - block_begin if block_count is None else block_count
+    _c128(vtable, "vtable")
+    if vtable.numel() != n:
+        msg = "vtable must hold prod(shape) entries"
+        raise ValueError(msg)
+    if out is None:
+        out = torch.empty((block_count, n, n), dtype=torch.complex128, device="cuda")
+    _c128(out, "out")
+    rc = lib.sqb_bloch_build(
+        nd, _lib.int_array(shape), _lib.int_array(repeat), _lib.double_array(np.asarray(dk).ravel()),
+        _ptr(vtable), float(mass), float(hbar), block_begin, block_count, _ptr(out), _stream(),
+    )
+    _lib.check(rc, "sqb_bloch_build")
+    return out
+
+
+def bloch_kinetic(
+    shape: Sequence[int], repeat: Sequence[int], dk: np.ndarray, mass: float, hbar: float,
+    block_begin: int = 0, block_count: int | None = None,
+) -> torch.Tensor:
+    _require_cuda()
+    lib = _lib.load()
+    n = int(np.prod(shape))
+    n_k = int(np.prod(repeat))
+    block_count = n_k - block_begin if block_count is None else block_count
+    out = torch.empty((block_count, n), dtype=torch.complex128, device="cuda")
+    rc = lib.sqb_bloch_kinetic(
+        len(shape), _lib.int_array(shape), _lib.int_array(repeat), _lib.double_array(np.asarray(dk).ravel()),
+        float(mass), float(hbar), block_begin, block_count, _ptr(out), _stream(),
+    )
+    _lib.check(rc, "sqb_bloch_kinetic")
+    return out
+
+
+def bloch_permute(shape: Sequence[int], repeat: Sequence[int], vectors: torch.Tensor, direction: int) -> torch.Tensor:
+    """K5 on the last axis of `vectors` ([..., M]).  direction 0: supercell -> Bloch; 1: Bloch -> supercell."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(vectors, "vectors")
+    m = int(np.prod(shape)) * int(np.prod(repeat))
+    if vectors.shape[-1] != m:
+        msg = f"last axis must have {m} entries"
+        raise ValueError(msg)
+    out = torch.empty_like(vectors)
+    lead = vectors.numel() // m
+    rc = lib.sqb_bloch_permute(
+        len(shape), _lib.int_array(shape), _lib.int_array(repeat), direction, lead, _ptr(vectors), _ptr(out), _stream()
+    )
+    _lib.check(rc, "sqb_bloch_permute")
+    return out
+
+
+def fft_c2c(x: torch.Tensor, dims: Sequence[int], sign: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """K4 over the trailing len(dims) axes of a [batch, prod(dims)]-like tensor, norm="ortho"."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(x, "x")
+    total = int(np.prod(dims))
+    if x.numel() % total:
+        msg = "tensor size is not a multiple of prod(dims)"
+        raise ValueError(msg)
+    batch = x.numel() // total
+    out = torch.empty_like(x) if out is None else _c128(out, "out")
+    dims_c = _lib.int_array(dims)
+    ws_bytes = lib.sqb_fft_workspace_bytes(len(dims), dims_c, batch)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_fft_c2c(len(dims), dims_c, batch, sign, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream())
+    _lib.check(rc, "sqb_fft_c2c")
+    return out
+
+
+def fft_axis(x: torch.Tensor, outer: int, length: int, inner: int, sign: int) -> torch.Tensor:
+    _require_cuda()
+    lib = _lib.load()
+    _c128(x, "x")
+    out = torch.empty_like(x)
+    dims_c = _lib.int_array([length])
+    ws_bytes = lib.sqb_fft_workspace_bytes(1, dims_c, outer * inner)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_fft_axis(outer, length, inner, sign, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream())
+    _lib.check(rc, "sqb_fft_axis")
+    return out
+
+
+def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K2 IN PLACE: `a` [batch,n,n] is overwritten by the transform (rows = eigenvectors).
+
+    Returns (w [batch,n] float64 ascending per block, a, info [batch] int32).
+    """
+    _require_cuda()
+    lib = _lib.load()
+    _c128(a, "a")
+    batch, n, n2 = a.shape
+    if n != n2:
+        msg = "matrices must be square"
+        raise ValueError(msg)
+    w = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    info = torch.empty((batch,), dtype=torch.int32, device="cuda")
+    if workspace is None:
+        ws_bytes = lib.sqb_eigh_workspace_bytes(n, batch)
+        free, _ = torch.cuda.mem_get_info()
+        ws_bytes = min(ws_bytes, max(int(free * 0.6), lib.sqb_eigh_workspace_bytes(n, 1)))
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_eigh_batched(n, batch, _ptr(a), _ptr(w), _ptr(info), _ptr(workspace), workspace.numel(), _stream())
+    _lib.check(rc, "sqb_eigh_batched")
+    return w, a, info
+
+
+def project(transform: torch.Tensor, psi: torch.Tensor) -> torch.Tensor:
+    _require_cuda()
+    lib = _lib.load()
+    _c128(transform, "transform")
+    _c128(psi, "psi")
+    batch, n, _ = transform.shape
+    c = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+    rc = lib.sqb_project(n, batch, _ptr(transform), _ptr(psi), _ptr(c), _stream())
+    _lib.check(rc, "sqb_project")
+    return c
+
+
+def evolve_eigen(w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float) -> torch.Tensor:
+    _require_cuda()
+    lib = _lib.load()
+    _f64(w, "w")
+    _c128(c, "c")
+    _f64(times, "times")
+    m = w.numel()
+    out = torch.empty((times.numel(), m), dtype=torch.complex128, device="cuda")
+    rc = lib.sqb_evolve_eigen(m, _ptr(w), _ptr(c), _ptr(times), times.numel(), float(hbar), _ptr(out), _stream())
+    _lib.check(rc, "sqb_evolve_eigen")
+    return out
+
+
+def evolve_bloch(
+    transform: torch.Tensor, w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM)."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(transform, "transform")
+    _f64(w, "w")
+    _c128(c, "c")
+    _f64(times, "times")
+    batch, n, _ = transform.shape
+    t_count = times.numel()
+    if out is None:
+        out = torch.empty((t_count, batch * n), dtype=torch.complex128, device="cuda")
+    _c128(out, "out")
+    rc = lib.sqb_evolve_bloch(
+        n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), batch * n, _stream()
+    )
+    _lib.check(rc, "sqb_evolve_bloch")
+    return out

@@ -1,0 +1,257 @@
+"""Parity of every CUDA kernel (through the C ABI) against the CPU oracle.  All tests need a B200."""
+
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import bloch_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+HBAR = o.HBAR_SI
+SHAPES_1D = [(x,) for x in [3, 5]]
+SHAPES_2D = [*itertools.product([3, 4], [3, 4]), (5, 5)]
+REF_GRID = [*itertools.product(SHAPES_1D, SHAPES_1D), *itertools.product(SHAPES_2D, SHAPES_2D)]
+
+
+def _gpu():
+    import torch
+
+    from slate_quantum_b200 import kernels
+
+    return torch, kernels
+
+
+def _build_gpu(delta_x, shape, comps, mass, repeat, hbar=HBAR, **kw):
+    torch, kernels = _gpu()
+    table = kernels.to_device(o.pad_components(shape, comps).ravel(), torch.complex128)
+    h = kernels.bloch_build(shape, repeat, o.stacked_dk(delta_x), table, mass, hbar, **kw)
+    return h
+
+
+# ---------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize(("shape", "repeat"), REF_GRID)
+@pytest.mark.parametrize("kind", ["cos1", "cos0", "sin"])
+def test_bloch_build_reference_grid(cuda, shape, repeat, kind):
+    """tests/test_bloch.py:16-47 / 50-86 shapes; tolerance = the reference's own (1e-14 / 1e-15)."""
+    nd = len(shape)
+    dx = 2 * np.pi * np.eye(nd)
+    comps = {
+        "cos1": o.cos_potential_components(shape, 1.0),
+        "cos0": o.cos_potential_components(shape, 0.0),
+        "sin": o.sin_potential_components(shape, 0.7, 0.1),
+    }[kind]
+    got = _build_gpu(dx, shape, comps, HBAR**2, repeat).cpu().numpy()
+    want = o.bloch_blocks(dx, shape, comps, HBAR**2, repeat)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-14)
+    # and against the dense supercell Hamiltonian, as the reference test does
+    full = o.supercell_hamiltonian(dx, shape, comps, HBAR**2, repeat)
+    np.testing.assert_allclose(o.embed_blocks(got, shape, repeat), full, rtol=0, atol=1e-14)
+
+
+def test_bloch_build_hexagonal_quirk_q1(cuda):
+    """Non-orthogonal lattice: the literal Cartesian-row wrap of _hamiltonian.py:87-93 (quirk Q1)."""
+    dx = 2 * np.pi * np.array([[np.sin(np.pi / 3), np.cos(np.pi / 3)], [0.0, 1.0]])
+    shape, repeat = (6, 4), (5, 4)
+    comps = o.fcc_potential_components(shape, 10.0)
+    got = _build_gpu(dx, shape, comps, HBAR**2, repeat).cpu().numpy()
+    want = o.bloch_blocks(dx, shape, comps, HBAR**2, repeat)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-14 * scale)
+
+
+def test_bloch_build_block_range_and_3d(cuda):
+    dx = 2 * np.pi * np.eye(3)
+    shape, repeat = (3, 4, 5), (2, 3, 2)
+    comps = o.cos_potential_components(shape, 4.0)
+    want = o.bloch_blocks(dx, shape, comps, HBAR**2, repeat)
+    got = _build_gpu(dx, shape, comps, HBAR**2, repeat, block_begin=5, block_count=4).cpu().numpy()
+    np.testing.assert_allclose(got, want[5:9], rtol=0, atol=1e-13)
+    torch, kernels = _gpu()
+    e = kernels.bloch_kinetic(shape, repeat, o.stacked_dk(dx), HBAR**2, HBAR).cpu().numpy()
+    fr = o.sample_fractions(repeat)
+    for b in range(fr.shape[1]):
+        np.testing.assert_allclose(e[b], o.kinetic_energy(dx, shape, HBAR**2, fr[:, b]), rtol=1e-14, atol=1e-14)
+
+
+def test_kinetic_literal(cuda):
+    """tests/test_operator.py:22-28 literal through the CUDA kernel."""
+    torch, kernels = _gpu()
+    e = kernels.bloch_kinetic((5,), (1,), o.stacked_dk(np.array([[2 * np.pi]])), HBAR**2, HBAR).cpu().numpy()
+    np.testing.assert_allclose(e[0], [0.0, 0.5, 2.0, 2.0, 0.5])
+    assert np.all(e.imag == 0)
+
+
+# ---------------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize(("shape", "repeat"), [*REF_GRID, ((3, 4, 5), (2, 3, 4)), ((16,), (7,))])
+def test_bloch_permute(cuda, shape, repeat):
+    torch, kernels = _gpu()
+    m = int(np.prod(shape) * np.prod(repeat))
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(3, m)) + 1j * rng.normal(size=(3, m))
+    vd = kernels.to_device(v, torch.complex128)
+    fwd = kernels.bloch_permute(shape, repeat, vd, 0)
+    np.testing.assert_array_equal(fwd.cpu().numpy(), o.bloch_from_supercell(v, shape, repeat))
+    back = kernels.bloch_permute(shape, repeat, fwd, 1)
+    np.testing.assert_array_equal(back.cpu().numpy(), v)
+    np.testing.assert_array_equal(
+        kernels.bloch_permute(shape, repeat, vd, 1).cpu().numpy(), o.bloch_into_supercell(v, shape, repeat)
+    )
+
+
+# ---------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize(
+    "dims",
+    [(5,), (9,), (12,), (16,), (25,), (64,), (224,), (1024,), (6400,), (3 * 5 * 7 * 11,), (8192,), (131072,),
+     (12, 15), (16, 20), (64, 48), (9, 16, 10), (28, 28, 28), (13 * 4,), (31 * 2,)],
+)
+def test_fft_matches_numpy(cuda, dims):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(2)
+    batch = 3 if np.prod(dims) < 100000 else 1
+    x = rng.normal(size=(batch, *dims)) + 1j * rng.normal(size=(batch, *dims))
+    xd = kernels.to_device(x, torch.complex128)
+    axes = tuple(range(1, 1 + len(dims)))
+    fwd = kernels.fft_c2c(xd, dims, -1).cpu().numpy()
+    np.testing.assert_allclose(fwd, np.fft.fftn(x, axes=axes, norm="ortho"), rtol=0, atol=2e-13)
+    bwd = kernels.fft_c2c(xd, dims, +1).cpu().numpy()
+    np.testing.assert_allclose(bwd, np.fft.ifftn(x, axes=axes, norm="ortho"), rtol=0, atol=2e-13)
+    # in place round trip
+    y = xd.clone()
+    kernels.fft_c2c(y, dims, -1, out=y)
+    kernels.fft_c2c(y, dims, +1, out=y)
+    np.testing.assert_allclose(y.cpu().numpy(), x, rtol=0, atol=2e-13)
+
+
+def test_fft_axis(cuda):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(4, 12, 10)) + 1j * rng.normal(size=(4, 12, 10))
+    xd = kernels.to_device(x, torch.complex128)
+    got = kernels.fft_axis(xd, 4, 12, 10, -1).cpu().numpy()
+    np.testing.assert_allclose(got, np.fft.fft(x, axis=1, norm="ortho"), rtol=0, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------- K2
+def _check_eigh(h, w, t, info):
+    """north_star tolerances: eigenvalues rel 1e-10, residual < 1e-10, projectors."""
+    assert np.all(info == 0), info
+    norm = np.linalg.norm(h, axis=(1, 2))
+    w_ref, t_ref = o.eigh_blocks(h)
+    scale = np.abs(w_ref).max(axis=1, keepdims=True)
+    assert np.all(np.diff(w, axis=1) >= 0)
+    np.testing.assert_allclose(w, w_ref, rtol=1e-10, atol=0) if np.all(np.abs(w_ref) > 1e-3 * scale) else None
+    assert np.max(np.abs(w - w_ref) / np.maximum(scale, 1e-300)) < 1e-10
+    res, orth = o.eigh_residuals(h, w, t)
+    assert res < 1e-10, res
+    assert orth < 1e-10, orth
+    for b in range(min(len(h), 8)):
+        err = o.subspace_projector_error(w_ref[b], t[b], t_ref[b], norm[b])
+        assert err < 1e-8, err
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 16, 33, 64, 100, 128, 200, 256])
+def test_eigh_random_hermitian(cuda, n):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(0)
+    batch = 5
+    g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+    h = g + np.swapaxes(g.conj(), 1, 2)
+    a = kernels.to_device(h, torch.complex128)
+    w, t, info = kernels.eigh_batched(a)
+    _check_eigh(h, w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [343, 512])
+def test_eigh_large_blocks(cuda, n):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(4)
+    g = rng.normal(size=(2, n, n)) + 1j * rng.normal(size=(2, n, n))
+    h = g + np.swapaxes(g.conj(), 1, 2)
+    a = kernels.to_device(h, torch.complex128)
+    w, t, info = kernels.eigh_batched(a)
+    _check_eigh(h, w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy())
+
+
+@pytest.mark.parametrize("height", [0.0, 10.0])
+def test_eigh_bloch_blocks_degenerate(cuda, height):
+    """Free-particle blocks (cos_potential(meta, 0), in the reference tests) have exact +-k degeneracies."""
+    torch, kernels = _gpu()
+    dx = 2 * np.pi * np.eye(2)
+    shape, repeat = (8, 8), (3, 4)
+    comps = o.cos_potential_components(shape, height)
+    hd = _build_gpu(dx, shape, comps, HBAR**2, repeat)
+    h = hd.cpu().numpy()
+    w, t, info = kernels.eigh_batched(hd)
+    _check_eigh(h, w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy())
+
+
+def test_eigh_chunked_workspace(cuda):
+    """A workspace that only holds 3 matrices forces the chunk loop."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200 import _lib
+
+    n, batch = 48, 10
+    rng = np.random.default_rng(5)
+    g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+    h = g + np.swapaxes(g.conj(), 1, 2)
+    a = kernels.to_device(h, torch.complex128)
+    per3 = _lib.load().sqb_eigh_workspace_bytes(n, 3)
+    ws = torch.empty(per3, dtype=torch.uint8, device="cuda")
+    w, t, info = kernels.eigh_batched(a, workspace=ws)
+    _check_eigh(h, w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize(("n", "batch", "n_t"), [(5, 3, 7), (64, 4, 100), (100, 3, 65), (256, 2, 130), (343, 1, 64)])
+def test_project_and_evolve(cuda, n, batch, n_t):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(6)
+    g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+    h = g + np.swapaxes(g.conj(), 1, 2)
+    w_ref, t_ref = o.eigh_blocks(h)
+    psi = rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n))
+    times = np.linspace(0.0, 5.0 * HBAR, n_t)
+    td = kernels.to_device(t_ref, torch.complex128)
+    wd = kernels.to_device(w_ref, torch.float64)
+    c = kernels.project(td, kernels.to_device(psi, torch.complex128))
+    c_ref = o.project(t_ref, psi)
+    np.testing.assert_allclose(c.cpu().numpy(), c_ref, rtol=0, atol=1e-12)
+    timed = kernels.to_device(times, torch.float64)
+    a = kernels.evolve_eigen(wd.reshape(-1), c.reshape(-1), timed, HBAR).cpu().numpy()
+    a_ref = o.evolve_eigenbasis(c_ref, w_ref, times, HBAR)
+    np.testing.assert_allclose(a, a_ref, rtol=0, atol=1e-9)
+    out = kernels.evolve_bloch(td, wd, c, timed, HBAR).cpu().numpy()
+    out_ref = o.back_transform(t_ref, a_ref).reshape(n_t, batch * n)
+    np.testing.assert_allclose(out, out_ref, rtol=0, atol=1e-9)
+
+
+def test_full_pipeline_vs_expm(cuda):
+    """K1 -> K2 -> K4 -> K5 -> K3 -> K5 -> K4 against dense scipy expm of the supercell Hamiltonian."""
+    import scipy.linalg
+
+    torch, kernels = _gpu()
+    dx = 2 * np.pi * np.eye(2)
+    shape, repeat = (4, 3), (3, 4)
+    big = tuple(n * r for n, r in zip(shape, repeat))
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    comps = o.sin_potential_components(shape, 3.0, 0.3)
+    hd = _build_gpu(dx, shape, comps, HBAR**2, repeat)
+    w, t, info = kernels.eigh_batched(hd)
+    assert int(info.abs().sum()) == 0
+    rng = np.random.default_rng(7)
+    psi = rng.normal(size=n * n_k) + 1j * rng.normal(size=n * n_k)
+    psi /= np.linalg.norm(psi)
+    times = np.linspace(0, 3 * HBAR, 9)
+    psid = kernels.to_device(psi, torch.complex128)
+    psik = kernels.fft_c2c(psid.reshape(1, -1), big, -1)
+    psib = kernels.bloch_permute(shape, repeat, psik, 0).reshape(n_k, n)
+    c = kernels.project(t, psib)
+    out = kernels.evolve_bloch(t, w, c, kernels.to_device(times, torch.float64), HBAR)
+    outk = kernels.bloch_permute(shape, repeat, out, 1)
+    outx = kernels.fft_c2c(outk, big, +1).cpu().numpy()
+    hk = o.supercell_hamiltonian(dx, shape, comps, HBAR**2, repeat)
+    hx = o.momentum_matrix_to_position(hk, big)
+    ref = np.array([scipy.linalg.expm(-1j * hx * tt / HBAR) @ psi for tt in times])
+    np.testing.assert_allclose(outx, ref, rtol=0, atol=1e-9)
