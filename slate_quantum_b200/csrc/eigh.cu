@@ -230,7 +230,7 @@ ql_kernel(int n, int64_t count, EighWs ws, double* __restrict__ w_out, int* __re
   extern __shared__ double smem_d[];
   double* d = smem_d;            // [n]
   double* e = d + n;             // [n]
-  double2* rbuf = reinterpret_cast<double2*>(e + n + (n & 1));  // [n]
+  double2* rbuf = reinterpret_cast<double2*>(d + 2 * n);  // [n], 16 B aligned since 2n doubles precede it
   const int lane = threadIdx.x;
   const int64_t b = blockIdx.x;
   if (b >= count) return;

@@ -15,6 +15,19 @@ import torch
 from slate_quantum_b200 import _lib
 
 
+LAUNCHES = 0  # kernels of libslate_b200.so launched through this module (bench.py reports it)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES  # noqa: PLW0603
+    LAUNCHES += n
+
+
+def _fft_launches(dims: Sequence[int]) -> int:
+    # per axis: twiddle-table kernel + pass kernel; lines longer than 4096 take two passes (four-step)
+    return sum(2 if d <= 4096 else 4 for d in dims)
+
+
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         msg = "slate_quantum_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback."
@@ -80,6 +93,7 @@ def bloch_build(
         _ptr(vtable), float(mass), float(hbar), block_begin, block_count, _ptr(out), _stream(),
     )
     _lib.check(rc, "sqb_bloch_build")
+    _count(1)
     return out
 
 
@@ -98,10 +112,13 @@ def bloch_kinetic(
         float(mass), float(hbar), block_begin, block_count, _ptr(out), _stream(),
     )
     _lib.check(rc, "sqb_bloch_kinetic")
+    _count(1)
     return out
 
 
-def bloch_permute(shape: Sequence[int], repeat: Sequence[int], vectors: torch.Tensor, direction: int) -> torch.Tensor:
+def bloch_permute(
+    shape: Sequence[int], repeat: Sequence[int], vectors: torch.Tensor, direction: int, out: torch.Tensor | None = None
+) -> torch.Tensor:
     """K5 on the last axis of `vectors` ([..., M]).  direction 0: supercell -> Bloch; 1: Bloch -> supercell."""
     _require_cuda()
     lib = _lib.load()
@@ -110,12 +127,13 @@ def bloch_permute(shape: Sequence[int], repeat: Sequence[int], vectors: torch.Te
     if vectors.shape[-1] != m:
         msg = f"last axis must have {m} entries"
         raise ValueError(msg)
-    out = torch.empty_like(vectors)
+    out = torch.empty_like(vectors) if out is None else _c128(out, "out")
     lead = vectors.numel() // m
     rc = lib.sqb_bloch_permute(
         len(shape), _lib.int_array(shape), _lib.int_array(repeat), direction, lead, _ptr(vectors), _ptr(out), _stream()
     )
     _lib.check(rc, "sqb_bloch_permute")
+    _count(1)
     return out
 
 
@@ -135,6 +153,7 @@ def fft_c2c(x: torch.Tensor, dims: Sequence[int], sign: int, out: torch.Tensor |
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     rc = lib.sqb_fft_c2c(len(dims), dims_c, batch, sign, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "sqb_fft_c2c")
+    _count(_fft_launches(dims))
     return out
 
 
@@ -148,6 +167,7 @@ def fft_axis(x: torch.Tensor, outer: int, length: int, inner: int, sign: int) ->
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     rc = lib.sqb_fft_axis(outer, length, inner, sign, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "sqb_fft_axis")
+    _count(_fft_launches([length]))
     return out
 
 
@@ -172,6 +192,9 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     rc = lib.sqb_eigh_batched(n, batch, _ptr(a), _ptr(w), _ptr(info), _ptr(workspace), workspace.numel(), _stream())
     _lib.check(rc, "sqb_eigh_batched")
+    per = lib.sqb_eigh_workspace_bytes(n, 1) - 4096
+    chunk = max(1, min(batch, (workspace.numel() - 4096) // per, 65535))
+    _count(4 * -(-batch // chunk))
     return w, a, info
 
 
@@ -184,6 +207,7 @@ def project(transform: torch.Tensor, psi: torch.Tensor) -> torch.Tensor:
     c = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
     rc = lib.sqb_project(n, batch, _ptr(transform), _ptr(psi), _ptr(c), _stream())
     _lib.check(rc, "sqb_project")
+    _count(1)
     return c
 
 
@@ -197,6 +221,7 @@ def evolve_eigen(w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: fl
     out = torch.empty((times.numel(), m), dtype=torch.complex128, device="cuda")
     rc = lib.sqb_evolve_eigen(m, _ptr(w), _ptr(c), _ptr(times), times.numel(), float(hbar), _ptr(out), _stream())
     _lib.check(rc, "sqb_evolve_eigen")
+    _count(1)
     return out
 
 
@@ -220,4 +245,5 @@ def evolve_bloch(
         n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), batch * n, _stream()
     )
     _lib.check(rc, "sqb_evolve_bloch")
+    _count(-(-batch // 65535))
     return out

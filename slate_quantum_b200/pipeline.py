@@ -1,0 +1,111 @@
+"""Device-resident driver of the hot path: K1 build -> K2 eigh -> K4/K5/K3a project -> K3c evolve -> K5/K4.
+
+This is the host-side engine the API mirror (slate_quantum_b200.bloch / operator / dynamics) sits on.
+It owns nothing but torch CUDA tensors and calls the C ABI for every arithmetic step.  A solver instance
+covers a contiguous range of k-blocks, which is how the path shards over GPUs (one process per GPU).
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from slate_quantum_b200 import kernels
+
+
+class BlochSolver:
+    """Bloch Hamiltonian blocks [block_begin, block_begin + block_count) of one periodic system.
+
+    Mirrors the reference call chain bloch.build.kinetic_hamiltonian (bloch/build.py:146-167) ->
+    operator.into_diagonal_hermitian (operator/_linalg.py:45-83) ->
+    dynamics.solve_schrodinger_equation_decomposition (dynamics/schrodinger.py:59-73).
+    """
+
+    def __init__(
+        self,
+        shape: Sequence[int],
+        repeat: Sequence[int],
+        dk: np.ndarray,
+        mass: float,
+        hbar: float,
+        block_begin: int = 0,
+        block_count: int | None = None,
+    ) -> None:
+        self.shape = tuple(int(s) for s in shape)
+        self.repeat = tuple(int(r) for r in repeat)
+        self.dk = np.asarray(dk, dtype=np.float64)
+        self.mass = float(mass)
+        self.hbar = float(hbar)
+        self.n = int(np.prod(self.shape))
+        self.n_k = int(np.prod(self.repeat))
+        self.block_begin = int(block_begin)
+        self.block_count = self.n_k - self.block_begin if block_count is None else int(block_count)
+        self.supercell = tuple(n * r for n, r in zip(self.shape, self.repeat, strict=True))
+        self.m = self.n * self.n_k
+        self.hamiltonian: torch.Tensor | None = None
+        self.eigenvalues: torch.Tensor | None = None
+        self.transform: torch.Tensor | None = None
+        self.info: torch.Tensor | None = None
+        self._eigh_ws: torch.Tensor | None = None
+
+    # ------------------------------------------------------------------ K1
+    def build(self, potential_table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        self.hamiltonian = kernels.bloch_build(
+            self.shape, self.repeat, self.dk, potential_table, self.mass, self.hbar,
+            self.block_begin, self.block_count, out=out,
+        )
+        return self.hamiltonian
+
+    # ------------------------------------------------------------------ K2
+    def diagonalise(self, hamiltonian: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """In place: the Hamiltonian buffer becomes the transform (rows = eigenvectors)."""
+        h = self.hamiltonian if hamiltonian is None else hamiltonian
+        if h is None:
+            msg = "build() first"
+            raise RuntimeError(msg)
+        if self._eigh_ws is None:
+            from slate_quantum_b200 import _lib
+
+            want = _lib.load().sqb_eigh_workspace_bytes(self.n, h.shape[0])
+            free, _ = torch.cuda.mem_get_info()
+            floor = _lib.load().sqb_eigh_workspace_bytes(self.n, 1)
+            self._eigh_ws = torch.empty(max(min(want, int(free * 0.5)), floor), dtype=torch.uint8, device="cuda")
+        w, v, info = kernels.eigh_batched(h, workspace=self._eigh_ws)
+        self.eigenvalues, self.transform, self.info = w, v, info
+        self.hamiltonian = None
+        return w, v
+
+    def release_workspace(self) -> None:
+        self._eigh_ws = None
+
+    # ------------------------------------------------------------------ K4 + K5 + K3a
+    def to_bloch(self, psi_position: torch.Tensor) -> torch.Tensor:
+        """Position-basis state(s) over the whole supercell [.., M] -> Bloch order [.., n_k, N]."""
+        flat = psi_position.reshape(-1, self.m)
+        psi_k = kernels.fft_c2c(flat, self.supercell, -1)
+        return kernels.bloch_permute(self.shape, self.repeat, psi_k, 0).reshape(-1, self.n_k, self.n)
+
+    def project(self, psi_position: torch.Tensor) -> torch.Tensor:
+        """c[b, e] for this solver's blocks from ONE position-basis state."""
+        psi_b = self.to_bloch(psi_position)[0, self.block_begin : self.block_begin + self.block_count].contiguous()
+        return kernels.project(self.transform, psi_b)
+
+    # ------------------------------------------------------------------ K3b / K3c
+    def evolve_eigen(self, coefficients: torch.Tensor, times: torch.Tensor) -> torch.Tensor:
+        """The reference's return value: [T, count*N] amplitudes in the eigenbasis (schrodinger.py:51-53)."""
+        return kernels.evolve_eigen(self.eigenvalues.reshape(-1), coefficients.reshape(-1), times, self.hbar)
+
+    def evolve_bloch(self, coefficients: torch.Tensor, times: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[T, count*N] states in the Bloch-ordered momentum basis (fused phase x eigenvector GEMM)."""
+        return kernels.evolve_bloch(self.transform, self.eigenvalues, coefficients, times, self.hbar, out=out)
+
+    # ------------------------------------------------------------------ K5 + K4
+    def bloch_to_position(self, states_bloch: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[T, M] Bloch order (ALL blocks) -> position basis.  Needs block_count == n_k."""
+        if states_bloch.shape[-1] != self.m:
+            msg = "bloch_to_position needs every k-block (gather or all-to-all the shards first)"
+            raise ValueError(msg)
+        states_k = kernels.bloch_permute(self.shape, self.repeat, states_bloch.contiguous(), 1)
+        return kernels.fft_c2c(states_k, self.supercell, +1, out=states_k if out is None else out)
