@@ -70,6 +70,11 @@ int sqb_bloch_kinetic(int nd, const int* shape_host, const int* repeat_host, con
                       double mass, double hbar, int64_t block_begin, int64_t block_count,
                       sqb_c128* E_out, void* stream);
 
+/* Kinetic diagonal of ONE cell for an explicit Bloch fraction (NULL = zero): E_out[N].
+ * Replaces operator/_build/_hamiltonian.py:149-158 `kinetic_energy(metadata, mass, bloch_fraction)`. */
+int sqb_kinetic_energy(int nd, const int* shape_host, const double* dk_host, const double* fraction_host,
+                       double mass, double hbar, sqb_c128* E_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  Bloch index permutation (BlochShiftedBasis per axis + BlochTransposedBasis).
  * Replaces: bloch/_shifted_basis.py:62-84 / 87-111 and bloch/_transposed_basis.py:102-133 / 136-167.
@@ -109,7 +114,7 @@ int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, const sqb_c128
  * w        [batch, n] eigenvalues, ascending within each matrix (quirk Q3: not globally sorted)
  * info     [batch] 0 = converged; k > 0 = the implicit-QL iteration failed on k eigenvalues or ran
  *          out of rotation storage (results for that matrix are undefined)
- * n <= 1024.  Algorithm: Householder tridiagonalisation, implicit-shift QL on the real tridiagonal
+ * n <= 512 (SQB_E_UNSUPPORTED above).  Algorithm: Householder tridiagonalisation, implicit-shift QL on the real tridiagonal
  * with recorded Givens rotations, rotation replay on shared-memory strips, Householder
  * back-transformation.
  * ---------------------------------------------------------------------------------------------- */
@@ -134,6 +139,12 @@ int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* in
  * ---------------------------------------------------------------------------------------------- */
 int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
                 void* stream);
+/* Generic explicit-basis conversion of a vector list [lead, batch*n] (ExplicitUnitaryBasis.__into_inner__ /
+ * __from_inner__, reached from state/_state.py:102-107 and :153-165):
+ *   mode 0: out[l,b,k] = sum_e in[l,b,e] transform[b,e,k]        (eigenbasis -> inner basis)
+ *   mode 1: out[l,b,e] = sum_k conj(transform[b,e,k]) in[l,b,k]  (inner basis -> eigenbasis)      */
+int sqb_apply_transform(int n, int64_t batch, int64_t lead, int mode, const sqb_c128* transform,
+                        const sqb_c128* in, sqb_c128* out, void* stream);
 int sqb_evolve_eigen(int64_t m, const double* w, const sqb_c128* c, const double* times,
                      int64_t n_times, double hbar, sqb_c128* out, void* stream);
 int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w,

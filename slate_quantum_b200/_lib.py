@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     "sqb_error_string",
     "sqb_bloch_build",
     "sqb_bloch_kinetic",
+    "sqb_kinetic_energy",
     "sqb_bloch_permute",
     "sqb_fft_workspace_bytes",
     "sqb_fft_c2c",
@@ -26,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "sqb_eigh_workspace_bytes",
     "sqb_eigh_batched",
     "sqb_project",
+    "sqb_apply_transform",
     "sqb_evolve_eigen",
     "sqb_evolve_bloch",
     "sqb_peak_dmma",
@@ -62,6 +64,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_bloch_build.argtypes = [c_int, ip, ip, dp, c_void_p, c_double, c_double, c_int64, c_int64, c_void_p, c_void_p]
     lib.sqb_bloch_kinetic.restype = c_int
     lib.sqb_bloch_kinetic.argtypes = [c_int, ip, ip, dp, c_double, c_double, c_int64, c_int64, c_void_p, c_void_p]
+    lib.sqb_kinetic_energy.restype = c_int
+    lib.sqb_kinetic_energy.argtypes = [c_int, ip, dp, dp, c_double, c_double, c_void_p, c_void_p]
     lib.sqb_bloch_permute.restype = c_int
     lib.sqb_bloch_permute.argtypes = [c_int, ip, ip, c_int, c_int64, c_void_p, c_void_p, c_void_p]
     lib.sqb_fft_workspace_bytes.restype = c_size_t
@@ -76,6 +80,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_eigh_batched.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_project.restype = c_int
     lib.sqb_project.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.sqb_apply_transform.restype = c_int
+    lib.sqb_apply_transform.argtypes = [c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sqb_evolve_eigen.restype = c_int
     lib.sqb_evolve_eigen.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]
     lib.sqb_evolve_bloch.restype = c_int

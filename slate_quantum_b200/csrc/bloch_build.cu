@@ -22,6 +22,8 @@ struct BuildParams {
   double half_delta[SQB_MAX_DIMS];     // |N_j dk_j| / 2   (norm of delta_k row j, halved)
   double mass, hbar;
   double inv_sqrt_n_den;               // sqrt(N)
+  int use_fraction;                    // 1: every block uses `fraction` instead of its own k-point
+  double fraction[SQB_MAX_DIMS];
 };
 
 // FFT-order signed integer of array index i on an axis of length n: [0,1,..,ceil(n/2)-1,-floor(n/2),..,-1]
@@ -48,7 +50,7 @@ __device__ double kinetic_value(const BuildParams& P, const int* pidx, const int
     for (int i = 0; i < nd; ++i) {
       const double dkij = P.dk[i * SQB_MAX_DIMS + j];
       const double ni = (double)fft_int(pidx[i], P.d.shape[i]);
-      const double fi = (double)fft_int(bidx[i], P.d.repeat[i]) / (double)P.d.repeat[i];
+      const double fi = P.use_fraction ? P.fraction[i] : (double)fft_int(bidx[i], P.d.repeat[i]) / (double)P.d.repeat[i];
       acc = __dadd_rn(acc, __dmul_rn(dkij, ni));
       phase = __dadd_rn(phase, __dmul_rn(dkij, fi));
     }
@@ -153,6 +155,8 @@ int fill_params(BuildParams& P, int nd, const int* shape, const int* repeat, con
   P.mass = mass;
   P.hbar = hbar;
   P.inv_sqrt_n_den = sqrt((double)n64);
+  P.use_fraction = 0;
+  for (int i = 0; i < SQB_MAX_DIMS; ++i) P.fraction[i] = 0.0;
   for (int i = 0; i < SQB_MAX_DIMS * SQB_MAX_DIMS; ++i) P.dk[i] = 0.0;
   for (int i = 0; i < nd; ++i)
     for (int j = 0; j < nd; ++j) P.dk[i * SQB_MAX_DIMS + j] = dk[i * nd + j];
@@ -209,6 +213,22 @@ extern "C" int sqb_bloch_kinetic(int nd, const int* shape_host, const int* repea
   const int grid = (int)sqb_min64((total + 255) / 256, 148 * 8);
   bloch_kinetic_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(P, block_begin, block_count,
                                                              reinterpret_cast<c128*>(E_out));
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+extern "C" int sqb_kinetic_energy(int nd, const int* shape_host, const double* dk_host, const double* fraction_host,
+                                  double mass, double hbar, sqb_c128* E_out, void* stream) {
+  BuildParams P;
+  int64_t nk;
+  const int ones[SQB_MAX_DIMS] = {1, 1, 1, 1};
+  int rc = fill_params(P, nd, shape_host, ones, dk_host, mass, hbar, &nk);
+  if (rc) return rc;
+  if (!E_out) return SQB_E_BADARG;
+  P.use_fraction = 1;
+  for (int i = 0; i < nd; ++i) P.fraction[i] = fraction_host ? fraction_host[i] : 0.0;
+  const int grid = (int)sqb_min64(((int64_t)P.n + 255) / 256, 148 * 8);
+  bloch_kinetic_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(P, 0, 1, reinterpret_cast<c128*>(E_out));
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }

@@ -351,13 +351,18 @@ ql_kernel(int n, int64_t count, EighWs ws, double* __restrict__ w_out, int* __re
 
 // ------------------------------------------------------------------------------------------------
 // (3) rotation replay on a 32-row strip of the identity; one warp per (strip, matrix).
-constexpr int kRotWindow = 64;
+// A lane owns one row; the strip lives in shared memory as zs[col][lane] (conflict free).  The only
+// loop-carried dependency of a sweep is ONE fma on `carry`, so rotations are processed in blocks of
+// kRotBlock with all their shared-memory loads hoisted in front of the chain.  The (c, s) stream is
+// staged through a 128-entry shared ring that is refilled 32 entries at a time, one refill ahead.
+constexpr int kRotBlock = 8;
+constexpr int kRing = 128;
 
 __global__ void __launch_bounds__(32)
 replay_kernel(int n, EighWs ws) {
   extern __shared__ double smem_d[];
   double* zs = smem_d;  // [n][32]  zs[col*32 + lane]
-  __shared__ double2 win[2][kRotWindow];
+  __shared__ double2 ring[kRing];
   const int lane = threadIdx.x;
   const int r0 = blockIdx.x * 32;
   const int64_t b = blockIdx.y;
@@ -368,53 +373,63 @@ replay_kernel(int n, EighWs ws) {
   double* qt = ws.qt + b * (int64_t)n * n;
 
   for (int col = 0; col < n; ++col) zs[col * 32 + lane] = (col == r0 + lane) ? 1.0 : 0.0;
-  __syncwarp();
 
-  // total rotations
   int64_t total = 0;
   if (nsw > 0) {
     const int4 last = sweeps[nsw - 1];
     total = (int64_t)last.w + last.z;
   }
-  // window prefetch: win[buf] holds rotations [wbase, wbase + kRotWindow)
-  int64_t wbase = 0;
-  int buf = 0;
-  for (int k = lane; k < kRotWindow; k += 32) win[0][k] = (k < total) ? rot[k] : make_double2(1.0, 0.0);
-  double2 pre[kRotWindow / 32];
-#pragma unroll
-  for (int q = 0; q < kRotWindow / 32; ++q) {
-    const int64_t idx = kRotWindow + q * 32 + lane;
-    pre[q] = idx < total ? rot[idx] : make_double2(1.0, 0.0);
-  }
+  const double2 ident = make_double2(1.0, 0.0);
+  // ring holds [loaded - kRing, loaded); `pre` holds [loaded, loaded + 32) in flight
+  int64_t loaded = 0;
+  for (; loaded < 96; loaded += 32) ring[(loaded + lane) & (kRing - 1)] = (loaded + lane < total) ? rot[loaded + lane] : ident;
+  double2 pre = (loaded + lane < total) ? rot[loaded + lane] : ident;
   __syncwarp();
 
+  int4 h = nsw > 0 ? sweeps[0] : make_int4(0, 0, 0, 0);
   for (int sw = 0; sw < nsw; ++sw) {
-    const int4 h = sweeps[sw];
+    const int4 hn = (sw + 1 < nsw) ? sweeps[sw + 1] : h;  // prefetch next header
     const int m = h.y, cnt = h.z;
     const int64_t off = h.w;
     double carry = zs[m * 32 + lane];
     int i = m - 1;
-    for (int k = 0; k < cnt; ++k, --i) {
+    int k = 0;
+    while (k < cnt) {
       const int64_t idx = off + k;
-      if (idx >= wbase + kRotWindow) {
-        // rotate windows: publish prefetched, fetch the one after
-        buf ^= 1;
-        wbase += kRotWindow;
-#pragma unroll
-        for (int q = 0; q < kRotWindow / 32; ++q) win[buf][q * 32 + lane] = pre[q];
-#pragma unroll
-        for (int q = 0; q < kRotWindow / 32; ++q) {
-          const int64_t nidx = wbase + kRotWindow + q * 32 + lane;
-          pre[q] = nidx < total ? rot[nidx] : make_double2(1.0, 0.0);
-        }
+      // keep at least kRotBlock + 32 entries ahead of idx published in the ring
+      if (idx + kRotBlock + 32 > loaded) {
+        ring[(loaded + lane) & (kRing - 1)] = pre;
+        loaded += 32;
+        pre = (loaded + lane < total) ? rot[loaded + lane] : ident;
         __syncwarp();
       }
-      const double2 cs = win[buf][idx - wbase];
-      const double zi = zs[i * 32 + lane];
-      zs[(i + 1) * 32 + lane] = fma(cs.y, zi, cs.x * carry);
-      carry = fma(-cs.y, carry, cs.x * zi);
+      if (cnt - k >= kRotBlock) {
+        double2 cs[kRotBlock];
+        double zi[kRotBlock];
+#pragma unroll
+        for (int j = 0; j < kRotBlock; ++j) {
+          cs[j] = ring[(idx + j) & (kRing - 1)];
+          zi[j] = zs[(i - j) * 32 + lane];
+        }
+#pragma unroll
+        for (int j = 0; j < kRotBlock; ++j) {
+          const double t = cs[j].x * zi[j];
+          zs[(i - j + 1) * 32 + lane] = fma(cs[j].y, zi[j], cs[j].x * carry);
+          carry = fma(-cs[j].y, carry, t);
+        }
+        i -= kRotBlock;
+        k += kRotBlock;
+      } else {
+        const double2 c1 = ring[idx & (kRing - 1)];
+        const double z1 = zs[i * 32 + lane];
+        zs[(i + 1) * 32 + lane] = fma(c1.y, z1, c1.x * carry);
+        carry = fma(-c1.y, carry, c1.x * z1);
+        --i;
+        ++k;
+      }
     }
     zs[(i + 1) * 32 + lane] = carry;
+    h = hn;
   }
   __syncwarp();
   if (r0 + lane < n) {

@@ -35,6 +35,39 @@ project_kernel(int n, int64_t rows, const c128* __restrict__ V, const c128* __re
   if (lane == 0) c[row] = acc;
 }
 
+// generic explicit-basis conversions for [lead, batch*n] vector lists (not the fused hot path):
+//   mode 0 (explicit -> inner): out[l,b,k] = sum_e in[l,b,e] V[b,e,k]
+//   mode 1 (inner -> explicit): out[l,b,e] = sum_k conj(V[b,e,k]) in[l,b,k]
+__global__ void __launch_bounds__(256)
+apply_transform_kernel(int n, int64_t batch, int64_t lead, int mode, const c128* __restrict__ V,
+                       const c128* __restrict__ in, c128* __restrict__ out) {
+  if (mode == 1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // (l, b, e)
+    if (row >= lead * batch * n) return;
+    const int64_t be = row % (batch * n), l = row / (batch * n);
+    const int64_t b = be / n;
+    const c128* v = V + be * n;
+    const c128* p = in + (l * batch + b) * n;
+    c128 acc = make_double2(0.0, 0.0);
+    for (int k = lane; k < n; k += 32) cfmac(acc, v[k], p[k]);
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) out[row] = acc;
+  } else {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (l, b, k)
+    if (g >= lead * batch * n) return;
+    const int k = (int)(g % n);
+    const int64_t lb = g / n;
+    const int64_t b = lb % batch;
+    const c128* v = V + b * (int64_t)n * n + k;
+    const c128* a = in + lb * n;
+    c128 acc = make_double2(0.0, 0.0);
+    for (int e = 0; e < n; ++e) cfma(acc, a[e], v[(int64_t)e * n]);
+    out[g] = acc;
+  }
+}
+
 // literal phase of dynamics/schrodinger.py:51-53: exp(-1j * E * t / hbar) with E real-valued complex128
 __device__ __forceinline__ c128 phase_factor(double w, double t, double hbar) {
   const double theta = -((w * t) / hbar);
@@ -239,6 +272,21 @@ extern "C" int sqb_project(int n, int64_t batch, const sqb_c128* transform, cons
   project_kernel<<<(unsigned)grid, 256, 0, sqb_stream(stream)>>>(n, rows, reinterpret_cast<const c128*>(transform),
                                                                 reinterpret_cast<const c128*>(psi),
                                                                 reinterpret_cast<c128*>(c));
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+extern "C" int sqb_apply_transform(int n, int64_t batch, int64_t lead, int mode, const sqb_c128* transform,
+                                   const sqb_c128* in, sqb_c128* out, void* stream) {
+  if (n < 1 || batch < 0 || lead < 0 || (mode != 0 && mode != 1) || !transform || !in || !out || in == out)
+    return SQB_E_BADARG;
+  const int64_t total = lead * batch * n;
+  if (total == 0) return SQB_OK;
+  const int64_t grid = mode == 1 ? (total + 7) / 8 : (total + 255) / 256;
+  if (grid > 2147483647LL) return SQB_E_UNSUPPORTED;
+  apply_transform_kernel<<<(unsigned)grid, 256, 0, sqb_stream(stream)>>>(
+      n, batch, lead, mode, reinterpret_cast<const c128*>(transform), reinterpret_cast<const c128*>(in),
+      reinterpret_cast<c128*>(out));
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }

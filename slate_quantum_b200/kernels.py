@@ -116,6 +116,23 @@ def bloch_kinetic(
     return out
 
 
+def kinetic_energy(
+    shape: Sequence[int], dk: np.ndarray, fraction: np.ndarray | None, mass: float, hbar: float
+) -> torch.Tensor:
+    """Kinetic diagonal E[N] of one cell for an explicit Bloch fraction (None = 0)."""
+    _require_cuda()
+    lib = _lib.load()
+    out = torch.empty((int(np.prod(shape)),), dtype=torch.complex128, device="cuda")
+    frac = None if fraction is None else _lib.double_array(np.asarray(fraction, dtype=np.float64).ravel())
+    rc = lib.sqb_kinetic_energy(
+        len(shape), _lib.int_array(shape), _lib.double_array(np.asarray(dk).ravel()), frac, float(mass), float(hbar),
+        _ptr(out), _stream(),
+    )
+    _lib.check(rc, "sqb_kinetic_energy")
+    _count(1)
+    return out
+
+
 def bloch_permute(
     shape: Sequence[int], repeat: Sequence[int], vectors: torch.Tensor, direction: int, out: torch.Tensor | None = None
 ) -> torch.Tensor:
@@ -209,6 +226,21 @@ def project(transform: torch.Tensor, psi: torch.Tensor) -> torch.Tensor:
     _lib.check(rc, "sqb_project")
     _count(1)
     return c
+
+
+def apply_transform(transform: torch.Tensor, vectors: torch.Tensor, mode: int) -> torch.Tensor:
+    """Generic explicit-basis conversion of [lead, batch*n] lists (mode 0: eigen -> inner, 1: inner -> eigen)."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(transform, "transform")
+    _c128(vectors, "vectors")
+    batch, n, _ = transform.shape
+    lead = vectors.numel() // (batch * n)
+    out = torch.empty_like(vectors)
+    rc = lib.sqb_apply_transform(n, batch, lead, mode, _ptr(transform), _ptr(vectors), _ptr(out), _stream())
+    _lib.check(rc, "sqb_apply_transform")
+    _count(1)
+    return out
 
 
 def evolve_eigen(w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float) -> torch.Tensor:

@@ -1,0 +1,94 @@
+"""Operator / OperatorList containers (reference: slate_quantum/operator/_operator.py:58-395)."""
+
+from __future__ import annotations
+
+from typing import Any, Iterable
+
+import numpy as np
+
+from slate_quantum_b200.core import basis as _basis
+from slate_quantum_b200.core.array import Array
+from slate_quantum_b200.core.basis import AsUpcast, Basis, FundamentalBasis, TupleBasis, are_dual_shapes
+
+
+def _assert_operator_basis(basis: Basis) -> None:
+    """reference operator/_operator.py:34-40."""
+    is_dual = basis.is_dual
+    if isinstance(is_dual, bool) or len(is_dual) != 2:  # noqa: PLR2004
+        msg = "Basis is not 2d"
+        raise TypeError(msg)
+    assert are_dual_shapes(is_dual[0], is_dual[1])
+
+
+def operator_basis(basis: Basis) -> TupleBasis:
+    return TupleBasis((basis, basis.dual_basis()))
+
+
+class Operator(Array):
+    """An operator: basis metadata = TupleMetadata((M, M)) (reference :58-75)."""
+
+    def __init__(self, basis: Basis, data: Any) -> None:
+        _assert_operator_basis(basis)
+        super().__init__(basis, data)
+
+    def with_basis(self, basis: Basis) -> "Operator":
+        assert basis.metadata() == self.basis.metadata()
+        data = self.basis.convert_vector_into(self.device_data.reshape(-1), basis, 0)
+        return Operator(basis, data)
+
+    def as_array(self) -> np.ndarray:
+        n = self.basis.metadata().children[0].fundamental_size
+        fund = self.basis.into_fundamental(self.device_data.to(dtype=_c128()).reshape(-1), 0)
+        return fund.detach().cpu().numpy().reshape(n, n)
+
+
+def _c128():
+    import torch
+
+    return torch.complex128
+
+
+def _assert_operator_list_basis(basis: Basis) -> None:
+    is_dual = basis.is_dual
+    if isinstance(is_dual, bool) or len(is_dual) != 2:  # noqa: PLR2004
+        msg = "Basis is not 2d"
+        raise TypeError(msg)
+
+
+class OperatorList(Array):
+    """A list of operators: basis = TupleBasis((list basis, operator basis)) (reference :239-395)."""
+
+    def __init__(self, basis: Basis, data: Any) -> None:
+        _assert_operator_list_basis(basis)
+        super().__init__(basis, data)
+
+    def with_basis(self, basis: Basis) -> "OperatorList":
+        assert basis.metadata() == self.basis.metadata()
+        data = self.basis.convert_vector_into(self.device_data.reshape(-1), basis, 0)
+        return OperatorList(basis, data)
+
+    def with_operator_basis(self, basis: Basis) -> "OperatorList":
+        """reference :268-284."""
+        lhs_basis = _basis.as_tuple(self.basis).children[0]
+        return self.with_basis(AsUpcast(TupleBasis((lhs_basis, basis)), self.basis.metadata()))
+
+    def with_list_basis(self, basis: Basis) -> "OperatorList":
+        """reference :315-327."""
+        rhs_basis = _basis.as_tuple(self.basis).children[1]
+        return self.with_basis(AsUpcast(TupleBasis((basis, rhs_basis)), self.basis.metadata()))
+
+    def __iter__(self):
+        tup = _basis.as_tuple(self.basis)
+        data = self.raw_data.reshape(tup.shape)
+        return (Operator(tup.children[1], row) for row in data)
+
+    def __len__(self) -> int:
+        return _basis.as_tuple(self.basis).children[0].size
+
+    @staticmethod
+    def from_operators(iter_: Iterable[Operator]) -> "OperatorList":
+        """reference :377-395."""
+        ops = list(iter_)
+        assert all(x.basis == ops[0].basis for x in ops)
+        list_basis = FundamentalBasis.from_size(len(ops))
+        return OperatorList(TupleBasis((list_basis, ops[0].basis)).upcast(), np.array([x.raw_data for x in ops]))

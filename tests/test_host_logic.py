@@ -1,0 +1,140 @@
+"""CPU: host-side logic - metadata, basis bookkeeping, workload configs, sharding (gloo, world_size 2),
+and the numpy model of the GPU eigensolver algorithm."""
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import bloch_oracle as o
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_metadata_and_bases_bookkeeping():
+    from slate_quantum_b200.bloch.build import BlochFractionMetadata, basis_from_metadata, get_sample_fractions
+    from slate_quantum_b200.core import basis, metadata
+    from slate_quantum_b200.metadata import RepeatedMetadata, repeat_volume_metadata, unit_cell_metadata
+
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(
+        (np.array([2 * np.pi, 0]), np.array([0, 2 * np.pi])), (4, 3)
+    )
+    assert meta.shape == (4, 3)
+    np.testing.assert_allclose(metadata.fundamental_stacked_dk(meta), np.eye(2), atol=1e-15)
+    np.testing.assert_allclose(metadata.fundamental_stacked_delta_k(meta), np.diag([4.0, 3.0]), atol=1e-15)
+    np.testing.assert_array_equal(metadata.fundamental_nk_points(5), [0, 1, 2, -2, -1])
+    rep = repeat_volume_metadata(meta, (3, 2))
+    assert isinstance(rep.children[0], RepeatedMetadata)
+    assert rep.shape == (12, 6)
+    assert rep.children[0].domain.delta == pytest.approx(3 * 2 * np.pi)
+    assert unit_cell_metadata(rep) == meta
+    assert rep == repeat_volume_metadata(meta, (3, 2))
+    assert rep != repeat_volume_metadata(meta, (2, 3))
+    fr = get_sample_fractions(BlochFractionMetadata.from_repeats((4, 2)))
+    np.testing.assert_array_equal(np.array(fr), o.sample_fractions((4, 2)))
+    bloch_basis = basis_from_metadata(rep)
+    assert bloch_basis.size == 72
+    assert bloch_basis.metadata() == rep
+    assert bloch_basis == basis_from_metadata(rep)
+    assert bloch_basis.dual_basis() != bloch_basis
+    assert bloch_basis.inner.supercell_momentum_basis() == basis.transformed_from_metadata(rep)
+    tb = basis.transformed_from_metadata(meta)
+    assert tb.is_dual == (False, False) and tb.dual_basis().is_dual == (True, True)
+
+
+def test_potential_descriptions_match_oracle():
+    from slate_quantum_b200.core import metadata
+    from slate_quantum_b200.operator import build
+
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(
+        (np.array([2 * np.pi, 0]), np.array([0, 2 * np.pi])), (8, 6)
+    )
+    np.testing.assert_allclose(build.cos_potential(meta, 3.0, offset=0.2).raw_data,
+                               o.cos_potential_components((8, 6), 3.0, 0.2).ravel())
+    np.testing.assert_allclose(build.sin_potential(meta, 3.0).raw_data, o.sin_potential_components((8, 6), 3.0).ravel())
+    np.testing.assert_allclose(build.fcc_potential(meta, 2.0).raw_data, o.fcc_potential_components((8, 6), 2.0).ravel())
+    pot = build.cos_potential(meta, 1.0)
+    assert pot.basis.size == 9
+    assert pot.basis.metadata().children[0] == meta
+
+
+def test_workload_configs():
+    from slate_quantum_b200.configs import CONFIGS, shard_blocks
+
+    c3 = CONFIGS["cfg3"]
+    assert (c3.n, c3.n_k, c3.m, c3.n_times) == (256, 4096, 1 << 20, 4096)
+    assert CONFIGS["cfg5"].n == 343 and CONFIGS["cfg4"].n == 512
+    np.testing.assert_allclose(c3.potential_table(), o.pad_components(c3.shape, o.cos_potential_components(c3.shape, 10.0)))
+    c4 = CONFIGS["cfg4"]
+    np.testing.assert_allclose(c4.dk(), o.stacked_dk(c4.vectors()))
+    psi = CONFIGS["cfg1"].initial_state()
+    assert psi.shape == (6400,) and abs(np.linalg.norm(psi) - 1) < 1e-12
+    for n_k, world in [(4096, 8), (10, 4), (7, 8)]:
+        ranges = [shard_blocks(n_k, r, world) for r in range(world)]
+        assert sum(c for _, c in ranges) == n_k
+        assert all(ranges[i][0] + ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 40])
+def test_eigensolver_algorithm_model(n):
+    from eigh_model import eigh_model
+
+    rng = np.random.default_rng(n)
+    g = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    h = g + g.conj().T
+    w, t, fails, nrot, _ = eigh_model(h)
+    assert fails == 0
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(h), atol=1e-12 * max(1.0, np.abs(h).max() * n))
+    v = t.T
+    assert np.linalg.norm(h @ v - v * w) / max(np.linalg.norm(h), 1e-300) < 1e-12
+    assert nrot <= 5 * n * n // 2 + 64 * n + 64  # rotation-record capacity of csrc/eigh.cu
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SQB_ROOT"])
+from oracle import bloch_oracle as o
+from slate_quantum_b200.configs import shard_blocks
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["SQB_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+shape, repeat = (4, 3), (3, 3)
+dx = 2 * np.pi * np.eye(2)
+comps = o.cos_potential_components(shape, 2.0)
+n_k = 9
+begin, count = shard_blocks(n_k, rank, 2)
+blocks = o.bloch_blocks(dx, shape, comps, o.HBAR_SI**2, repeat, block_begin=begin, block_count=count)
+w, _ = o.eigh_blocks(blocks)
+# ragged all-gather of eigenvalues, as bench.py / the solver do with NCCL
+counts = [shard_blocks(n_k, r, 2)[1] for r in range(2)]
+pad = max(counts)
+mine = torch.zeros((pad, 12), dtype=torch.float64)
+mine[:count] = torch.from_numpy(w)
+gathered = [torch.zeros_like(mine) for _ in range(2)]
+dist.all_gather(gathered, mine)
+full = torch.cat([g[:c] for g, c in zip(gathered, counts)]).numpy()
+w_all, _ = o.eigh_blocks(o.bloch_blocks(dx, shape, comps, o.HBAR_SI**2, repeat))
+assert np.abs(full - w_all).max() < 1e-13, np.abs(full - w_all).max()
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_block_sharding_and_eigenvalue_gather_world_size_2(tmp_path):
+    """N>1 path on CPU: contiguous k-block ranges + all-gather of eigenvalues over gloo, world_size 2."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), SQB_ROOT=str(ROOT), SQB_PORT=port, MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
