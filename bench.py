@@ -232,6 +232,7 @@ def run_ours(args) -> None:
     table = table_h.cuda(non_blocking=True)
     psi0 = psi_h.cuda(non_blocking=True)
     times = times_h.cuda(non_blocking=True)
+    dt_uniform = kernels.uniform_step(cfg.times())  # SpacedTimeMetadata-style uniform grid -> phase recurrence
 
     # ---- measured FP64 tensor (DMMA) and FMA peaks for the roofline denominators
     sink = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -262,15 +263,16 @@ def run_ours(args) -> None:
     free, _ = torch.cuda.mem_get_info()
     row_bytes = n_k_local * n * 16
     t_tile = T
-    budget = int(free * (0.42 if with_position else 0.8))
+    budget = int((free - (n_k_local * n * n * 16 if with_position else 0)) * (0.42 if with_position else 0.8))
     while t_tile * row_bytes > budget and t_tile > 64:
         t_tile //= 2
     states = torch.empty((t_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
-    pos_tile = min(t_tile, max(1, (int(free * 0.3)) // row_bytes)) if with_position else 0
+    pos_out = torch.empty_like(states) if with_position else None
+    folded_buf = torch.empty_like(h_buf) if with_position else None
     eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    stage_names = ["build", "eigh", "project", "evolve", "position"]
+    stage_names = ["build", "eigh", "fold", "project", "evolve", "position"]
 
     def step(record: list | None = None) -> None:
         """One pass of the hot path.  `record` collects (stage, start_event, end_event) triples."""
@@ -293,14 +295,17 @@ def run_ours(args) -> None:
                 dist.all_gather_into_tensor(eig_all, solver.eigenvalues.reshape(-1))
 
         timed("eigh", eigh)
+        if with_position:
+            # eigenvectors -> in-cell position basis + Bloch twiddle, once per eigensolve (K4 on N-point cells)
+            timed("fold", lambda: solver.fold(out=folded_buf))
         c = timed("project", lambda: solver.project(psi0))
         for t0 in range(0, T, t_tile):
             tt = min(t_tile, T - t0)
-            timed("evolve", lambda: solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt]))
             if with_position:
-                for p0 in range(0, tt, pos_tile):
-                    pt = min(pos_tile, tt - p0)
-                    timed("position", lambda: solver.bloch_to_position(states[p0 : p0 + pt], out=states[p0 : p0 + pt]))
+                timed("evolve", lambda: solver.evolve_cell(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
+                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
+            else:
+                timed("evolve", lambda: solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
 
     def sync_all() -> None:
         torch.cuda.synchronize()
@@ -350,6 +355,7 @@ def run_ours(args) -> None:
         eig_host = torch.empty((n_k_local * n,), dtype=torch.float64).pin_memory()
         tile_free = [torch.cuda.Event(), torch.cuda.Event()]
         pos_tmp = torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda") if with_position else None
+        e_src = pos_out if with_position else states
         h2d = table_h.numel() * 16 + psi_h.numel() * 16 + times_h.numel() * 8
         d2h = eig_host.numel() * 8 + T * row_bytes
 
@@ -361,16 +367,19 @@ def run_ours(args) -> None:
             solver.build(tb, out=h_buf)
             solver.diagonalise()
             eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
+            if with_position:
+                solver.fold(out=folded_buf)
             c = solver.project(ps)
             k = 0
             for i_tile, t0 in enumerate(range(0, T, e_tile)):
                 tt = min(e_tile, T - t0)
-                buf = states[(i_tile & 1) * e_tile : (i_tile & 1) * e_tile + tt]
+                buf = e_src[(i_tile & 1) * e_tile : (i_tile & 1) * e_tile + tt]
                 cur.wait_event(tile_free[i_tile & 1])  # the D2H of the tile that used this buffer is done
-                solver.evolve_bloch(c, tm[t0 : t0 + tt], out=buf)
                 if with_position:
-                    kernels.bloch_permute(solver.shape, solver.repeat, buf, 1, out=pos_tmp[:tt])
-                    kernels.fft_c2c(pos_tmp[:tt], solver.supercell, +1, out=buf)
+                    solver.evolve_cell(c, tm[t0 : t0 + tt], out=pos_tmp[:tt], uniform_dt=dt_uniform)
+                    solver.cell_to_position(pos_tmp[:tt], out=buf)
+                else:
+                    solver.evolve_bloch(c, tm[t0 : t0 + tt], out=buf, uniform_dt=dt_uniform)
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 copy_stream.wait_event(ready)
@@ -440,7 +449,8 @@ def run_ours(args) -> None:
                 "parallelism": f"k-block sharding x{world}" + (", NCCL all-gather of eigenvalues" if world > 1 else ""),
             },
             "blocks_diagonalised_per_s": n_k_global / ((stage_ms["build"] + stage_ms["eigh"]) * 1e-3),
-            "state_time_evolutions_per_s": T / ((stage_ms["project"] + stage_ms["evolve"] + stage_ms["position"]) * 1e-3),
+            "state_time_evolutions_per_s": T
+            / ((stage_ms["fold"] + stage_ms["project"] + stage_ms["evolve"] + stage_ms["position"]) * 1e-3),
             "stage_ms": stage_ms,
             "roofline": {
                 "kernel": "evolve_bloch_kernel (K3c fused phase x eigenvector complex GEMM, DMMA.8x8x4)",

@@ -103,6 +103,31 @@ int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, const sqb_c128
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K4b  Bloch "cell FFT": the supercell FFT of Bloch-ordered data, factorised.
+ * With s_a = k_a R_a + q_a (supercell momentum) and x_a = c_a N_a + j_a (supercell position)
+ *   exp(2 pi i s_a x_a/L_a) = exp(2 pi i k_a j_a/N_a) * exp(2 pi i q_a j_a/L_a) * exp(2 pi i q_a c_a/R_a)
+ * so TransformedBasis o BlochShiftedBasis o BlochTransposedBasis (the chain of bloch/build.py:79-88 that a
+ * StateList.with_state_basis(position basis) walks, state/_state.py:153-165) = N-point FFT inside each
+ * block, a twiddle, and an R-point FFT across blocks.
+ *
+ * sqb_fold_transform: folded[b,e,j] = exp(+2 pi i sum_a q_a(b) j_a / L_a) * ifftn_ortho_N(transform[b,e,:])[j]
+ *   (eigenvectors moved ONCE to the in-cell position basis with the Bloch twiddle applied; feeding `folded`
+ *   to sqb_evolve_bloch yields states in the "cell layout" [T, n_k, N(j)]).  Blocks
+ *   [block_begin, block_begin+batch) of the k-grid `repeat`.  workspace: sqb_fft_workspace_bytes(nd, shape, batch*N).
+ * sqb_cell_fft: [lead, n_k, N] cell layout <-> [lead, M] supercell position order, ortho over n_k.
+ *   direction 1: cell -> position (sign +1).  For nd > 1 `in_scratch` is CLOBBERED (used in place for the
+ *                first nd-1 axes); the last axis scatters into `out`.
+ *   direction 0: position -> cell (sign -1); `in_scratch` is only read.
+ *   in_scratch != out for nd > 1.  Every repeat[a] <= 4096 with prime factors <= 31.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host);
+int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
+                 sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes, void* stream);
+int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, int64_t block_begin,
+                       int64_t batch, const sqb_c128* transform, sqb_c128* folded, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K2  Batched Hermitian eigensolver, complex128, one problem per k-block.
  * Replaces: slate_core.linalg.into_diagonal_hermitian (np.linalg.eigh / LAPACK zheevd per block),
  * call site operator/_linalg.py:56 (`into_diagonal_hermitian`), bloch/_linalg.py:72-84.
@@ -137,6 +162,13 @@ int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* in
  *                    Rows t in [t_begin, t_begin+t_count) of `times` are produced; `out` points at
  *                    row t_begin's storage, row stride = out_row_stride elements (>= batch*n).
  * ---------------------------------------------------------------------------------------------- */
+/* sqb_evolve_bloch_uniform: same result as sqb_evolve_bloch for a UNIFORM grid times[i] = times[0] + i*dt (the
+ * caller guarantees it, e.g. SpacedTimeMetadata): rows 8 apart differ by exp(-1j*w*8*dt/hbar), tabulated once per
+ * eigenvalue in step_workspace ([batch*n] complex128), so the GEMM's producer warps need one sincos per 8 rows.
+ * Accuracy: 7 extra complex multiplications per element (<= 1e-15 relative). */
+int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
+                             const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
+                             sqb_c128* out, int64_t out_row_stride, sqb_c128* step_workspace, void* stream);
 int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
                 void* stream);
 /* Generic explicit-basis conversion of a vector list [lead, batch*n] (ExplicitUnitaryBasis.__into_inner__ /

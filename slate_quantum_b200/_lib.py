@@ -24,12 +24,16 @@ EXPORTED_SYMBOLS = (
     "sqb_fft_workspace_bytes",
     "sqb_fft_c2c",
     "sqb_fft_axis",
+    "sqb_cell_fft_workspace_bytes",
+    "sqb_cell_fft",
+    "sqb_fold_transform",
     "sqb_eigh_workspace_bytes",
     "sqb_eigh_batched",
     "sqb_project",
     "sqb_apply_transform",
     "sqb_evolve_eigen",
     "sqb_evolve_bloch",
+    "sqb_evolve_bloch_uniform",
     "sqb_peak_dmma",
     "sqb_peak_dfma",
 )
@@ -74,6 +78,12 @@ def load() -> ctypes.CDLL:
     lib.sqb_fft_c2c.argtypes = [c_int, ip, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_fft_axis.restype = c_int
     lib.sqb_fft_axis.argtypes = [c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_cell_fft_workspace_bytes.restype = c_size_t
+    lib.sqb_cell_fft_workspace_bytes.argtypes = [c_int, ip]
+    lib.sqb_cell_fft.restype = c_int
+    lib.sqb_cell_fft.argtypes = [c_int, ip, ip, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_fold_transform.restype = c_int
+    lib.sqb_fold_transform.argtypes = [c_int, ip, ip, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_eigh_workspace_bytes.restype = c_size_t
     lib.sqb_eigh_workspace_bytes.argtypes = [c_int, c_int64]
     lib.sqb_eigh_batched.restype = c_int
@@ -87,6 +97,11 @@ def load() -> ctypes.CDLL:
     lib.sqb_evolve_bloch.restype = c_int
     lib.sqb_evolve_bloch.argtypes = [
         c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_int64, c_void_p,
+    ]
+    lib.sqb_evolve_bloch_uniform.restype = c_int
+    lib.sqb_evolve_bloch_uniform.argtypes = [
+        c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_int64,
+        c_void_p, c_void_p,
     ]
     lib.sqb_peak_dmma.restype = c_int
     lib.sqb_peak_dmma.argtypes = [c_int64, c_void_p, dp, c_void_p]

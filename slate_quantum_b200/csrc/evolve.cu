@@ -86,15 +86,30 @@ evolve_eigen_kernel(int64_t m, const double* __restrict__ w, const c128* __restr
   }
 }
 
+// step[i] = exp(-1j * w[i] * dt8 / hbar): the factor between time rows 8 apart on a uniform grid
+__global__ void __launch_bounds__(256)
+phase_step_kernel(int64_t m, const double* __restrict__ w, double dt8, double hbar, c128* __restrict__ step) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    step[i] = phase_factor(w[i], dt8, hbar);
+}
+
 // ------------------------------------------------------------------------------------------------
-// fused phase x eigenvector GEMM
+// fused phase x eigenvector GEMM, warp specialised:
+//   warps 0..7   consumers: 32 x 32 complex warp tiles (2 x 4 over the 64 x 128 CTA tile), DMMA.8x8x4 only
+//   warps 8..11  producers: generate the A chunk (c_e * exp(-i w_e t / hbar), one sincos per element) into
+//                shared memory and issue the 1-D bulk (TMA) copies of the B chunk (eigenvector rows)
+// kGemmStages-deep ring, full/empty mbarriers; the tensor pipe never waits for sincos or for L2.
 constexpr int TM = 64;    // times per CTA tile
 constexpr int TN = 128;   // components per CTA tile
 constexpr int KC = 16;    // eigen-index chunk
 constexpr int LDA = KC + 4;   // complex elements; == 4 (mod 8) -> conflict-free 16 B fragment loads
 constexpr int LDB = TN + 2;   // == 2 (mod 8)
-constexpr int kGemmThreads = 256;
-constexpr size_t kGemmSmem = (size_t)2 * (TM * LDA + KC * LDB) * sizeof(c128) + 64;
+constexpr int kGemmStages = 3;
+constexpr int kConsumerThreads = 256;
+constexpr int kProducerThreads = 128;
+constexpr int kGemmThreads = kConsumerThreads + kProducerThreads;
+constexpr int kStageElems = TM * LDA + KC * LDB;
+constexpr size_t kGemmSmem = (size_t)kGemmStages * kStageElems * sizeof(c128) + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,7 +117,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -133,71 +151,108 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 evolve_bloch_kernel(int n, const c128* __restrict__ V, const double* __restrict__ w, const c128* __restrict__ coef,
                     const double* __restrict__ times, int64_t t_count, double hbar, c128* __restrict__ out,
-                    int64_t out_row_stride) {
+                    int64_t out_row_stride, const c128* __restrict__ step8) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  c128* As = reinterpret_cast<c128*>(smem_raw);        // [2][TM][LDA]
-  c128* Bs = As + 2 * TM * LDA;                         // [2][KC][LDB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 2 * KC * LDB);  // [2]
+  c128* stage0 = reinterpret_cast<c128*>(smem_raw);  // [stages][ A: TM x LDA | B: KC x LDB ]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + kGemmStages * kStageElems);  // [stages]
+  uint64_t* empty = full + kGemmStages;                                               // [stages]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p0 = blockIdx.x * TN;
   const int64_t t0 = (int64_t)blockIdx.y * TM;
   const int64_t b = blockIdx.z;
   const c128* Vb = V + b * (int64_t)n * n;
-  const double* wb = w + b * n;
-  const c128* cb = coef + b * n;
   const int ncols = min(TN, n - p0);
   const int nchunks = (n + KC - 1) / KC;
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(&full[s], kProducerThreads);
+      mbar_init(&empty[s], kConsumerThreads / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // A generation mapping: thread -> (e_local = tid % KC, rows j = tid / KC + 16*q, q < TM/16)
-  const int ge = tid % KC;
-  const int gj = tid / KC;  // 0..15
-  double tj[TM / 16];
+  if (warp >= kConsumerThreads / 32) {
+    // ============================== producers ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int ptid = tid - kConsumerThreads;
+    const int ge = ptid % KC;   // eigen index inside the chunk
+    const int gj = ptid / KC;   // 0..7 ; rows gj + 8 q
+    const double* wb = w + b * n;
+    const c128* cb = coef + b * n;
+    double tj[TM / 8];
 #pragma unroll
-  for (int q = 0; q < TM / 16; ++q) {
-    const int64_t t = t0 + gj + 16 * q;
-    tj[q] = t < t_count ? times[t] : 0.0;
+    for (int q = 0; q < TM / 8; ++q) {
+      const int64_t t = t0 + gj + 8 * q;
+      tj[q] = t < t_count ? times[t] : 0.0;
+    }
+    // uniform time grids: rows gj, gj+8, gj+16, .. differ by the constant factor step8[e] = exp(-i w_e 8 dt / hbar)
+    // (precomputed per eigenvalue), so a thread needs ONE sincos per chunk instead of TM/8.
+    const c128* sb = step8 ? step8 + b * n : nullptr;
+    double we_next = 0.0;
+    c128 ce_next = make_double2(0.0, 0.0), se_next = make_double2(1.0, 0.0);
+    if (ge < n) {
+      we_next = wb[ge];
+      ce_next = cb[ge];
+      if (sb) se_next = sb[ge];
+    }
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % kGemmStages;
+      const uint32_t ph = (uint32_t)((kc / kGemmStages) & 1);
+      c128* As = stage0 + s * kStageElems;
+      c128* Bs = As + TM * LDA;
+      const double we = we_next;
+      const c128 ce = ce_next, se = se_next;
+      const int e = kc * KC + ge;
+      {  // prefetch the next chunk's eigenvalue / coefficient
+        const int en = e + KC;
+        we_next = 0.0;
+        ce_next = make_double2(0.0, 0.0);
+        if (en < n) {
+          we_next = wb[en];
+          ce_next = cb[en];
+          if (sb) se_next = sb[en];
+        }
+      }
+      mbar_wait(&empty[s], ph ^ 1u);
+      const int e0 = kc * KC;
+      const int nrows = min(KC, n - e0);
+      if (ptid == 0) {
+        mbar_expect_tx(&full[s], (uint32_t)(nrows * ncols * sizeof(c128)));
+        for (int r = 0; r < nrows; ++r)
+          bulk_g2s(Bs + r * LDB, Vb + (int64_t)(e0 + r) * n + p0, (uint32_t)(ncols * sizeof(c128)), &full[s]);
+      }
+      if (nrows < KC) {
+        for (int idx = ptid; idx < (KC - nrows) * LDB; idx += kProducerThreads)
+          Bs[nrows * LDB + idx] = make_double2(0.0, 0.0);
+      }
+      if (sb) {
+        c128 v = make_double2(0.0, 0.0);
+        if (e < n) v = cmul(ce, phase_factor(we, tj[0], hbar));
+#pragma unroll
+        for (int q = 0; q < TM / 8; ++q) {
+          const int j = gj + 8 * q;
+          As[j * LDA + ge] = (t0 + j < t_count) ? v : make_double2(0.0, 0.0);
+          v = cmul(v, se);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < TM / 8; ++q) {
+          const int j = gj + 8 * q;
+          c128 v = make_double2(0.0, 0.0);
+          if (e < n && t0 + j < t_count) v = cmul(ce, phase_factor(we, tj[q], hbar));
+          As[j * LDA + ge] = v;
+        }
+      }
+      mbar_arrive(&full[s]);
+    }
+    return;
   }
 
-  auto issue_b = [&](int kc, int s) {
-    // thread 0: bulk copies of the rows e in [kc*KC, kc*KC+KC) that exist; others are zero-filled by all
-    const int e0 = kc * KC;
-    const int nrows = min(KC, n - e0);
-    if (tid == 0) {
-      mbar_expect_tx(&bars[s], (uint32_t)(nrows * ncols * sizeof(c128)));
-      for (int r = 0; r < nrows; ++r)
-        bulk_g2s(Bs + (s * KC + r) * LDB, Vb + (int64_t)(e0 + r) * n + p0, (uint32_t)(ncols * sizeof(c128)), &bars[s]);
-    }
-    if (nrows < KC) {
-      for (int idx = tid; idx < (KC - nrows) * LDB; idx += kGemmThreads)
-        Bs[(s * KC + nrows) * LDB + idx] = make_double2(0.0, 0.0);
-    }
-  };
-  auto gen_a = [&](int kc, int s) {
-    const int e = kc * KC + ge;
-    double we = 0.0;
-    c128 ce = make_double2(0.0, 0.0);
-    if (e < n) {
-      we = wb[e];
-      ce = cb[e];
-    }
-#pragma unroll
-    for (int q = 0; q < TM / 16; ++q) {
-      const int j = gj + 16 * q;
-      c128 v = make_double2(0.0, 0.0);
-      if (e < n && t0 + j < t_count) v = cmul(ce, phase_factor(we, tj[q], hbar));
-      As[(s * TM + j) * LDA + ge] = v;
-    }
-  };
-
-  // warp tile: 32 (t) x 32 (k);  8 warps = 2 (t) x 4 (k)
+  // ============================== consumers ==============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int wm = (warp & 1) * 32;
   const int wn = (warp >> 1) * 32;
   double cr[4][4][2], ci[4][4][2];
@@ -208,41 +263,48 @@ evolve_bloch_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       cr[a][c][0] = cr[a][c][1] = 0.0;
       ci[a][c][0] = ci[a][c][1] = 0.0;
     }
-
-  issue_b(0, 0);
-  gen_a(0, 0);
-  __syncthreads();
-
   const int frow = lane >> 2, fcol = lane & 3;
   for (int kc = 0; kc < nchunks; ++kc) {
-    const int s = kc & 1;
-    if (kc + 1 < nchunks) {
-      issue_b(kc + 1, s ^ 1);
-      gen_a(kc + 1, s ^ 1);
-    }
-    mbar_wait(&bars[s], (uint32_t)((kc >> 1) & 1));
-    const c128* Asb = As + s * TM * LDA;
-    const c128* Bsb = Bs + s * KC * LDB;
+    const int s = kc % kGemmStages;
+    const uint32_t ph = (uint32_t)((kc / kGemmStages) & 1);
+    const c128* Asb = stage0 + s * kStageElems;
+    const c128* Bsb = Asb + TM * LDA;
+    mbar_wait(&full[s], ph);
+    // fragments are double buffered in registers; the two products of a complex MAC that hit the same
+    // accumulator are issued a full sweep (32 DMMAs) apart so no DMMA waits on its predecessor
+    c128 af[2][4], bf[2][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) af[0][a] = Asb[(wm + a * 8 + frow) * LDA + fcol];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bf[0][c] = Bsb[fcol * LDB + wn + c * 8 + frow];
 #pragma unroll
     for (int k4 = 0; k4 < KC; k4 += 4) {
-      c128 af[4], bf[4];
+      const int cur = (k4 >> 2) & 1, nxt = cur ^ 1;
+      if (k4 + 4 < KC) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) af[a] = Asb[(wm + a * 8 + frow) * LDA + k4 + fcol];
+        for (int a = 0; a < 4; ++a) af[nxt][a] = Asb[(wm + a * 8 + frow) * LDA + k4 + 4 + fcol];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bf[c] = Bsb[(k4 + fcol) * LDB + wn + c * 8 + frow];
+        for (int c = 0; c < 4; ++c) bf[nxt][c] = Bsb[(k4 + 4 + fcol) * LDB + wn + c * 8 + frow];
+      }
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double nai = -af[a].y;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          dmma(cr[a][c][0], cr[a][c][1], af[a].x, bf[c].x);
-          dmma(ci[a][c][0], ci[a][c][1], af[a].x, bf[c].y);
-          dmma(cr[a][c][0], cr[a][c][1], nai, bf[c].y);
-          dmma(ci[a][c][0], ci[a][c][1], af[a].y, bf[c].x);
+          dmma(cr[a][c][0], cr[a][c][1], af[cur][a].x, bf[cur][c].x);
+          dmma(ci[a][c][0], ci[a][c][1], af[cur][a].x, bf[cur][c].y);
+        }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double nai = -af[cur][a].y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          dmma(cr[a][c][0], cr[a][c][1], nai, bf[cur][c].y);
+          dmma(ci[a][c][0], ci[a][c][1], af[cur][a].y, bf[cur][c].x);
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // epilogue: lane holds C[row = frow][cols 2*fcol, 2*fcol+1] of each 8x8 tile
@@ -303,9 +365,10 @@ extern "C" int sqb_evolve_eigen(int64_t m, const double* w, const sqb_c128* c, c
   return SQB_OK;
 }
 
-extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
-                                const double* times, int64_t t_count, double hbar, sqb_c128* out,
-                                int64_t out_row_stride, void* stream) {
+namespace {
+int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
+                        const double* times, int64_t t_count, double hbar, sqb_c128* out, int64_t out_row_stride,
+                        const c128* step8, void* stream) {
   if (n < 1 || batch < 0 || t_count < 0 || !transform || !w || !c || !times || !out || hbar == 0.0 ||
       out_row_stride < batch * n)
     return SQB_E_BADARG;
@@ -321,8 +384,28 @@ extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform,
     evolve_bloch_kernel<<<grid, kGemmThreads, kGemmSmem, sqb_stream(stream)>>>(
         n, reinterpret_cast<const c128*>(transform) + b0 * (int64_t)n * n, w + b0 * n,
         reinterpret_cast<const c128*>(c) + b0 * n, times, t_count, hbar, reinterpret_cast<c128*>(out) + b0 * n,
-        out_row_stride);
+        out_row_stride, step8 ? step8 + b0 * n : nullptr);
     SQB_LAUNCH_CHECK();
   }
   return SQB_OK;
+}
+}  // namespace
+
+extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
+                                const double* times, int64_t t_count, double hbar, sqb_c128* out,
+                                int64_t out_row_stride, void* stream) {
+  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, nullptr, stream);
+}
+
+extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
+                                        const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
+                                        sqb_c128* out, int64_t out_row_stride, sqb_c128* step_workspace, void* stream) {
+  if (!step_workspace || n < 1 || batch < 0 || !w || hbar == 0.0) return SQB_E_BADARG;
+  if (batch == 0 || t_count == 0) return SQB_OK;
+  const int64_t m = batch * n;
+  const int grid = (int)sqb_min64((m + 255) / 256, 148 * 8);
+  phase_step_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, 8.0 * dt, hbar, reinterpret_cast<c128*>(step_workspace));
+  SQB_LAUNCH_CHECK();
+  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride,
+                             reinterpret_cast<const c128*>(step_workspace), stream);
 }

@@ -1,9 +1,21 @@
-// K4: complex128 FFT, norm="ortho", shared-memory mixed-radix Stockham.
+// K4: complex128 FFT, norm="ortho", shared-memory mixed-radix Stockham, plus the Bloch "cell FFT".
 //
 // One CTA transforms `lines_per_cta` 1-D lines that it first stages into shared memory (HBM traffic:
 // one read + one write of the array per axis pass: 32 B per element per pass).  Lines longer than
 // kMaxSmemLen are split L = L1*L2 (four-step: strided L1-point pass with the inter-stage twiddle fused
 // into its store, then contiguous L2-point pass with a transposed store).
+//
+// Line addressing is generic: a line is identified by (outer index o, inner index i); both are decomposed
+// into up to 4 mixed-radix digits with independent element strides on the input and on the output side.
+// That lets the LAST pass of the Bloch cell FFT scatter straight into supercell position order
+// (x_a = c_a*N_a + j_a) without a separate transpose pass.
+//
+// Cell FFT (sqb_cell_fft): with supercell momentum s_a = k_a*R_a + q_a and position x_a = c_a*N_a + j_a,
+//   exp(2 pi i s_a x_a / L_a) = exp(2 pi i k_a j_a / N_a) * exp(2 pi i q_a j_a / L_a) * exp(2 pi i q_a c_a / R_a)
+// so the supercell inverse FFT of Bloch-ordered data factorises into an N-point FFT inside every block, a
+// twiddle, and an R-point FFT ACROSS blocks.  The first two are folded into the eigenvectors once
+// (sqb_fold_transform), which leaves only the R-point passes per evolved state: they read/write
+// N-element contiguous runs instead of gathering 16 B elements (replaces K5 + the big K4 on the way out).
 //
 // Convention (reference): position -> momentum on a ket index = np.fft.fft(norm="ortho"),
 // momentum -> position = np.fft.ifft(norm="ortho")  (tests/test_operator.py:197-204).
@@ -14,23 +26,40 @@
 namespace {
 
 constexpr int kFftThreads = 256;
-constexpr int kMaxSmemLen = 4096;       // complex elements of one ping-pong buffer
+constexpr int kMaxSmemLen = 4096;   // complex elements of one ping-pong buffer
 constexpr int kMaxStages = 24;
 constexpr int kMaxRadix = 31;
+constexpr int kMaxLines = 64;       // lines per CTA (always a power of two)
+constexpr int kDigits = 4;
+
+struct Digits {  // flat index (C order over dims, last fastest) -> sum digit * stride
+  int nd;
+  int dims[kDigits];
+  int64_t strides[kDigits];
+};
+
+__host__ __device__ inline int64_t digits_offset(const Digits& d, int64_t flat) {
+  int64_t off = 0;
+  for (int a = d.nd - 1; a >= 0; --a) {
+    off += (flat % d.dims[a]) * d.strides[a];
+    flat /= d.dims[a];
+  }
+  return off;
+}
 
 struct FftPass {
   int len;                 // transform length of this pass
   int n_stages;
   int radix[kMaxStages];
-  int64_t n_outer, n_inner;  // lines = n_outer * n_inner
-  int64_t in_so, in_sl, in_si;     // element strides of (outer, position-in-line, inner) on input
-  int64_t out_so, out_sl, out_si;  // ... on output
+  int64_t n_outer, n_inner;  // lines = n_outer * n_inner, line id = o * n_inner + i
+  Digits in_outer, in_inner, out_outer, out_inner;
+  int64_t in_sl, out_sl;   // element stride of the position inside a line
   int lines_per_cta;
   int inner_fastest;       // load order: 1 = a CTA's lines are adjacent in memory (coalesce across lines)
   int out_inner_fastest;   // same for the store
   int sign;                // -1 forward, +1 backward
   double scale;            // multiplied into every output
-  int64_t tw_len;          // 0 = none; else multiply output (k, inner=i) by exp(sign*2*pi*i*k*i/tw_len)
+  int64_t tw_len;          // 0 = none; else multiply output (pos k, inner i) by exp(sign*2*pi*i*k*i/tw_len)
 };
 
 __device__ __forceinline__ c128 tw_lookup(const c128* tab, int idx, int sign) {
@@ -46,19 +75,18 @@ __device__ __forceinline__ void dft_small(c128* x, int sign, const c128* tab, in
 #pragma unroll
   for (int j = 1; j < R; ++j) w[j] = tw_lookup(tab, j * root_stride, sign);
   c128 y[R];
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-    c128 acc = x[0];
-#pragma unroll
-    for (int t = 1; t < R; ++t) cfma(acc, x[t], w[(t * k) % R == 0 ? 1 : (t * k) % R]);
-    y[k] = acc;
-  }
-  // k = 0 row must use w^0 = 1 (the ternary above only dodges an out-of-range index at compile time)
   {
     c128 acc = x[0];
 #pragma unroll
     for (int t = 1; t < R; ++t) acc = cadd(acc, x[t]);
     y[0] = acc;
+  }
+#pragma unroll
+  for (int k = 1; k < R; ++k) {
+    c128 acc = x[0];
+#pragma unroll
+    for (int t = 1; t < R; ++t) cfma(acc, x[t], w[(t * k) % R == 0 ? 1 : (t * k) % R]);
+    y[k] = acc;
   }
 #pragma unroll
   for (int k = 0; k < R; ++k) x[k] = y[k];
@@ -71,7 +99,7 @@ __device__ __forceinline__ void dft_small<2>(c128* x, int, const c128*, int) {
   x[1] = csub(a, b);
 }
 
-// multiply by -i*sign... helper: rotate by exp(sign * i*pi/2) = sign*i
+// multiply by exp(sign * i*pi/2) = sign*i
 __device__ __forceinline__ c128 mul_i_sign(c128 a, int sign) {
   return sign > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
 }
@@ -86,7 +114,37 @@ __device__ __forceinline__ void dft_small<4>(c128* x, int sign, const c128*, int
   x[3] = csub(b, d);
 }
 
-// Generic small DFT of prime (or any) radix r using the root table: roots[j] = exp(-2 pi i j / r).
+template <>
+__device__ __forceinline__ void dft_small<8>(c128* x, int sign, const c128*, int) {
+  const double h = 0.70710678118654752440;
+  c128 a[4], b[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    a[m] = cadd(x[m], x[m + 4]);
+    b[m] = csub(x[m], x[m + 4]);
+  }
+  // b[m] *= exp(sign * 2 pi i m / 8)
+  {
+    const c128 t1 = b[1], t3 = b[3];
+    if (sign > 0) {
+      b[1] = make_double2(h * (t1.x - t1.y), h * (t1.x + t1.y));    // * (1+i)/sqrt2
+      b[3] = make_double2(-h * (t3.x + t3.y), h * (t3.x - t3.y));   // * (-1+i)/sqrt2
+    } else {
+      b[1] = make_double2(h * (t1.x + t1.y), h * (t1.y - t1.x));    // * (1-i)/sqrt2
+      b[3] = make_double2(h * (t3.y - t3.x), -h * (t3.x + t3.y));   // * (-1-i)/sqrt2
+    }
+    b[2] = mul_i_sign(b[2], sign);
+  }
+  dft_small<4>(a, sign, nullptr, 0);
+  dft_small<4>(b, sign, nullptr, 0);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    x[2 * m] = a[m];
+    x[2 * m + 1] = b[m];
+  }
+}
+
+// Generic small DFT of any radix r using the root table: roots[j] = exp(-2 pi i j / r).
 __device__ __forceinline__ void dft_generic(c128* x, int r, const c128* tab, int tab_stride, int sign) {
   c128 y[kMaxRadix];
   for (int k = 0; k < r; ++k) {
@@ -109,28 +167,87 @@ __global__ void fft_table_kernel(c128* tab, int len) {
   }
 }
 
+// (w / d, w % d) with a shift fast path when d is a power of two (shift >= 0)
+__device__ __forceinline__ void fast_divmod(int w, int d, int shift, int& q, int& r) {
+  if (shift >= 0) {
+    q = w >> shift;
+    r = w & (d - 1);
+  } else {
+    q = w / d;
+    r = w - q * d;
+  }
+}
+__device__ __forceinline__ int pow2_shift(int d) { return (d & (d - 1)) == 0 ? 31 - __clz(d) : -1; }
+
+struct StageIo {
+  const c128* src;          // shared source (unused by the first stage)
+  c128* dst;                // shared destination (unused by the last stage)
+  const c128* gin;          // global input / output
+  c128* gout;
+  const int64_t* in_base;   // per-line element offsets (shared)
+  const int64_t* out_base;
+  const int64_t* inner_idx;
+  bool first, last, line_fastest;
+};
+
+// One Stockham stage of radix R over `lines` lines held by the CTA.  The first stage reads its butterfly
+// inputs straight from global memory and the last one writes straight to global memory, so an FFT of S
+// stages makes S-1 round trips through shared memory instead of S+1.
 template <int R>
-__device__ __forceinline__ void stage_fixed(const c128* src, c128* dst, int len, int ns, int lines,
-                                            const c128* tab, int sign) {
+__device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io, int ns, int lines, const c128* tab) {
+  const int len = P.len, sign = P.sign, lpc = P.lines_per_cta;
   const int per_line = len / R;
-  const int work = per_line * lines;
   const int tw_step = len / (ns * R);
+  const int pl_shift = pow2_shift(per_line), ns_shift = pow2_shift(ns);
+  const int lshift = 31 - __clz(lpc);
+  const int work = per_line * (io.line_fastest ? lpc : lines);
   for (int w = threadIdx.x; w < work; w += kFftThreads) {
-    const int line = w / per_line;
-    const int j = w - line * per_line;
-    const int k = j % ns;
+    int line, j, jq, k;
+    if (io.line_fastest) {
+      line = w & (lpc - 1);
+      j = w >> lshift;
+      if (line >= lines) continue;
+    } else {
+      fast_divmod(w, per_line, pl_shift, line, j);
+    }
+    fast_divmod(j, ns, ns_shift, jq, k);
     c128 x[R];
+    if (io.first) {
+      const int64_t base = io.in_base[line];
 #pragma unroll
-    for (int t = 0; t < R; ++t) x[t] = src[line * len + j + t * per_line];
+      for (int t = 0; t < R; ++t) x[t] = io.gin[base + (int64_t)(j + t * per_line) * P.in_sl];
+    } else {
 #pragma unroll
-    for (int t = 1; t < R; ++t) x[t] = cmul(x[t], tw_lookup(tab, t * k * tw_step, sign));
+      for (int t = 0; t < R; ++t) x[t] = io.src[line * len + j + t * per_line];
+    }
+    if (ns > 1) {
+#pragma unroll
+      for (int t = 1; t < R; ++t) x[t] = cmul(x[t], tw_lookup(tab, t * k * tw_step, sign));
+    }
     dft_small<R>(x, sign, tab, len / R);
-    const int base = line * len + (j - k) * R + k;
+    const int pos0 = (j - k) * R + k;
+    if (io.last) {
+      const int64_t base = io.out_base[line];
 #pragma unroll
-    for (int t = 0; t < R; ++t) dst[base + t * ns] = x[t];
+      for (int t = 0; t < R; ++t) {
+        const int pos = pos0 + t * ns;
+        c128 v = cscale(x[t], P.scale);
+        if (P.tw_len) {
+          double sn, cs;
+          const int64_t prod = ((int64_t)pos * io.inner_idx[line]) % P.tw_len;
+          sincospi((double)sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
+          v = cmul(v, make_double2(cs, sn));
+        }
+        io.gout[base + (int64_t)pos * P.out_sl] = v;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < R; ++t) io.dst[line * len + pos0 + t * ns] = x[t];
+    }
   }
 }
 
+// Any radix (primes 11..31): shared memory on both sides (the caller brackets it with copy stages).
 __device__ __forceinline__ void stage_generic(const c128* src, c128* dst, int len, int ns, int r, int lines,
                                               const c128* tab, int sign) {
   const int per_line = len / r;
@@ -152,95 +269,141 @@ __device__ __forceinline__ void stage_generic(const c128* src, c128* dst, int le
   }
 }
 
-__global__ void __launch_bounds__(kFftThreads)
+__device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; }
+
+__global__ void __launch_bounds__(kFftThreads, 3)
 fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
   extern __shared__ c128 smem[];
+  __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
   const int len = P.len;
   const int lpc = P.lines_per_cta;
-  c128* buf0 = smem;
-  c128* buf1 = smem + (size_t)lpc * len;
-  c128* tab = buf1 + (size_t)lpc * len;  // [len]
+  c128* tab = smem;                       // [len]
+  c128* buf0 = smem + len;                // [lpc][len]
+  c128* buf1 = buf0 + (size_t)lpc * len;  // [lpc][len]  (only when the pass needs it, see launch_pass)
 
   const int64_t n_lines = P.n_outer * P.n_inner;
   const int64_t line0 = (int64_t)blockIdx.x * lpc;
   const int lines = (int)sqb_min64(lpc, n_lines - line0);
   if (lines <= 0) return;
 
-  for (int j = threadIdx.x; j < len; j += kFftThreads) tab[j] = tab_g[j];
-
-  // ---- load
-  const int total = lines * len;
-  if (P.inner_fastest) {
-    for (int e = threadIdx.x; e < total; e += kFftThreads) {
-      const int pos = e / lines, l = e - pos * lines;
-      const int64_t line = line0 + l;
-      const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
-      buf0[l * len + pos] = in[o * P.in_so + pos * P.in_sl + i * P.in_si];
-    }
-  } else {
-    for (int e = threadIdx.x; e < total; e += kFftThreads) {
-      const int l = e / len, pos = e - l * len;
-      const int64_t line = line0 + l;
-      const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
-      buf0[l * len + pos] = in[o * P.in_so + pos * P.in_sl + i * P.in_si];
-    }
+  if (threadIdx.x < lines) {
+    const int64_t line = line0 + threadIdx.x;
+    const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
+    s_in_base[threadIdx.x] = digits_offset(P.in_outer, o) + digits_offset(P.in_inner, i);
+    s_out_base[threadIdx.x] = digits_offset(P.out_outer, o) + digits_offset(P.out_inner, i);
+    s_inner_idx[threadIdx.x] = i;
   }
+  for (int j = threadIdx.x; j < len; j += kFftThreads) tab[j] = tab_g[j];
   __syncthreads();
 
-  // ---- stages
+  const int lshift = 31 - __clz(lpc);
+  // A generic-radix stage at either end (or a length-1 transform) cannot touch global memory itself:
+  // stage the data through shared memory with plain copies in that case.
+  const bool copy_in = P.n_stages == 0 || !radix_is_fixed(P.radix[0]);
+  const bool copy_out = P.n_stages == 0 || !radix_is_fixed(P.radix[P.n_stages - 1]);
   c128* src = buf0;
   c128* dst = buf1;
+  if (copy_in) {
+    if (P.inner_fastest) {
+      const int l = threadIdx.x & (lpc - 1);
+      if (l < lines)
+        for (int pos = threadIdx.x >> lshift; pos < len; pos += kFftThreads >> lshift)
+          buf0[l * len + pos] = in[s_in_base[l] + (int64_t)pos * P.in_sl];
+    } else {
+      for (int e = threadIdx.x; e < lines * len; e += kFftThreads) {
+        const int l = e / len, pos = e - l * len;
+        buf0[l * len + pos] = in[s_in_base[l] + (int64_t)pos * P.in_sl];
+      }
+    }
+    __syncthreads();
+  }
+
   int ns = 1;
   for (int s = 0; s < P.n_stages; ++s) {
     const int r = P.radix[s];
+    StageIo io;
+    io.first = (s == 0) && !copy_in;
+    io.last = (s == P.n_stages - 1) && !copy_out;
+    io.src = src;
+    io.dst = io.first ? buf0 : dst;
+    io.gin = in;
+    io.gout = out;
+    io.in_base = s_in_base;
+    io.out_base = s_out_base;
+    io.inner_idx = s_inner_idx;
+    io.line_fastest = (io.first && P.inner_fastest) || (io.last && P.out_inner_fastest);
     switch (r) {
-      case 2: stage_fixed<2>(src, dst, len, ns, lines, tab, P.sign); break;
-      case 4: stage_fixed<4>(src, dst, len, ns, lines, tab, P.sign); break;
-      case 3: stage_fixed<3>(src, dst, len, ns, lines, tab, P.sign); break;
-      case 5: stage_fixed<5>(src, dst, len, ns, lines, tab, P.sign); break;
-      case 7: stage_fixed<7>(src, dst, len, ns, lines, tab, P.sign); break;
+      case 8: stage_fixed<8>(P, io, ns, lines, tab); break;
+      case 4: stage_fixed<4>(P, io, ns, lines, tab); break;
+      case 2: stage_fixed<2>(P, io, ns, lines, tab); break;
+      case 3: stage_fixed<3>(P, io, ns, lines, tab); break;
+      case 5: stage_fixed<5>(P, io, ns, lines, tab); break;
+      case 7: stage_fixed<7>(P, io, ns, lines, tab); break;
       default: stage_generic(src, dst, len, ns, r, lines, tab, P.sign); break;
     }
+    if (io.last) return;
     __syncthreads();
-    c128* t = src; src = dst; dst = t;
+    if (io.first) {
+      src = buf0;  // first stage wrote buf0
+      dst = buf1;
+    } else {
+      c128* t = src; src = dst; dst = t;
+    }
     ns *= r;
   }
 
-  // ---- store (optionally with the four-step twiddle)
+  // ---- copy out (generic last stage / length 1)
+  auto emit = [&](int l, int pos) {
+    c128 v = cscale(src[l * len + pos], P.scale);
+    if (P.tw_len) {
+      double sn, cs;
+      const int64_t prod = ((int64_t)pos * s_inner_idx[l]) % P.tw_len;
+      sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
+      v = cmul(v, make_double2(cs, sn));
+    }
+    out[s_out_base[l] + (int64_t)pos * P.out_sl] = v;
+  };
   if (P.out_inner_fastest) {
-    for (int e = threadIdx.x; e < total; e += kFftThreads) {
-      const int pos = e / lines, l = e - pos * lines;
-      const int64_t line = line0 + l;
-      const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
-      c128 v = cscale(src[l * len + pos], P.scale);
-      if (P.tw_len) {
-        double sn, cs;
-        const int64_t prod = ((int64_t)pos * i) % P.tw_len;
-        sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
-        v = cmul(v, make_double2(cs, sn));
-      }
-      out[o * P.out_so + pos * P.out_sl + i * P.out_si] = v;
-    }
+    const int l = threadIdx.x & (lpc - 1);
+    if (l < lines)
+      for (int pos = threadIdx.x >> lshift; pos < len; pos += kFftThreads >> lshift) emit(l, pos);
   } else {
-    for (int e = threadIdx.x; e < total; e += kFftThreads) {
-      const int l = e / len, pos = e - l * len;
-      const int64_t line = line0 + l;
-      const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
-      c128 v = cscale(src[l * len + pos], P.scale);
-      if (P.tw_len) {
-        double sn, cs;
-        const int64_t prod = ((int64_t)pos * i) % P.tw_len;
-        sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
-        v = cmul(v, make_double2(cs, sn));
-      }
-      out[o * P.out_so + pos * P.out_sl + i * P.out_si] = v;
+    for (int e = threadIdx.x; e < lines * len; e += kFftThreads) {
+      const int l = e / len;
+      emit(l, e - l * len);
     }
+  }
+}
+
+// Bloch twiddle folded into the (already in-cell transformed) eigenvectors:
+//   W[b, e, j] *= prod_a exp(sign * 2 pi i q_a(b) j_a / L_a),  q_a = FFT-order signed block index
+__global__ void fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int sign, c128* __restrict__ W) {
+  const int64_t total = batch * n * (int64_t)n;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(g % n);
+    int64_t b = block_begin + g / ((int64_t)n * n);
+    int jj = j;
+    double phase = 0.0;  // in turns
+    for (int a = d.nd - 1; a >= 0; --a) {
+      const int ja = jj % d.shape[a];
+      jj /= d.shape[a];
+      const int ba = (int)(b % d.repeat[a]);
+      b /= d.repeat[a];
+      const int qa = ba < (d.repeat[a] + 1) / 2 ? ba : ba - d.repeat[a];
+      const int64_t big = (int64_t)d.shape[a] * d.repeat[a];
+      const int64_t prod = ((int64_t)qa * ja) % big;
+      phase += (double)prod / (double)big;
+    }
+    double sn, cs;
+    sincospi((double)sign * 2.0 * phase, &sn, &cs);
+    W[g] = cmul(W[g], make_double2(cs, sn));
   }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 bool factorize(int len, int* radix, int* n_stages) {
   int n = 0, rem = len;
+  while (rem % 8 == 0) { radix[n++] = 8; rem /= 8; if (n >= kMaxStages) return false; }
   while (rem % 4 == 0) { radix[n++] = 4; rem /= 4; if (n >= kMaxStages) return false; }
   while (rem % 2 == 0) { radix[n++] = 2; rem /= 2; if (n >= kMaxStages) return false; }
   for (int p = 3; p <= kMaxRadix && rem > 1; p += 2) {
@@ -267,38 +430,37 @@ bool split_len(int len, int* l1, int* l2) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// workspace layout: [twiddle table: max_len c128][scratch: total elements c128 (only for long lines)]
-struct AxisPlan {
-  bool long_line;
-  int l1, l2;
-};
+Digits digits1(int64_t dim, int64_t stride) {
+  Digits d{};
+  d.nd = 1;
+  d.dims[0] = (int)dim;  // callers keep every digit below 2^31
+  d.strides[0] = stride;
+  return d;
+}
 
-bool plan_axis(int len, AxisPlan* ap) {
+bool smooth(int len) {
   int radix[kMaxStages], ns;
-  if (len <= kMaxSmemLen) {
-    ap->long_line = false;
-    ap->l1 = len;
-    ap->l2 = 1;
-    return factorize(len, radix, &ns);
-  }
-  ap->long_line = true;
-  if (!split_len(len, &ap->l1, &ap->l2)) return false;
-  return factorize(ap->l1, radix, &ns) && factorize(ap->l2, radix, &ns);
+  return factorize(len, radix, &ns);
 }
 
 int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t st) {
   if (!factorize(P.len, P.radix, &P.n_stages)) return SQB_E_UNSUPPORTED;
-  int lpc = kMaxSmemLen / P.len;
-  if (lpc < 1) lpc = 1;
-  if (lpc > 16) lpc = 16;
+  if (P.len > kMaxSmemLen) return SQB_E_UNSUPPORTED;
+  // lines per CTA (power of two): enough for 128..256 B coalesced runs across lines and >= 1024 elements of
+  // work per CTA, small enough for several CTAs per SM
+  int lpc = 1;
+  while (lpc * 2 <= kMaxLines && lpc * 2 * P.len <= 2048) lpc *= 2;
+  if ((P.inner_fastest || P.out_inner_fastest) && lpc < 8 && P.len * 8 <= kMaxSmemLen) lpc = 8;
   const int64_t n_lines = P.n_outer * P.n_inner;
-  if (P.inner_fastest) {
-    // a CTA's lines must share `outer`: make lines_per_cta divide n_inner
-    while (lpc > 1 && (P.n_inner % lpc)) --lpc;
-  }
-  if (lpc > n_lines) lpc = (int)n_lines;
+  while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
   P.lines_per_cta = lpc;
-  const size_t smem = ((size_t)2 * lpc * P.len + P.len) * sizeof(c128);
+  // buffers: first fixed-radix stage reads global, last writes global -> S-1 shared round trips
+  auto fixed = [](int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; };
+  const bool copy_in = P.n_stages == 0 || !fixed(P.radix[0]);
+  const bool copy_out = P.n_stages == 0 || !fixed(P.radix[P.n_stages - 1]);
+  const int smem_writes = P.n_stages - 1 + (copy_in ? 1 : 0) + (copy_out ? 1 : 0);  // stages writing shared
+  const int n_buf = smem_writes >= 2 ? 2 : 1;
+  const size_t smem = ((size_t)n_buf * lpc * P.len + P.len) * sizeof(c128);
   cudaError_t e = cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   fft_table_kernel<<<(P.len + 255) / 256, 256, 0, st>>>(tab, P.len);
@@ -309,19 +471,18 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   return SQB_OK;
 }
 
-// One axis of a [outer, len, inner] array, in -> out (in == out allowed when !long_line).
+// One axis of a [outer, len, inner] array, in -> out (in == out allowed when the line fits shared memory).
 int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, const c128* in, c128* out,
                  c128* tab, c128* scratch, cudaStream_t st) {
-  AxisPlan ap;
-  if (!plan_axis(len, &ap)) return SQB_E_UNSUPPORTED;
-  if (!ap.long_line) {
+  if (outer >= (1LL << 31) || inner >= (1LL << 31)) return SQB_E_UNSUPPORTED;
+  if (len <= kMaxSmemLen) {
     FftPass P{};
     P.len = len;
     P.n_outer = outer;
     P.n_inner = inner;
-    P.in_so = P.out_so = (int64_t)len * inner;
+    P.in_outer = P.out_outer = digits1(outer, (int64_t)len * inner);
+    P.in_inner = P.out_inner = digits1(inner, 1);
     P.in_sl = P.out_sl = inner;
-    P.in_si = P.out_si = 1;
     P.inner_fastest = P.out_inner_fastest = inner > 1;
     P.sign = sign;
     P.scale = scale;
@@ -329,21 +490,19 @@ int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, 
     return launch_pass(P, in, out, tab, st);
   }
   // four-step: view the line as [l1, l2] (n = n1*l2 + n2).
-  // pass A: l1-point transforms over n1 for every (outer, n2, inner), twiddle W_len^(k1*n2), in -> scratch
-  // pass B: l2-point transforms over n2 for every (outer, k1, inner), output index k1 + l1*k2, scratch -> out
-  const int l1 = ap.l1, l2 = ap.l2;
-  if (inner != 1) {
-    // treat (n2, inner) as the combined inner index for pass A; twiddle needs n2 alone -> only inner == 1 here
-    return SQB_E_UNSUPPORTED;
-  }
+  // pass A: l1-point transforms over n1 for every (outer, n2), twiddle W_len^(k1*n2), in -> scratch
+  // pass B: l2-point transforms over n2 for every (outer, k1), output index k1 + l1*k2, scratch -> out
+  int l1, l2;
+  if (!split_len(len, &l1, &l2) || !smooth(l1) || !smooth(l2)) return SQB_E_UNSUPPORTED;
+  if (inner != 1 || !scratch) return SQB_E_UNSUPPORTED;  // long strided lines are not needed by the Bloch path
   {
     FftPass P{};
     P.len = l1;
     P.n_outer = outer;
     P.n_inner = l2;
-    P.in_so = P.out_so = len;
+    P.in_outer = P.out_outer = digits1(outer, len);
+    P.in_inner = P.out_inner = digits1(l2, 1);
     P.in_sl = P.out_sl = l2;
-    P.in_si = P.out_si = 1;
     P.inner_fastest = P.out_inner_fastest = 1;
     P.sign = sign;
     P.scale = 1.0;
@@ -355,13 +514,12 @@ int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, 
     FftPass P{};
     P.len = l2;
     P.n_outer = outer;
-    P.n_inner = l1;  // "inner" index = k1, but lines are contiguous in n2: strides below
-    P.in_so = len;
+    P.n_inner = l1;  // inner index = k1; lines are contiguous in n2
+    P.in_outer = P.out_outer = digits1(outer, len);
+    P.in_inner = digits1(l1, l2);
+    P.out_inner = digits1(l1, 1);
     P.in_sl = 1;
-    P.in_si = l2;
-    P.out_so = len;
     P.out_sl = l1;
-    P.out_si = 1;
     P.inner_fastest = 0;
     P.out_inner_fastest = 1;
     P.sign = sign;
@@ -433,4 +591,128 @@ extern "C" int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, con
                                           align_up((size_t)len * sizeof(c128), 256));
   return fft_one_axis(outer, len, inner, sign, 1.0 / sqrt((double)len), reinterpret_cast<const c128*>(in),
                       reinterpret_cast<c128*>(out), tab, scratch, sqb_stream(stream));
+}
+
+extern "C" size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host) {
+  if (nd < 1 || nd > SQB_MAX_DIMS || !repeat_host) return 0;
+  int max_len = 1;
+  for (int a = 0; a < nd; ++a)
+    if (repeat_host[a] > max_len) max_len = repeat_host[a];
+  return align_up((size_t)max_len * sizeof(c128), 256) + 256;
+}
+
+extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
+                            sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  SqbDims d;
+  int64_t n, nk;
+  int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
+  if (rc) return rc;
+  if (!in_scratch || !out || lead < 0 || (direction != 0 && direction != 1)) return SQB_E_BADARG;
+  if (!workspace || workspace_bytes < sqb_cell_fft_workspace_bytes(nd, repeat_host)) return SQB_E_WORKSPACE;
+  if (nd > 1 && in_scratch == out) return SQB_E_BADARG;  // the scatter / gather pass is out of place
+  for (int a = 0; a < nd; ++a)
+    if (d.repeat[a] > kMaxSmemLen || !smooth(d.repeat[a])) return SQB_E_UNSUPPORTED;
+  if (lead == 0) return SQB_OK;
+  if (lead >= (1LL << 31)) return SQB_E_UNSUPPORTED;
+  c128* tab = reinterpret_cast<c128*>(workspace);
+  cudaStream_t st = sqb_stream(stream);
+  const int64_t m = n * nk;
+  const double scale = 1.0 / sqrt((double)nk);
+  c128* src = reinterpret_cast<c128*>(in_scratch);
+  c128* dst = reinterpret_cast<c128*>(out);
+
+  // supercell strides S_a = prod_{a' > a} L_a'
+  int64_t S[SQB_MAX_DIMS];
+  {
+    int64_t s = 1;
+    for (int a = nd - 1; a >= 0; --a) {
+      S[a] = s;
+      s *= (int64_t)d.shape[a] * d.repeat[a];
+    }
+  }
+  // "cell layout" [lead][b_0..b_{nd-1}][j]  <->  "position layout" [lead][x_0..x_{nd-1}], x_a = c_a N_a + j_a.
+  // direction 1 (cell -> position, sign +1): axes 0..nd-2 in place on the cell layout (this CLOBBERS
+  //   in_scratch), the last axis scatters into `out`.
+  // direction 0 (position -> cell, sign -1): the last axis gathers from the position layout into `out`,
+  //   then the other axes run in place on `out`.
+  auto scatter_pass = [&](const c128* pin, c128* pout, bool cell_is_input) -> int {
+    const int a = nd - 1;
+    FftPass P{};
+    P.len = d.repeat[a];
+    P.n_outer = lead * (nk / d.repeat[a]);
+    P.n_inner = n;
+    const Digits cell_outer = digits1(P.n_outer, (int64_t)d.repeat[a] * n);
+    const Digits cell_inner = digits1(n, 1);
+    Digits pos_outer{}, pos_inner{};
+    pos_outer.nd = nd;  // digits (lead, c_0 .. c_{nd-2})
+    pos_outer.dims[0] = (int)lead;
+    pos_outer.strides[0] = m;
+    for (int q = 0; q < nd - 1; ++q) {
+      pos_outer.dims[q + 1] = d.repeat[q];
+      pos_outer.strides[q + 1] = (int64_t)d.shape[q] * S[q];
+    }
+    pos_inner.nd = nd;  // digits (j_0 .. j_{nd-1})
+    for (int q = 0; q < nd; ++q) {
+      pos_inner.dims[q] = d.shape[q];
+      pos_inner.strides[q] = S[q];
+    }
+    const int64_t cell_sl = n, pos_sl = d.shape[a];
+    if (cell_is_input) {
+      P.in_outer = cell_outer; P.in_inner = cell_inner; P.in_sl = cell_sl;
+      P.out_outer = pos_outer; P.out_inner = pos_inner; P.out_sl = pos_sl;
+      P.sign = +1;
+    } else {
+      P.in_outer = pos_outer; P.in_inner = pos_inner; P.in_sl = pos_sl;
+      P.out_outer = cell_outer; P.out_inner = cell_inner; P.out_sl = cell_sl;
+      P.sign = -1;
+    }
+    P.inner_fastest = P.out_inner_fastest = 1;
+    P.scale = scale;
+    P.tw_len = 0;
+    return launch_pass(P, pin, pout, tab, st);
+  };
+  auto inplace_axis = [&](int a, c128* p, int sign) -> int {
+    int64_t inner = n;
+    for (int q = a + 1; q < nd; ++q) inner *= d.repeat[q];
+    int64_t outer = lead;
+    for (int q = 0; q < a; ++q) outer *= d.repeat[q];
+    return fft_one_axis(outer, d.repeat[a], inner, sign, 1.0, p, p, tab, nullptr, st);
+  };
+
+  if (direction == 1) {
+    for (int a = 0; a < nd - 1; ++a) {
+      rc = inplace_axis(a, src, +1);
+      if (rc) return rc;
+    }
+    return scatter_pass(src, dst, true);
+  }
+  rc = scatter_pass(src, dst, false);
+  if (rc) return rc;
+  for (int a = 0; a < nd - 1; ++a) {
+    rc = inplace_axis(a, dst, -1);
+    if (rc) return rc;
+  }
+  return SQB_OK;
+}
+
+extern "C" int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, int64_t block_begin,
+                                  int64_t batch, const sqb_c128* transform, sqb_c128* folded, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  SqbDims d;
+  int64_t n, nk;
+  int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
+  if (rc) return rc;
+  if (!transform || !folded || batch < 0 || block_begin < 0 || block_begin + batch > nk) return SQB_E_BADARG;
+  if (batch == 0) return SQB_OK;
+  // (1) in-cell inverse FFT of every eigenvector: [batch*n, shape...] ortho, momentum -> position
+  rc = sqb_fft_c2c(nd, shape_host, batch * n, +1, transform, folded, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  // (2) Bloch twiddle exp(+2 pi i q_a j_a / L_a)
+  const int64_t total = batch * n * n;
+  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
+  fold_twiddle_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(d, (int)n, block_begin, batch, +1,
+                                                           reinterpret_cast<c128*>(folded));
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
 }

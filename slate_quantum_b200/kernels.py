@@ -188,6 +188,49 @@ def fft_axis(x: torch.Tensor, outer: int, length: int, inner: int, sign: int) ->
     return out
 
 
+def cell_fft(
+    shape: Sequence[int], repeat: Sequence[int], x: torch.Tensor, direction: int, out: torch.Tensor | None = None
+) -> torch.Tensor:
+    """K4b: [lead, n_k, N] cell layout <-> [lead, M] position order. direction 1 CLOBBERS `x` when nd > 1."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(x, "x")
+    m = int(np.prod(shape)) * int(np.prod(repeat))
+    lead = x.numel() // m
+    out = torch.empty_like(x) if out is None else _c128(out, "out")
+    rep_c = _lib.int_array(repeat)
+    ws_bytes = lib.sqb_cell_fft_workspace_bytes(len(repeat), rep_c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_cell_fft(
+        len(shape), _lib.int_array(shape), rep_c, direction, lead, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream()
+    )
+    _lib.check(rc, "sqb_cell_fft")
+    _count(2 * len(shape))
+    return out
+
+
+def fold_transform(
+    shape: Sequence[int], repeat: Sequence[int], transform: torch.Tensor, block_begin: int = 0,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """Eigenvectors -> in-cell position basis with the Bloch twiddle folded in (see include/slate_b200.h)."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(transform, "transform")
+    batch, n, _ = transform.shape
+    out = torch.empty_like(transform) if out is None else _c128(out, "out")
+    shape_c = _lib.int_array(shape)
+    ws_bytes = lib.sqb_fft_workspace_bytes(len(shape), shape_c, batch * n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_fold_transform(
+        len(shape), shape_c, _lib.int_array(repeat), block_begin, batch, _ptr(transform), _ptr(out), _ptr(ws),
+        ws_bytes, _stream(),
+    )
+    _lib.check(rc, "sqb_fold_transform")
+    _count(_fft_launches(shape) + 1)
+    return out
+
+
 def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """K2 IN PLACE: `a` [batch,n,n] is overwritten by the transform (rows = eigenvectors).
 
@@ -257,11 +300,24 @@ def evolve_eigen(w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: fl
     return out
 
 
+def uniform_step(times: np.ndarray | Sequence[float]) -> float | None:
+    """dt if `times` (host values) is a uniform grid to within a few ulp, else None."""
+    t = np.asarray(times, dtype=np.float64)
+    if t.size < 2:
+        return None
+    dt = (t[-1] - t[0]) / (t.size - 1)
+    err = np.abs(t - (t[0] + dt * np.arange(t.size))).max()
+    return float(dt) if err <= 4 * np.finfo(np.float64).eps * max(np.abs(t).max(), abs(dt)) else None
+
+
 def evolve_bloch(
     transform: torch.Tensor, w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float,
-    out: torch.Tensor | None = None,
+    out: torch.Tensor | None = None, uniform_dt: float | None = None,
 ) -> torch.Tensor:
-    """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM)."""
+    """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM).
+
+    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`) to use the cheaper
+    phase recurrence in the GEMM's producer warps."""
     _require_cuda()
     lib = _lib.load()
     _c128(transform, "transform")
@@ -273,9 +329,19 @@ def evolve_bloch(
     if out is None:
         out = torch.empty((t_count, batch * n), dtype=torch.complex128, device="cuda")
     _c128(out, "out")
-    rc = lib.sqb_evolve_bloch(
-        n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), batch * n, _stream()
-    )
-    _lib.check(rc, "sqb_evolve_bloch")
-    _count(-(-batch // 65535))
+    if uniform_dt is None:
+        rc = lib.sqb_evolve_bloch(
+            n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), batch * n,
+            _stream(),
+        )
+        _lib.check(rc, "sqb_evolve_bloch")
+        _count(-(-batch // 65535))
+    else:
+        step = torch.empty((batch * n,), dtype=torch.complex128, device="cuda")
+        rc = lib.sqb_evolve_bloch_uniform(
+            n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(uniform_dt), float(hbar),
+            _ptr(out), batch * n, _ptr(step), _stream(),
+        )
+        _lib.check(rc, "sqb_evolve_bloch_uniform")
+        _count(1 - (-batch // 65535))
     return out

@@ -49,6 +49,7 @@ class BlochSolver:
         self.transform: torch.Tensor | None = None
         self.info: torch.Tensor | None = None
         self._eigh_ws: torch.Tensor | None = None
+        self.transform_folded: torch.Tensor | None = None
 
     # ------------------------------------------------------------------ K1
     def build(self, potential_table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -75,7 +76,16 @@ class BlochSolver:
         w, v, info = kernels.eigh_batched(h, workspace=self._eigh_ws)
         self.eigenvalues, self.transform, self.info = w, v, info
         self.hamiltonian = None
+        self.transform_folded = None
         return w, v
+
+    def fold(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Eigenvectors in the in-cell POSITION basis with the Bloch twiddle applied (done once per eigh)."""
+        if self.transform_folded is None or out is not None:
+            self.transform_folded = kernels.fold_transform(
+                self.shape, self.repeat, self.transform, self.block_begin, out=out
+            )
+        return self.transform_folded
 
     def release_workspace(self) -> None:
         self._eigh_ws = None
@@ -97,9 +107,37 @@ class BlochSolver:
         """The reference's return value: [T, count*N] amplitudes in the eigenbasis (schrodinger.py:51-53)."""
         return kernels.evolve_eigen(self.eigenvalues.reshape(-1), coefficients.reshape(-1), times, self.hbar)
 
-    def evolve_bloch(self, coefficients: torch.Tensor, times: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def evolve_bloch(
+        self, coefficients: torch.Tensor, times: torch.Tensor, out: torch.Tensor | None = None,
+        uniform_dt: float | None = None,
+    ) -> torch.Tensor:
         """[T, count*N] states in the Bloch-ordered momentum basis (fused phase x eigenvector GEMM)."""
-        return kernels.evolve_bloch(self.transform, self.eigenvalues, coefficients, times, self.hbar, out=out)
+        return kernels.evolve_bloch(
+            self.transform, self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt
+        )
+
+    def evolve_cell(
+        self, coefficients: torch.Tensor, times: torch.Tensor, out: torch.Tensor | None = None,
+        uniform_dt: float | None = None,
+    ) -> torch.Tensor:
+        """[T, count*N] states in the cell layout (block, in-cell POSITION); cell_to_position finishes the job."""
+        return kernels.evolve_bloch(
+            self.fold(), self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt
+        )
+
+    def cell_to_position(self, states_cell: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[T, M] cell layout (ALL blocks) -> supercell position basis: R-point FFTs across blocks only.
+        `states_cell` is used as scratch."""
+        if states_cell.shape[-1] != self.m:
+            msg = "cell_to_position needs every k-block (all-to-all the k-shards into time-shards first)"
+            raise ValueError(msg)
+        return kernels.cell_fft(self.shape, self.repeat, states_cell, 1, out=out)
+
+    def evolve_position(
+        self, coefficients: torch.Tensor, times: torch.Tensor, uniform_dt: float | None = None
+    ) -> torch.Tensor:
+        """Position-basis states [T, M] (needs block_count == n_k)."""
+        return self.cell_to_position(self.evolve_cell(coefficients, times, uniform_dt=uniform_dt))
 
     # ------------------------------------------------------------------ K5 + K4
     def bloch_to_position(self, states_bloch: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -225,6 +225,12 @@ def test_project_and_evolve(cuda, n, batch, n_t):
     out = kernels.evolve_bloch(td, wd, c, timed, HBAR).cpu().numpy()
     out_ref = o.back_transform(t_ref, a_ref).reshape(n_t, batch * n)
     np.testing.assert_allclose(out, out_ref, rtol=0, atol=1e-9)
+    # uniform-grid fast path (phase recurrence in the producer warps) must agree to the same tolerance
+    dt = kernels.uniform_step(times)
+    assert dt is not None
+    out_u = kernels.evolve_bloch(td, wd, c, timed, HBAR, uniform_dt=dt).cpu().numpy()
+    np.testing.assert_allclose(out_u, out_ref, rtol=0, atol=1e-9)
+    assert kernels.uniform_step(times**2 / max(times[-1], 1e-300)) is None
 
 
 def test_full_pipeline_vs_expm(cuda):
@@ -255,3 +261,62 @@ def test_full_pipeline_vs_expm(cuda):
     hx = o.momentum_matrix_to_position(hk, big)
     ref = np.array([scipy.linalg.expm(-1j * hx * tt / HBAR) @ psi for tt in times])
     np.testing.assert_allclose(outx, ref, rtol=0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------- K4b cell FFT
+@pytest.mark.parametrize(("shape", "repeat"), [((5,), (4,)), ((8,), (6,)), ((4, 3), (3, 4)), ((4, 4), (8, 2)),
+                                                ((3, 4, 5), (2, 3, 4)), ((7, 7, 7), (2, 4, 2))])
+def test_cell_fft_and_fold_equal_permute_plus_supercell_fft(cuda, shape, repeat):
+    """fold(V) + cell FFT must equal K5 + supercell ifftn (the literal reference chain) on the same data."""
+    torch, kernels = _gpu()
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    big = tuple(a * b for a, b in zip(shape, repeat))
+    rng = np.random.default_rng(8)
+    v = rng.normal(size=(n_k, n, n)) + 1j * rng.normal(size=(n_k, n, n))  # any "transform"
+    a = rng.normal(size=(3, n_k, n)) + 1j * rng.normal(size=(3, n_k, n))  # amplitudes per (t, block, e)
+    bloch = np.einsum("tbe,bek->tbk", a, v).reshape(3, -1)
+    want = o.momentum_to_position(o.bloch_into_supercell(bloch, shape, repeat), big)
+    vd = kernels.to_device(v, torch.complex128)
+    folded = kernels.fold_transform(shape, repeat, vd)
+    cell = kernels.apply_transform(folded, kernels.to_device(a.reshape(3, -1), torch.complex128), 0)
+    got = kernels.cell_fft(shape, repeat, cell, 1).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    # direction 0 is the inverse map
+    back = kernels.cell_fft(shape, repeat, kernels.to_device(want, torch.complex128), 0)
+    cell_ref = kernels.apply_transform(folded, kernels.to_device(a.reshape(3, -1), torch.complex128), 0)
+    np.testing.assert_allclose(back.cpu().numpy(), cell_ref.cpu().numpy(), rtol=0, atol=1e-12)
+
+
+def test_fold_transform_block_range(cuda):
+    torch, kernels = _gpu()
+    shape, repeat = (4, 3), (3, 4)
+    n, n_k = 12, 12
+    rng = np.random.default_rng(9)
+    v = rng.normal(size=(n_k, n, n)) + 1j * rng.normal(size=(n_k, n, n))
+    vd = kernels.to_device(v, torch.complex128)
+    full = kernels.fold_transform(shape, repeat, vd).cpu().numpy()
+    part = kernels.fold_transform(shape, repeat, vd[5:9].contiguous(), block_begin=5).cpu().numpy()
+    np.testing.assert_array_equal(part, full[5:9])
+
+
+def test_evolve_position_pipeline(cuda):
+    """BlochSolver.evolve_position (folded eigenvectors + cell FFT) against the oracle chain."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    dx = 2 * np.pi * np.eye(2)
+    shape, repeat = (6, 4), (4, 6)
+    comps = o.sin_potential_components(shape, 4.0, 0.2)
+    solver = BlochSolver(shape, repeat, o.stacked_dk(dx), HBAR**2, HBAR)
+    solver.build(kernels.to_device(o.pad_components(shape, comps).ravel(), torch.complex128))
+    blocks = solver.hamiltonian.cpu().numpy()
+    solver.diagonalise()
+    rng = np.random.default_rng(10)
+    psi = rng.normal(size=solver.m) + 1j * rng.normal(size=solver.m)
+    psi /= np.linalg.norm(psi)
+    times = np.linspace(0, 5 * HBAR, 11)
+    c = solver.project(kernels.to_device(psi, torch.complex128))
+    got = solver.evolve_position(c, kernels.to_device(times, torch.float64)).cpu().numpy()
+    w_ref, t_ref = o.eigh_blocks(blocks)
+    want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
