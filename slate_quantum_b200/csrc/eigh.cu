@@ -438,17 +438,83 @@ replay_kernel(int n, EighWs ws) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// (4) Householder back-transformation.  Warp = 2 eigenvectors; lane: kg = lane & 15 owns components
-// k = kk*LPE + kg (kk < KPT) of eigenvector e, all in registers (LPE = 16 lanes per eigenvector, 32 for n > 256).
+// (4) Householder back-transformation.  Warp = 32/LPE eigenvectors; lane kg = lane % LPE owns components
+// k = kk*LPE + kg (kk < KPT) of eigenvector e, all in registers (LPE = 16 lanes per eigenvector, 32 for
+// n > 256).  The reflectors are streamed through a kBtStages-deep shared-memory ring by 1-D bulk (TMA)
+// copies issued by a dedicated producer warp; consumer warps never touch global memory inside the loop.
+constexpr int kBtStages = 8;
+constexpr int kBtConsumerWarps = 8;
+
+__device__ __forceinline__ uint32_t bt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bt_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bt_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bt_mbar_arrive_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bt_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bt_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bt_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bt_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bt_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(bt_smem_u32(bar))
+      : "memory");
+}
+
 template <int KPT, int LPE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * (kBtConsumerWarps + 1), 2)
 backtransform_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
+  extern __shared__ __align__(16) unsigned char bt_smem[];
+  c128* ring = reinterpret_cast<c128*>(bt_smem);                        // [stages][n]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kBtStages * n);   // [stages]
+  uint64_t* empty = full + kBtStages;                                   // [stages]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int kg = lane % LPE;
-  const int e = (blockIdx.x * 8 + warp) * (32 / LPE) + (lane / LPE);
   const int64_t b = blockIdx.y;
   const c128* Y = ws.y + b * (int64_t)n * n;
   const c128* tau = ws.tau + b * n;
+  const int n_refl = n - 1;  // reflectors n-2 .. 0, iteration it <-> reflector i = n-2-it
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBtStages; ++s) {
+      bt_mbar_init(&full[s], 1);
+      bt_mbar_init(&empty[s], kBtConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kBtConsumerWarps) {
+    // ---- producer warp: one lane issues the bulk copies
+    if (lane == 0) {
+      for (int it = 0; it < n_refl; ++it) {
+        const int s = it % kBtStages;
+        const uint32_t ph = (uint32_t)((it / kBtStages) & 1);
+        bt_mbar_wait(&empty[s], ph ^ 1u);
+        const int i = n - 2 - it;
+        const uint32_t bytes = (uint32_t)((n - i - 1) * sizeof(c128));
+        bt_mbar_arrive_tx(&full[s], bytes);
+        bt_bulk_g2s(ring + s * n + i + 1, Y + (int64_t)i * n + i + 1, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  const int kg = lane % LPE;
+  const int e = (blockIdx.x * kBtConsumerWarps + warp) * (32 / LPE) + (lane / LPE);
   const double* qt = ws.qt + b * (int64_t)n * n;
   c128* out = A_all + b * (int64_t)n * n;
   const bool valid = e < n;
@@ -459,33 +525,45 @@ backtransform_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
     const int k = kk * LPE + kg;
     z[kk] = make_double2((valid && k < n) ? qt[(int64_t)e * n + k] : 0.0, 0.0);
   }
-  // reflectors n-2 .. 0 ; reflector i touches rows >= i+1.  Group by q = (i+1)/16 so that the chunk loop
-  // [q, KPT) has compile-time bounds (registers stay statically indexed).
+  // Group reflectors by q = (i+1)/LPE so that the chunk loop [q, KPT) has compile-time bounds
+  // (registers stay statically indexed) while skipping the rows above the reflector's support.
+  int it = 0;
 #pragma unroll
   for (int q = KPT - 1; q >= 0; --q) {
-    int i_hi = min(n - 2, q * LPE + LPE - 2);  // i+1 <= q*LPE + LPE-1
-    int i_lo = max(0, q * LPE - 1);            // i+1 >= q*LPE
-    for (int i = i_hi; i >= i_lo; --i) {
+    const int i_hi = min(n - 2, q * LPE + LPE - 2);  // i+1 <= q*LPE + LPE-1
+    const int i_lo = max(0, q * LPE - 1);            // i+1 >= q*LPE
+    for (int i = i_hi; i >= i_lo; --i, ++it) {
+      const int s = it % kBtStages;
+      const uint32_t ph = (uint32_t)((it / kBtStages) & 1);
       const c128 t = tau[i];
-      if (t.x == 0.0 && t.y == 0.0) continue;
-      const c128* yi = Y + (int64_t)i * n;
-      c128 v[KPT];
-      c128 dot = make_double2(0.0, 0.0);
+      bt_mbar_wait(&full[s], ph);
+      if (t.x != 0.0 || t.y != 0.0) {
+        const c128* yi = ring + s * n;
+        c128 dot = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int kk = q; kk < KPT; ++kk) {
-        const int k = kk * LPE + kg;
-        v[kk] = (k >= i + 1 && k < n) ? yi[k] : make_double2(0.0, 0.0);
-        cfmac(dot, v[kk], z[kk]);
+        for (int kk = q; kk < KPT; ++kk) {
+          const int k = kk * LPE + kg;
+          const c128 v = (k >= i + 1 && k < n) ? yi[k] : make_double2(0.0, 0.0);
+          cfmac(dot, v, z[kk]);
+        }
+#pragma unroll
+        for (int o = LPE / 2; o > 0; o >>= 1) {
+          dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o);
+          dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
+        }
+        const c128 sc = cmul(t, dot);
+        const c128 ms = make_double2(-sc.x, -sc.y);
+        // second sweep re-reads the reflector from shared memory (cheaper than 2*KPT more registers:
+        // keeps the kernel at 2 CTAs / SM)
+#pragma unroll
+        for (int kk = q; kk < KPT; ++kk) {
+          const int k = kk * LPE + kg;
+          const c128 v = (k >= i + 1 && k < n) ? yi[k] : make_double2(0.0, 0.0);
+          cfma(z[kk], v, ms);
+        }
       }
-#pragma unroll
-      for (int o = LPE / 2; o > 0; o >>= 1) {
-        dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o);
-        dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
-      }
-      const c128 s = cmul(t, dot);
-      const c128 ms = make_double2(-s.x, -s.y);
-#pragma unroll
-      for (int kk = q; kk < KPT; ++kk) cfma(z[kk], v[kk], ms);
+      __syncwarp();
+      if (lane == 0) bt_mbar_arrive(&empty[s]);
     }
   }
   if (valid) {
@@ -543,9 +621,12 @@ int launch_tridiag(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t
 
 template <int KPT, int LPE>
 int launch_back(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st) {
-  const int per_cta = 8 * (32 / LPE);
+  const int per_cta = kBtConsumerWarps * (32 / LPE);
   dim3 grid((unsigned)((n + per_cta - 1) / per_cta), (unsigned)count);
-  backtransform_kernel<KPT, LPE><<<grid, 256, 0, st>>>(n, A, ws);
+  const size_t smem = (size_t)kBtStages * n * sizeof(c128) + 2 * kBtStages * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(backtransform_kernel<KPT, LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  backtransform_kernel<KPT, LPE><<<grid, 32 * (kBtConsumerWarps + 1), smem, st>>>(n, A, ws);
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }
