@@ -202,7 +202,7 @@ def run_ours(args) -> None:
     import torch.distributed as dist
 
     from slate_quantum_b200 import _lib, kernels
-    from slate_quantum_b200.pipeline import BlochSolver
+    from slate_quantum_b200.pipeline import BlochSolver, exchange_k_to_time
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +214,7 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
     cfg = CONFIGS[args.config]
-    with_position = bool(args.position) and world == 1
+    with_position = bool(args.position)
 
     # weak scaling: the k-grid grows along axis 0 with the number of GPUs; rank r owns n_k contiguous blocks
     repeat_global = (cfg.repeat[0] * world, *cfg.repeat[1:])
@@ -238,16 +238,16 @@ def run_ours(args) -> None:
     sink = torch.zeros(8, dtype=torch.float64, device="cuda")
     fl = ctypes.c_double(0.0)
 
-    def peak(fn) -> float:
+    def peak(fn, *lead) -> float:
         best = 0.0
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for _ in range(3):  # warm the clocks up: the first launches after idle run below boost
-            fn(20000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), st)
+        for _ in range(2):
+            fn(*lead, 20000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), st)
         torch.cuda.synchronize()
-        for _ in range(6):
+        for _ in range(4):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            fn(20000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), st)
+            fn(*lead, 20000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), st)
             b.record()
             torch.cuda.synchronize()
             best = max(best, fl.value / a.elapsed_time(b) / 1e9)
@@ -260,16 +260,19 @@ def run_ours(args) -> None:
     free, _ = torch.cuda.mem_get_info()
     row_bytes = n_k_local * n * 16
     t_tile = T
-    budget = int((free - (n_k_local * n * n * 16 if with_position else 0)) * (0.42 if with_position else 0.8))
+    # buffers of one time tile: states (+ position output; + all-to-all receive/transposed copies at N > 1)
+    n_tiles_buf = (2 if world == 1 else 4) if with_position else 1
+    budget = int((free - (n_k_local * n * n * 16 if with_position else 0)) * 0.85 / n_tiles_buf)
     while t_tile * row_bytes > budget and t_tile > 64:
         t_tile //= 2
     states = torch.empty((t_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
-    pos_out = torch.empty_like(states) if with_position else None
+    # position output: time rows [*, M_global]; at N > 1 a rank keeps t_tile / world rows of every block
+    pos_out = torch.empty((t_tile // world, n_k_global * n), dtype=torch.complex128, device="cuda") if with_position else None
     folded_buf = torch.empty_like(h_buf) if with_position else None
     eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    stage_names = ["build", "eigh", "fold", "project", "evolve", "position"]
+    stage_names = ["build", "eigh", "fold", "project", "evolve", "exchange", "position"]
 
     def step(record: list | None = None) -> None:
         """One pass of the hot path.  `record` collects (stage, start_event, end_event) triples."""
@@ -300,7 +303,12 @@ def run_ours(args) -> None:
             tt = min(t_tile, T - t0)
             if with_position:
                 timed("evolve", lambda: solver.evolve_cell(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
-                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
+                if world == 1:
+                    timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
+                else:
+                    # k-shards -> time-shards (NCCL all-to-all over NVLink), then the across-block cell FFT
+                    full = timed("exchange", lambda: exchange_k_to_time(states[:tt]))
+                    timed("position", lambda: solver.cell_to_position(full, out=pos_out[: tt // world]))
             else:
                 timed("evolve", lambda: solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
 
@@ -315,7 +323,8 @@ def run_ours(args) -> None:
     sync_all()
     assert int(solver.info.abs().sum().item()) == 0, "eigensolver reported non-convergence"
     # roofline denominators, measured now that the warm-up steps have brought the clocks up
-    dmma_peak = peak(lib.sqb_peak_dmma)
+    dmma_variants = [peak(lib.sqb_peak_dmma, v) for v in range(3)]  # 4 / 8 / 16 chains per warp
+    dmma_peak = max(dmma_variants)
     dfma_peak = peak(lib.sqb_peak_dfma)
 
     # ---- device-resident timed region: exactly K steps
@@ -354,8 +363,12 @@ def run_ours(args) -> None:
         stage_buf = [torch.empty((d2h_rows, n_k_local * n), dtype=torch.complex128).pin_memory() for _ in range(2)]
         eig_host = torch.empty((n_k_local * n,), dtype=torch.float64).pin_memory()
         tile_free = [torch.cuda.Event(), torch.cuda.Event()]
-        pos_tmp = torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda") if with_position else None
-        e_src = pos_out if with_position else states
+        pos_tmp = (
+            torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
+            if with_position and world == 1 else None
+        )
+        e2e_position = with_position and world == 1  # at N > 1 the e2e leg returns k-sharded momentum-basis states
+        e_src = pos_out if e2e_position else states
         h2d = table_h.numel() * 16 + psi_h.numel() * 16 + times_h.numel() * 8
         d2h = eig_host.numel() * 8 + T * row_bytes
 
@@ -367,7 +380,7 @@ def run_ours(args) -> None:
             solver.build(tb, out=h_buf)
             solver.diagonalise()
             eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
-            if with_position:
+            if e2e_position:
                 solver.fold(out=folded_buf)
             c = solver.project(ps)
             k = 0
@@ -375,7 +388,7 @@ def run_ours(args) -> None:
                 tt = min(e_tile, T - t0)
                 buf = e_src[(i_tile & 1) * e_tile : (i_tile & 1) * e_tile + tt]
                 cur.wait_event(tile_free[i_tile & 1])  # the D2H of the tile that used this buffer is done
-                if with_position:
+                if e2e_position:
                     solver.evolve_cell(c, tm[t0 : t0 + tt], out=pos_tmp[:tt], uniform_dt=dt_uniform)
                     solver.cell_to_position(pos_tmp[:tt], out=buf)
                 else:
@@ -446,11 +459,14 @@ def run_ours(args) -> None:
                 "time_tile": t_tile,
                 "l2_policy": "inputs larger than L2: every step rebuilds and re-reads the "
                 f"{n_k_local * n * n * 16 / 1e9:.2f} GB block array (L2 = 126 MB)",
-                "parallelism": f"k-block sharding x{world}" + (", NCCL all-gather of eigenvalues" if world > 1 else ""),
+                "parallelism": f"k-block sharding x{world}"
+                + (", NCCL all-gather of eigenvalues, NCCL all-to-all (k-shards -> time-shards) before the cell FFT"
+                   if world > 1 else ""),
             },
             "blocks_diagonalised_per_s": n_k_global / ((stage_ms["build"] + stage_ms["eigh"]) * 1e-3),
             "state_time_evolutions_per_s": T
-            / ((stage_ms["fold"] + stage_ms["project"] + stage_ms["evolve"] + stage_ms["position"]) * 1e-3),
+            * world
+            / ((stage_ms["fold"] + stage_ms["project"] + stage_ms["evolve"] + stage_ms["exchange"] + stage_ms["position"]) * 1e-3),
             "stage_ms": stage_ms,
             "roofline": {
                 "kernel": "evolve_bloch_kernel (K3c fused phase x eigenvector complex GEMM, DMMA.8x8x4)",
@@ -460,8 +476,9 @@ def run_ours(args) -> None:
                 "unit": "TFLOP/s",
                 "frac": ach / dmma_peak,
                 "traffic": None,
-                "peak_source": "FP64 DMMA issue-rate micro-benchmark sqb_peak_dmma measured in this run "
-                "(MEASURED_PEAKS.json carries only bf16 and HBM); plain DFMA peak measured "
+                "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
+                f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
+                "warm-up (MEASURED_PEAKS.json carries only bf16 and HBM); plain DFMA peak measured "
                 f"{dfma_peak:.1f} TFLOP/s",
                 "algorithmic_flops_per_launch": flops_evolve * min(t_tile, T) / T,
             },

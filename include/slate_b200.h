@@ -185,11 +185,12 @@ int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const doub
 
 /* ------------------------------------------------------------------------------------------------
  * Measured-peak micro-benchmarks (used by bench.py for the roofline denominators; not on the path).
- *   sqb_peak_dmma : runs `iters` dependent-free DMMA.8x8x4 chains on every SM; returns 0 and the
- *                   number of real FP64 flops executed in *flops_host.  Time it with CUDA events.
+ *   sqb_peak_dmma : `iters` rounds of independent DMMA.8x8x4 chains on every SM (variant 0/1/2 = 4/8/16
+ *                   chains per warp; the loop is sensitive to chain count and code placement, so the
+ *                   caller times every variant and takes the best); *flops_host = real FP64 flops executed.
  *   sqb_peak_dfma : same with plain DFMA.
  * ---------------------------------------------------------------------------------------------- */
-int sqb_peak_dmma(int64_t iters, double* sink, double* flops_host, void* stream);
+int sqb_peak_dmma(int variant, int64_t iters, double* sink, double* flops_host, void* stream);
 int sqb_peak_dfma(int64_t iters, double* sink, double* flops_host, void* stream);
 
 #ifdef __cplusplus

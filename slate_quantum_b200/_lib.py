@@ -104,7 +104,7 @@ def load() -> ctypes.CDLL:
         c_void_p, c_void_p,
     ]
     lib.sqb_peak_dmma.restype = c_int
-    lib.sqb_peak_dmma.argtypes = [c_int64, c_void_p, dp, c_void_p]
+    lib.sqb_peak_dmma.argtypes = [c_int, c_int64, c_void_p, dp, c_void_p]
     lib.sqb_peak_dfma.restype = c_int
     lib.sqb_peak_dfma.argtypes = [c_int64, c_void_p, dp, c_void_p]
     _lib = lib

@@ -147,3 +147,42 @@ class BlochSolver:
             raise ValueError(msg)
         states_k = kernels.bloch_permute(self.shape, self.repeat, states_bloch.contiguous(), 1)
         return kernels.fft_c2c(states_k, self.supercell, +1, out=states_k if out is None else out)
+
+
+def exchange_k_to_time(states: torch.Tensor, group=None) -> torch.Tensor:
+    """All-to-all re-sharding of evolved states: k-sharded [T, count*N] -> time-sharded [T/G, G*count*N].
+
+    Rank r owns a contiguous range of k-blocks, so concatenating the ranks' block ranges
+    in rank order IS the global block order.  After the exchange rank g holds time rows
+    [g*T/G, (g+1)*T/G) of EVERY block, which is what the across-block cell FFT (sqb_cell_fft) needs.
+    The only data-path collective of the position-basis output; NCCL all_to_all over NVLink (a grouped
+    send/recv fallback is used on backends without all_to_all, e.g. gloo in the CPU tests).
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if world == 1:
+        return states
+    t, width = states.shape
+    if t % world:
+        msg = f"the time tile ({t}) must be divisible by the number of ranks ({world})"
+        raise ValueError(msg)
+    rows = t // world
+    send = torch.view_as_real(states.contiguous()).reshape(world, rows, width, 2)
+    recv = torch.empty_like(send)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, group=group)
+    else:
+        rank = dist.get_rank(group)
+        ops = []
+        for peer in range(world):
+            if peer == rank:
+                recv[peer].copy_(send[peer])
+            else:
+                ops.append(dist.P2POp(dist.isend, send[peer].contiguous(), peer, group))
+                ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    # [src rank, rows, width] -> [rows, src rank * width]
+    out = torch.view_as_complex(recv.permute(1, 0, 2, 3).contiguous())
+    return out.reshape(rows, world * width)

@@ -119,6 +119,15 @@ dist.all_gather(gathered, mine)
 full = torch.cat([g[:c] for g, c in zip(gathered, counts)]).numpy()
 w_all, _ = o.eigh_blocks(o.bloch_blocks(dx, shape, comps, o.HBAR_SI**2, repeat))
 assert np.abs(full - w_all).max() < 1e-13, np.abs(full - w_all).max()
+# k-shards -> time-shards exchange used before the across-block cell FFT (NCCL all_to_all on GPUs;
+# grouped send/recv here).  Equal block counts per rank as in bench.py's weak-scaling layout.
+from slate_quantum_b200.pipeline import exchange_k_to_time
+T, width = 6, 5
+glob = np.arange(T * 2 * width).reshape(T, 2 * width) * (1 + 0.5j)
+mine_k = torch.from_numpy(glob[:, rank * width:(rank + 1) * width].copy())
+got = exchange_k_to_time(mine_k).numpy()
+want = glob[rank * (T // 2):(rank + 1) * (T // 2)]
+assert got.shape == want.shape and np.array_equal(got, want), (got, want)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

@@ -27,9 +27,9 @@ res={}
 if a.peaks:
     lib=_lib.load(); import ctypes
     sink=torch.zeros(8,dtype=torch.float64,device="cuda"); fl=ctypes.c_double(0)
-    for name,fn in (("dmma",lib.sqb_peak_dmma),("dfma",lib.sqb_peak_dfma)):
+    for name,fn,lead in (("dmma0",lib.sqb_peak_dmma,(0,)),("dmma1",lib.sqb_peak_dmma,(1,)),("dmma2",lib.sqb_peak_dmma,(2,)),("dfma",lib.sqb_peak_dfma,())):
         it=20000
-        def run(): fn(it, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        def run(): fn(*lead, it, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(fl), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         ms=timeit(run,reps=5,warm=2)
         res[f"peak_{name}_tflops"]=fl.value/ms/1e9
 dk=2*np.pi*np.linalg.inv(2*np.pi*np.eye(nd)).T
