@@ -257,18 +257,23 @@ def run_ours(args) -> None:
     h_buf = torch.empty((n_k_local, n, n), dtype=torch.complex128, device="cuda")
     ws_bytes = lib.sqb_eigh_workspace_bytes(n, n_k_local)
     solver._eigh_ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")  # noqa: SLF001
+    folded_buf = torch.empty_like(h_buf) if with_position else None
     free, _ = torch.cuda.mem_get_info()
     row_bytes = n_k_local * n * 16
     t_tile = T
     # buffers of one time tile: states (+ position output; + all-to-all receive/transposed copies at N > 1)
-    n_tiles_buf = (2 if world == 1 else 4) if with_position else 1
-    budget = int((free - (n_k_local * n * n * 16 if with_position else 0)) * 0.85 / n_tiles_buf)
+    gathered = world > 1 and with_position  # time-sharded evolve over all-gathered eigenvectors
+    w_all = torch.empty((n_k_global, n, n), dtype=torch.complex128, device="cuda") if gathered else None
+    c_all = torch.empty((n_k_global * n,), dtype=torch.complex128, device="cuda") if gathered else None
+    free, _ = torch.cuda.mem_get_info()
+    if gathered:
+        row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
+        t_tile = T // world
+    budget = int(free * 0.8 / (2 if with_position else 1))
     while t_tile * row_bytes > budget and t_tile > 64:
         t_tile //= 2
-    states = torch.empty((t_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
-    # position output: time rows [*, M_global]; at N > 1 a rank keeps t_tile / world rows of every block
-    pos_out = torch.empty((t_tile // world, n_k_global * n), dtype=torch.complex128, device="cuda") if with_position else None
-    folded_buf = torch.empty_like(h_buf) if with_position else None
+    states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
+    pos_out = torch.empty_like(states) if with_position else None
     eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -299,16 +304,31 @@ def run_ours(args) -> None:
             # eigenvectors -> in-cell position basis + Bloch twiddle, once per eigensolve (K4 on N-point cells)
             timed("fold", lambda: solver.fold(out=folded_buf))
         c = timed("project", lambda: solver.project(psi0))
+        if world > 1 and with_position:
+            # Position output at N > 1: the across-block cell FFT needs every block of a time sample on one GPU.
+            # Instead of re-sharding the evolved STATES (all-to-all of T*M*16 B per step) the ranks all-gather the
+            # folded EIGENVECTORS (+ eigenvalues, coefficients) once per eigensolve - (G-1)/G * n_k*N^2*16 B received
+            # per rank, 2x less than the states at cfg3 and NVLS-friendly - and then evolve their own T/G time
+            # samples for ALL blocks locally (same flops per rank), followed by the local cell FFT.
+            def gather():
+                dist.all_gather_into_tensor(torch.view_as_real(w_all), torch.view_as_real(folded_buf))
+                dist.all_gather_into_tensor(torch.view_as_real(c_all), torch.view_as_real(c.reshape(-1)))
+
+            timed("exchange", gather)
+            t_lo = rank * (T // world)
+            for t0 in range(0, T // world, t_tile):
+                tt = min(t_tile, T // world - t0)
+                tsl = times[t_lo + t0 : t_lo + t0 + tt]
+                timed("evolve", lambda: kernels.evolve_bloch(
+                    w_all, eig_all.reshape(n_k_global, n), c_all.reshape(n_k_global, n), tsl, HBAR,
+                    out=states[:tt], uniform_dt=dt_uniform))
+                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
+            return
         for t0 in range(0, T, t_tile):
             tt = min(t_tile, T - t0)
             if with_position:
                 timed("evolve", lambda: solver.evolve_cell(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
-                if world == 1:
-                    timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
-                else:
-                    # k-shards -> time-shards (NCCL all-to-all over NVLink), then the across-block cell FFT
-                    full = timed("exchange", lambda: exchange_k_to_time(states[:tt]))
-                    timed("position", lambda: solver.cell_to_position(full, out=pos_out[: tt // world]))
+                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
             else:
                 timed("evolve", lambda: solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
 
@@ -358,19 +378,20 @@ def run_ours(args) -> None:
     e2e = None
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream()
-        e_tile = max(1, min(t_tile // 2, (4 << 30) // row_bytes))  # two device tiles ping-pong inside `states`
-        d2h_rows = max(1, min(e_tile, (1 << 30) // row_bytes))      # <= 1 GiB pinned staging buffers, ping-pong
+        # self-contained buffers (the device-resident leg's big tiles are released first)
+        del states, pos_out
+        torch.cuda.empty_cache()
+        row_e = n_k_local * n * 16
+        e_tile = max(1, min(T // 2, (4 << 30) // row_e))          # two device tiles ping-pong
+        d2h_rows = max(1, min(e_tile, (1 << 30) // row_e))        # <= 1 GiB pinned staging buffers, ping-pong
+        e2e_position = with_position and world == 1  # at N > 1 the e2e leg returns k-sharded momentum-basis states
+        e_src = torch.empty((2 * e_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
+        pos_tmp = torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda") if e2e_position else None
         stage_buf = [torch.empty((d2h_rows, n_k_local * n), dtype=torch.complex128).pin_memory() for _ in range(2)]
         eig_host = torch.empty((n_k_local * n,), dtype=torch.float64).pin_memory()
         tile_free = [torch.cuda.Event(), torch.cuda.Event()]
-        pos_tmp = (
-            torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
-            if with_position and world == 1 else None
-        )
-        e2e_position = with_position and world == 1  # at N > 1 the e2e leg returns k-sharded momentum-basis states
-        e_src = pos_out if e2e_position else states
         h2d = table_h.numel() * 16 + psi_h.numel() * 16 + times_h.numel() * 8
-        d2h = eig_host.numel() * 8 + T * row_bytes
+        d2h = eig_host.numel() * 8 + T * row_e
 
         def e2e_step() -> None:
             cur = torch.cuda.current_stream()
@@ -427,7 +448,7 @@ def run_ours(args) -> None:
             "steps": n_e2e,
             "note": "host potential table + psi0 + times in pinned memory -> C ABI -> eigenvalues and every "
             "evolved state copied back to pinned host staging buffers (PCIe-bound: the state list is "
-            f"{T * row_bytes / 1e9:.1f} GB per rank)",
+            f"{T * row_e / 1e9:.1f} GB per rank)",
         }
 
     if rank == 0:

@@ -123,6 +123,13 @@ int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, const sqb_c128
 size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host);
 int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
                  sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes, void* stream);
+/* sqb_cell_fft_sharded: direction 1 (cell -> position) reading the RECEIVE BUFFER of the k-shard -> time-shard
+ * all-to-all directly: in_scratch is [ranks][lead][n_k/ranks][N] (rank r contributed blocks
+ * [r n_k/ranks, (r+1) n_k/ranks), i.e. block axis 0 split in `ranks` contiguous pieces; repeat[0] % ranks == 0).
+ * Saves the transposition copy between the collective and the FFT. */
+int sqb_cell_fft_sharded(int nd, const int* shape_host, const int* repeat_host, int64_t lead, int ranks,
+                         sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, int64_t block_begin,
                        int64_t batch, const sqb_c128* transform, sqb_c128* folded, void* workspace,
                        size_t workspace_bytes, void* stream);

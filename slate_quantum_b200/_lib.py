@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "sqb_fft_axis",
     "sqb_cell_fft_workspace_bytes",
     "sqb_cell_fft",
+    "sqb_cell_fft_sharded",
     "sqb_fold_transform",
     "sqb_eigh_workspace_bytes",
     "sqb_eigh_batched",
@@ -82,6 +83,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_cell_fft_workspace_bytes.argtypes = [c_int, ip]
     lib.sqb_cell_fft.restype = c_int
     lib.sqb_cell_fft.argtypes = [c_int, ip, ip, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_cell_fft_sharded.restype = c_int
+    lib.sqb_cell_fft_sharded.argtypes = [c_int, ip, ip, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_fold_transform.restype = c_int
     lib.sqb_fold_transform.argtypes = [c_int, ip, ip, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_eigh_workspace_bytes.restype = c_size_t

@@ -30,7 +30,7 @@ constexpr int kMaxSmemLen = 4096;   // complex elements of one ping-pong buffer
 constexpr int kMaxStages = 24;
 constexpr int kMaxRadix = 31;
 constexpr int kMaxLines = 64;       // lines per CTA (always a power of two)
-constexpr int kDigits = 4;
+constexpr int kDigits = 6;
 
 struct Digits {  // flat index (C order over dims, last fastest) -> sum digit * stride
   int nd;
@@ -54,6 +54,12 @@ struct FftPass {
   int64_t n_outer, n_inner;  // lines = n_outer * n_inner, line id = o * n_inner + i
   Digits in_outer, in_inner, out_outer, out_inner;
   int64_t in_sl, out_sl;   // element stride of the position inside a line
+  // optional two-level position stride on the input: pos -> (pos / in_split) * in_sl_hi + (pos % in_split) * in_sl
+  // (a line that crosses rank-major chunks of an all-to-all receive buffer); in_split == 0: plain pos * in_sl
+  int in_split;
+  int64_t in_sl_hi;
+  int out_split;
+  int64_t out_sl_hi;
   int lines_per_cta;
   int inner_fastest;       // load order: 1 = a CTA's lines are adjacent in memory (coalesce across lines)
   int out_inner_fastest;   // same for the store
@@ -179,6 +185,12 @@ __device__ __forceinline__ void fast_divmod(int w, int d, int shift, int& q, int
 }
 __device__ __forceinline__ int pow2_shift(int d) { return (d & (d - 1)) == 0 ? 31 - __clz(d) : -1; }
 
+__device__ __forceinline__ int64_t pos_offset(int pos, int split, int64_t sl_hi, int64_t sl) {
+  if (split == 0) return (int64_t)pos * sl;
+  const int hi = pos / split;
+  return (int64_t)hi * sl_hi + (int64_t)(pos - hi * split) * sl;
+}
+
 struct StageIo {
   const c128* src;          // shared source (unused by the first stage)
   c128* dst;                // shared destination (unused by the last stage)
@@ -215,7 +227,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
     if (io.first) {
       const int64_t base = io.in_base[line];
 #pragma unroll
-      for (int t = 0; t < R; ++t) x[t] = io.gin[base + (int64_t)(j + t * per_line) * P.in_sl];
+      for (int t = 0; t < R; ++t) x[t] = io.gin[base + pos_offset(j + t * per_line, P.in_split, P.in_sl_hi, P.in_sl)];
     } else {
 #pragma unroll
       for (int t = 0; t < R; ++t) x[t] = io.src[line * len + j + t * per_line];
@@ -238,7 +250,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
           sincospi((double)sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
           v = cmul(v, make_double2(cs, sn));
         }
-        io.gout[base + (int64_t)pos * P.out_sl] = v;
+        io.gout[base + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
       }
     } else {
 #pragma unroll
@@ -308,11 +320,11 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       const int l = threadIdx.x & (lpc - 1);
       if (l < lines)
         for (int pos = threadIdx.x >> lshift; pos < len; pos += kFftThreads >> lshift)
-          buf0[l * len + pos] = in[s_in_base[l] + (int64_t)pos * P.in_sl];
+          buf0[l * len + pos] = in[s_in_base[l] + pos_offset(pos, P.in_split, P.in_sl_hi, P.in_sl)];
     } else {
       for (int e = threadIdx.x; e < lines * len; e += kFftThreads) {
         const int l = e / len, pos = e - l * len;
-        buf0[l * len + pos] = in[s_in_base[l] + (int64_t)pos * P.in_sl];
+        buf0[l * len + pos] = in[s_in_base[l] + pos_offset(pos, P.in_split, P.in_sl_hi, P.in_sl)];
       }
     }
     __syncthreads();
@@ -361,7 +373,7 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
       v = cmul(v, make_double2(cs, sn));
     }
-    out[s_out_base[l] + (int64_t)pos * P.out_sl] = v;
+    out[s_out_base[l] + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
   };
   if (P.out_inner_fastest) {
     const int l = threadIdx.x & (lpc - 1);
@@ -601,9 +613,9 @@ extern "C" size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host) {
   return align_up((size_t)max_len * sizeof(c128), 256) + 256;
 }
 
-extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
-                            sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
+                         int ranks, sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   SqbDims d;
   int64_t n, nk;
   int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
@@ -613,12 +625,18 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
   if (nd > 1 && in_scratch == out) return SQB_E_BADARG;  // the scatter / gather pass is out of place
   for (int a = 0; a < nd; ++a)
     if (d.repeat[a] > kMaxSmemLen || !smooth(d.repeat[a])) return SQB_E_UNSUPPORTED;
+  if (ranks < 1 || d.repeat[0] % ranks || (ranks > 1 && direction != 1)) return SQB_E_BADARG;
   if (lead == 0) return SQB_OK;
   if (lead >= (1LL << 31)) return SQB_E_UNSUPPORTED;
   c128* tab = reinterpret_cast<c128*>(workspace);
   cudaStream_t st = sqb_stream(stream);
   const int64_t m = n * nk;
   const double scale = 1.0 / sqrt((double)nk);
+  // rank-major input (ranks > 1): [ranks][lead][n_k / ranks][N], the receive buffer of the k-shard -> time-shard
+  // all-to-all; block axis 0 is split as b_0 = r * P0 + b_0l with P0 = R_0 / ranks.
+  const int P0 = d.repeat[0] / ranks;
+  const int64_t chunk = (nk / ranks) * n;       // elements of one (rank, lead) slab
+  const int64_t inner0 = (nk / d.repeat[0]) * n;  // stride of b_0l inside a slab
   c128* src = reinterpret_cast<c128*>(in_scratch);
   c128* dst = reinterpret_cast<c128*>(out);
 
@@ -642,8 +660,22 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
     P.len = d.repeat[a];
     P.n_outer = lead * (nk / d.repeat[a]);
     P.n_inner = n;
-    const Digits cell_outer = digits1(P.n_outer, (int64_t)d.repeat[a] * n);
+    Digits cell_outer = digits1(P.n_outer, (int64_t)d.repeat[a] * n);
     const Digits cell_inner = digits1(n, 1);
+    if (ranks > 1 && nd > 1) {
+      // outer index o = (lead, c_0 = (r, c_0l), c_1 .. c_{nd-2}) in C order; slab strides for (r, lead)
+      cell_outer.nd = nd + 1;
+      cell_outer.dims[0] = (int)lead;  cell_outer.strides[0] = chunk;
+      cell_outer.dims[1] = ranks;      cell_outer.strides[1] = lead * chunk;
+      cell_outer.dims[2] = P0;         cell_outer.strides[2] = inner0;
+      int64_t st_q = inner0;
+      for (int q = 1; q < nd - 1; ++q) {
+        st_q /= d.repeat[q];
+        cell_outer.dims[q + 2] = d.repeat[q];
+        cell_outer.strides[q + 2] = st_q;
+      }
+    }
+    if (ranks > 1 && nd == 1) cell_outer = digits1(lead, chunk);
     Digits pos_outer{}, pos_inner{};
     pos_outer.nd = nd;  // digits (lead, c_0 .. c_{nd-2})
     pos_outer.dims[0] = (int)lead;
@@ -662,6 +694,10 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
       P.in_outer = cell_outer; P.in_inner = cell_inner; P.in_sl = cell_sl;
       P.out_outer = pos_outer; P.out_inner = pos_inner; P.out_sl = pos_sl;
       P.sign = +1;
+      if (ranks > 1 && nd == 1) {  // the scattered axis is the rank-split axis itself
+        P.in_split = P0;
+        P.in_sl_hi = lead * chunk;
+      }
     } else {
       P.in_outer = pos_outer; P.in_inner = pos_inner; P.in_sl = pos_sl;
       P.out_outer = cell_outer; P.out_inner = cell_inner; P.out_sl = cell_sl;
@@ -677,6 +713,24 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
     for (int q = a + 1; q < nd; ++q) inner *= d.repeat[q];
     int64_t outer = lead;
     for (int q = 0; q < a; ++q) outer *= d.repeat[q];
+    if (ranks > 1 && a == 0) {
+      // lines along b_0 cross the rank slabs: two-level position stride, one line per (lead, inner index)
+      FftPass P{};
+      P.len = d.repeat[0];
+      P.n_outer = lead;
+      P.n_inner = inner;
+      P.in_outer = P.out_outer = digits1(lead, chunk);
+      P.in_inner = P.out_inner = digits1(inner, 1);
+      P.in_sl = P.out_sl = inner;
+      P.in_split = P.out_split = P0;
+      P.in_sl_hi = P.out_sl_hi = lead * chunk;
+      P.inner_fastest = P.out_inner_fastest = 1;
+      P.sign = sign;
+      P.scale = 1.0;
+      P.tw_len = 0;
+      return launch_pass(P, p, p, tab, st);
+    }
+    // axes >= 1 never cross a slab: the order of the outer index is irrelevant for an in-place pass
     return fft_one_axis(outer, d.repeat[a], inner, sign, 1.0, p, p, tab, nullptr, st);
   };
 
@@ -694,6 +748,20 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
     if (rc) return rc;
   }
   return SQB_OK;
+}
+
+extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
+                            sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return cell_fft_impl(nd, shape_host, repeat_host, direction, lead, 1, in_scratch, out, workspace, workspace_bytes,
+                       stream);
+}
+
+extern "C" int sqb_cell_fft_sharded(int nd, const int* shape_host, const int* repeat_host, int64_t lead, int ranks,
+                                    sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  return cell_fft_impl(nd, shape_host, repeat_host, 1, lead, ranks, in_scratch, out, workspace, workspace_bytes,
+                       stream);
 }
 
 extern "C" int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, int64_t block_begin,

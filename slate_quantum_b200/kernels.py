@@ -189,21 +189,32 @@ def fft_axis(x: torch.Tensor, outer: int, length: int, inner: int, sign: int) ->
 
 
 def cell_fft(
-    shape: Sequence[int], repeat: Sequence[int], x: torch.Tensor, direction: int, out: torch.Tensor | None = None
+    shape: Sequence[int], repeat: Sequence[int], x: torch.Tensor, direction: int, out: torch.Tensor | None = None,
+    ranks: int = 1,
 ) -> torch.Tensor:
-    """K4b: [lead, n_k, N] cell layout <-> [lead, M] position order. direction 1 CLOBBERS `x` when nd > 1."""
+    """K4b: [lead, n_k, N] cell layout <-> [lead, M] position order. direction 1 CLOBBERS `x` when nd > 1.
+
+    ranks > 1 (direction 1 only): `x` is the all-to-all receive buffer [ranks, lead, n_k/ranks, N]."""
     _require_cuda()
     lib = _lib.load()
     _c128(x, "x")
     m = int(np.prod(shape)) * int(np.prod(repeat))
     lead = x.numel() // m
-    out = torch.empty_like(x) if out is None else _c128(out, "out")
+    if out is None:
+        out = torch.empty((lead, m), dtype=torch.complex128, device="cuda")
+    _c128(out, "out")
     rep_c = _lib.int_array(repeat)
     ws_bytes = lib.sqb_cell_fft_workspace_bytes(len(repeat), rep_c)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-    rc = lib.sqb_cell_fft(
-        len(shape), _lib.int_array(shape), rep_c, direction, lead, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream()
-    )
+    if ranks > 1:
+        rc = lib.sqb_cell_fft_sharded(
+            len(shape), _lib.int_array(shape), rep_c, lead, ranks, _ptr(x), _ptr(out), _ptr(ws), ws_bytes, _stream()
+        )
+    else:
+        rc = lib.sqb_cell_fft(
+            len(shape), _lib.int_array(shape), rep_c, direction, lead, _ptr(x), _ptr(out), _ptr(ws), ws_bytes,
+            _stream(),
+        )
     _lib.check(rc, "sqb_cell_fft")
     _count(2 * len(shape))
     return out

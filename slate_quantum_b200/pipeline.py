@@ -125,13 +125,16 @@ class BlochSolver:
             self.fold(), self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt
         )
 
-    def cell_to_position(self, states_cell: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def cell_to_position(
+        self, states_cell: torch.Tensor, out: torch.Tensor | None = None, ranks: int = 1
+    ) -> torch.Tensor:
         """[T, M] cell layout (ALL blocks) -> supercell position basis: R-point FFTs across blocks only.
-        `states_cell` is used as scratch."""
-        if states_cell.shape[-1] != self.m:
+        `states_cell` is used as scratch.  ranks > 1: `states_cell` is the rank-major all-to-all receive
+        buffer [ranks, T, n_k/ranks * N] (see exchange_k_to_time(..., transpose=False))."""
+        if states_cell.numel() % self.m:
             msg = "cell_to_position needs every k-block (all-to-all the k-shards into time-shards first)"
             raise ValueError(msg)
-        return kernels.cell_fft(self.shape, self.repeat, states_cell, 1, out=out)
+        return kernels.cell_fft(self.shape, self.repeat, states_cell, 1, out=out, ranks=ranks)
 
     def evolve_position(
         self, coefficients: torch.Tensor, times: torch.Tensor, uniform_dt: float | None = None
@@ -149,7 +152,7 @@ class BlochSolver:
         return kernels.fft_c2c(states_k, self.supercell, +1, out=states_k if out is None else out)
 
 
-def exchange_k_to_time(states: torch.Tensor, group=None) -> torch.Tensor:
+def exchange_k_to_time(states: torch.Tensor, group=None, *, transpose: bool = True) -> torch.Tensor:
     """All-to-all re-sharding of evolved states: k-sharded [T, count*N] -> time-sharded [T/G, G*count*N].
 
     Rank r owns a contiguous range of k-blocks, so concatenating the ranks' block ranges
@@ -183,6 +186,9 @@ def exchange_k_to_time(states: torch.Tensor, group=None) -> torch.Tensor:
                 ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+    if not transpose:
+        # rank-major receive buffer [src rank, rows, width]: sqb_cell_fft_sharded reads it in place
+        return torch.view_as_complex(recv)
     # [src rank, rows, width] -> [rows, src rank * width]
     out = torch.view_as_complex(recv.permute(1, 0, 2, 3).contiguous())
     return out.reshape(rows, world * width)

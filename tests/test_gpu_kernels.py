@@ -320,3 +320,19 @@ def test_evolve_position_pipeline(cuda):
     w_ref, t_ref = o.eigh_blocks(blocks)
     want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize(("shape", "repeat", "ranks"), [((5,), (6,), 2), ((4, 3), (4, 3), 2), ((4, 4), (8, 2), 4),
+                                                         ((3, 2, 3), (4, 3, 2), 2)])
+def test_cell_fft_sharded_reads_rank_major_buffer(cuda, shape, repeat, ranks):
+    """The all-to-all receive buffer [ranks, lead, n_k/ranks, N] must transform like the transposed copy."""
+    torch, kernels = _gpu()
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    lead = 3
+    rng = np.random.default_rng(11)
+    cell = rng.normal(size=(lead, n_k, n)) + 1j * rng.normal(size=(lead, n_k, n))
+    want = kernels.cell_fft(shape, repeat, kernels.to_device(cell.reshape(lead, -1), torch.complex128), 1).cpu().numpy()
+    per = n_k // ranks
+    rank_major = np.ascontiguousarray(cell.reshape(lead, ranks, per, n).transpose(1, 0, 2, 3))
+    got = kernels.cell_fft(shape, repeat, kernels.to_device(rank_major.reshape(-1), torch.complex128), 1, ranks=ranks)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-13)
