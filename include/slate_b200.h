@@ -139,7 +139,7 @@ int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, in
  * Replaces: slate_core.linalg.into_diagonal_hermitian (np.linalg.eigh / LAPACK zheevd per block),
  * call site operator/_linalg.py:56 (`into_diagonal_hermitian`), bloch/_linalg.py:72-84.
  *
- * A_inout  [batch, n, n] in:  H_b (row-major, Hermitian; both triangles are read)
+ * A_inout  [batch, n, n] in:  H_b (row-major, Hermitian; only the UPPER triangle H[r<=c] is read)
  *                        out: transform_b[e, k] = component k of eigenvector e (ROWS = eigenvectors,
  *                             i.e. np.linalg.eigh(H_b)[1].T - the layout of the reference's
  *                             EigenstateBasis transform, bloch/_linalg.py:35-57)

@@ -7,7 +7,8 @@
 //                          (LAPACK zhetd2 recurrences, lower/column form) carried out in the column-major
 //                          view of the row-major input, i.e. on conj(H).  The rank-2 update of step i-1 is
 //                          deferred and fused with the matrix-vector product of step i, so every step
-//                          streams the trailing block exactly once (16 B read + 16 B write per element);
+//                          streams the LOWER TRIANGLE of the trailing block exactly once (16 B read + 16 B
+//                          write per element, Hermitian symmetry supplies the other half of the product);
 //                          the block lives in L2.  Reflectors go to workspace Y, so A is dead afterwards.
 //   (2) ql_kernel          one warp per matrix.  Implicit-shift QL (EISPACK imtql2 recurrences) on (d, e):
 //                          latency-bound scalar chain run by lane 0 for thousands of matrices at once; the
@@ -65,7 +66,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch, int nwarp
 // (1) Householder tridiagonalisation.  Threads = 256*RG; warp w: row group rg = w % RG, column group
 // cg = w / RG (8 column groups).  Lane rows: r = (c*RG + rg)*32 + lane, c < NR.
 template <int NR, int RG>
-__global__ void __launch_bounds__(256 * RG)
+__global__ void __launch_bounds__(256 * RG, RG == 1 ? 2 : 1)
 tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
   constexpr int kThreads = 256 * RG;
   constexpr int kWarps = kThreads / 32;
@@ -73,8 +74,9 @@ tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
   c128* vo = reinterpret_cast<c128*>(smem_d);  // pending update vectors (rows >= i)
   c128* wo = vo + n;
   c128* vn = wo + n;                            // new reflector
-  c128* red = vn + n;                           // [8][n] partial A22*v sums per column group
-  double* scratch = reinterpret_cast<double*>(red + 8 * n);  // [40]
+  c128* red = vn + n;                           // [8][n] partial A22*v sums per column group (rows >= column)
+  c128* redc = red + 8 * n;                     // [RG][n] mirrored (upper triangle) contributions per column
+  double* scratch = reinterpret_cast<double*>(redc + RG * n);  // [40]
   // scalars: scratch[34..39]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rg = warp % RG, cg = warp / RG;
@@ -142,7 +144,10 @@ tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
     }
     __syncthreads();
 
-    // ---- phase B: apply pending update to trailing block, accumulate A22 * vn
+    // ---- phase B: apply the pending update to the LOWER triangle of the trailing block (rows r >= column j)
+    // and accumulate p = A22 * vn using Hermitian symmetry: element a = A(r,j) contributes a*vn[j] to p[r]
+    // and, for r > j, conj(a)*vn[r] to p[j].  Only the lower triangle is ever read or written, which halves
+    // the L2/HBM traffic of the reduction (it is bandwidth bound).
     c128 acc[NR];
 #pragma unroll
     for (int c = 0; c < NR; ++c) acc[c] = make_double2(0.0, 0.0);
@@ -155,26 +160,31 @@ tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
       for (int c = 0; c < NR; ++c) {
         rows[c] = (c * RG + rg) * 32 + lane;
         cur[c] = make_double2(0.0, 0.0);
-        if (j < n && rows[c] >= lo && rows[c] < n) cur[c] = A[(int64_t)j * n + rows[c]];
+        if (j < n && rows[c] >= j && rows[c] < n) cur[c] = A[(int64_t)j * n + rows[c]];
       }
       for (; j < n; j += 8) {
         const int jn = j + 8;
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
           nxt[c] = make_double2(0.0, 0.0);
-          if (jn < n && rows[c] >= lo && rows[c] < n) nxt[c] = A[(int64_t)jn * n + rows[c]];
+          if (jn < n && rows[c] >= jn && rows[c] < n) nxt[c] = A[(int64_t)jn * n + rows[c]];
         }
         const c128 cw = cconj(wo[j]), cv = cconj(vo[j]), vj = vn[j];
+        c128 dotj = make_double2(0.0, 0.0);
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
-          if (rows[c] >= lo && rows[c] < n) {
+          if (rows[c] >= j && rows[c] < n) {
             c128 a = cur[c];
             a = csub(a, cmul(vo[rows[c]], cw));
             a = csub(a, cmul(wo[rows[c]], cv));
             A[(int64_t)j * n + rows[c]] = a;
             cfma(acc[c], a, vj);
+            if (rows[c] > j) cfmac(dotj, a, vn[rows[c]]);
           }
         }
+        dotj.x = warp_sum(dotj.x);
+        dotj.y = warp_sum(dotj.y);
+        if (lane == 0) redc[rg * n + j] = dotj;
 #pragma unroll
         for (int c = 0; c < NR; ++c) cur[c] = nxt[c];
       }
@@ -191,6 +201,8 @@ tridiag_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
       c128 s = red[r];
 #pragma unroll
       for (int g = 1; g < 8; ++g) s = cadd(s, red[g * n + r]);
+#pragma unroll
+      for (int g = 0; g < RG; ++g) s = cadd(s, redc[g * n + r]);
       p = cmul(tau, s);
       const c128 v = vn[r];
       // conj(p) * v
@@ -611,7 +623,7 @@ void carve(EighWs& ws, void* base, int n, int64_t chunk) {
 
 template <int NR, int RG>
 int launch_tridiag(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st) {
-  const size_t smem = (size_t)(3 + 8) * n * sizeof(c128) + 40 * sizeof(double);
+  const size_t smem = (size_t)(3 + 8 + RG) * n * sizeof(c128) + 40 * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(tridiag_kernel<NR, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   tridiag_kernel<NR, RG><<<(unsigned)count, 256 * RG, smem, st>>>(n, A, ws);
