@@ -671,33 +671,64 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     cudaError_t e = cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 32 * 8);
     if (e != cudaSuccess) return (int)e;
   }
-  for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+  // Two chunks are kept in flight on two internal streams (each with its own half of the workspace): the
+  // latency-bound QL stage of one chunk then overlaps the bandwidth / FP64-bound stages of the other.
+  const bool two_lanes = batch >= 512 && chunk >= 256;
+  const int n_lanes = two_lanes ? 2 : 1;
+  if (two_lanes) chunk = sqb_min64(chunk / 2, (batch + 1) / 2);
+  const size_t lane_bytes = align_up(per * (size_t)chunk, 256);
+  cudaStream_t lanes[2] = {st, st};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  if (two_lanes) {
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
+    cudaEventRecord(fork, st);
+    for (int l = 0; l < 2; ++l) {
+      if (cudaStreamCreateWithFlags(&lanes[l], cudaStreamNonBlocking) != cudaSuccess) return (int)cudaGetLastError();
+      cudaStreamWaitEvent(lanes[l], fork, 0);
+    }
+  }
+  int status = SQB_OK;
+  int which = 0;
+  for (int64_t b0 = 0; b0 < batch && status == SQB_OK; b0 += chunk, which ^= 1) {
     const int64_t cnt = sqb_min64(chunk, batch - b0);
+    const int l = two_lanes ? which : 0;
+    cudaStream_t ls = lanes[l];
     EighWs ws;
-    carve(ws, base, n, chunk);
+    carve(ws, reinterpret_cast<char*>(base) + (size_t)l * lane_bytes, n, chunk);
     c128* Ab = A + b0 * (int64_t)n * n;
     int rc;
-    if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, st);
-    else if (n <= 64) rc = launch_tridiag<2, 1>(n, cnt, Ab, ws, st);
-    else if (n <= 128) rc = launch_tridiag<4, 1>(n, cnt, Ab, ws, st);
-    else if (n <= 256) rc = launch_tridiag<8, 1>(n, cnt, Ab, ws, st);
-    else rc = launch_tridiag<8, 2>(n, cnt, Ab, ws, st);
-    if (rc) return rc;
+    if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, ls);
+    else if (n <= 64) rc = launch_tridiag<2, 1>(n, cnt, Ab, ws, ls);
+    else if (n <= 128) rc = launch_tridiag<4, 1>(n, cnt, Ab, ws, ls);
+    else if (n <= 256) rc = launch_tridiag<8, 1>(n, cnt, Ab, ws, ls);
+    else rc = launch_tridiag<8, 2>(n, cnt, Ab, ws, ls);
+    if (rc) { status = rc; break; }
 
     const size_t ql_smem = (size_t)(2 * n + 2) * 8 + (size_t)n * 16;
-    ql_kernel<<<(unsigned)cnt, 32, ql_smem, st>>>(n, cnt, ws, w + b0 * n, info + b0);
-    SQB_LAUNCH_CHECK();
+    ql_kernel<<<(unsigned)cnt, 32, ql_smem, ls>>>(n, cnt, ws, w + b0 * n, info + b0);
+    if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
 
     dim3 rgrid((unsigned)((n + 31) / 32), (unsigned)cnt);
-    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8, st>>>(n, ws);
-    SQB_LAUNCH_CHECK();
+    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8, ls>>>(n, ws);
+    if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
 
-    if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, st);
-    else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, st);
-    else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, st);
-    else if (n <= 384) rc = launch_back<12, 32>(n, cnt, Ab, ws, st);
-    else rc = launch_back<16, 32>(n, cnt, Ab, ws, st);
-    if (rc) return rc;
+    if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
+    else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, ls);
+    else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, ls);
+    else if (n <= 384) rc = launch_back<12, 32>(n, cnt, Ab, ws, ls);
+    else rc = launch_back<16, 32>(n, cnt, Ab, ws, ls);
+    if (rc) { status = rc; break; }
   }
-  return SQB_OK;
+  if (two_lanes) {
+    for (int l = 0; l < 2; ++l) {
+      if (cudaEventCreateWithFlags(&join[l], cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(join[l], lanes[l]);
+        cudaStreamWaitEvent(st, join[l], 0);
+        cudaEventDestroy(join[l]);
+      }
+      cudaStreamDestroy(lanes[l]);  // deferred by the runtime until the enqueued work has drained
+    }
+    cudaEventDestroy(fork);
+  }
+  return status;
 }

@@ -65,7 +65,8 @@ struct FftPass {
   int out_inner_fastest;   // same for the store
   int sign;                // -1 forward, +1 backward
   double scale;            // multiplied into every output
-  int64_t tw_len;          // 0 = none; else multiply output (pos k, inner i) by exp(sign*2*pi*i*k*i/tw_len)
+  int64_t tw_len;          // 0 = none; else multiply output (pos k, inner i) by exp(sign*2*pi*i*k*(i/tw_div)/tw_len)
+  int64_t tw_div;          // divisor applied to the inner index before the twiddle (>= 1)
 };
 
 __device__ __forceinline__ c128 tw_lookup(const c128* tab, int idx, int sign) {
@@ -246,7 +247,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
         c128 v = cscale(x[t], P.scale);
         if (P.tw_len) {
           double sn, cs;
-          const int64_t prod = ((int64_t)pos * io.inner_idx[line]) % P.tw_len;
+          const int64_t prod = ((int64_t)pos * (io.inner_idx[line] / P.tw_div)) % P.tw_len;
           sincospi((double)sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
           v = cmul(v, make_double2(cs, sn));
         }
@@ -369,7 +370,7 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
     c128 v = cscale(src[l * len + pos], P.scale);
     if (P.tw_len) {
       double sn, cs;
-      const int64_t prod = ((int64_t)pos * s_inner_idx[l]) % P.tw_len;
+      const int64_t prod = ((int64_t)pos * (s_inner_idx[l] / P.tw_div)) % P.tw_len;
       sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
       v = cmul(v, make_double2(cs, sn));
     }
@@ -499,26 +500,28 @@ int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, 
     P.sign = sign;
     P.scale = scale;
     P.tw_len = 0;
+    P.tw_div = 1;
     return launch_pass(P, in, out, tab, st);
   }
-  // four-step: view the line as [l1, l2] (n = n1*l2 + n2).
-  // pass A: l1-point transforms over n1 for every (outer, n2), twiddle W_len^(k1*n2), in -> scratch
-  // pass B: l2-point transforms over n2 for every (outer, k1), output index k1 + l1*k2, scratch -> out
+  // four-step: view the line as [l1, l2] (n = n1*l2 + n2), every element carrying `inner` trailing entries.
+  // pass A: l1-point transforms over n1 for every (outer, n2, i), twiddle W_len^(k1*n2), in -> scratch
+  // pass B: l2-point transforms over n2 for every (outer, k1, i), output index k1 + l1*k2, scratch -> out
   int l1, l2;
   if (!split_len(len, &l1, &l2) || !smooth(l1) || !smooth(l2)) return SQB_E_UNSUPPORTED;
-  if (inner != 1 || !scratch) return SQB_E_UNSUPPORTED;  // long strided lines are not needed by the Bloch path
+  if (!scratch || (int64_t)l2 * inner >= (1LL << 31) || (int64_t)l1 * inner >= (1LL << 31)) return SQB_E_UNSUPPORTED;
   {
     FftPass P{};
     P.len = l1;
     P.n_outer = outer;
-    P.n_inner = l2;
-    P.in_outer = P.out_outer = digits1(outer, len);
-    P.in_inner = P.out_inner = digits1(l2, 1);
-    P.in_sl = P.out_sl = l2;
+    P.n_inner = (int64_t)l2 * inner;  // combined (n2, i), contiguous
+    P.in_outer = P.out_outer = digits1(outer, (int64_t)len * inner);
+    P.in_inner = P.out_inner = digits1(P.n_inner, 1);
+    P.in_sl = P.out_sl = (int64_t)l2 * inner;
     P.inner_fastest = P.out_inner_fastest = 1;
     P.sign = sign;
     P.scale = 1.0;
     P.tw_len = len;
+    P.tw_div = inner;
     int rc = launch_pass(P, in, scratch, tab, st);
     if (rc) return rc;
   }
@@ -526,17 +529,26 @@ int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, 
     FftPass P{};
     P.len = l2;
     P.n_outer = outer;
-    P.n_inner = l1;  // inner index = k1; lines are contiguous in n2
-    P.in_outer = P.out_outer = digits1(outer, len);
-    P.in_inner = digits1(l1, l2);
-    P.out_inner = digits1(l1, 1);
-    P.in_sl = 1;
-    P.out_sl = l1;
-    P.inner_fastest = 0;
+    P.n_inner = (int64_t)l1 * inner;  // (k1, i)
+    P.in_outer = P.out_outer = digits1(outer, (int64_t)len * inner);
+    Digits din{}, dout{};
+    din.nd = dout.nd = 2;
+    din.dims[0] = dout.dims[0] = l1;
+    din.dims[1] = dout.dims[1] = (int)inner;
+    din.strides[0] = (int64_t)l2 * inner;
+    din.strides[1] = 1;
+    dout.strides[0] = inner;
+    dout.strides[1] = 1;
+    P.in_inner = din;
+    P.out_inner = dout;
+    P.in_sl = inner;
+    P.out_sl = (int64_t)l1 * inner;
+    P.inner_fastest = inner > 1;
     P.out_inner_fastest = 1;
     P.sign = sign;
     P.scale = scale;
     P.tw_len = 0;
+    P.tw_div = 1;
     return launch_pass(P, scratch, out, tab, st);
   }
 }
@@ -706,6 +718,7 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
     P.inner_fastest = P.out_inner_fastest = 1;
     P.scale = scale;
     P.tw_len = 0;
+    P.tw_div = 1;
     return launch_pass(P, pin, pout, tab, st);
   };
   auto inplace_axis = [&](int a, c128* p, int sign) -> int {
@@ -728,6 +741,7 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
       P.sign = sign;
       P.scale = 1.0;
       P.tw_len = 0;
+      P.tw_div = 1;
       return launch_pass(P, p, p, tab, st);
     }
     // axes >= 1 never cross a slab: the order of the outer index is irrelevant for an in-place pass

@@ -265,6 +265,8 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
     _lib.check(rc, "sqb_eigh_batched")
     per = lib.sqb_eigh_workspace_bytes(n, 1) - 4096
     chunk = max(1, min(batch, (workspace.numel() - 4096) // per, 65535))
+    if batch >= 512 and chunk >= 256:  # two chunks in flight on two internal streams (csrc/eigh.cu)
+        chunk = min(chunk // 2, (batch + 1) // 2)
     _count(4 * -(-batch // chunk))
     return w, a, info
 

@@ -104,7 +104,7 @@ def test_bloch_permute(cuda, shape, repeat):
 @pytest.mark.parametrize(
     "dims",
     [(5,), (9,), (12,), (16,), (25,), (64,), (224,), (1024,), (6400,), (3 * 5 * 7 * 11,), (8192,), (131072,),
-     (12, 15), (16, 20), (64, 48), (9, 16, 10), (28, 28, 28), (13 * 4,), (31 * 2,)],
+     (12, 15), (16, 20), (64, 48), (9, 16, 10), (28, 28, 28), (13 * 4,), (31 * 2,), (8192, 6), (6400, 3, 2)],
 )
 def test_fft_matches_numpy(cuda, dims):
     torch, kernels = _gpu()
