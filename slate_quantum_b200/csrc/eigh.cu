@@ -327,7 +327,9 @@ ql_kernel(int n, int64_t count, EighWs ws, double* __restrict__ w_out, int* __re
       }
       cnt = __shfl_sync(0xffffffffu, cnt, 0);
       __syncwarp();
-      // flush this sweep's rotations (coalesced) and its header
+      // flush this sweep's rotations (coalesced) and its header; every sweep starts at a multiple of 8 in
+      // the record so that the replay kernel's 8-rotation blocks never wrap inside its ring
+      nrot = (nrot + 7) & ~(int64_t)7;
       if (nsw < scap && nrot + cnt <= rcap) {
         for (int k = lane; k < cnt; k += 32) rot[nrot + k] = rbuf[k];
         if (lane == 0) sweeps[nsw] = make_int4(l, m, cnt, (int)nrot);
@@ -363,18 +365,31 @@ ql_kernel(int n, int64_t count, EighWs ws, double* __restrict__ w_out, int* __re
 
 // ------------------------------------------------------------------------------------------------
 // (3) rotation replay on a 32-row strip of the identity; one warp per (strip, matrix).
-// A lane owns one row; the strip lives in shared memory as zs[col][lane] (conflict free).  The only
-// loop-carried dependency of a sweep is ONE fma on `carry`, so rotations are processed in blocks of
-// kRotBlock with all their shared-memory loads hoisted in front of the chain.  The (c, s) stream is
-// staged through a 128-entry shared ring that is refilled 32 entries at a time, one refill ahead.
+// A lane owns one row; the strip lives in shared memory as zs[col][lane] (conflict free).  Within a QL
+// sweep the rotations form a chain with ONE dependent FMA per rotation, so a single sweep is bound by the
+// FP64 FMA latency, not by throughput.  The kernel therefore keeps TWO sweeps in flight as a rolling
+// pipeline: a leader and, when the next sweep ends at the same column m, a follower that trails the leader
+// by >= 16 rotations.  The follower then only reads columns the leader finished in an earlier block, so a
+// "dual block" (8 rotations of each) is straight-line code with two independent chains and all its
+// shared-memory loads hoisted in front.  The (c, s) record is one contiguous stream; leader and follower
+// read it through ONE shared ring (2 cursors, at most n entries apart) refilled 32 entries at a time with
+// four refills in flight.
 constexpr int kRotBlock = 8;
-constexpr int kRing = 128;
+constexpr int kFollowLag = 16;
+
+struct SweepState {
+  int m, cnt, r;       // upper column, rotations, next rotation to apply
+  int off;             // first rotation in the record (multiple of 8)
+  double carry;        // pending value of column m - r (per lane)
+  bool active;
+};
 
 __global__ void __launch_bounds__(32)
-replay_kernel(int n, EighWs ws) {
+replay_kernel(int n, int ring_size, EighWs ws) {
   extern __shared__ double smem_d[];
-  double* zs = smem_d;  // [n][32]  zs[col*32 + lane]
-  __shared__ double2 ring[kRing];
+  double* zs = smem_d;                                            // [n][32]  zs[col*32 + lane]
+  double2* ring = reinterpret_cast<double2*>(zs + (size_t)n * 32);  // [ring_size], index = record index & mask
+  const int mask = ring_size - 1;
   const int lane = threadIdx.x;
   const int r0 = blockIdx.x * 32;
   const int64_t b = blockIdx.y;
@@ -391,57 +406,135 @@ replay_kernel(int n, EighWs ws) {
     const int4 last = sweeps[nsw - 1];
     total = (int64_t)last.w + last.z;
   }
-  const double2 ident = make_double2(1.0, 0.0);
-  // ring holds [loaded - kRing, loaded); `pre` holds [loaded, loaded + 32) in flight
-  int64_t loaded = 0;
-  for (; loaded < 96; loaded += 32) ring[(loaded + lane) & (kRing - 1)] = (loaded + lane < total) ? rot[loaded + lane] : ident;
-  double2 pre = (loaded + lane < total) ? rot[loaded + lane] : ident;
-  __syncwarp();
+  // The ring holds record entries [loaded - ring_size, loaded).  Refills go global -> shared with cp.async
+  // (no registers, no waiting moves): 32 entries per commit group, and the most recent kPend groups may
+  // still be in flight, i.e. entries below `loaded - 32*kPend` are readable after cp.async.wait_group kPend.
+  // The record lives in HBM (far larger than L2), so the prefetch distance has to cover DRAM latency.
+  constexpr int kPend = 3;
+  const int rcap = (int)rot_capacity(n);
+  int loaded = 0;
+  auto refill = [&]() {
+    const int idx = loaded + lane;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (idx & mask));
+    const double2* src = rot + (idx < rcap ? idx : rcap - 1);  // beyond `total` the values are never used
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    loaded += 32;
+  };
+  for (int q = 0; q < 6; ++q) refill();
+  (void)total;
 
-  int4 h = nsw > 0 ? sweeps[0] : make_int4(0, 0, 0, 0);
-  for (int sw = 0; sw < nsw; ++sw) {
-    const int4 hn = (sw + 1 < nsw) ? sweeps[sw + 1] : h;  // prefetch next header
-    const int m = h.y, cnt = h.z;
-    const int64_t off = h.w;
-    double carry = zs[m * 32 + lane];
-    int i = m - 1;
-    int k = 0;
-    while (k < cnt) {
-      const int64_t idx = off + k;
-      // keep at least kRotBlock + 32 entries ahead of idx published in the ring
-      if (idx + kRotBlock + 32 > loaded) {
-        ring[(loaded + lane) & (kRing - 1)] = pre;
-        loaded += 32;
-        pre = (loaded + lane < total) ? rot[loaded + lane] : ident;
-        __syncwarp();
-      }
-      if (cnt - k >= kRotBlock) {
-        double2 cs[kRotBlock];
-        double zi[kRotBlock];
-#pragma unroll
-        for (int j = 0; j < kRotBlock; ++j) {
-          cs[j] = ring[(idx + j) & (kRing - 1)];
-          zi[j] = zs[(i - j) * 32 + lane];
-        }
-#pragma unroll
-        for (int j = 0; j < kRotBlock; ++j) {
-          const double t = cs[j].x * zi[j];
-          zs[(i - j + 1) * 32 + lane] = fma(cs[j].y, zi[j], cs[j].x * carry);
-          carry = fma(-cs[j].y, carry, t);
-        }
-        i -= kRotBlock;
-        k += kRotBlock;
+  SweepState L, F;
+  L.active = false;
+  F.active = false;
+  L.m = L.cnt = L.r = 0; L.off = 0; L.carry = 0.0;
+  F = L;
+  int next_sw = 0;
+  int4 hn = nsw > 0 ? sweeps[0] : make_int4(0, 0, 0, 0);  // header of sweep `next_sw`, prefetched
+
+  auto take_next = [&](SweepState& s) {
+    s.m = hn.y;
+    s.cnt = hn.z;
+    s.off = hn.w;
+    s.r = 0;
+    s.active = true;
+    s.carry = zs[s.m * 32 + lane];
+    ++next_sw;
+    if (next_sw < nsw) hn = sweeps[next_sw];
+  };
+
+  while (true) {
+    if (!L.active) {
+      if (F.active) {
+        L = F;
+        F.active = false;
+      } else if (next_sw < nsw) {
+        take_next(L);
       } else {
-        const double2 c1 = ring[idx & (kRing - 1)];
-        const double z1 = zs[i * 32 + lane];
-        zs[(i + 1) * 32 + lane] = fma(c1.y, z1, c1.x * carry);
-        carry = fma(-c1.y, carry, c1.x * z1);
-        --i;
-        ++k;
+        break;
       }
     }
-    zs[(i + 1) * 32 + lane] = carry;
-    h = hn;
+    if (!F.active && next_sw < nsw && hn.y == L.m && L.r >= kFollowLag) take_next(F);
+
+    // keep the ring ahead of the furthest cursor (never overwriting the leader's unread entries):
+    // `target` is a prefetch goal (the follower's cursor, or the start of the next sweep when there is no
+    // follower yet), `need` is what this iteration will certainly read.
+    {
+      const int lead_pos = L.off + L.r;
+      const int target = (F.active ? F.off + F.r : L.off + L.cnt) + kRotBlock + 32 + 32 * kPend;
+      int need = lead_pos + kRotBlock;
+      if (F.active) need = max(need, F.off + F.r + kRotBlock);
+      need += 32 * kPend;
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep)
+        if (target > loaded) refill();
+      while (need > loaded) refill();
+      asm volatile("cp.async.wait_group 3;" ::: "memory");
+      __syncwarp();
+    }
+
+    const int left_l = L.cnt - L.r;
+    if (F.active && left_l >= kRotBlock && F.cnt - F.r >= kRotBlock && L.r >= F.r + kFollowLag) {
+      // ---- dual block: two independent chains, all loads first
+      double2 cl[kRotBlock], cf[kRotBlock];
+      double zl[kRotBlock], zf[kRotBlock];
+      const double2* rl = ring + ((L.off + L.r) & mask);  // 8-aligned: no wrap inside the block
+      const double2* rf = ring + ((F.off + F.r) & mask);
+      const int coll = L.m - 1 - L.r, colf = F.m - 1 - F.r;
+#pragma unroll
+      for (int j = 0; j < kRotBlock; ++j) {
+        cl[j] = rl[j];
+        cf[j] = rf[j];
+        zl[j] = zs[(coll - j) * 32 + lane];
+        zf[j] = zs[(colf - j) * 32 + lane];
+      }
+      double ca = L.carry, cb = F.carry;
+#pragma unroll
+      for (int j = 0; j < kRotBlock; ++j) {
+        const double tl = cl[j].x * zl[j];
+        const double tf = cf[j].x * zf[j];
+        zs[(coll - j + 1) * 32 + lane] = fma(cl[j].y, zl[j], cl[j].x * ca);
+        zs[(colf - j + 1) * 32 + lane] = fma(cf[j].y, zf[j], cf[j].x * cb);
+        ca = fma(-cl[j].y, ca, tl);
+        cb = fma(-cf[j].y, cb, tf);
+      }
+      L.carry = ca;
+      F.carry = cb;
+      L.r += kRotBlock;
+      F.r += kRotBlock;
+    } else if (left_l >= kRotBlock) {
+      // ---- single full block on the leader
+      double2 cl[kRotBlock];
+      double zl[kRotBlock];
+      const double2* rl = ring + ((L.off + L.r) & mask);
+      const int coll = L.m - 1 - L.r;
+#pragma unroll
+      for (int j = 0; j < kRotBlock; ++j) {
+        cl[j] = rl[j];
+        zl[j] = zs[(coll - j) * 32 + lane];
+      }
+      double ca = L.carry;
+#pragma unroll
+      for (int j = 0; j < kRotBlock; ++j) {
+        const double tl = cl[j].x * zl[j];
+        zs[(coll - j + 1) * 32 + lane] = fma(cl[j].y, zl[j], cl[j].x * ca);
+        ca = fma(-cl[j].y, ca, tl);
+      }
+      L.carry = ca;
+      L.r += kRotBlock;
+    } else {
+      // ---- leader tail (< 8 rotations) and finalisation
+      double ca = L.carry;
+      for (int k = 0; k < left_l; ++k) {
+        const double2 c1 = ring[((L.off + L.r) & mask) + k];
+        const int col = L.m - 1 - L.r - k;
+        const double z1 = zs[col * 32 + lane];
+        zs[(col + 1) * 32 + lane] = fma(c1.y, z1, c1.x * ca);
+        ca = fma(-c1.y, ca, c1.x * z1);
+      }
+      zs[(L.m - L.cnt) * 32 + lane] = ca;
+      L.active = false;
+    }
   }
   __syncwarp();
   if (r0 + lane < n) {
@@ -590,6 +683,13 @@ backtransform_kernel(int n, c128* __restrict__ A_all, EighWs ws) {
 // ------------------------------------------------------------------------------------------------
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ring of the replay kernel: a power of two >= n + 240 record entries (two cursors at most n apart + refills)
+int replay_ring_size(int n) {
+  int r = 256;
+  while (r < n + 240) r *= 2;
+  return r;
+}
+
 size_t per_matrix_bytes(int n) {
   size_t s = 0;
   s += align_up((size_t)n * 8, 256) * 2;                       // d, e
@@ -668,7 +768,8 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
 
   {
-    cudaError_t e = cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 32 * 8);
+    cudaError_t e = cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         n * 32 * 8 + replay_ring_size(n) * 16);
     if (e != cudaSuccess) return (int)e;
   }
   // Two chunks are kept in flight on two internal streams (each with its own half of the workspace): the
@@ -709,7 +810,7 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
 
     dim3 rgrid((unsigned)((n + 31) / 32), (unsigned)cnt);
-    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8, ls>>>(n, ws);
+    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8 + (size_t)replay_ring_size(n) * 16, ls>>>(n, replay_ring_size(n), ws);
     if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
 
     if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
