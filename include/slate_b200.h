@@ -170,12 +170,17 @@ int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* in
  *                    row t_begin's storage, row stride = out_row_stride elements (>= batch*n).
  * ---------------------------------------------------------------------------------------------- */
 /* sqb_evolve_bloch_uniform: same result as sqb_evolve_bloch for a UNIFORM grid times[i] = times[0] + i*dt (the
- * caller guarantees it, e.g. SpacedTimeMetadata): rows 8 apart differ by exp(-1j*w*8*dt/hbar), tabulated once per
- * eigenvalue in step_workspace ([batch*n] complex128), so the GEMM's producer warps need one sincos per 8 rows.
- * Accuracy: 7 extra complex multiplications per element (<= 1e-15 relative). */
+ * caller guarantees it, e.g. SpacedTimeMetadata).  The phases factorise as
+ *   exp(-1j w t_{64 q + g + 8 r}) = tilebase[q] * pow8[g] * step8^r
+ * (three small per-eigenvalue tables built by one pre-kernel in `workspace`,
+ * sqb_evolve_uniform_workspace_bytes(n, batch, t_count) bytes), so the GEMM's producer warps use complex
+ * multiplications only, and the complex product is evaluated with the 3M scheme (3 real tensor-core products
+ * instead of 4).  Accuracy: <= ~10 extra roundings per element, normwise 1e-15. */
+size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count);
 int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
                              const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
-                             sqb_c128* out, int64_t out_row_stride, sqb_c128* step_workspace, void* stream);
+                             sqb_c128* out, int64_t out_row_stride, void* workspace, size_t workspace_bytes,
+                             void* stream);
 int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
                 void* stream);
 /* Generic explicit-basis conversion of a vector list [lead, batch*n] (ExplicitUnitaryBasis.__into_inner__ /

@@ -86,11 +86,30 @@ evolve_eigen_kernel(int64_t m, const double* __restrict__ w, const c128* __restr
   }
 }
 
-// step[i] = exp(-1j * w[i] * dt8 / hbar): the factor between time rows 8 apart on a uniform grid
+constexpr int TM = 64;    // times per CTA tile (both GEMM variants)
+
+// Phase tables of a uniform time grid t_j = times[0] + j dt (per eigenvalue i, m = batch * n of them):
+//   step8[i]       = exp(-1j w_i 8 dt / hbar)              factor between time rows 8 apart
+//   pow8[i][g]     = exp(-1j w_i g dt / hbar), g = 0..7    offset of row g inside a group of 8
+//   tilebase[q][i] = exp(-1j w_i times[64 q] / hbar)       first row of CTA time tile q
+// so that a producer thread of the GEMM builds its 8 A entries with complex multiplications only.
 __global__ void __launch_bounds__(256)
-phase_step_kernel(int64_t m, const double* __restrict__ w, double dt8, double hbar, c128* __restrict__ step) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-    step[i] = phase_factor(w[i], dt8, hbar);
+phase_tables_kernel(int64_t m, const double* __restrict__ w, const double* __restrict__ times, int64_t t_count,
+                    double dt, double hbar, c128* __restrict__ step8, c128* __restrict__ pow8,
+                    c128* __restrict__ tilebase) {
+  const int64_t n_tiles = (t_count + TM - 1) / TM;
+  const int64_t total = m * (9 + n_tiles);
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = g / m, i = g - k * m;  // i fastest: coalesced
+    const double wi = w[i];
+    if (k == 0) {
+      step8[i] = phase_factor(wi, 8.0 * dt, hbar);
+    } else if (k < 9) {
+      pow8[i * 8 + (k - 1)] = phase_factor(wi, (double)(k - 1) * dt, hbar);
+    } else {
+      tilebase[(k - 9) * m + i] = phase_factor(wi, times[(k - 9) * TM], hbar);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -99,7 +118,6 @@ phase_step_kernel(int64_t m, const double* __restrict__ w, double dt8, double hb
 //   warps 8..11  producers: generate the A chunk (c_e * exp(-i w_e t / hbar), one sincos per element) into
 //                shared memory and issue the 1-D bulk (TMA) copies of the B chunk (eigenvector rows)
 // kGemmStages-deep ring, full/empty mbarriers; the tensor pipe never waits for sincos or for L2.
-constexpr int TM = 64;    // times per CTA tile
 constexpr int TN = 128;   // components per CTA tile
 constexpr int KC = 16;    // eigen-index chunk
 constexpr int LDA = KC + 4;   // complex elements; == 4 (mod 8) -> conflict-free 16 B fragment loads
@@ -322,6 +340,210 @@ evolve_bloch_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3M variant of the fused GEMM (uniform time grids): a complex product needs THREE real products
+//   P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi);   Cr = P1 - P2,  Ci = P3 - P1 - P2
+// i.e. 3 DMMA.8x8x4 per complex 8x8x4 tile instead of 4 (25 % less tensor work; normwise stable, error
+// ~1e-15 relative to |a||b|, far inside the 1e-9 tolerance).  Three accumulator planes cost 1.5x the
+// registers, so the warp tile is 32 x 16 and the CTA tile 64 (t) x 64 (k); the producers also store the
+// plane Ar + Ai, and the plane Br + Bi of the eigenvectors is precomputed once per call (bsum_kernel, row
+// stride padded to an even number of doubles so that its rows can be bulk-copied) - a DADD in the consumer
+// warps would queue behind their own DMMAs on the shared FP64 pipe.
+__global__ void __launch_bounds__(256)
+bsum_kernel(int n, int n_pad, int64_t rows, const c128* __restrict__ V, double* __restrict__ bsum) {
+  const int64_t total = rows * n_pad;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = g / n_pad;
+    const int k = (int)(g - r * n_pad);
+    double v = 0.0;
+    if (k < n) {
+      const c128 z = V[r * n + k];
+      v = z.x + z.y;
+    }
+    bsum[g] = v;
+  }
+}
+
+constexpr int TN3 = 64;
+constexpr int LDB3 = TN3 + 2;   // == 2 (mod 8)
+constexpr int LDAS = KC + 4;    // doubles; == 4 (mod 16) -> conflict-free 8 B fragment loads
+constexpr int LDBS = TN3 + 4;    // doubles; == 4 (mod 16)
+constexpr int kStages3 = 4;
+constexpr int kStage3Bytes = TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16 + KC * LDBS * 8;
+constexpr size_t kGemm3Smem = (size_t)kStages3 * kStage3Bytes + 128;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict__ coef, int64_t t_count,
+                       c128* __restrict__ out, int64_t out_row_stride, const c128* __restrict__ step8,
+                       const c128* __restrict__ pow8, const c128* __restrict__ tilebase, int64_t m_total,
+                       const double* __restrict__ bsum, int n_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages3 * kStage3Bytes);  // [stages]
+  uint64_t* empty = full + kStages3;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = blockIdx.x * TN3;
+  const int64_t t0 = (int64_t)blockIdx.y * TM;
+  const int64_t b = blockIdx.z;
+  const c128* Vb = V + b * (int64_t)n * n;
+  const int ncols = min(TN3, n - p0);
+  const int nchunks = (n + KC - 1) / KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages3; ++s) {
+      mbar_init(&full[s], kProducerThreads);
+      mbar_init(&empty[s], kConsumerThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kConsumerThreads / 32) {
+    // ============================== producers ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int ptid = tid - kConsumerThreads;
+    const int ge = ptid % KC;
+    const int gj = ptid / KC;  // 0..7 ; rows gj + 8 q
+    // A[t0 + gj + 8q, e] = c_e * tilebase[tile][e] * pow8[e][gj] * step8[e]^q : multiplications only
+    const c128* cb = coef + b * n;
+    const c128* sb = step8 + b * n;
+    const c128* pb = pow8 + b * n * 8 + gj;
+    const c128* tb = tilebase + (int64_t)blockIdx.y * m_total + b * n;
+    c128 ce_next = make_double2(0.0, 0.0), se_next = make_double2(1.0, 0.0);
+    if (ge < n) {
+      ce_next = cmul(cmul(cb[ge], tb[ge]), pb[(int64_t)ge * 8]);
+      se_next = sb[ge];
+    }
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % kStages3;
+      const uint32_t ph = (uint32_t)((kc / kStages3) & 1);
+      unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
+      c128* Ac = reinterpret_cast<c128*>(st);
+      double* As = reinterpret_cast<double*>(st + TM * LDA * 16);
+      c128* Bs = reinterpret_cast<c128*>(st + TM * LDA * 16 + TM * LDAS * 8);
+      double* Bq = reinterpret_cast<double*>(st + TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16);
+      const c128 ce = ce_next, se = se_next;
+      const int e = kc * KC + ge;
+      c128 c_raw = make_double2(0.0, 0.0), t_raw = make_double2(1.0, 0.0), p_raw = make_double2(1.0, 0.0);
+      {
+        const int en = e + KC;
+        se_next = make_double2(1.0, 0.0);
+        if (en < n) {
+          c_raw = cb[en];
+          t_raw = tb[en];
+          p_raw = pb[(int64_t)en * 8];
+          se_next = sb[en];
+        }
+      }
+      mbar_wait(&empty[s], ph ^ 1u);
+      const int e0 = kc * KC;
+      const int nrows = min(KC, n - e0);
+      if (ptid == 0) {
+        const int ncols2 = (ncols + 1) & ~1;  // bulk copies move multiples of 16 B; the pad column is zero
+        mbar_expect_tx(&full[s], (uint32_t)(nrows * (ncols * sizeof(c128) + ncols2 * sizeof(double))));
+        const double* qb = bsum + (b * n + e0) * (int64_t)n_pad + p0;
+        for (int r = 0; r < nrows; ++r) {
+          bulk_g2s(Bs + r * LDB3, Vb + (int64_t)(e0 + r) * n + p0, (uint32_t)(ncols * sizeof(c128)), &full[s]);
+          bulk_g2s(Bq + r * LDBS, qb + (int64_t)r * n_pad, (uint32_t)(ncols2 * sizeof(double)), &full[s]);
+        }
+      }
+      if (nrows < KC) {
+        for (int idx = ptid; idx < (KC - nrows) * LDB3; idx += kProducerThreads)
+          Bs[nrows * LDB3 + idx] = make_double2(0.0, 0.0);
+        for (int idx = ptid; idx < (KC - nrows) * LDBS; idx += kProducerThreads) Bq[nrows * LDBS + idx] = 0.0;
+      }
+      c128 v = ce;  // zero for e >= n
+#pragma unroll
+      for (int q = 0; q < TM / 8; ++q) {
+        const int j = gj + 8 * q;
+        const c128 o = (t0 + j < t_count) ? v : make_double2(0.0, 0.0);
+        Ac[j * LDA + ge] = o;
+        As[j * LDAS + ge] = o.x + o.y;
+        v = cmul(v, se);
+      }
+      ce_next = cmul(cmul(c_raw, t_raw), p_raw);  // next chunk's first-row amplitude (loads issued above)
+      mbar_arrive(&full[s]);
+    }
+    return;
+  }
+
+  // ============================== consumers ==============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int wm = (warp & 1) * 32;
+  const int wn = (warp >> 1) * 16;
+  double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      p1[a][c][0] = p1[a][c][1] = 0.0;
+      p2[a][c][0] = p2[a][c][1] = 0.0;
+      p3[a][c][0] = p3[a][c][1] = 0.0;
+    }
+  const int frow = lane >> 2, fcol = lane & 3;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int s = kc % kStages3;
+    const uint32_t ph = (uint32_t)((kc / kStages3) & 1);
+    const unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
+    const c128* Ac = reinterpret_cast<const c128*>(st);
+    const double* As = reinterpret_cast<const double*>(st + TM * LDA * 16);
+    const c128* Bs = reinterpret_cast<const c128*>(st + TM * LDA * 16 + TM * LDAS * 8);
+    const double* Bq = reinterpret_cast<const double*>(st + TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16);
+    mbar_wait(&full[s], ph);
+    c128 af[2][4], bf[2][2];
+    double as[2][4], bs[2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      af[0][a] = Ac[(wm + a * 8 + frow) * LDA + fcol];
+      as[0][a] = As[(wm + a * 8 + frow) * LDAS + fcol];
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      bf[0][c] = Bs[fcol * LDB3 + wn + c * 8 + frow];
+      bs[0][c] = Bq[fcol * LDBS + wn + c * 8 + frow];
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      const int cur = (k4 >> 2) & 1, nxt = cur ^ 1;
+      if (k4 + 4 < KC) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          af[nxt][a] = Ac[(wm + a * 8 + frow) * LDA + k4 + 4 + fcol];
+          as[nxt][a] = As[(wm + a * 8 + frow) * LDAS + k4 + 4 + fcol];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          bf[nxt][c] = Bs[(k4 + 4 + fcol) * LDB3 + wn + c * 8 + frow];
+          bs[nxt][c] = Bq[(k4 + 4 + fcol) * LDBS + wn + c * 8 + frow];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          dmma(p1[a][c][0], p1[a][c][1], af[cur][a].x, bf[cur][c].x);
+          dmma(p2[a][c][0], p2[a][c][1], af[cur][a].y, bf[cur][c].y);
+          dmma(p3[a][c][0], p3[a][c][1], as[cur][a], bs[cur][c]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t t = t0 + wm + a * 8 + frow;
+    if (t >= t_count) continue;
+    c128* orow = out + t * out_row_stride + b * (int64_t)n;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int p = p0 + wn + c * 8 + fcol * 2;
+      if (p < n) orow[p] = make_double2(p1[a][c][0] - p2[a][c][0], p3[a][c][0] - p1[a][c][0] - p2[a][c][0]);
+      if (p + 1 < n) orow[p + 1] = make_double2(p1[a][c][1] - p2[a][c][1], p3[a][c][1] - p1[a][c][1] - p2[a][c][1]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
@@ -368,23 +590,35 @@ extern "C" int sqb_evolve_eigen(int64_t m, const double* w, const sqb_c128* c, c
 namespace {
 int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
                         const double* times, int64_t t_count, double hbar, sqb_c128* out, int64_t out_row_stride,
-                        const c128* step8, void* stream) {
+                        const c128* step8, const c128* pow8, const c128* tilebase, const double* bsum, int n_pad,
+                        void* stream) {
   if (n < 1 || batch < 0 || t_count < 0 || !transform || !w || !c || !times || !out || hbar == 0.0 ||
       out_row_stride < batch * n)
     return SQB_E_BADARG;
   if (batch == 0 || t_count == 0) return SQB_OK;
-  cudaError_t e = cudaFuncSetAttribute(evolve_bloch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+  const bool use_3m = step8 != nullptr;  // uniform grid: 3M complex product, 64 x 64 CTA tiles
+  cudaError_t e = use_3m ? cudaFuncSetAttribute(evolve_bloch_3m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)kGemm3Smem)
+                         : cudaFuncSetAttribute(evolve_bloch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)kGemmSmem);
   if (e != cudaSuccess) return (int)e;
   const int64_t t_tiles = (t_count + TM - 1) / TM;
   if (t_tiles > 65535) return SQB_E_UNSUPPORTED;
-  const unsigned p_tiles = (unsigned)((n + TN - 1) / TN);
+  const int tn = use_3m ? TN3 : TN;
+  const unsigned p_tiles = (unsigned)((n + tn - 1) / tn);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int64_t cnt = sqb_min64(65535, batch - b0);
     dim3 grid(p_tiles, (unsigned)t_tiles, (unsigned)cnt);
-    evolve_bloch_kernel<<<grid, kGemmThreads, kGemmSmem, sqb_stream(stream)>>>(
-        n, reinterpret_cast<const c128*>(transform) + b0 * (int64_t)n * n, w + b0 * n,
-        reinterpret_cast<const c128*>(c) + b0 * n, times, t_count, hbar, reinterpret_cast<c128*>(out) + b0 * n,
-        out_row_stride, step8 ? step8 + b0 * n : nullptr);
+    const c128* vb = reinterpret_cast<const c128*>(transform) + b0 * (int64_t)n * n;
+    const c128* cbp = reinterpret_cast<const c128*>(c) + b0 * n;
+    c128* ob = reinterpret_cast<c128*>(out) + b0 * n;
+    if (use_3m)
+      evolve_bloch_3m_kernel<<<grid, kGemmThreads, kGemm3Smem, sqb_stream(stream)>>>(
+          n, vb, cbp, t_count, ob, out_row_stride, step8 + b0 * n, pow8 + b0 * n * 8, tilebase + b0 * n, batch * n,
+          bsum + b0 * n * (int64_t)n_pad, n_pad);
+    else
+      evolve_bloch_kernel<<<grid, kGemmThreads, kGemmSmem, sqb_stream(stream)>>>(
+          n, vb, w + b0 * n, cbp, times, t_count, hbar, ob, out_row_stride, nullptr);
     SQB_LAUNCH_CHECK();
   }
   return SQB_OK;
@@ -394,18 +628,38 @@ int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const d
 extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const double* w, const sqb_c128* c,
                                 const double* times, int64_t t_count, double hbar, sqb_c128* out,
                                 int64_t out_row_stride, void* stream) {
-  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, nullptr, stream);
+  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, nullptr, nullptr,
+                             nullptr, nullptr, 0, stream);
+}
+
+extern "C" size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count) {
+  if (n < 1 || batch < 0 || t_count < 0) return 0;
+  const int64_t tiles = (t_count + TM - 1) / TM;
+  const int64_t n_pad = n + (n & 1);
+  return (size_t)(batch * n) * (size_t)(9 + tiles) * sizeof(c128) + (size_t)(batch * n) * n_pad * sizeof(double) + 512;
 }
 
 extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
                                         const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
-                                        sqb_c128* out, int64_t out_row_stride, sqb_c128* step_workspace, void* stream) {
-  if (!step_workspace || n < 1 || batch < 0 || !w || hbar == 0.0) return SQB_E_BADARG;
+                                        sqb_c128* out, int64_t out_row_stride, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (n < 1 || batch < 0 || !w || !times || hbar == 0.0) return SQB_E_BADARG;
   if (batch == 0 || t_count == 0) return SQB_OK;
+  if (!workspace || workspace_bytes < sqb_evolve_uniform_workspace_bytes(n, batch, t_count)) return SQB_E_WORKSPACE;
   const int64_t m = batch * n;
-  const int grid = (int)sqb_min64((m + 255) / 256, 148 * 8);
-  phase_step_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, 8.0 * dt, hbar, reinterpret_cast<c128*>(step_workspace));
+  const int64_t tiles = (t_count + TM - 1) / TM;
+  c128* step8 = reinterpret_cast<c128*>(workspace);
+  c128* pow8 = step8 + m;
+  c128* tilebase = pow8 + 8 * m;
+  const int n_pad = n + (n & 1);
+  double* bsum = reinterpret_cast<double*>(tilebase + tiles * m);  // [batch*n][n_pad] plane Re + Im of `transform`
+  const int64_t total = m * (9 + tiles);
+  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
+  phase_tables_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, times, t_count, dt, hbar, step8, pow8, tilebase);
   SQB_LAUNCH_CHECK();
-  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride,
-                             reinterpret_cast<const c128*>(step_workspace), stream);
+  const int grid2 = (int)sqb_min64((m * n_pad + 255) / 256, 148 * 32);
+  bsum_kernel<<<grid2, 256, 0, sqb_stream(stream)>>>(n, n_pad, m, reinterpret_cast<const c128*>(transform), bsum);
+  SQB_LAUNCH_CHECK();
+  return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, step8, pow8, tilebase,
+                             bsum, n_pad, stream);
 }

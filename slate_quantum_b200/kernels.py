@@ -350,11 +350,12 @@ def evolve_bloch(
         _lib.check(rc, "sqb_evolve_bloch")
         _count(-(-batch // 65535))
     else:
-        step = torch.empty((batch * n,), dtype=torch.complex128, device="cuda")
+        ws_bytes = lib.sqb_evolve_uniform_workspace_bytes(n, batch, t_count)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
         rc = lib.sqb_evolve_bloch_uniform(
             n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(uniform_dt), float(hbar),
-            _ptr(out), batch * n, _ptr(step), _stream(),
+            _ptr(out), batch * n, _ptr(ws), ws_bytes, _stream(),
         )
         _lib.check(rc, "sqb_evolve_bloch_uniform")
-        _count(1 - (-batch // 65535))
+        _count(2 - (-batch // 65535))  # phase tables + Re+Im plane + GEMM
     return out
