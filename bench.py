@@ -265,6 +265,10 @@ def run_ours(args) -> None:
     gathered = world > 1 and with_position  # time-sharded evolve over all-gathered eigenvectors
     w_all = torch.empty((n_k_global, n, n), dtype=torch.complex128, device="cuda") if gathered else None
     c_all = torch.empty((n_k_global * n,), dtype=torch.complex128, device="cuda") if gathered else None
+    evolve_ws = (
+        torch.empty(kernels.evolve_uniform_workspace_bytes(n, n_k_global, T // world), dtype=torch.uint8, device="cuda")
+        if gathered else None
+    )
     free, _ = torch.cuda.mem_get_info()
     if gathered:
         row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
@@ -316,12 +320,12 @@ def run_ours(args) -> None:
 
             timed("exchange", gather)
             t_lo = rank * (T // world)
-            for t0 in range(0, T // world, t_tile):
+            for i_tile, t0 in enumerate(range(0, T // world, t_tile)):
                 tt = min(t_tile, T // world - t0)
                 tsl = times[t_lo + t0 : t_lo + t0 + tt]
                 timed("evolve", lambda: kernels.evolve_bloch(
                     w_all, eig_all.reshape(n_k_global, n), c_all.reshape(n_k_global, n), tsl, HBAR,
-                    out=states[:tt], uniform_dt=dt_uniform))
+                    out=states[:tt], uniform_dt=dt_uniform, workspace=evolve_ws, reuse_plane=i_tile > 0))
                 timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
             return
         for t0 in range(0, T, t_tile):

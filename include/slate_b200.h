@@ -175,12 +175,15 @@ int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* in
  * (three small per-eigenvalue tables built by one pre-kernel in `workspace`,
  * sqb_evolve_uniform_workspace_bytes(n, batch, t_count) bytes), so the GEMM's producer warps use complex
  * multiplications only, and the complex product is evaluated with the 3M scheme (3 real tensor-core products
- * instead of 4).  Accuracy: <= ~10 extra roundings per element, normwise 1e-15. */
+ * instead of 4).  Accuracy: <= ~10 extra roundings per element, normwise 1e-15.
+ * The workspace also holds the plane Re+Im of `transform` (the third operand of 3M).  It only depends on
+ * `transform`: pass reuse_transform_plane = 1 on later calls with the SAME transform, n, batch and workspace
+ * (e.g. the next time tile) to skip recomputing it. */
 size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count);
 int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
                              const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
                              sqb_c128* out, int64_t out_row_stride, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             int reuse_transform_plane, void* stream);
 int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
                 void* stream);
 /* Generic explicit-basis conversion of a vector list [lead, batch*n] (ExplicitUnitaryBasis.__into_inner__ /

@@ -107,7 +107,7 @@ def load() -> ctypes.CDLL:
     lib.sqb_evolve_bloch_uniform.restype = c_int
     lib.sqb_evolve_bloch_uniform.argtypes = [
         c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_int64,
-        c_void_p, c_size_t, c_void_p,
+        c_void_p, c_size_t, c_int, c_void_p,
     ]
     lib.sqb_peak_dmma.restype = c_int
     lib.sqb_peak_dmma.argtypes = [c_int, c_int64, c_void_p, dp, c_void_p]

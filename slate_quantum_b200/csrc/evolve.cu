@@ -642,24 +642,28 @@ extern "C" size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64
 extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
                                         const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,
                                         sqb_c128* out, int64_t out_row_stride, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+                                        size_t workspace_bytes, int reuse_transform_plane, void* stream) {
   if (n < 1 || batch < 0 || !w || !times || hbar == 0.0) return SQB_E_BADARG;
   if (batch == 0 || t_count == 0) return SQB_OK;
   if (!workspace || workspace_bytes < sqb_evolve_uniform_workspace_bytes(n, batch, t_count)) return SQB_E_WORKSPACE;
   const int64_t m = batch * n;
   const int64_t tiles = (t_count + TM - 1) / TM;
-  c128* step8 = reinterpret_cast<c128*>(workspace);
+  // workspace layout: [bsum: m * n_pad doubles][step8: m][pow8: 8 m][tilebase: tiles * m]; bsum first so that
+  // its position does not depend on t_count and it can be reused across calls on the same transform
+  const int n_pad = n + (n & 1);
+  double* bsum = reinterpret_cast<double*>(workspace);  // [batch*n][n_pad] plane Re + Im of `transform`
+  c128* step8 = reinterpret_cast<c128*>(bsum + (m * n_pad + (m * n_pad & 1)));
   c128* pow8 = step8 + m;
   c128* tilebase = pow8 + 8 * m;
-  const int n_pad = n + (n & 1);
-  double* bsum = reinterpret_cast<double*>(tilebase + tiles * m);  // [batch*n][n_pad] plane Re + Im of `transform`
   const int64_t total = m * (9 + tiles);
   const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
   phase_tables_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, times, t_count, dt, hbar, step8, pow8, tilebase);
   SQB_LAUNCH_CHECK();
-  const int grid2 = (int)sqb_min64((m * n_pad + 255) / 256, 148 * 32);
-  bsum_kernel<<<grid2, 256, 0, sqb_stream(stream)>>>(n, n_pad, m, reinterpret_cast<const c128*>(transform), bsum);
-  SQB_LAUNCH_CHECK();
+  if (!reuse_transform_plane) {
+    const int grid2 = (int)sqb_min64((m * n_pad + 255) / 256, 148 * 32);
+    bsum_kernel<<<grid2, 256, 0, sqb_stream(stream)>>>(n, n_pad, m, reinterpret_cast<const c128*>(transform), bsum);
+    SQB_LAUNCH_CHECK();
+  }
   return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, step8, pow8, tilebase,
                              bsum, n_pad, stream);
 }

@@ -459,20 +459,26 @@ bool smooth(int len) {
 int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t st) {
   if (!factorize(P.len, P.radix, &P.n_stages)) return SQB_E_UNSUPPORTED;
   if (P.len > kMaxSmemLen) return SQB_E_UNSUPPORTED;
-  // lines per CTA (power of two): enough for 128..256 B coalesced runs across lines and >= 1024 elements of
-  // work per CTA, small enough for several CTAs per SM
-  int lpc = 1;
-  while (lpc * 2 <= kMaxLines && lpc * 2 * P.len <= 2048) lpc *= 2;
-  if ((P.inner_fastest || P.out_inner_fastest) && lpc < 8 && P.len * 8 <= kMaxSmemLen) lpc = 8;
-  const int64_t n_lines = P.n_outer * P.n_inner;
-  while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
-  P.lines_per_cta = lpc;
   // buffers: first fixed-radix stage reads global, last writes global -> S-1 shared round trips
   auto fixed = [](int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; };
   const bool copy_in = P.n_stages == 0 || !fixed(P.radix[0]);
   const bool copy_out = P.n_stages == 0 || !fixed(P.radix[P.n_stages - 1]);
   const int smem_writes = P.n_stages - 1 + (copy_in ? 1 : 0) + (copy_out ? 1 : 0);  // stages writing shared
   const int n_buf = smem_writes >= 2 ? 2 : 1;
+  // lines per CTA (power of two): enough for 128..256 B coalesced runs across lines and >= 1024 elements of
+  // work per CTA, small enough for several CTAs per SM (<= ~72 KB of shared memory when possible)
+  int lpc = 1;
+  while (lpc * 2 <= kMaxLines && lpc * 2 * P.len <= 2048) lpc *= 2;
+  if (P.inner_fastest || P.out_inner_fastest) {
+    // strided lines: at least 4 adjacent lines (64 B runs), 8 when the buffers stay small
+    int want = 8;
+    while (want > 1 && (size_t)want * P.len * n_buf * sizeof(c128) > 72 * 1024) want /= 2;
+    if (want < 4 && (size_t)4 * P.len * n_buf * sizeof(c128) <= 160 * 1024) want = 4;
+    if (lpc < want) lpc = want;
+  }
+  const int64_t n_lines = P.n_outer * P.n_inner;
+  while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
+  P.lines_per_cta = lpc;
   const size_t smem = ((size_t)n_buf * lpc * P.len + P.len) * sizeof(c128);
   cudaError_t e = cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;

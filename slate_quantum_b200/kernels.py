@@ -323,14 +323,20 @@ def uniform_step(times: np.ndarray | Sequence[float]) -> float | None:
     return float(dt) if err <= 4 * np.finfo(np.float64).eps * max(np.abs(t).max(), abs(dt)) else None
 
 
+def evolve_uniform_workspace_bytes(n: int, batch: int, t_count: int) -> int:
+    return int(_lib.load().sqb_evolve_uniform_workspace_bytes(n, batch, t_count))
+
+
 def evolve_bloch(
     transform: torch.Tensor, w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float,
     out: torch.Tensor | None = None, uniform_dt: float | None = None,
+    workspace: torch.Tensor | None = None, reuse_plane: bool = False,
 ) -> torch.Tensor:
     """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM).
 
-    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`) to use the cheaper
-    phase recurrence in the GEMM's producer warps."""
+    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`) to use the 3M kernel with
+    table-driven phases.  workspace / reuse_plane: a caller-owned workspace (>= evolve_uniform_workspace_bytes)
+    lets consecutive calls on the SAME transform (time tiles) skip recomputing the Re+Im plane."""
     _require_cuda()
     lib = _lib.load()
     _c128(transform, "transform")
@@ -351,11 +357,12 @@ def evolve_bloch(
         _count(-(-batch // 65535))
     else:
         ws_bytes = lib.sqb_evolve_uniform_workspace_bytes(n, batch, t_count)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        if workspace is None or workspace.numel() < ws_bytes:
+            workspace, reuse_plane = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda"), False
         rc = lib.sqb_evolve_bloch_uniform(
             n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(uniform_dt), float(hbar),
-            _ptr(out), batch * n, _ptr(ws), ws_bytes, _stream(),
+            _ptr(out), batch * n, _ptr(workspace), workspace.numel(), int(bool(reuse_plane)), _stream(),
         )
         _lib.check(rc, "sqb_evolve_bloch_uniform")
-        _count(2 - (-batch // 65535))  # phase tables + Re+Im plane + GEMM
+        _count((1 if reuse_plane else 2) - (-batch // 65535))  # phase tables (+ Re+Im plane) + GEMM
     return out

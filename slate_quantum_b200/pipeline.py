@@ -50,6 +50,8 @@ class BlochSolver:
         self.info: torch.Tensor | None = None
         self._eigh_ws: torch.Tensor | None = None
         self.transform_folded: torch.Tensor | None = None
+        self._evolve_ws: torch.Tensor | None = None
+        self._evolve_ws_for: tuple | None = None  # (data_ptr of the transform whose Re+Im plane the workspace holds)
 
     # ------------------------------------------------------------------ K1
     def build(self, potential_table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -77,6 +79,7 @@ class BlochSolver:
         self.eigenvalues, self.transform, self.info = w, v, info
         self.hamiltonian = None
         self.transform_folded = None
+        self._evolve_ws_for = None
         return w, v
 
     def fold(self, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -85,7 +88,26 @@ class BlochSolver:
             self.transform_folded = kernels.fold_transform(
                 self.shape, self.repeat, self.transform, self.block_begin, out=out
             )
+            self._evolve_ws_for = None
         return self.transform_folded
+
+    def _evolve(self, transform, coefficients, times, out, uniform_dt):
+        """K3c on `transform` with a persistent workspace: the Re+Im plane of the 3M kernel is computed once per
+        (eigensolve, transform) and reused by every later time tile."""
+        if uniform_dt is None:
+            return kernels.evolve_bloch(transform, self.eigenvalues, coefficients, times, self.hbar, out=out)
+        need = kernels.evolve_uniform_workspace_bytes(self.n, transform.shape[0], times.numel())
+        if self._evolve_ws is None or self._evolve_ws.numel() < need:
+            self._evolve_ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+            self._evolve_ws_for = None
+        key = (transform.data_ptr(),)
+        reuse = self._evolve_ws_for == key
+        res = kernels.evolve_bloch(
+            transform, self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt,
+            workspace=self._evolve_ws, reuse_plane=reuse,
+        )
+        self._evolve_ws_for = key
+        return res
 
     def release_workspace(self) -> None:
         self._eigh_ws = None
@@ -112,18 +134,14 @@ class BlochSolver:
         uniform_dt: float | None = None,
     ) -> torch.Tensor:
         """[T, count*N] states in the Bloch-ordered momentum basis (fused phase x eigenvector GEMM)."""
-        return kernels.evolve_bloch(
-            self.transform, self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt
-        )
+        return self._evolve(self.transform, coefficients, times, out, uniform_dt)
 
     def evolve_cell(
         self, coefficients: torch.Tensor, times: torch.Tensor, out: torch.Tensor | None = None,
         uniform_dt: float | None = None,
     ) -> torch.Tensor:
         """[T, count*N] states in the cell layout (block, in-cell POSITION); cell_to_position finishes the job."""
-        return kernels.evolve_bloch(
-            self.fold(), self.eigenvalues, coefficients, times, self.hbar, out=out, uniform_dt=uniform_dt
-        )
+        return self._evolve(self.fold(), coefficients, times, out, uniform_dt)
 
     def cell_to_position(
         self, states_cell: torch.Tensor, out: torch.Tensor | None = None, ranks: int = 1
