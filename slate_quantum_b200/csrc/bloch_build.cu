@@ -71,39 +71,61 @@ __device__ __forceinline__ void unravel(int64_t flat, const int* dims, int nd, i
 }
 
 constexpr int kBuildThreads = 256;
-constexpr int kRowsPerCta = 16;
+constexpr int kRowsPerCta = 32;
+
+// 32-bit unravel (n <= 2^20)
+__device__ __forceinline__ void unravel32(int flat, const int* dims, int nd, int* out) {
+  for (int a = nd - 1; a >= 0; --a) {
+    const int q = flat / dims[a];
+    out[a] = flat - q * dims[a];
+    flat = q;
+  }
+}
 
 __global__ void __launch_bounds__(kBuildThreads)
 bloch_build_kernel(BuildParams P, const c128* __restrict__ vtable, int64_t block_begin, c128* __restrict__ H) {
-  extern __shared__ c128 s_tab[];
+  extern __shared__ c128 s_tab[];                 // [n] potential table / sqrt(N)
+  __shared__ int s_ridx[kRowsPerCta][SQB_MAX_DIMS];  // multi index of each row of the tile
+  __shared__ double s_kin[kRowsPerCta];              // kinetic energy of each row of the tile
   const int n = P.n;
   const int nd = P.d.nd;
   for (int i = threadIdx.x; i < n; i += kBuildThreads) {
     c128 v = vtable[i];
     s_tab[i] = make_double2(__ddiv_rn(v.x, P.inv_sqrt_n_den), __ddiv_rn(v.y, P.inv_sqrt_n_den));
   }
+  const int64_t b_local = blockIdx.x;
+  const int row0 = blockIdx.y * kRowsPerCta;
+  const int rows = min(kRowsPerCta, n - row0);
+  if (threadIdx.x < rows) {
+    int bidx[SQB_MAX_DIMS], ridx[SQB_MAX_DIMS];
+    unravel(block_begin + b_local, P.d.repeat, nd, bidx);
+    unravel32(row0 + threadIdx.x, P.d.shape, nd, ridx);
+    for (int a = 0; a < SQB_MAX_DIMS; ++a) s_ridx[threadIdx.x][a] = a < nd ? ridx[a] : 0;
+    s_kin[threadIdx.x] = kinetic_value(P, ridx, bidx);
+  }
   __syncthreads();
 
-  const int64_t b_local = blockIdx.x;
-  int bidx[SQB_MAX_DIMS];
-  unravel(block_begin + b_local, P.d.repeat, nd, bidx);
-  const int row0 = blockIdx.y * kRowsPerCta;
-  c128* Hb = H + b_local * (int64_t)n * n;
-
+  c128* Hb = H + b_local * (int64_t)n * n + (int64_t)row0 * n;
+  int stride[SQB_MAX_DIMS];
+  {
+    int st = 1;
+    for (int a = nd - 1; a >= 0; --a) {
+      stride[a] = st;
+      st *= P.d.shape[a];
+    }
+  }
   for (int c = threadIdx.x; c < n; c += kBuildThreads) {
     int cidx[SQB_MAX_DIMS];
-    unravel(c, P.d.shape, nd, cidx);
-    for (int r = row0; r < min(row0 + kRowsPerCta, n); ++r) {
-      int ridx[SQB_MAX_DIMS];
-      unravel(r, P.d.shape, nd, ridx);
+    unravel32(c, P.d.shape, nd, cidx);
+    for (int r = 0; r < rows; ++r) {
       int flat = 0;
       for (int a = 0; a < nd; ++a) {
-        int dlt = cidx[a] - ridx[a];
+        int dlt = cidx[a] - s_ridx[r][a];
         if (dlt < 0) dlt += P.d.shape[a];
-        flat = flat * P.d.shape[a] + dlt;
+        flat += dlt * stride[a];
       }
       c128 v = s_tab[flat];
-      if (c == r) v.x = __dadd_rn(v.x, kinetic_value(P, ridx, bidx));
+      if (c == row0 + r) v.x = __dadd_rn(v.x, s_kin[r]);
       Hb[(int64_t)r * n + c] = v;
     }
   }
