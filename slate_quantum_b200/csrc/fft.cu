@@ -201,6 +201,7 @@ struct StageIo {
   const int64_t* out_base;
   const int64_t* inner_idx;
   bool first, last, line_fastest;
+  bool line_major;          // shared layout: true = [pos][line] (line fastest), false = [line][pos]
 };
 
 // One Stockham stage of radix R over `lines` lines held by the CTA.  The first stage reads its butterfly
@@ -214,6 +215,10 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
   const int pl_shift = pow2_shift(per_line), ns_shift = pow2_shift(ns);
   const int lshift = 31 - __clz(lpc);
   const int work = per_line * (io.line_fastest ? lpc : lines);
+  // shared-memory index of (line, pos): with the [pos][line] layout a warp that walks 32 adjacent lines at one
+  // position touches 32 consecutive elements (conflict free); [line][pos] would be a 32-way bank conflict there
+  const int s_line = io.line_major ? 1 : len;
+  const int s_pos = io.line_major ? lpc : 1;
   for (int w = threadIdx.x; w < work; w += kFftThreads) {
     int line, j, jq, k;
     if (io.line_fastest) {
@@ -231,7 +236,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
       for (int t = 0; t < R; ++t) x[t] = io.gin[base + pos_offset(j + t * per_line, P.in_split, P.in_sl_hi, P.in_sl)];
     } else {
 #pragma unroll
-      for (int t = 0; t < R; ++t) x[t] = io.src[line * len + j + t * per_line];
+      for (int t = 0; t < R; ++t) x[t] = io.src[line * s_line + (j + t * per_line) * s_pos];
     }
     if (ns > 1) {
 #pragma unroll
@@ -255,7 +260,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
       }
     } else {
 #pragma unroll
-      for (int t = 0; t < R; ++t) io.dst[line * len + pos0 + t * ns] = x[t];
+      for (int t = 0; t < R; ++t) io.dst[line * s_line + (pos0 + t * ns) * s_pos] = x[t];
     }
   }
 }
@@ -284,7 +289,12 @@ __device__ __forceinline__ void stage_generic(const c128* src, c128* dst, int le
 
 __device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; }
 
-__global__ void __launch_bounds__(kFftThreads, 3)
+// kGeneric = false: every radix is one of {2,3,4,5,7,8} (the common case; no local-memory radix arrays are
+// compiled in, which keeps the register count down for 4 CTAs / SM)
+// kVariant 0: radices {2,4,8} only (power-of-two lengths, the hot cell-FFT passes); 1: {2,3,4,5,7,8};
+// 2: any radix <= 31 (local-memory arrays).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
+template <int kVariant>
+__global__ void __launch_bounds__(kFftThreads, kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))
 fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
   extern __shared__ c128 smem[];
   __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
@@ -310,6 +320,11 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
   __syncthreads();
 
   const int lshift = 31 - __clz(lpc);
+  // [pos][line] shared layout (and line-fastest work mapping in every stage) whenever the CTA's lines are
+  // adjacent in memory; the generic-radix / copy paths below keep the plain [line][pos] layout
+  bool all_fixed = P.n_stages > 0;
+  for (int s = 0; s < P.n_stages; ++s) all_fixed = all_fixed && radix_is_fixed(P.radix[s]);
+  const bool line_major = all_fixed && P.inner_fastest && P.out_inner_fastest;
   // A generic-radix stage at either end (or a length-1 transform) cannot touch global memory itself:
   // stage the data through shared memory with plain copies in that case.
   const bool copy_in = P.n_stages == 0 || !radix_is_fixed(P.radix[0]);
@@ -344,15 +359,18 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
     io.in_base = s_in_base;
     io.out_base = s_out_base;
     io.inner_idx = s_inner_idx;
-    io.line_fastest = (io.first && P.inner_fastest) || (io.last && P.out_inner_fastest);
+    io.line_major = line_major;
+    io.line_fastest = line_major || (io.first && P.inner_fastest) || (io.last && P.out_inner_fastest);
     switch (r) {
       case 8: stage_fixed<8>(P, io, ns, lines, tab); break;
       case 4: stage_fixed<4>(P, io, ns, lines, tab); break;
       case 2: stage_fixed<2>(P, io, ns, lines, tab); break;
-      case 3: stage_fixed<3>(P, io, ns, lines, tab); break;
-      case 5: stage_fixed<5>(P, io, ns, lines, tab); break;
-      case 7: stage_fixed<7>(P, io, ns, lines, tab); break;
-      default: stage_generic(src, dst, len, ns, r, lines, tab, P.sign); break;
+      case 3: if constexpr (kVariant >= 1) stage_fixed<3>(P, io, ns, lines, tab); break;
+      case 5: if constexpr (kVariant >= 1) stage_fixed<5>(P, io, ns, lines, tab); break;
+      case 7: if constexpr (kVariant >= 1) stage_fixed<7>(P, io, ns, lines, tab); break;
+      default:
+        if constexpr (kVariant == 2) stage_generic(src, dst, len, ns, r, lines, tab, P.sign);
+        break;
     }
     if (io.last) return;
     __syncthreads();
@@ -480,12 +498,19 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
   P.lines_per_cta = lpc;
   const size_t smem = ((size_t)n_buf * lpc * P.len + P.len) * sizeof(c128);
-  cudaError_t e = cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  int variant = 0;
+  for (int q = 0; q < P.n_stages; ++q) {
+    const int r = P.radix[q];
+    if (!fixed(r)) variant = 2;
+    else if ((r == 3 || r == 5 || r == 7) && variant < 1) variant = 1;
+  }
+  auto* kern = variant == 0 ? fft_pass_kernel<0> : (variant == 1 ? fft_pass_kernel<1> : fft_pass_kernel<2>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   fft_table_kernel<<<(P.len + 255) / 256, 256, 0, st>>>(tab, P.len);
   const int64_t grid = (n_lines + lpc - 1) / lpc;
   if (grid > 2147483647LL) return SQB_E_UNSUPPORTED;
-  fft_pass_kernel<<<(unsigned)grid, kFftThreads, smem, st>>>(P, in, out, tab);
+  kern<<<(unsigned)grid, kFftThreads, smem, st>>>(P, in, out, tab);
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }
