@@ -183,7 +183,7 @@ def run_reference(args) -> None:
         "warmup": args.warmup,
         "ms_per_step": best["step_s_extrapolated"] * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "c128 (f64)",
         "data": "synthetic",
@@ -216,9 +216,14 @@ def run_ours(args) -> None:
     cfg = CONFIGS[args.config]
     with_position = bool(args.position)
 
-    # weak scaling: the k-grid grows along axis 0 with the number of GPUs; rank r owns n_k contiguous blocks
-    repeat_global = (cfg.repeat[0] * world, *cfg.repeat[1:])
-    n, n_k_local, T = cfg.n, cfg.n_k, cfg.n_times
+    # weak scaling (default): the k-grid grows along axis 0 with the number of GPUs, rank r owns n_k contiguous
+    # blocks.  strong scaling (--scaling strong): the config's own k-grid is split into `world` contiguous ranges.
+    strong = args.scaling == "strong"
+    if strong and cfg.n_k % world:
+        raise SystemExit(f"--scaling strong needs n_k={cfg.n_k} divisible by the number of GPUs")
+    repeat_global = tuple(cfg.repeat) if strong else (cfg.repeat[0] * world, *cfg.repeat[1:])
+    n, T = cfg.n, cfg.n_times
+    n_k_local = cfg.n_k // world if strong else cfg.n_k
     n_k_global = n_k_local * world
     solver = BlochSolver(cfg.shape, repeat_global, cfg.dk(), cfg.mass(), HBAR, rank * n_k_local, n_k_local)
     supercell = solver.supercell
@@ -468,7 +473,7 @@ def run_ours(args) -> None:
             "warmup": args.warmup,
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None,
             "dtype": "c128 (f64)",
             "data": "synthetic",
@@ -566,6 +571,8 @@ def main() -> None:
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--position", type=int, default=1, help="include K5+K4 to the position basis (N=1 only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU owns the config's k-grid (default); strong: the config is split over the GPUs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
