@@ -336,3 +336,83 @@ def test_cell_fft_sharded_reads_rank_major_buffer(cuda, shape, repeat, ranks):
     rank_major = np.ascontiguousarray(cell.reshape(lead, ranks, per, n).transpose(1, 0, 2, 3))
     got = kernels.cell_fft(shape, repeat, kernels.to_device(rank_major.reshape(-1), torch.complex128), 1, ranks=ranks)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------- edge cases
+def test_eigh_special_matrices(cuda):
+    """Zero, identity, diagonal (incl. repeated entries), rank-one and 2x2 complex matrices."""
+    torch, kernels = _gpu()
+    n = 24
+    rng = np.random.default_rng(12)
+    u = rng.normal(size=n) + 1j * rng.normal(size=n)
+    mats = [
+        np.zeros((n, n), dtype=complex),
+        np.eye(n, dtype=complex),
+        np.diag(np.repeat(np.arange(n // 4), 4)).astype(complex),
+        np.diag(rng.normal(size=n)).astype(complex),
+        np.outer(u, u.conj()),
+        np.diag(np.geomspace(1e-8, 1e8, n)).astype(complex),
+    ]
+    h = np.stack(mats)
+    w, t, info = kernels.eigh_batched(kernels.to_device(h, torch.complex128))
+    w, t, info = w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy()
+    assert np.all(info == 0)
+    w_ref = np.linalg.eigvalsh(h)
+    scale = np.maximum(np.abs(w_ref).max(axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(w - w_ref) / scale) < 1e-12
+    v = np.swapaxes(t, 1, 2)
+    assert np.abs(np.swapaxes(v.conj(), 1, 2) @ v - np.eye(n)).max() < 1e-12
+    res = np.abs(h @ v - v * w[:, None, :]).max(axis=(1, 2)) / scale[:, 0]
+    assert res.max() < 1e-12
+    h2 = np.array([[[1.0, 2 - 3j], [2 + 3j, -1.0]]])
+    w2, t2, info2 = kernels.eigh_batched(kernels.to_device(h2, torch.complex128))
+    np.testing.assert_allclose(w2.cpu().numpy()[0], np.linalg.eigvalsh(h2[0]), atol=1e-14)
+
+
+@pytest.mark.parametrize(("n", "n_t"), [(7, 1), (9, 63), (130, 65), (64, 129)])
+def test_evolve_ragged_sizes(cuda, n, n_t):
+    """Block sizes / time counts that are not multiples of the GEMM tiles, general and uniform-grid kernels."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(13)
+    batch = 3
+    g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+    w_ref, t_ref = o.eigh_blocks(g + np.swapaxes(g.conj(), 1, 2))
+    c = rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n))
+    times = 0.3 * HBAR + np.arange(n_t) * 0.17 * HBAR
+    want = o.back_transform(t_ref, o.evolve_eigenbasis(c, w_ref, times, HBAR)).reshape(n_t, batch * n)
+    args = (kernels.to_device(t_ref, torch.complex128), kernels.to_device(w_ref, torch.float64),
+            kernels.to_device(c, torch.complex128), kernels.to_device(times, torch.float64), HBAR)
+    np.testing.assert_allclose(kernels.evolve_bloch(*args).cpu().numpy(), want, rtol=0, atol=1e-9)
+    if n_t > 1:
+        got = kernels.evolve_bloch(*args, uniform_dt=kernels.uniform_step(times)).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("dims", [(11,), (13 * 17,), (19 * 2,), (23, 4), (29,), (31, 3), (1,), (2, 1, 3)])
+def test_fft_generic_primes_and_unit_axes(cuda, dims):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(14)
+    x = rng.normal(size=(2, *dims)) + 1j * rng.normal(size=(2, *dims))
+    axes = tuple(range(1, 1 + len(dims)))
+    got = kernels.fft_c2c(kernels.to_device(x, torch.complex128), dims, -1).cpu().numpy()
+    np.testing.assert_allclose(got, np.fft.fftn(x, axes=axes, norm="ortho"), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize(("shape", "repeat"), [((4,), (1,)), ((3, 4), (1, 5)), ((3, 4), (5, 1)), ((2, 3, 4), (3, 1, 2))])
+def test_unit_repeats(cuda, shape, repeat):
+    """repeat = 1 along an axis: permutation, cell FFT and build must degrade gracefully."""
+    torch, kernels = _gpu()
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    big = tuple(a * b for a, b in zip(shape, repeat))
+    rng = np.random.default_rng(15)
+    v = rng.normal(size=(2, n * n_k)) + 1j * rng.normal(size=(2, n * n_k))
+    vd = kernels.to_device(v, torch.complex128)
+    np.testing.assert_array_equal(kernels.bloch_permute(shape, repeat, vd, 0).cpu().numpy(),
+                                  o.bloch_from_supercell(v, shape, repeat))
+    tr = rng.normal(size=(n_k, n, n)) + 1j * rng.normal(size=(n_k, n, n))
+    a = rng.normal(size=(2, n_k, n)) + 1j * rng.normal(size=(2, n_k, n))
+    bloch = np.einsum("tbe,bek->tbk", a, tr).reshape(2, -1)
+    want = o.momentum_to_position(o.bloch_into_supercell(bloch, shape, repeat), big)
+    folded = kernels.fold_transform(shape, repeat, kernels.to_device(tr, torch.complex128))
+    cell = kernels.apply_transform(folded, kernels.to_device(a.reshape(2, -1), torch.complex128), 0)
+    np.testing.assert_allclose(kernels.cell_fft(shape, repeat, cell, 1).cpu().numpy(), want, rtol=0, atol=1e-12)
