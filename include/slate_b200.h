@@ -146,13 +146,23 @@ int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, in
  * w        [batch, n] eigenvalues, ascending within each matrix (quirk Q3: not globally sorted)
  * info     [batch] 0 = converged; k > 0 = the implicit-QL iteration failed on k eigenvalues or ran
  *          out of rotation storage (results for that matrix are undefined)
- * n <= 512 (SQB_E_UNSUPPORTED above).  Algorithm: Householder tridiagonalisation, implicit-shift QL on the real tridiagonal
- * with recorded Givens rotations, rotation replay on shared-memory strips, Householder
- * back-transformation.
+ * n <= 512 (SQB_E_UNSUPPORTED above).  Algorithm: Householder tridiagonalisation; divide and conquer on the
+ * real tridiagonal (QL leaves of <= 32 rows, dlaed2-style deflation, secular equation per root, Gu/Eisenstat
+ * vectors, merge products on the FP64 tensor cores); Householder back-transformation.  With the environment
+ * variable SQB_EIGH_TRIDIAG_SOLVER=ql the tridiagonal stage is implicit-shift QL with recorded Givens
+ * rotations replayed on shared-memory strips instead (info then also reports rotation-storage overflow).
+ *
+ * sqb_tridiag_eigh_batched is the tridiagonal stage on its own: T_b = tridiag(e_b, d_b, e_b) real symmetric,
+ * d [batch, n], e [batch, n] (e[b, i] couples rows i and i+1; e[b, n-1] is ignored), w [batch, n] ascending,
+ * q_rows [batch, n, n] with ROWS = eigenvectors.  batch <= 65535 per call.
  * ---------------------------------------------------------------------------------------------- */
 size_t sqb_eigh_workspace_bytes(int n, int64_t batch);
 int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double* w, int* info, void* workspace,
                      size_t workspace_bytes, void* stream);
+size_t sqb_tridiag_eigh_workspace_bytes(int n, int64_t batch);
+int sqb_tridiag_eigh_batched(int n, int64_t batch, const double* d, const double* e, double* w,
+                             double* q_rows, int* info, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  Eigenbasis projection, phase evolution, back-transformation.

@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "sqb_fold_transform",
     "sqb_eigh_workspace_bytes",
     "sqb_eigh_batched",
+    "sqb_tridiag_eigh_workspace_bytes",
+    "sqb_tridiag_eigh_batched",
     "sqb_project",
     "sqb_apply_transform",
     "sqb_evolve_eigen",
@@ -92,6 +94,12 @@ def load() -> ctypes.CDLL:
     lib.sqb_eigh_workspace_bytes.argtypes = [c_int, c_int64]
     lib.sqb_eigh_batched.restype = c_int
     lib.sqb_eigh_batched.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_tridiag_eigh_workspace_bytes.restype = c_size_t
+    lib.sqb_tridiag_eigh_workspace_bytes.argtypes = [c_int, c_int64]
+    lib.sqb_tridiag_eigh_batched.restype = c_int
+    lib.sqb_tridiag_eigh_batched.argtypes = [
+        c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
     lib.sqb_project.restype = c_int
     lib.sqb_project.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sqb_apply_transform.restype = c_int

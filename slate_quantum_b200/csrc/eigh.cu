@@ -20,10 +20,15 @@
 //                          reflectors, conjugates (undoing the conj(H) view) and writes rows = eigenvectors
 //                          into A.
 //
-// The algorithm is modelled step by step in tests/eigh_model.py (numpy).
+// Stages (2)+(3) are the fallback (environment SQB_EIGH_TRIDIAG_SOLVER=ql); by default the tridiagonal
+// eigenproblem is solved by the divide-and-conquer kernels of eigh_dc.cuh (DMMA merge GEMMs), which write the
+// same Q_T layout.  The algorithms are modelled step by step in tests/eigh_model.py and tests/dc_model.py.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "sqb_common.cuh"
+#include "eigh_dc.cuh"
 
 namespace {
 
@@ -43,7 +48,18 @@ struct EighWs {  // per-chunk workspace pointers (each array is [chunk, ...])
   double2* rot;   // [chunk, rot_capacity]    {c, s}
   c128* y;        // [chunk, n, n]  reflector i at y[i*n + r]
   double* qt;     // [chunk, n, n]  qt[e*n + k]
+  DcWs dc;        // divide-and-conquer arrays (dc.q[0] == qt)
 };
+
+// tridiagonal solver: 1 = divide and conquer (default), 0 = implicit QL + rotation replay
+int eigh_use_dc() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* v = getenv("SQB_EIGH_TRIDIAG_SOLVER");
+    cached = (v && strcmp(v, "ql") == 0) ? 0 : 1;
+  }
+  return cached;
+}
 
 // ------------------------------------------------------------------------------------------------
 // block-wide sum of a double over `nthreads` (multiple of 32) threads; result broadcast to all.
@@ -690,35 +706,75 @@ int replay_ring_size(int n) {
   return r;
 }
 
+size_t dc_per_matrix_bytes(int n) {
+  size_t s = 0;
+  s += 256;                                                    // scale (amortised)
+  s += align_up((size_t)n * 8, 256) * 3;                       // lam[2], invnorm
+  s += align_up((size_t)n * 4, 256) * 3;                       // src_row, out_row, kcount
+  s += align_up((size_t)n * n * 8, 256) * 2;                   // q[1], u   (q[0] is qt)
+  return s;
+}
+
 size_t per_matrix_bytes(int n) {
   size_t s = 0;
   s += align_up((size_t)n * 8, 256) * 2;                       // d, e
   s += align_up((size_t)n * 16, 256);                          // tau
-  s += align_up((size_t)n * 4, 256);                           // rank
-  s += 256;                                                    // nsweeps (amortised)
-  s += align_up((size_t)sweep_capacity(n) * 16, 256);          // sweeps
-  s += align_up((size_t)rot_capacity(n) * 16, 256);            // rot
   s += align_up((size_t)n * n * 16, 256);                      // y
   s += align_up((size_t)n * n * 8, 256);                       // qt
+  if (eigh_use_dc()) {
+    s += dc_per_matrix_bytes(n);
+  } else {
+    s += align_up((size_t)n * 4, 256);                         // rank
+    s += 256;                                                  // nsweeps (amortised)
+    s += align_up((size_t)sweep_capacity(n) * 16, 256);        // sweeps
+    s += align_up((size_t)rot_capacity(n) * 16, 256);          // rot
+  }
   return s;
 }
 
-void carve(EighWs& ws, void* base, int n, int64_t chunk) {
-  char* p = reinterpret_cast<char*>(base);
-  auto take = [&](size_t bytes_per, int64_t cnt) {
+struct Carver {
+  char* p;
+  char* take(size_t bytes_per, int64_t cnt) {
     char* r = p;
     p += align_up(bytes_per * (size_t)cnt, 256);
     return r;
-  };
-  ws.d = reinterpret_cast<double*>(take((size_t)n * 8, chunk));
-  ws.e = reinterpret_cast<double*>(take((size_t)n * 8, chunk));
-  ws.tau = reinterpret_cast<c128*>(take((size_t)n * 16, chunk));
-  ws.rank = reinterpret_cast<int*>(take((size_t)n * 4, chunk));
-  ws.nsweeps = reinterpret_cast<int*>(take(4, chunk));
-  ws.sweeps = reinterpret_cast<int4*>(take((size_t)sweep_capacity(n) * 16, chunk));
-  ws.rot = reinterpret_cast<double2*>(take((size_t)rot_capacity(n) * 16, chunk));
-  ws.y = reinterpret_cast<c128*>(take((size_t)n * n * 16, chunk));
-  ws.qt = reinterpret_cast<double*>(take((size_t)n * n * 8, chunk));
+  }
+};
+
+void carve_dc(DcWs& dc, Carver& cv, int n, int64_t chunk, const double* d, const double* e, double* q0) {
+  dc.d = d;
+  dc.e = e;
+  dc.q[0] = q0;
+  dc.scale = reinterpret_cast<double*>(cv.take(8, chunk));
+  dc.lam[0] = reinterpret_cast<double*>(cv.take((size_t)n * 8, chunk));
+  dc.lam[1] = reinterpret_cast<double*>(cv.take((size_t)n * 8, chunk));
+  dc.invnorm = reinterpret_cast<double*>(cv.take((size_t)n * 8, chunk));
+  dc.src_row = reinterpret_cast<int*>(cv.take((size_t)n * 4, chunk));
+  dc.out_row = reinterpret_cast<int*>(cv.take((size_t)n * 4, chunk));
+  dc.kcount = reinterpret_cast<int*>(cv.take((size_t)n * 4, chunk));
+  dc.q[1] = reinterpret_cast<double*>(cv.take((size_t)n * n * 8, chunk));
+  dc.u = reinterpret_cast<double*>(cv.take((size_t)n * n * 8, chunk));
+}
+
+void carve(EighWs& ws, void* base, int n, int64_t chunk) {
+  Carver cv{reinterpret_cast<char*>(base)};
+  ws.d = reinterpret_cast<double*>(cv.take((size_t)n * 8, chunk));
+  ws.e = reinterpret_cast<double*>(cv.take((size_t)n * 8, chunk));
+  ws.tau = reinterpret_cast<c128*>(cv.take((size_t)n * 16, chunk));
+  ws.y = reinterpret_cast<c128*>(cv.take((size_t)n * n * 16, chunk));
+  ws.qt = reinterpret_cast<double*>(cv.take((size_t)n * n * 8, chunk));
+  ws.rank = nullptr;
+  ws.nsweeps = nullptr;
+  ws.sweeps = nullptr;
+  ws.rot = nullptr;
+  if (eigh_use_dc()) {
+    carve_dc(ws.dc, cv, n, chunk, ws.d, ws.e, ws.qt);
+  } else {
+    ws.rank = reinterpret_cast<int*>(cv.take((size_t)n * 4, chunk));
+    ws.nsweeps = reinterpret_cast<int*>(cv.take(4, chunk));
+    ws.sweeps = reinterpret_cast<int4*>(cv.take((size_t)sweep_capacity(n) * 16, chunk));
+    ws.rot = reinterpret_cast<double2*>(cv.take((size_t)rot_capacity(n) * 16, chunk));
+  }
 }
 
 template <int NR, int RG>
@@ -805,13 +861,18 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     else rc = launch_tridiag<8, 2>(n, cnt, Ab, ws, ls);
     if (rc) { status = rc; break; }
 
-    const size_t ql_smem = (size_t)(2 * n + 2) * 8 + (size_t)n * 16;
-    ql_kernel<<<(unsigned)cnt, 32, ql_smem, ls>>>(n, cnt, ws, w + b0 * n, info + b0);
-    if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
+    if (eigh_use_dc()) {
+      rc = dc_solve(n, cnt, ws.dc, w + b0 * n, info + b0, ls);
+      if (rc) { status = rc; break; }
+    } else {
+      const size_t ql_smem = (size_t)(2 * n + 2) * 8 + (size_t)n * 16;
+      ql_kernel<<<(unsigned)cnt, 32, ql_smem, ls>>>(n, cnt, ws, w + b0 * n, info + b0);
+      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
 
-    dim3 rgrid((unsigned)((n + 31) / 32), (unsigned)cnt);
-    replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8 + (size_t)replay_ring_size(n) * 16, ls>>>(n, replay_ring_size(n), ws);
-    if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
+      dim3 rgrid((unsigned)((n + 31) / 32), (unsigned)cnt);
+      replay_kernel<<<rgrid, 32, (size_t)n * 32 * 8 + (size_t)replay_ring_size(n) * 16, ls>>>(n, replay_ring_size(n), ws);
+      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
+    }
 
     if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, ls);
@@ -832,4 +893,24 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     cudaEventDestroy(fork);
   }
   return status;
+}
+
+// real symmetric tridiagonal eigenproblems on their own (the divide-and-conquer stage of sqb_eigh_batched)
+extern "C" size_t sqb_tridiag_eigh_workspace_bytes(int n, int64_t batch) {
+  if (n < 1 || n > kMaxN || batch < 0) return 0;
+  return dc_per_matrix_bytes(n) * (size_t)(batch < 1 ? 1 : batch) + 4096;
+}
+
+extern "C" int sqb_tridiag_eigh_batched(int n, int64_t batch, const double* d, const double* e, double* w,
+                                        double* q_rows, int* info, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  if (n < 1 || batch < 0 || !d || !e || !w || !q_rows || !info) return SQB_E_BADARG;
+  if (n > kMaxN) return SQB_E_UNSUPPORTED;
+  if (batch == 0) return SQB_OK;
+  if (batch > 65535) return SQB_E_UNSUPPORTED;  // grid.y / grid.z limit of the merge kernels
+  if (!workspace || workspace_bytes < sqb_tridiag_eigh_workspace_bytes(n, batch)) return SQB_E_WORKSPACE;
+  Carver cv{reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256))};
+  DcWs dc;
+  carve_dc(dc, cv, n, batch, d, e, q_rows);
+  return dc_solve(n, batch, dc, w, info, sqb_stream(stream));
 }

@@ -267,8 +267,50 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
     chunk = max(1, min(batch, (workspace.numel() - 4096) // per, 65535))
     if batch >= 512 and chunk >= 256:  # two chunks in flight on two internal streams (csrc/eigh.cu)
         chunk = min(chunk // 2, (batch + 1) // 2)
-    _count(4 * -(-batch // chunk))
+    _count(_eigh_launches_per_chunk(n) * -(-batch // chunk))
     return w, a, info
+
+
+def _dc_depth(n: int) -> int:
+    depth = 0
+    while ((n + (1 << depth) - 1) >> depth) > 32:
+        depth += 1
+    return depth
+
+
+def _eigh_launches_per_chunk(n: int) -> int:
+    """Kernels per chunk of matrices: tridiagonalisation + back-transformation + the tridiagonal solver."""
+    import os
+
+    if os.environ.get("SQB_EIGH_TRIDIAG_SOLVER") == "ql":
+        return 4  # ql + replay
+    return 2 + 1 + 2 * _dc_depth(n)  # leaves + (set-up, GEMM) per merge level
+
+
+def tridiag_eigh_batched(d: torch.Tensor, e: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Divide-and-conquer stage of K2 on its own: real symmetric tridiagonals (d [batch,n], e [batch,n]).
+
+    Returns (w [batch,n] ascending, q [batch,n,n] with rows = eigenvectors, info [batch]).
+    """
+    _require_cuda()
+    lib = _lib.load()
+    if d.dtype != torch.float64 or e.dtype != torch.float64 or d.shape != e.shape or d.dim() != 2:
+        msg = "d and e must be float64 [batch, n]"
+        raise ValueError(msg)
+    if not (d.is_cuda and e.is_cuda and d.is_contiguous() and e.is_contiguous()):
+        msg = "d and e must be contiguous CUDA tensors"
+        raise ValueError(msg)
+    batch, n = d.shape
+    w = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    q = torch.empty((batch, n, n), dtype=torch.float64, device="cuda")
+    info = torch.empty((batch,), dtype=torch.int32, device="cuda")
+    workspace = torch.empty(lib.sqb_tridiag_eigh_workspace_bytes(n, batch), dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_tridiag_eigh_batched(
+        n, batch, _ptr(d), _ptr(e), _ptr(w), _ptr(q), _ptr(info), _ptr(workspace), workspace.numel(), _stream()
+    )
+    _lib.check(rc, "sqb_tridiag_eigh_batched")
+    _count(1 + 2 * _dc_depth(n))
+    return w, q, info
 
 
 def project(transform: torch.Tensor, psi: torch.Tensor) -> torch.Tensor:

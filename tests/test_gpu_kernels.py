@@ -416,3 +416,56 @@ def test_unit_repeats(cuda, shape, repeat):
     folded = kernels.fold_transform(shape, repeat, kernels.to_device(tr, torch.complex128))
     cell = kernels.apply_transform(folded, kernels.to_device(a.reshape(2, -1), torch.complex128), 0)
     np.testing.assert_allclose(kernels.cell_fft(shape, repeat, cell, 1).cpu().numpy(), want, rtol=0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# divide-and-conquer tridiagonal stage of K2 on its own (csrc/eigh_dc.cuh; model: tests/dc_model.py)
+def _run_tridiag(d, e):
+    torch, kernels = _gpu()
+    dd = kernels.to_device(np.ascontiguousarray(d), torch.float64)
+    ee = kernels.to_device(np.ascontiguousarray(e), torch.float64)
+    w, q, info = kernels.tridiag_eigh_batched(dd, ee)
+    return w.cpu().numpy(), q.cpu().numpy(), info.cpu().numpy()
+
+
+def test_tridiag_dc_hard_cases(cuda):
+    from test_dc_model import CASES, check_tridiagonal
+
+    for name in sorted(CASES):
+        d, e = CASES[name]
+        w, q, info = _run_tridiag(d[None, :], e[None, :])
+        assert info[0] == 0, name
+        check_tridiagonal(d, e, w[0], q[0], tol_scale=2.0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 32, 33, 64, 100, 256, 343, 512])
+def test_tridiag_dc_random_batches(cuda, n):
+    from test_dc_model import check_tridiagonal
+
+    rng = np.random.default_rng(n)
+    batch = 5
+    d = rng.normal(size=(batch, n))
+    e = rng.normal(size=(batch, n))
+    w, q, info = _run_tridiag(d, e)
+    assert not info.any()
+    for b in range(batch):
+        check_tridiagonal(d[b], e[b], w[b], q[b], tol_scale=2.0)
+
+
+def test_tridiag_dc_matches_model_eigenvalues(cuda):
+    import dc_model
+
+    rng = np.random.default_rng(11)
+    d, e = rng.normal(size=(1, 200)), rng.normal(size=(1, 200))
+    w, q, info = _run_tridiag(d, e)
+    w_model, _ = dc_model.dc_eigh_tridiagonal(d[0], e[0])
+    assert info[0] == 0
+    assert np.abs(w[0] - w_model).max() < 1e-13 * np.abs(w_model).max()
+
+
+def test_tridiag_dc_nan_input_is_flagged(cuda):
+    d = np.ones((2, 70))
+    e = np.full((2, 70), 0.5)
+    d[1, 40] = np.nan
+    w, q, info = _run_tridiag(d, e)
+    assert info[0] == 0 and info[1] != 0
