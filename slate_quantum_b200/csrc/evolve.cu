@@ -391,86 +391,99 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
 
   if (tid == 0) {
     for (int s = 0; s < kStages3; ++s) {
-      mbar_init(&full[s], kProducerThreads);
+      mbar_init(&full[s], 32);
       mbar_init(&empty[s], kConsumerThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp >= kConsumerThreads / 32) {
+  // Producers are the lowest warp ids and each producer warp OWNS one ring stage: warp w generates the whole A
+  // chunk (and issues the TMA copies) of chunks w, w+4, ...  ncu showed that the FP64 pipe is handed over only
+  // when its current owner stalls: a producer waited ~1700 cycles for the consumers' DMMA burst to end before
+  // its own short burst could start, and with all four producer warps contributing to EVERY chunk the
+  // consumers waited for the slowest of four such hand-overs per chunk (21 % of their time on the full
+  // barrier).  With one warp per stage a producer needs one hand-over per FOUR chunk times.
+  static_assert(kProducerThreads / 32 == kStages3, "one producer warp per ring stage");
+  if (warp < kProducerThreads / 32) {
     // ============================== producers ==============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    const int ptid = tid - kConsumerThreads;
-    const int ge = ptid % KC;
-    const int gj = ptid / KC;  // 0..7 ; rows gj + 8 q
-    // A[t0 + gj + 8q, e] = c_e * tilebase[tile][e] * pow8[e][gj] * step8[e]^q : multiplications only
+    const int s = warp;
+    const int ge = lane & 15;          // eigen index inside the chunk
+    const int gh = (lane >> 4) * 4;    // rows gh + g + 8 q, g < 4, q < 8
+    // A[t0 + j + 8q, e] = c_e * tilebase[tile][e] * pow8[e][j] * step8[e]^q : multiplications only
     const c128* cb = coef + b * n;
     const c128* sb = step8 + b * n;
-    const c128* pb = pow8 + b * n * 8 + gj;
+    const c128* pb = pow8 + b * n * 8 + gh;
     const c128* tb = tilebase + (int64_t)blockIdx.y * m_total + b * n;
-    c128 ce_next = make_double2(0.0, 0.0), se_next = make_double2(1.0, 0.0);
-    if (ge < n) {
-      ce_next = cmul(cmul(cb[ge], tb[ge]), pb[(int64_t)ge * 8]);
-      se_next = sb[ge];
-    }
-    for (int kc = 0; kc < nchunks; ++kc) {
-      const int s = kc % kStages3;
+    unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
+    c128* Ac = reinterpret_cast<c128*>(st);
+    double* As = reinterpret_cast<double*>(st + TM * LDA * 16);
+    c128* Bs = reinterpret_cast<c128*>(st + TM * LDA * 16 + TM * LDAS * 8);
+    double* Bq = reinterpret_cast<double*>(st + TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16);
+    for (int kc = s; kc < nchunks; kc += kStages3) {
       const uint32_t ph = (uint32_t)((kc / kStages3) & 1);
-      unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
-      c128* Ac = reinterpret_cast<c128*>(st);
-      double* As = reinterpret_cast<double*>(st + TM * LDA * 16);
-      c128* Bs = reinterpret_cast<c128*>(st + TM * LDA * 16 + TM * LDAS * 8);
-      double* Bq = reinterpret_cast<double*>(st + TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16);
-      const c128 ce = ce_next, se = se_next;
       const int e = kc * KC + ge;
-      c128 c_raw = make_double2(0.0, 0.0), t_raw = make_double2(1.0, 0.0), p_raw = make_double2(1.0, 0.0);
-      {
-        const int en = e + KC;
-        se_next = make_double2(1.0, 0.0);
-        if (en < n) {
-          c_raw = cb[en];
-          t_raw = tb[en];
-          p_raw = pb[(int64_t)en * 8];
-          se_next = sb[en];
-        }
+      c128 base = make_double2(0.0, 0.0), se = make_double2(1.0, 0.0);
+      c128 pw[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pw[g] = make_double2(0.0, 0.0);
+      if (e < n) {
+        const c128 c_raw = cb[e], t_raw = tb[e];
+        se = sb[e];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pw[g] = pb[(int64_t)e * 8 + g];
+        base = cmul(c_raw, t_raw);
       }
       mbar_wait(&empty[s], ph ^ 1u);
       const int e0 = kc * KC;
       const int nrows = min(KC, n - e0);
-      if (ptid == 0) {
+      {
+        // one bulk copy pair per eigenvector row, issued by 16 lanes at once (a single lane looping over the
+        // 32 copies of a chunk cost ~8 ms per step); the expected byte count is registered first
         const int ncols2 = (ncols + 1) & ~1;  // bulk copies move multiples of 16 B; the pad column is zero
-        mbar_expect_tx(&full[s], (uint32_t)(nrows * (ncols * sizeof(c128) + ncols2 * sizeof(double))));
-        const double* qb = bsum + (b * n + e0) * (int64_t)n_pad + p0;
-        for (int r = 0; r < nrows; ++r) {
-          bulk_g2s(Bs + r * LDB3, Vb + (int64_t)(e0 + r) * n + p0, (uint32_t)(ncols * sizeof(c128)), &full[s]);
-          bulk_g2s(Bq + r * LDBS, qb + (int64_t)r * n_pad, (uint32_t)(ncols2 * sizeof(double)), &full[s]);
+        if (lane == 0)
+          mbar_expect_tx(&full[s], (uint32_t)(nrows * (ncols * sizeof(c128) + ncols2 * sizeof(double))));
+        __syncwarp();
+        if (lane < nrows) {
+          const double* qb = bsum + (b * n + e0 + lane) * (int64_t)n_pad + p0;
+          bulk_g2s(Bs + lane * LDB3, Vb + (int64_t)(e0 + lane) * n + p0, (uint32_t)(ncols * sizeof(c128)), &full[s]);
+          bulk_g2s(Bq + lane * LDBS, qb, (uint32_t)(ncols2 * sizeof(double)), &full[s]);
         }
       }
       if (nrows < KC) {
-        for (int idx = ptid; idx < (KC - nrows) * LDB3; idx += kProducerThreads)
-          Bs[nrows * LDB3 + idx] = make_double2(0.0, 0.0);
-        for (int idx = ptid; idx < (KC - nrows) * LDBS; idx += kProducerThreads) Bq[nrows * LDBS + idx] = 0.0;
+        for (int idx = lane; idx < (KC - nrows) * LDB3; idx += 32) Bs[nrows * LDB3 + idx] = make_double2(0.0, 0.0);
+        for (int idx = lane; idx < (KC - nrows) * LDBS; idx += 32) Bq[nrows * LDBS + idx] = 0.0;
       }
-      c128 v = ce;  // zero for e >= n
+      // powers of the step factor by squaring: the 8 rows of a column are then products of depth <= 3 instead
+      // of an 8-deep recurrence (the FP64 pipe is held for the whole latency-bound burst, see above)
+      const c128 se2 = cmul(se, se);
+      const c128 se4 = cmul(se2, se2);
 #pragma unroll
-      for (int q = 0; q < TM / 8; ++q) {
-        const int j = gj + 8 * q;
-        const c128 o = (t0 + j < t_count) ? v : make_double2(0.0, 0.0);
-        Ac[j * LDA + ge] = o;
-        As[j * LDAS + ge] = o.x + o.y;
-        v = cmul(v, se);
+      for (int g = 0; g < 4; ++g) {
+        c128 v[TM / 8];
+        v[0] = cmul(base, pw[g]);  // zero for e >= n
+        v[1] = cmul(v[0], se);
+        v[2] = cmul(v[0], se2);
+        v[3] = cmul(v[1], se2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[4 + q] = cmul(v[q], se4);
+#pragma unroll
+        for (int q = 0; q < TM / 8; ++q) {
+          const int j = gh + g + 8 * q;
+          const c128 o = (t0 + j < t_count) ? v[q] : make_double2(0.0, 0.0);
+          Ac[j * LDA + ge] = o;
+          As[j * LDAS + ge] = o.x + o.y;
+        }
       }
-      ce_next = cmul(cmul(c_raw, t_raw), p_raw);  // next chunk's first-row amplitude (loads issued above)
       mbar_arrive(&full[s]);
     }
     return;
   }
 
   // ============================== consumers ==============================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-  const int wm = (warp & 1) * 32;
-  const int wn = (warp >> 1) * 16;
+  const int cwarp = warp - kProducerThreads / 32;
+  const int wm = (cwarp & 1) * 32;
+  const int wn = (cwarp >> 1) * 16;
   double p1[4][2][2], p2[4][2][2], p3[4][2][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
