@@ -13,6 +13,7 @@
 // Reference: slate_quantum/dynamics/schrodinger.py:31-56; ExplicitUnitaryBasis conversions reached from
 // state/_state.py:37-43 (projection) and :153-165 (back-transform).
 #include <math.h>
+#include <stdlib.h>
 
 #include "sqb_common.cuh"
 
@@ -376,14 +377,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict__ coef, int64_t t_count,
                        c128* __restrict__ out, int64_t out_row_stride, const c128* __restrict__ step8,
                        const c128* __restrict__ pow8, const c128* __restrict__ tilebase, int64_t m_total,
-                       const double* __restrict__ bsum, int n_pad) {
+                       const double* __restrict__ bsum, int n_pad, int tiles_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages3 * kStage3Bytes);  // [stages]
   uint64_t* empty = full + kStages3;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p0 = blockIdx.x * TN3;
-  const int64_t t0 = (int64_t)blockIdx.y * TM;
+  // a CTA walks tiles_per_cta consecutive time tiles of its (block, column tile): the ring keeps flowing across
+  // tiles, so the producers' start-up latency and the consumers' epilogue overlap with the neighbouring tile
+  // (with one tile per CTA and one CTA per SM they were exposed: ~12 ms per step)
+  const int64_t tile_first = (int64_t)blockIdx.y * tiles_per_cta;
+  const int64_t n_t_tiles = (t_count + TM - 1) / TM;
+  const int my_tiles = (int)sqb_min64(tiles_per_cta, n_t_tiles - tile_first);
   const int64_t b = blockIdx.z;
   const c128* Vb = V + b * (int64_t)n * n;
   const int ncols = min(TN3, n - p0);
@@ -414,14 +420,19 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
     const c128* cb = coef + b * n;
     const c128* sb = step8 + b * n;
     const c128* pb = pow8 + b * n * 8 + gh;
-    const c128* tb = tilebase + (int64_t)blockIdx.y * m_total + b * n;
+    const c128* tb0 = tilebase + tile_first * m_total + b * n;
     unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
     c128* Ac = reinterpret_cast<c128*>(st);
     double* As = reinterpret_cast<double*>(st + TM * LDA * 16);
     c128* Bs = reinterpret_cast<c128*>(st + TM * LDA * 16 + TM * LDAS * 8);
     double* Bq = reinterpret_cast<double*>(st + TM * LDA * 16 + TM * LDAS * 8 + KC * LDB3 * 16);
-    for (int kc = s; kc < nchunks; kc += kStages3) {
-      const uint32_t ph = (uint32_t)((kc / kStages3) & 1);
+    const int total_chunks = my_tiles * nchunks;
+    for (int kg = s; kg < total_chunks; kg += kStages3) {
+      const uint32_t ph = (uint32_t)((kg / kStages3) & 1);
+      const int tile = kg / nchunks;
+      const int kc = kg - tile * nchunks;
+      const int64_t t0 = (tile_first + tile) * TM;
+      const c128* tb = tb0 + (int64_t)tile * m_total;
       const int e = kc * KC + ge;
       c128 base = make_double2(0.0, 0.0), se = make_double2(1.0, 0.0);
       c128 pw[4];
@@ -484,6 +495,10 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
   const int cwarp = warp - kProducerThreads / 32;
   const int wm = (cwarp & 1) * 32;
   const int wn = (cwarp >> 1) * 16;
+  const int frow = lane >> 2, fcol = lane & 3;
+  int kg = 0;
+  for (int tile = 0; tile < my_tiles; ++tile) {
+  const int64_t t0 = (tile_first + tile) * TM;
   double p1[4][2][2], p2[4][2][2], p3[4][2][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -493,10 +508,9 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
       p2[a][c][0] = p2[a][c][1] = 0.0;
       p3[a][c][0] = p3[a][c][1] = 0.0;
     }
-  const int frow = lane >> 2, fcol = lane & 3;
-  for (int kc = 0; kc < nchunks; ++kc) {
-    const int s = kc % kStages3;
-    const uint32_t ph = (uint32_t)((kc / kStages3) & 1);
+  for (int kc = 0; kc < nchunks; ++kc, ++kg) {
+    const int s = kg % kStages3;
+    const uint32_t ph = (uint32_t)((kg / kStages3) & 1);
     const unsigned char* st = smem_raw + (size_t)s * kStage3Bytes;
     const c128* Ac = reinterpret_cast<const c128*>(st);
     const double* As = reinterpret_cast<const double*>(st + TM * LDA * 16);
@@ -555,6 +569,7 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
       if (p + 1 < n) orow[p + 1] = make_double2(p1[a][c][1] - p2[a][c][1], p3[a][c][1] - p1[a][c][1] - p2[a][c][1]);
     }
   }
+  }  // tiles
 }
 
 }  // namespace
@@ -615,7 +630,10 @@ int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const d
                          : cudaFuncSetAttribute(evolve_bloch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)kGemmSmem);
   if (e != cudaSuccess) return (int)e;
-  const int64_t t_tiles = (t_count + TM - 1) / TM;
+  int64_t t_tiles = (t_count + TM - 1) / TM;
+  static const int tiles_env = getenv("SQB_EVOLVE_TILES_PER_CTA") ? atoi(getenv("SQB_EVOLVE_TILES_PER_CTA")) : 0;
+  const int tiles_per_cta = tiles_env > 0 ? tiles_env : 8;
+  if (use_3m) t_tiles = (t_tiles + tiles_per_cta - 1) / tiles_per_cta;  // CTAs walk several time tiles
   if (t_tiles > 65535) return SQB_E_UNSUPPORTED;
   const int tn = use_3m ? TN3 : TN;
   const unsigned p_tiles = (unsigned)((n + tn - 1) / tn);
@@ -628,7 +646,7 @@ int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const d
     if (use_3m)
       evolve_bloch_3m_kernel<<<grid, kGemmThreads, kGemm3Smem, sqb_stream(stream)>>>(
           n, vb, cbp, t_count, ob, out_row_stride, step8 + b0 * n, pow8 + b0 * n * 8, tilebase + b0 * n, batch * n,
-          bsum + b0 * n * (int64_t)n_pad, n_pad);
+          bsum + b0 * n * (int64_t)n_pad, n_pad, tiles_per_cta);
     else
       evolve_bloch_kernel<<<grid, kGemmThreads, kGemmSmem, sqb_stream(stream)>>>(
           n, vb, w + b0 * n, cbp, times, t_count, hbar, ob, out_row_stride, nullptr);
