@@ -515,11 +515,13 @@ def run_ours(args) -> None:
                     "frac": (0.75 if dt_uniform is not None else 1.0) * ach / dmma_peak,
                     "note": "3 real DMMA products per complex MAC (3M) instead of 4: executed = 0.75 x algorithmic flop",
                 },
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from profiles/r01_c_evolve_bloch_cfg3_raw.csv
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from profiles/r01_s2_evolve3m_cfg3_raw.csv
                 # (ncu --set full, cfg3, 2048-sample time tile); null for other shapes (not captured)
-                "traffic": 38.713316e9 if (cfg.name.startswith("cfg3") and min(t_tile, T) == 2048 and world == 1) else None,
+                "traffic": 41.518867e9 if (cfg.name.startswith("cfg3") and min(t_tile, T) == 2048 and world == 1) else None,
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "algorithmic_bytes_per_launch": (16.0 * n * min(t_tile, T) + 16.0 * n * n) * n_k_local,
+                # states written + eigenvectors read once (+ their Re+Im plane for the 3M kernel)
+                "algorithmic_bytes_per_launch": (16.0 * n * min(t_tile, T) + (24.0 if dt_uniform is not None else 16.0) * n * n)
+                * n_k_local,
                 "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
                 f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
                 "warm-up (MEASURED_PEAKS.json carries only bf16 and HBM); plain DFMA peak measured "

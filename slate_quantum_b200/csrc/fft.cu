@@ -408,11 +408,17 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
 
 // Bloch twiddle folded into the (already in-cell transformed) eigenvectors:
 //   W[b, e, j] *= prod_a exp(sign * 2 pi i q_a(b) j_a / L_a),  q_a = FFT-order signed block index
-__global__ void fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int sign, c128* __restrict__ W) {
-  const int64_t total = batch * n * (int64_t)n;
-  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(g % n);
-    int64_t b = block_begin + g / ((int64_t)n * n);
+// The twiddle depends on (block, j) only: a CTA computes the n factors of its block once into shared memory
+// (one sincospi per j instead of per element) and streams kFoldRows eigenvector rows through them.
+constexpr int kFoldRows = 32;
+__global__ void __launch_bounds__(256)
+fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int sign, c128* __restrict__ W) {
+  extern __shared__ __align__(16) unsigned char fold_smem[];
+  c128* tw = reinterpret_cast<c128*>(fold_smem);  // [n]
+  const int64_t bl = blockIdx.y;                   // block inside the batch
+  if (bl >= batch) return;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int64_t b = block_begin + bl;
     int jj = j;
     double phase = 0.0;  // in turns
     for (int a = d.nd - 1; a >= 0; --a) {
@@ -427,7 +433,15 @@ __global__ void fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64
     }
     double sn, cs;
     sincospi((double)sign * 2.0 * phase, &sn, &cs);
-    W[g] = cmul(W[g], make_double2(cs, sn));
+    tw[j] = make_double2(cs, sn);
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * kFoldRows;
+  const int r1 = min(n, r0 + kFoldRows);
+  c128* Wb = W + bl * (int64_t)n * n;
+  for (int r = r0; r < r1; ++r) {
+    c128* row = Wb + (int64_t)r * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) row[j] = cmul(row[j], tw[j]);
   }
 }
 
@@ -822,10 +836,13 @@ extern "C" int sqb_fold_transform(int nd, const int* shape_host, const int* repe
   rc = sqb_fft_c2c(nd, shape_host, batch * n, +1, transform, folded, workspace, workspace_bytes, stream);
   if (rc) return rc;
   // (2) Bloch twiddle exp(+2 pi i q_a j_a / L_a)
-  const int64_t total = batch * n * n;
-  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
-  fold_twiddle_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(d, (int)n, block_begin, batch, +1,
-                                                           reinterpret_cast<c128*>(folded));
-  SQB_LAUNCH_CHECK();
+  // grid.y is limited to 65535 blocks per launch
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t cnt = sqb_min64(65535, batch - b0);
+    const dim3 grid((unsigned)((n + kFoldRows - 1) / kFoldRows), (unsigned)cnt);
+    fold_twiddle_kernel<<<grid, 256, (size_t)n * sizeof(c128), sqb_stream(stream)>>>(
+        d, (int)n, block_begin + b0, cnt, +1, reinterpret_cast<c128*>(folded) + b0 * n * n);
+    SQB_LAUNCH_CHECK();
+  }
   return SQB_OK;
 }

@@ -369,7 +369,8 @@ def test_eigh_special_matrices(cuda):
     np.testing.assert_allclose(w2.cpu().numpy()[0], np.linalg.eigvalsh(h2[0]), atol=1e-14)
 
 
-@pytest.mark.parametrize(("n", "n_t"), [(7, 1), (9, 63), (130, 65), (64, 129)])
+# n_t = 513 / 1100: the uniform-grid kernel walks 8 time tiles of 64 rows per CTA (one full group + a ragged one)
+@pytest.mark.parametrize(("n", "n_t"), [(7, 1), (9, 63), (130, 65), (64, 129), (40, 513), (70, 1100)])
 def test_evolve_ragged_sizes(cuda, n, n_t):
     """Block sizes / time counts that are not multiples of the GEMM tiles, general and uniform-grid kernels."""
     torch, kernels = _gpu()
