@@ -218,6 +218,27 @@ int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const doub
 int sqb_peak_dmma(int variant, int64_t iters, double* sink, double* flops_host, void* stream);
 int sqb_peak_dfma(int64_t iters, double* sink, double* flops_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6  Observables of position-basis state lists ("next" row of the scope table).
+ * Replaces the diagonal-operator expectations of slate_quantum.operator.measure: all_x
+ * (operator/_measure.py:191-210, x operator operator/_build/_position.py:228-242), all_periodic_x (:242-268,
+ * scattering operator :213-239), all_variance_x (:271-292 with variance_x :140-163) and all_coherent_width
+ * (:295-305); normalisation as state.normalize_each (state/_state.py:294-308).
+ *
+ * states  [lead, M] complex128 in the position basis of a grid `grid_host` (C order, M = prod grid).
+ * out     [lead, 5] doubles per state t:
+ *           { sum |psi|^2, sum x |psi|^2, sum x^2 |psi|^2, sum cos(2 pi n/N) |psi|^2, sum sin(2 pi n/N) |psi|^2 }
+ *         with n the index along `axis`, N = grid_host[axis], x = n * spacing + offsets[t] (offsets may be
+ *         NULL = 0), folded into [-length/2, length/2) when `wrapped` != 0 (length = |delta_x[axis]|).
+ * From these: <x> = out1/out0, periodic <x> = mod(atan2(out4, out3), 2 pi) * length / (2 pi), variance =
+ * out2/out0 of a second call with offsets[t] = -periodic <x>_t and wrapped = 1.
+ * Orthogonal axes only; grid_host[axis] <= 4096 (SQB_E_UNSUPPORTED above).  One CTA per state, deterministic
+ * summation order.
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c128* states, int axis,
+                        double spacing, double length, const double* offsets, int wrapped, double* out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

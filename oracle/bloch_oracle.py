@@ -537,3 +537,95 @@ def subspace_projector_error(
             worst = max(worst, float(np.linalg.norm(pa - pb)))
             start = i
     return worst
+
+
+# ---------------------------------------------------------------------------------------------
+# Observables on position-basis state lists (reference operator/_measure.py).
+# PINNED by the reference's tests/test_measure.py (position eigenstates, coherent states: x, periodic x with
+# its sign, wrapped x, variance / width) re-expressed in tests/test_measure_oracle.py.  The wrap interval
+# convention of slate_core's fundamental_stacked_x_points (which side of +-L/2 is closed) is NOT visible from
+# the reference (assumption U9): the half-open interval [-L/2, L/2) is used, as everywhere else in the path.
+def stacked_x_points(
+    delta_x: np.ndarray, shape: Sequence[int], offset: Sequence[float] | None = None, wrapped: bool = False
+) -> np.ndarray:
+    """Cartesian coordinates [nd, prod(shape)] of the grid points, C-order ravel.
+
+    ``offset`` is a Cartesian displacement added to every point (operator/_build/_position.py:236-239 builds it
+    from the scalar ``offset`` of measure.x); ``wrapped`` folds the fractional coordinates into [-1/2, 1/2).
+    """
+    delta_x = np.asarray(delta_x, dtype=np.float64)
+    nd = len(shape)
+    a = delta_x[:nd, :nd]
+    idx = np.array([g.ravel() for g in np.meshgrid(*(np.arange(n) for n in shape), indexing="ij")], dtype=np.float64)
+    dx = a / np.asarray(shape, dtype=np.float64)[:, None]  # fundamental_stacked_dx: lattice vector / points
+    points = np.einsum("ij,ik->jk", dx, idx)  # x = sum_i n_i dx_i: exactly i*dx in 1-D (tests/test_measure.py:15)
+    if offset is not None:
+        points = points + np.asarray(offset, dtype=np.float64)[:nd, None]
+    if wrapped:
+        frac = np.linalg.solve(a.T, points)
+        points = points - np.einsum("ij,ik->jk", a, np.floor(frac + 0.5))
+    return points
+
+
+def _normalised_density(states: np.ndarray) -> np.ndarray:
+    """|psi|^2 / sum |psi|^2 per state: normalize_each (state/_state.py:294-308) + a diagonal expectation."""
+    density = np.square(np.abs(np.atleast_2d(states)))
+    return density / density.sum(axis=1, keepdims=True)
+
+
+def measure_all_x(
+    states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int, offset: float = 0.0, wrapped: bool = False
+) -> np.ndarray:
+    """operator.measure.all_x (operator/_measure.py:191-210): <x_axis> of every normalised state."""
+    inner_offset = [offset if i == axis else 0.0 for i in range(len(shape))]
+    points = stacked_x_points(delta_x, shape, inner_offset, wrapped)[axis]
+    return _normalised_density(states) @ points
+
+
+def measure_all_scatter(states: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """<exp(+i q x)> for the fundamental q of ``axis`` (_get_all_fundamental_scatter, operator/_measure.py:213-239).
+
+    Only its ANGLE is used downstream and pinned (tests/test_measure.py:33-38 fixes the sign); the modulus
+    convention of slate_core's single-coefficient transformed operator (a 1/sqrt(N) factor) is not visible.
+    """
+    idx = np.unravel_index(np.arange(int(np.prod(shape))), shape)[axis]
+    return _normalised_density(states) @ np.exp(2j * np.pi * idx / shape[axis])
+
+
+def measure_all_periodic_x(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_periodic_x (operator/_measure.py:242-268)."""
+    angle = np.angle(measure_all_scatter(states, shape, axis))
+    wrapped = np.mod(angle, 2 * np.pi)
+    return wrapped * (np.linalg.norm(np.asarray(delta_x)[axis]) / (2 * np.pi))
+
+
+def measure_all_variance_x(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_variance_x (operator/_measure.py:271-292, variance_x :140-163):
+    <x_w^2> with x_w the position wrapped around each state's own periodic <x>."""
+    states = np.atleast_2d(states)
+    centre = measure_all_periodic_x(states, delta_x, shape, axis)
+    density = _normalised_density(states)
+    out = np.empty(len(states))
+    for i, x0 in enumerate(centre):
+        inner_offset = [-x0 if a == axis else 0.0 for a in range(len(shape))]
+        points = stacked_x_points(delta_x, shape, inner_offset, True)[axis]
+        out[i] = density[i] @ np.square(points)
+    return out
+
+
+def measure_all_coherent_width(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_coherent_width (operator/_measure.py:295-305): sqrt(2 variance)."""
+    return np.sqrt(2.0 * measure_all_variance_x(states, delta_x, shape, axis))
+
+
+def coherent_state(
+    delta_x: np.ndarray, shape: Sequence[int], x_0: Sequence[float], k_0: Sequence[float], sigma_0: Sequence[float]
+) -> np.ndarray:
+    """state.build.coherent (state/_build.py:79-99): periodic Gaussian wavepacket, normalised."""
+    nd = len(shape)
+    a = np.asarray(delta_x, dtype=np.float64)[:nd, :nd]
+    disp = stacked_x_points(a, shape, [-x for x in x_0], True)
+    distance = np.linalg.norm([d / s for d, s in zip(disp, sigma_0)], axis=0)
+    phi = np.einsum("ij,i->j", disp, np.asarray(k_0, dtype=np.float64)[:nd])
+    data = np.exp(1j * phi - np.square(distance) / 2)
+    return data / np.sqrt(np.sum(np.square(np.abs(data))))

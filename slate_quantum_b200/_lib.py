@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "sqb_evolve_bloch",
     "sqb_evolve_uniform_workspace_bytes",
     "sqb_evolve_bloch_uniform",
+    "sqb_measure_moments",
     "sqb_peak_dmma",
     "sqb_peak_dfma",
 )
@@ -94,6 +95,10 @@ def load() -> ctypes.CDLL:
     lib.sqb_eigh_workspace_bytes.argtypes = [c_int, c_int64]
     lib.sqb_eigh_batched.restype = c_int
     lib.sqb_eigh_batched.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_measure_moments.restype = c_int
+    lib.sqb_measure_moments.argtypes = [
+        c_int, c_void_p, c_int64, c_void_p, c_int, c_double, c_double, c_void_p, c_int, c_void_p, c_void_p,
+    ]
     lib.sqb_tridiag_eigh_workspace_bytes.restype = c_size_t
     lib.sqb_tridiag_eigh_workspace_bytes.argtypes = [c_int, c_int64]
     lib.sqb_tridiag_eigh_batched.restype = c_int

@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libslate_b200.so"
-SOURCES = ["abi.cu", "bloch_build.cu", "fft.cu", "eigh.cu", "evolve.cu", "peaks.cu"]
+SOURCES = ["abi.cu", "bloch_build.cu", "fft.cu", "eigh.cu", "evolve.cu", "measure.cu", "peaks.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -34,7 +34,11 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     mtime = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "sqb_common.cuh", HERE.parent / "include" / "slate_b200.h"]
+    deps = [CSRC / s for s in SOURCES] + [
+        CSRC / "sqb_common.cuh",
+        CSRC / "eigh_dc.cuh",
+        HERE.parent / "include" / "slate_b200.h",
+    ]
     return any(d.stat().st_mtime > mtime for d in deps)
 
 

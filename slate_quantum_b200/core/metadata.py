@@ -250,17 +250,25 @@ class volume:  # noqa: N801 - mirrors the module name slate_core.metadata.volume
     def fundamental_stacked_x_points(
         metadata: TupleMetadata, *, offset: Sequence[float] | None = None, wrapped: bool = False
     ) -> tuple[np.ndarray, ...]:
-        """Cartesian coordinates of every grid point, C-order ravel."""
-        fractions = np.meshgrid(
-            *(np.arange(c.fundamental_size) / c.fundamental_size for c in metadata.children), indexing="ij"
-        )
-        frac = np.array([f.ravel() for f in fractions])
-        if offset is not None:
-            frac = frac + np.asarray(offset, dtype=np.float64)[:, None]
-        if wrapped:
-            frac = (frac + 0.5) % 1.0 - 0.5
+        """Cartesian coordinates of every grid point, C-order ravel.
+
+        ``offset`` is a Cartesian displacement (the reference passes lengths, tests/test_measure.py:40-42);
+        ``wrapped`` folds the fractional coordinates into [-1/2, 1/2).
+        """
         a = volume.fundamental_stacked_delta_x(metadata)
-        return tuple(np.einsum("ij,ik->jk", a, frac))
+        nd = len(metadata.children)
+        a = a[:nd, :nd]
+        shape = np.array([c.fundamental_size for c in metadata.children], dtype=np.float64)
+        idx = np.array(
+            [g.ravel() for g in np.meshgrid(*(np.arange(int(n)) for n in shape), indexing="ij")], dtype=np.float64
+        )
+        points = np.einsum("ij,ik->jk", a / shape[:, None], idx)
+        if offset is not None:
+            points = points + np.asarray(offset, dtype=np.float64)[:nd, None]
+        if wrapped:
+            frac = np.linalg.solve(a.T, points)
+            points = points - np.einsum("ij,ik->jk", a, np.floor(frac + 0.5))
+        return tuple(points)
 
 
 fundamental_stacked_dk = volume.fundamental_stacked_dk

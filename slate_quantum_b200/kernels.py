@@ -408,3 +408,41 @@ def evolve_bloch(
         _lib.check(rc, "sqb_evolve_bloch_uniform")
         _count((1 if reuse_plane else 2) - (-batch // 65535))  # phase tables (+ Re+Im plane) + GEMM
     return out
+
+
+def measure_moments(
+    states: torch.Tensor,
+    grid: Sequence[int],
+    axis: int,
+    spacing: float,
+    length: float,
+    offsets: torch.Tensor | None = None,
+    wrapped: bool = False,
+) -> torch.Tensor:
+    """K6: per-state sums {|psi|^2, x|psi|^2, x^2|psi|^2, cos(2 pi n/N)|psi|^2, sin(2 pi n/N)|psi|^2} -> [lead, 5].
+
+    `states` [lead, prod(grid)] complex128 in the position basis; x = n_axis * spacing + offsets[t], folded into
+    [-length/2, length/2) when `wrapped` (reference operator/_measure.py:191-305).
+    """
+    _require_cuda()
+    lib = _lib.load()
+    _c128(states, "states")
+    m = int(np.prod(grid))
+    if states.numel() % m:
+        msg = "states must hold whole vectors over the grid"
+        raise ValueError(msg)
+    lead = states.numel() // m
+    if offsets is not None:
+        _f64(offsets, "offsets")
+        if offsets.numel() != lead:
+            msg = "one offset per state"
+            raise ValueError(msg)
+    out = torch.empty((lead, 5), dtype=torch.float64, device="cuda")
+    g = (ctypes.c_int * len(grid))(*[int(x) for x in grid])
+    rc = lib.sqb_measure_moments(
+        len(grid), g, lead, _ptr(states), int(axis), float(spacing), float(length),
+        _ptr(offsets) if offsets is not None else None, int(bool(wrapped)), _ptr(out), _stream(),
+    )
+    _lib.check(rc, "sqb_measure_moments")
+    _count(1)
+    return out

@@ -1,6 +1,6 @@
 """Mirror of slate_quantum.operator for the hot path (reference: slate_quantum/operator/__init__.py)."""
 
-from slate_quantum_b200.operator import build
+from slate_quantum_b200.operator import build, measure
 from slate_quantum_b200.operator._diagonal import (
     momentum_operator_basis,
     position_operator_basis,
@@ -17,6 +17,7 @@ __all__ = [
     "get_eigenstates_hermitian",
     "into_diagonal",
     "into_diagonal_hermitian",
+    "measure",
     "momentum_operator_basis",
     "operator_basis",
     "position_operator_basis",

@@ -1,0 +1,139 @@
+"""Observables on states / state lists (reference: slate_quantum/operator/_measure.py:105-305).
+
+Every quantity here is a diagonal expectation in the position basis, ``sum_x f(x) |psi(x)|^2 / sum_x |psi(x)|^2``
+(the reference normalises with ``state.normalize_each`` and contracts a dense diagonal operator).  One CUDA
+kernel (``sqb_measure_moments``) reads the ``[T, M]`` state list ONCE and returns the sums for x, x^2 and the
+fundamental scattering phase together; nothing is computed on the CPU and only ``[T]`` floats ever leave the
+GPU - which is what makes the observables of a 68.7 GB evolved state list cheap to bring back to the host.
+
+Orthogonal axes only (x along ``axis`` must depend on that axis' index alone).
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from slate_quantum_b200 import kernels
+from slate_quantum_b200.core import basis as _basis
+from slate_quantum_b200.core.array import Array
+from slate_quantum_b200.core.metadata import TupleMetadata, volume
+from slate_quantum_b200.state._state import State, StateList
+
+
+def _position_data(states: Array, space: TupleMetadata) -> torch.Tensor:
+    """[lead, M] device tensor of the states in the fundamental (position) basis of ``space``."""
+    position = _basis.from_metadata(space).upcast()
+    if isinstance(states, StateList):
+        converted = states.with_state_basis(position)
+    else:
+        converted = states.with_basis(position)
+    data = converted.device_data
+    if not data.is_complex():
+        data = data.to(torch.complex128)
+    return data.reshape(-1, space.fundamental_size).contiguous()
+
+
+def _axis_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
+    delta_x = np.asarray(volume.fundamental_stacked_delta_x(space), dtype=np.float64)
+    nd = len(space.children)
+    a = delta_x[:nd, :nd]
+    off_axis = a[axis].copy()
+    off_axis[axis] = 0.0
+    if np.abs(off_axis).max(initial=0.0) > 1e-12 * np.abs(a).max() or np.abs(a[:, axis]).sum() - abs(a[axis, axis]) > 1e-12 * np.abs(a).max():
+        msg = "operator.measure on the B200 path needs an axis orthogonal to the others"
+        raise NotImplementedError(msg)
+    grid = tuple(int(c.fundamental_size) for c in space.children)
+    length = float(np.linalg.norm(delta_x[axis]))
+    return grid, float(a[axis, axis]) / grid[axis], length
+
+
+def _moments(pos: torch.Tensor, space: TupleMetadata, axis: int, offsets: torch.Tensor | None, wrapped: bool) -> torch.Tensor:
+    grid, spacing, length = _axis_geometry(space, axis)
+    return kernels.measure_moments(pos, grid, axis, spacing, length, offsets, wrapped)
+
+
+def _list_array(states: StateList, values: torch.Tensor) -> Array:
+    list_basis = _basis.from_metadata(states.basis.metadata().children[0])
+    return Array(list_basis, values)
+
+
+def _all_x(pos: torch.Tensor, space: TupleMetadata, axis: int, offset: float, wrapped: bool) -> torch.Tensor:
+    offsets = torch.full((pos.shape[0],), float(offset), dtype=torch.float64, device="cuda") if offset else None
+    mom = _moments(pos, space, axis, offsets, wrapped)
+    return mom[:, 1] / mom[:, 0]
+
+
+def _all_periodic_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch.Tensor:
+    _, _, length = _axis_geometry(space, axis)
+    mom = _moments(pos, space, axis, None, False)
+    angle = torch.atan2(mom[:, 4], mom[:, 3])
+    return torch.remainder(angle, 2 * np.pi) * (length / (2 * np.pi))
+
+
+def _all_variance_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch.Tensor:
+    centre = _all_periodic_x(pos, space, axis)
+    mom = _moments(pos, space, axis, (-centre).contiguous(), True)
+    return mom[:, 2] / mom[:, 0]
+
+
+def all_x(states: StateList, *, axis: int, offset: float = 0, wrapped: bool = False) -> Array:
+    """Position of all states (reference operator/_measure.py:191-210)."""
+    space = states.basis.metadata().children[1]
+    return _list_array(states, _all_x(_position_data(states, space), space, axis, offset, wrapped))
+
+
+def all_periodic_x(states: StateList, *, axis: int) -> Array:
+    """Periodic position coordinate of all states (reference operator/_measure.py:242-268)."""
+    space = states.basis.metadata().children[1]
+    return _list_array(states, _all_periodic_x(_position_data(states, space), space, axis))
+
+
+def all_variance_x(states: StateList, *, axis: int) -> Array:
+    """<x^2> around each state's periodic position (reference operator/_measure.py:271-292)."""
+    space = states.basis.metadata().children[1]
+    return _list_array(states, _all_variance_x(_position_data(states, space), space, axis))
+
+
+def all_coherent_width(states: StateList, *, axis: int) -> Array:
+    """Width of a Gaussian wavepacket, sqrt(2 variance) (reference operator/_measure.py:295-305)."""
+    space = states.basis.metadata().children[1]
+    variance = _all_variance_x(_position_data(states, space), space, axis)
+    return _list_array(states, torch.sqrt(2.0 * variance))
+
+
+def x(state: State, *, axis: int, offset: float = 0, wrapped: bool = False) -> float:
+    """reference operator/_measure.py:105-121."""
+    space = state.basis.metadata()
+    return float(_all_x(_position_data(state, space), space, axis, offset, wrapped)[0])
+
+
+def periodic_x(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:124-138."""
+    space = state.basis.metadata()
+    return float(_all_periodic_x(_position_data(state, space), space, axis)[0])
+
+
+def variance_x(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:140-163."""
+    space = state.basis.metadata()
+    return float(_all_variance_x(_position_data(state, space), space, axis)[0])
+
+
+def coherent_width(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:166-188."""
+    return float(np.sqrt(2.0 * variance_x(state, axis=axis)))
+
+
+__all__: list[Any] = [
+    "all_coherent_width",
+    "all_periodic_x",
+    "all_variance_x",
+    "all_x",
+    "coherent_width",
+    "periodic_x",
+    "variance_x",
+    "x",
+]

@@ -270,3 +270,29 @@ def test_get_eigenstates_hermitian_bloch(cuda):
     del vecs
     res = h_dense @ vk.T - vk.T * energies[None, :]
     assert np.abs(res).max() < 1e-10
+
+
+def test_measure_api_coherent_states(cuda):
+    """operator.measure mirror on the reference's own coherent-state checks (tests/test_measure.py:18-66)."""
+    from slate_quantum_b200 import operator, state
+    from slate_quantum_b200.core.metadata import spaced_volume_metadata_from_stacked_delta_x
+
+    n = 300
+    metadata = spaced_volume_metadata_from_stacked_delta_x((np.array([2 * np.pi]),), (n,))
+    dx = 2 * np.pi / n
+    sigma_0 = (0.1 * np.pi,)
+    centre = state.build.coherent(metadata, (150 * dx,), (0,), sigma_0)
+    np.testing.assert_allclose(operator.measure.x(centre, axis=0), 150 * dx, rtol=1e-3)
+    np.testing.assert_allclose(operator.measure.coherent_width(centre, axis=0), sigma_0[0], atol=1e-7 * dx)
+    states = state.StateList.from_states(
+        [state.build.coherent(metadata, (i * dx,), (0,), sigma_0) for i in range(0, n, 11)]
+    )
+    expected = np.arange(0, n, 11) * dx
+    periodic = operator.measure.all_periodic_x(states, axis=0).raw_data
+    difference = (periodic - expected + np.pi) % (2 * np.pi) - np.pi
+    np.testing.assert_allclose(difference, 0, atol=1e-7 * dx)
+    widths = operator.measure.all_coherent_width(states, axis=0).raw_data
+    np.testing.assert_allclose(widths, sigma_0[0], atol=1e-7 * dx)
+    for i, s in enumerate(states):
+        wrapped = operator.measure.x(s, axis=0, offset=-expected[i], wrapped=True)
+        np.testing.assert_allclose(wrapped, 0, atol=1e-7 * dx)

@@ -470,3 +470,74 @@ def test_tridiag_dc_nan_input_is_flagged(cuda):
     d[1, 40] = np.nan
     w, q, info = _run_tridiag(d, e)
     assert info[0] == 0 and info[1] != 0
+
+
+# ---------------------------------------------------------------------------------------------
+# K6 observables (csrc/measure.cu) against the oracle restatement of operator/_measure.py
+@pytest.mark.parametrize(("grid", "axis"), [((300,), 0), ((24, 36), 0), ((24, 36), 1), ((5, 7, 6), 1), ((4096,), 0)])
+def test_measure_moments_against_oracle(cuda, grid, axis):
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(21)
+    m = int(np.prod(grid))
+    lead = 5
+    states = rng.normal(size=(lead, m)) + 1j * rng.normal(size=(lead, m))
+    states *= np.exp(-np.linspace(-3, 3, m) ** 2)[None, :]  # localised, un-normalised
+    lengths = np.array([2 * np.pi, 3.0, 1.7])[: len(grid)]
+    delta_x = np.diag(lengths)
+    dev = kernels.to_device(states, torch.complex128)
+    spacing = lengths[axis] / grid[axis]
+    mom = kernels.measure_moments(dev, grid, axis, spacing, lengths[axis]).cpu().numpy()
+    x = mom[:, 1] / mom[:, 0]
+    np.testing.assert_allclose(x, o.measure_all_x(states, delta_x, grid, axis), rtol=1e-12, atol=1e-13)
+    periodic = np.mod(np.arctan2(mom[:, 4], mom[:, 3]), 2 * np.pi) * lengths[axis] / (2 * np.pi)
+    want_p = o.measure_all_periodic_x(states, delta_x, grid, axis)
+    np.testing.assert_allclose(periodic, want_p, rtol=1e-11, atol=1e-12)
+    off = kernels.to_device(-want_p, torch.float64)
+    mom2 = kernels.measure_moments(dev, grid, axis, spacing, lengths[axis], off, True).cpu().numpy()
+    np.testing.assert_allclose(mom2[:, 2] / mom2[:, 0], o.measure_all_variance_x(states, delta_x, grid, axis),
+                               rtol=1e-10, atol=1e-13)
+    # shifted, unwrapped x (measure.all_x(offset=...))
+    mom3 = kernels.measure_moments(dev, grid, axis, spacing, lengths[axis],
+                                   kernels.to_device(np.full(lead, 0.37), torch.float64), False).cpu().numpy()
+    np.testing.assert_allclose(mom3[:, 1] / mom3[:, 0], o.measure_all_x(states, delta_x, grid, axis, offset=0.37),
+                               rtol=1e-12, atol=1e-13)
+
+
+def test_measure_position_eigenstates_exact(cuda):
+    """reference tests/test_measure.py:8-15 through the CUDA kernel: <x> of |i> is exactly i dx."""
+    torch, kernels = _gpu()
+    n = 50
+    dx = 2 * np.pi / n
+    mom = kernels.measure_moments(kernels.to_device(np.eye(n, dtype=np.complex128), torch.complex128), (n,), 0, dx,
+                                  2 * np.pi).cpu().numpy()
+    np.testing.assert_array_equal(mom[:, 1] / mom[:, 0], np.arange(n) * dx)
+
+
+def test_measure_on_evolved_bloch_states(cuda):
+    """K1 -> K2 -> K3 -> cell FFT -> K6: observables of the evolved wavepacket against the oracle chain."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    shape, repeat = (8, 8), (4, 3)
+    big = tuple(s * r for s, r in zip(shape, repeat))
+    dx = 2 * np.pi * np.eye(2)
+    big_dx = dx * np.array(repeat)[:, None]
+    comps = o.cos_potential_components(shape, 10.0)
+    solver = BlochSolver(shape, repeat, o.stacked_dk(dx), HBAR**2, HBAR)
+    solver.build(kernels.to_device(o.pad_components(shape, comps).ravel(), torch.complex128))
+    solver.diagonalise()
+    psi = o.coherent_state(big_dx, big, (np.pi * repeat[0], np.pi * repeat[1]), (0.0, 0.3), (2.0, 2.5))
+    times = np.linspace(0, 6 * HBAR, 24)
+    c = solver.project(kernels.to_device(psi, torch.complex128))
+    pos = solver.bloch_to_position(solver.evolve_bloch(c, kernels.to_device(times, torch.float64)))
+    blocks = o.bloch_blocks(dx, shape, comps, HBAR**2, repeat)
+    w_ref, t_ref = o.eigh_blocks(blocks)
+    ref = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
+    for axis in (0, 1):
+        length = big_dx[axis, axis]
+        mom = kernels.measure_moments(pos.reshape(len(times), -1).contiguous(), big, axis, length / big[axis],
+                                      length).cpu().numpy()
+        np.testing.assert_allclose(mom[:, 0], 1.0, atol=1e-9)  # unitary evolution keeps the norm
+        got = np.mod(np.arctan2(mom[:, 4], mom[:, 3]), 2 * np.pi) * length / (2 * np.pi)
+        np.testing.assert_allclose(got, o.measure_all_periodic_x(ref, big_dx, big, axis), atol=1e-8)
+        np.testing.assert_allclose(mom[:, 1] / mom[:, 0], o.measure_all_x(ref, big_dx, big, axis), atol=1e-8)
