@@ -383,6 +383,34 @@ def run_ours(args) -> None:
         stage_ms = dict(zip(stage_names, st.tolist()))
     value = n_k_global / (ms_per_step * 1e-3)
 
+    # ---- K6 (SURVEY 8f "next" row, outside the step): observables of the position-basis states of the last time
+    # tile, one pass over the tile; reported beside the step, extrapolated to all T samples
+    observables = None
+    if with_position and world == 1:
+        big = cfg.supercell
+        length0 = float(np.linalg.norm(cfg.vectors()[0])) * cfg.repeat[0]
+        tt = min(t_tile, T)
+        kernels.measure_moments(pos_out[:tt], big, 0, length0 / big[0], length0)
+        torch.cuda.synchronize()
+        a_ev, b_ev = ev(), ev()
+        a_ev.record()
+        mom = kernels.measure_moments(pos_out[:tt], big, 0, length0 / big[0], length0)
+        b_ev.record()
+        torch.cuda.synchronize()
+        obs_ms = a_ev.elapsed_time(b_ev)
+        obs_gbs = tt * n_k_local * n * 16 / (obs_ms * 1e-3) / 1e9
+        observables = {
+            "kernel": "measure_moments_kernel (norm, <x>, <x^2>, scattering phase of every state in one pass)",
+            "ms_for_all_times": obs_ms * T / tt,
+            "bound": "hbm",
+            "achieved": obs_gbs,
+            "peak": _hbm_peak(),
+            "unit": "GB/s",
+            "frac": obs_gbs / _hbm_peak(),
+            "d2h_bytes": T * 5 * 8,
+            "norm_drift_max": float((mom[:, 0] - mom[0, 0]).abs().max().item()),
+        }
+
     # ---- end-to-end through the C ABI with HOST buffers (H2D of inputs, D2H of eigenvalues and states)
     e2e = None
     if not args.no_e2e:
@@ -554,6 +582,8 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        if observables is not None:
+            line["observables"] = observables
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
