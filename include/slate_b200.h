@@ -232,8 +232,8 @@ int sqb_peak_dfma(int64_t iters, double* sink, double* flops_host, void* stream)
  *         NULL = 0), folded into [-length/2, length/2) when `wrapped` != 0 (length = |delta_x[axis]|).
  * From these: <x> = out1/out0, periodic <x> = mod(atan2(out4, out3), 2 pi) * length / (2 pi), variance =
  * out2/out0 of a second call with offsets[t] = -periodic <x>_t and wrapped = 1.
- * Orthogonal axes only; grid_host[axis] <= 4096 (SQB_E_UNSUPPORTED above).  One CTA per state, deterministic
- * summation order.
+ * Orthogonal axes only.  One CTA per state, deterministic summation order (axes of up to 4096 points use a
+ * shared-memory table of positions and phases, longer ones evaluate them per element).
  * ---------------------------------------------------------------------------------------------- */
 int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c128* states, int axis,
                         double spacing, double length, const double* offsets, int wrapped, double* out,

@@ -32,7 +32,8 @@ measure_moments_kernel(int64_t m_total, int len, int64_t inner, double spacing, 
   __shared__ double red[5][kMeasureThreads / 32];
   const int64_t t = blockIdx.x;
   const double off = offsets ? offsets[t] : 0.0;
-  for (int i = threadIdx.x; i < len; i += kMeasureThreads) {
+  const bool table = len <= kMeasureMaxTable;  // longer axes (cfg2: 131072 points) evaluate x / sincospi per element
+  for (int i = threadIdx.x; table && i < len; i += kMeasureThreads) {
     double x = (double)i * spacing + off;
     if (wrapped) x -= length * floor(x / length + 0.5);
     xs[i] = x;
@@ -51,12 +52,21 @@ measure_moments_kernel(int64_t m_total, int len, int64_t inner, double spacing, 
     int i;
     if (small) i = (int)(((uint32_t)m / (uint32_t)inner) % (uint32_t)len);
     else i = (int)((m / inner) % len);
-    const double x = xs[i];
+    double x, c, sv;
+    if (table) {
+      x = xs[i];
+      c = cs[i];
+      sv = sn[i];
+    } else {
+      x = (double)i * spacing + off;
+      if (wrapped) x -= length * floor(x / length + 0.5);
+      sincospi(2.0 * (double)i / (double)len, &sv, &c);
+    }
     a0 += w;
     a1 = fma(w, x, a1);
     a2 = fma(w * x, x, a2);
-    a3 = fma(w, cs[i], a3);
-    a4 = fma(w, sn[i], a4);
+    a3 = fma(w, c, a3);
+    a4 = fma(w, sv, a4);
   }
   double v[5] = {a0, a1, a2, a3, a4};
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -90,10 +100,9 @@ extern "C" int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, c
     m_total *= grid_host[a];
     if (a > axis) inner *= grid_host[a];
   }
-  if (grid_host[axis] > kMeasureMaxTable) return SQB_E_UNSUPPORTED;
   if (lead == 0) return SQB_OK;
   if (lead >= (1LL << 31)) return SQB_E_UNSUPPORTED;
-  const size_t smem = (size_t)3 * grid_host[axis] * sizeof(double);
+  const size_t smem = grid_host[axis] <= kMeasureMaxTable ? (size_t)3 * grid_host[axis] * sizeof(double) : 0;
   cudaError_t e = cudaFuncSetAttribute(measure_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   measure_moments_kernel<<<(unsigned)lead, kMeasureThreads, smem, sqb_stream(stream)>>>(

@@ -474,7 +474,7 @@ def test_tridiag_dc_nan_input_is_flagged(cuda):
 
 # ---------------------------------------------------------------------------------------------
 # K6 observables (csrc/measure.cu) against the oracle restatement of operator/_measure.py
-@pytest.mark.parametrize(("grid", "axis"), [((300,), 0), ((24, 36), 0), ((24, 36), 1), ((5, 7, 6), 1), ((4096,), 0)])
+@pytest.mark.parametrize(("grid", "axis"), [((300,), 0), ((24, 36), 0), ((24, 36), 1), ((5, 7, 6), 1), ((4096,), 0), ((5000,), 0)])
 def test_measure_moments_against_oracle(cuda, grid, axis):
     torch, kernels = _gpu()
     rng = np.random.default_rng(21)
