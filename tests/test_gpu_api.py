@@ -296,3 +296,40 @@ def test_measure_api_coherent_states(cuda):
     for i, s in enumerate(states):
         wrapped = operator.measure.x(s, axis=0, offset=-expected[i], wrapped=True)
         np.testing.assert_allclose(wrapped, 0, atol=1e-7 * dx)
+
+
+@pytest.mark.parametrize("shape", [(24,), (6, 5)])
+def test_dense_hamiltonian_schrodinger_evolution_and_observables(cuda, shape):
+    """the reference's examples/schrodinger.py on ONE cell (no Bloch decomposition):
+    operator.build.kinetic_hamiltonian -> into_diagonal_hermitian (batch of one matrix) -> decomposition
+    solver -> position basis -> operator.measure, against scipy.linalg.expm and the oracle's observables."""
+    import scipy.linalg
+
+    _, dynamics, operator, state, _, basis, metadata = _api()
+    from slate_quantum_b200.core import FundamentalBasis
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata
+
+    nd = len(shape)
+    vectors = 2 * np.pi * np.eye(nd)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(tuple(vectors[i] for i in range(nd)), shape)
+    potential = operator.build.cos_potential(meta, 4.0)
+    hamiltonian = operator.build.kinetic_hamiltonian(potential, hbar**2)
+    comps = o.cos_potential_components(shape, 4.0)
+    h_k = o.dense_hamiltonian(vectors, shape, o.pad_components(shape, comps), hbar**2)
+    diagonal = operator.into_diagonal_hermitian(hamiltonian)
+    np.testing.assert_allclose(np.sort(diagonal.raw_data.real), np.linalg.eigvalsh(h_k), atol=1e-10)
+
+    initial_state = state.build.coherent(meta, (np.pi,) * nd, (1.0,) + (0.0,) * (nd - 1), (0.8,) * nd)
+    times = FundamentalBasis(SpacedTimeMetadata(9, domain=Domain(delta=2 * hbar)))
+    evolution = dynamics.solve_schrodinger_equation_decomposition(initial_state, times, hamiltonian)
+    in_position_list = evolution.with_state_basis(basis.from_metadata(meta).upcast())
+    in_position = in_position_list.raw_data.reshape(9, -1)
+    h_x = o.momentum_matrix_to_position(h_k, shape)
+    ref = np.array([scipy.linalg.expm(-1j * h_x * t / hbar) @ initial_state.raw_data for t in times.metadata().values])
+    np.testing.assert_allclose(in_position, ref, atol=1e-9)
+    for axis in range(nd):
+        got = operator.measure.all_periodic_x(in_position_list, axis=axis).raw_data
+        np.testing.assert_allclose(got, o.measure_all_periodic_x(ref, vectors, shape, axis), atol=1e-8)
+        got_w = operator.measure.all_coherent_width(in_position_list, axis=axis).raw_data
+        np.testing.assert_allclose(got_w, o.measure_all_coherent_width(ref, vectors, shape, axis), atol=1e-8)
