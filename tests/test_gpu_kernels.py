@@ -541,3 +541,36 @@ def test_measure_on_evolved_bloch_states(cuda):
         got = np.mod(np.arctan2(mom[:, 4], mom[:, 3]), 2 * np.pi) * length / (2 * np.pi)
         np.testing.assert_allclose(got, o.measure_all_periodic_x(ref, big_dx, big, axis), atol=1e-8)
         np.testing.assert_allclose(mom[:, 1] / mom[:, 0], o.measure_all_x(ref, big_dx, big, axis), atol=1e-8)
+
+
+def test_eigensystem_shard_dump_and_resume(cuda, tmp_path):
+    """(E, V) shard dump: a fresh solver resumed from the shard evolves identically, and a
+    shard of a different problem / a corrupted shard is refused."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    shape, repeat = (6, 5), (3, 4)
+    dx = 2 * np.pi * np.eye(2)
+    comps = o.cos_potential_components(shape, 7.0)
+    table = kernels.to_device(o.pad_components(shape, comps).ravel(), torch.complex128)
+
+    def make(mass=HBAR**2):
+        return BlochSolver(shape, repeat, o.stacked_dk(dx), mass, HBAR, block_begin=2, block_count=7)
+
+    a = make()
+    a.build(table)
+    a.diagonalise()
+    a.save_eigensystem(str(tmp_path), tag="rank0")
+    b = make()
+    b.load_eigensystem(str(tmp_path), tag="rank0")
+    rng = np.random.default_rng(5)
+    c = kernels.to_device(rng.normal(size=(7, a.n)) + 1j * rng.normal(size=(7, a.n)), torch.complex128)
+    times = kernels.to_device(np.linspace(0, 3 * HBAR, 20), torch.float64)
+    np.testing.assert_array_equal(a.evolve_bloch(c, times).cpu().numpy(), b.evolve_bloch(c, times).cpu().numpy())
+    with pytest.raises(ValueError, match="different problem"):
+        make(mass=2 * HBAR**2).load_eigensystem(str(tmp_path), tag="rank0")
+    w = np.load(tmp_path / "rank0.eigenvalues.npy")
+    w[0, 0] += 1.0
+    np.save(tmp_path / "rank0.eigenvalues.npy", w)
+    with pytest.raises(ValueError, match="checksum"):
+        make().load_eigensystem(str(tmp_path), tag="rank0")
