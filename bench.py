@@ -270,10 +270,18 @@ def run_ours(args) -> None:
     gathered = world > 1 and with_position  # time-sharded evolve over all-gathered eigenvectors
     w_all = torch.empty((n_k_global, n, n), dtype=torch.complex128, device="cuda") if gathered else None
     c_all = torch.empty((n_k_global * n,), dtype=torch.complex128, device="cuda") if gathered else None
-    evolve_ws = (
-        torch.empty(kernels.evolve_uniform_workspace_bytes(n, n_k_global, T // world), dtype=torch.uint8, device="cuda")
-        if gathered else None
+    # block segments of the time-sharded evolve: this rank's own blocks (local eigenvectors, no exchange needed),
+    # then the blocks below / above them out of the all-gathered buffer; one 3M workspace per segment
+    seg_ranges = (
+        [(rank * n_k_local, n_k_local), (0, rank * n_k_local), ((rank + 1) * n_k_local, (world - rank - 1) * n_k_local)]
+        if gathered else []
     )
+    seg_ws = [
+        torch.empty(kernels.evolve_uniform_workspace_bytes(n, cnt, T // world), dtype=torch.uint8, device="cuda")
+        if cnt > 0 else None
+        for _, cnt in seg_ranges
+    ]
+    comm_stream = torch.cuda.Stream() if gathered else None
     free, _ = torch.cuda.mem_get_info()
     if gathered:
         row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
@@ -319,18 +327,41 @@ def run_ours(args) -> None:
             # folded EIGENVECTORS (+ eigenvalues, coefficients) once per eigensolve - (G-1)/G * n_k*N^2*16 B received
             # per rank, 2x less than the states at cfg3 and NVLS-friendly - and then evolve their own T/G time
             # samples for ALL blocks locally (same flops per rank), followed by the local cell FFT.
+            # The all-gather runs on a side stream, launched BEFORE the evolve of this rank's own blocks: the NCCL
+            # CTAs take their SMs first (an evolve CTA owns a whole SM's register file, so the two cannot share
+            # one) and the collective hides behind the own-block GEMM instead of serialising with it.
             def gather():
                 dist.all_gather_into_tensor(torch.view_as_real(w_all), torch.view_as_real(folded_buf))
                 dist.all_gather_into_tensor(torch.view_as_real(c_all), torch.view_as_real(c.reshape(-1)))
 
-            timed("exchange", gather)
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            comm_stream.wait_event(ready)
+            with torch.cuda.stream(comm_stream):
+                timed("exchange", gather)
+                gathered_ev = torch.cuda.Event()
+                gathered_ev.record(comm_stream)
+            eig_g = eig_all.reshape(n_k_global, n)
+            c_g = c_all.reshape(n_k_global, n)
             t_lo = rank * (T // world)
+            waited = False
             for i_tile, t0 in enumerate(range(0, T // world, t_tile)):
                 tt = min(t_tile, T // world - t0)
                 tsl = times[t_lo + t0 : t_lo + t0 + tt]
-                timed("evolve", lambda: kernels.evolve_bloch(
-                    w_all, eig_all.reshape(n_k_global, n), c_all.reshape(n_k_global, n), tsl, HBAR,
-                    out=states[:tt], uniform_dt=dt_uniform, workspace=evolve_ws, reuse_plane=i_tile > 0))
+                for i_seg, (b0, cnt) in enumerate(seg_ranges):
+                    if cnt == 0:
+                        continue
+                    if i_seg == 0:
+                        tr, ww, cc = folded_buf, solver.eigenvalues, c
+                    else:
+                        if not waited:
+                            cur.wait_event(gathered_ev)  # the other ranks' eigenvectors have arrived
+                            waited = True
+                        tr, ww, cc = w_all[b0 : b0 + cnt], eig_g[b0 : b0 + cnt], c_g[b0 : b0 + cnt]
+                    timed("evolve", lambda: kernels.evolve_bloch(
+                        tr, ww, cc, tsl, HBAR, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=dt_uniform,
+                        workspace=seg_ws[i_seg], reuse_plane=i_tile > 0))
                 timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
             return
         for t0 in range(0, T, t_tile):

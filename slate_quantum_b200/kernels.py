@@ -389,10 +389,21 @@ def evolve_bloch(
     t_count = times.numel()
     if out is None:
         out = torch.empty((t_count, batch * n), dtype=torch.complex128, device="cuda")
-    _c128(out, "out")
+    # `out` may be a column slice of a wider [T, width] buffer (row stride > batch*n): the blocks of one rank
+    # inside the states of all ranks
+    if not (out.is_cuda and out.dtype == torch.complex128):
+        msg = "out must be a CUDA complex128 tensor"
+        raise TypeError(msg)
+    if out.is_contiguous():
+        row_stride = batch * n
+    elif out.dim() == 2 and out.stride(1) == 1 and out.shape[1] == batch * n and out.stride(0) >= batch * n:
+        row_stride = out.stride(0)
+    else:
+        msg = "out must be contiguous or a column slice [T, batch*n] of a wider row-major buffer"
+        raise TypeError(msg)
     if uniform_dt is None:
         rc = lib.sqb_evolve_bloch(
-            n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), batch * n,
+            n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(hbar), _ptr(out), row_stride,
             _stream(),
         )
         _lib.check(rc, "sqb_evolve_bloch")
@@ -403,7 +414,7 @@ def evolve_bloch(
             workspace, reuse_plane = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda"), False
         rc = lib.sqb_evolve_bloch_uniform(
             n, batch, _ptr(transform), _ptr(w), _ptr(c), _ptr(times), t_count, float(uniform_dt), float(hbar),
-            _ptr(out), batch * n, _ptr(workspace), workspace.numel(), int(bool(reuse_plane)), _stream(),
+            _ptr(out), row_stride, _ptr(workspace), workspace.numel(), int(bool(reuse_plane)), _stream(),
         )
         _lib.check(rc, "sqb_evolve_bloch_uniform")
         _count((1 if reuse_plane else 2) - (-batch // 65535))  # phase tables (+ Re+Im plane) + GEMM
