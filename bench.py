@@ -270,15 +270,13 @@ def run_ours(args) -> None:
     gathered = world > 1 and with_position  # time-sharded evolve over all-gathered eigenvectors
     w_all = torch.empty((n_k_global, n, n), dtype=torch.complex128, device="cuda") if gathered else None
     c_all = torch.empty((n_k_global * n,), dtype=torch.complex128, device="cuda") if gathered else None
-    # block segments of the time-sharded evolve: this rank's own blocks (local eigenvectors, no exchange needed),
-    # then the blocks below / above them out of the all-gathered buffer; one 3M workspace per segment
-    seg_ranges = (
-        [(rank * n_k_local, n_k_local), (0, rank * n_k_local), ((rank + 1) * n_k_local, (world - rank - 1) * n_k_local)]
-        if gathered else []
-    )
+    # block segments of the time-sharded evolve: this rank's own blocks first (local eigenvectors, no exchange
+    # needed), then the other ranks' blocks in the order their eigenvectors arrive (ring: rank-1, rank-2, ...);
+    # one 3M workspace per segment
+    seg_src = [(rank - k) % world for k in range(world)] if gathered else []
+    seg_ranges = [(src * n_k_local, n_k_local) for src in seg_src]
     seg_ws = [
         torch.empty(kernels.evolve_uniform_workspace_bytes(n, cnt, T // world), dtype=torch.uint8, device="cuda")
-        if cnt > 0 else None
         for _, cnt in seg_ranges
     ]
     comm_stream = torch.cuda.Stream() if gathered else None
@@ -327,37 +325,46 @@ def run_ours(args) -> None:
             # folded EIGENVECTORS (+ eigenvalues, coefficients) once per eigensolve - (G-1)/G * n_k*N^2*16 B received
             # per rank, 2x less than the states at cfg3 and NVLS-friendly - and then evolve their own T/G time
             # samples for ALL blocks locally (same flops per rank), followed by the local cell FFT.
-            # The all-gather runs on a side stream, launched BEFORE the evolve of this rank's own blocks: the NCCL
-            # CTAs take their SMs first (an evolve CTA owns a whole SM's register file, so the two cannot share
-            # one) and the collective hides behind the own-block GEMM instead of serialising with it.
-            def gather():
-                dist.all_gather_into_tensor(torch.view_as_real(w_all), torch.view_as_real(folded_buf))
+            # The exchange runs on a side stream, enqueued BEFORE the evolve of this rank's own blocks (which needs
+            # only local eigenvectors): the NCCL CTAs take their SMs first (an evolve CTA owns a whole SM's register
+            # file, so the two cannot share one).  It is a ring of G-1 send/recv steps (step k: receive rank-k's
+            # eigenvectors, send ours to rank+k) with one event per step, so the evolve of a peer's blocks starts
+            # as soon as THAT peer's eigenvectors are in: after the first step everything hides behind the GEMMs.
+            w_all_r = torch.view_as_real(w_all)
+            folded_r = torch.view_as_real(folded_buf)
+            arrived: list = [None] * world
+
+            def exchange():
                 dist.all_gather_into_tensor(torch.view_as_real(c_all), torch.view_as_real(c.reshape(-1)))
+                for k in range(1, world):
+                    src, dst = (rank - k) % world, (rank + k) % world
+                    ops = [
+                        dist.P2POp(dist.isend, folded_r, dst),
+                        dist.P2POp(dist.irecv, w_all_r[src * n_k_local : (src + 1) * n_k_local], src),
+                    ]
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                    arrived[k] = torch.cuda.Event()
+                    arrived[k].record(comm_stream)
 
             cur = torch.cuda.current_stream()
             ready = torch.cuda.Event()
             ready.record(cur)
             comm_stream.wait_event(ready)
             with torch.cuda.stream(comm_stream):
-                timed("exchange", gather)
-                gathered_ev = torch.cuda.Event()
-                gathered_ev.record(comm_stream)
+                timed("exchange", exchange)
             eig_g = eig_all.reshape(n_k_global, n)
             c_g = c_all.reshape(n_k_global, n)
             t_lo = rank * (T // world)
-            waited = False
             for i_tile, t0 in enumerate(range(0, T // world, t_tile)):
                 tt = min(t_tile, T // world - t0)
                 tsl = times[t_lo + t0 : t_lo + t0 + tt]
                 for i_seg, (b0, cnt) in enumerate(seg_ranges):
-                    if cnt == 0:
-                        continue
                     if i_seg == 0:
                         tr, ww, cc = folded_buf, solver.eigenvalues, c
                     else:
-                        if not waited:
-                            cur.wait_event(gathered_ev)  # the other ranks' eigenvectors have arrived
-                            waited = True
+                        if i_tile == 0:
+                            cur.wait_event(arrived[i_seg])  # that rank's eigenvectors (and c_all) have arrived
                         tr, ww, cc = w_all[b0 : b0 + cnt], eig_g[b0 : b0 + cnt], c_g[b0 : b0 + cnt]
                     timed("evolve", lambda: kernels.evolve_bloch(
                         tr, ww, cc, tsl, HBAR, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=dt_uniform,
