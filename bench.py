@@ -446,6 +446,7 @@ def run_ours(args) -> None:
             "unit": "GB/s",
             "frac": obs_gbs / _hbm_peak(),
             "d2h_bytes": T * 5 * 8,
+            "note": "read-only pass: `peak` is the driver's copy figure (a read+write mix), which a pure read can exceed",
             "norm_drift_max": float((mom[:, 0] - mom[0, 0]).abs().max().item()),
         }
 
