@@ -134,8 +134,11 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
     if (r >= i && r < n) {
       const c128 cw = cconj(wo[i]), cv = cconj(vo[i]);
       c128 a = i >= jres ? res[tri_off(n, jres, i) + r] : A[(int64_t)i * n + r];
-      a = csub(a, cmul(vo[r], cw));
-      a = csub(a, cmul(wo[r], cv));
+      {
+        c128 t = cmul(vo[r], cw);  // the correction is formed independently of `a`: one ADD on its chain
+        cfma(t, wo[r], cv);
+        a = csub(a, t);
+      }
       colv = a;
       if (r >= i + 2) part = a.x * a.x + a.y * a.y;
       if (r == i) dd[i] = a.x;
@@ -211,8 +214,9 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
         for (int c = 0; c < NR; ++c) {
           if (rows[c] >= j && rows[c] < n) {
             c128 a = cur[c];
-            a = csub(a, cmul(vo[rows[c]], cw));
-            a = csub(a, cmul(wo[rows[c]], cv));
+            c128 t = cmul(vo[rows[c]], cw);
+            cfma(t, wo[rows[c]], cv);
+            a = csub(a, t);
             A[(int64_t)j * n + rows[c]] = a;
             cfma(acc[c], a, vj);
             if (rows[c] > j) cfmac(dotj, a, vn[rows[c]]);
@@ -244,8 +248,9 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
         for (int c = 0; c < NR; ++c) {
           if (rows[c] >= j && rows[c] < n) {
             c128 a = col[rows[c]];
-            a = csub(a, cmul(vor[c], cw));
-            a = csub(a, cmul(wor[c], cv));
+            c128 t = cmul(vor[c], cw);
+            cfma(t, wor[c], cv);
+            a = csub(a, t);
             col[rows[c]] = a;
             cfma(acc[c], a, vj);
             if (rows[c] > j) cfmac(dotj, a, vnr[c]);
