@@ -574,3 +574,86 @@ def test_eigensystem_shard_dump_and_resume(cuda, tmp_path):
     np.save(tmp_path / "rank0.eigenvalues.npy", w)
     with pytest.raises(ValueError, match="checksum"):
         make().load_eigensystem(str(tmp_path), tag="rank0")
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes through size-independent properties (the oracle cannot run these in seconds)
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_full_size_properties(cuda, name):
+    """cfg2 (1024 x N=128) / cfg3 (4096 x N=256): trace and ordering of every block's spectrum, residual and
+    orthogonality of sampled blocks, t = 0 round trip position -> Bloch -> eigenbasis -> position, unitarity
+    (norm of every evolved state), and the observables' normalisation."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.configs import CONFIGS
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    cfg = CONFIGS[name]
+    n, n_k = cfg.n, cfg.n_k
+    solver = BlochSolver(cfg.shape, cfg.repeat, cfg.dk(), cfg.mass(), HBAR)
+    table = kernels.to_device(cfg.potential_table().ravel(), torch.complex128)
+    h = solver.build(table)
+    trace = torch.diagonal(h, dim1=1, dim2=2).real.sum(dim=1).clone()
+    h_norm = torch.linalg.matrix_norm(h).clone()
+    rng = np.random.default_rng(31)
+    sample = torch.as_tensor(np.sort(rng.choice(n_k, size=48, replace=False)), device="cuda")
+    h_sample = h[sample].clone()
+    w, v = solver.diagonalise()
+    assert int(solver.info.abs().sum()) == 0
+    # every block: ascending eigenvalues whose sum is the trace of the block
+    assert bool((w[:, 1:] >= w[:, :-1]).all())
+    assert float(((w.sum(dim=1) - trace).abs() / h_norm).max()) < 1e-12
+    # sampled blocks: residual and orthogonality (rows of v = eigenvectors)
+    vs = v[sample]
+    vcols = vs.transpose(1, 2)
+    resid = torch.linalg.matrix_norm(h_sample @ vcols - vcols * w[sample][:, None, :]) / h_norm[sample]
+    assert float(resid.max()) < 1e-10
+    eye = torch.eye(n, dtype=torch.complex128, device="cuda")
+    assert float(torch.linalg.matrix_norm(vs.conj() @ vcols - eye).max()) < 1e-10
+    del h_sample, vs, vcols
+    # evolution: t = 0 reproduces psi0, every later state has the same norm
+    psi0 = kernels.to_device(cfg.initial_state(), torch.complex128)
+    c = solver.project(psi0)
+    n_t = 64
+    times = kernels.to_device(cfg.times()[:n_t].copy(), torch.float64)
+    assert float(times[0]) == 0.0
+    pos = solver.evolve_position(c, times, uniform_dt=kernels.uniform_step(cfg.times()[:n_t]))
+    assert float((pos[0] - psi0.reshape(-1)).abs().max()) < 1e-9
+    norms = torch.linalg.vector_norm(pos, dim=1)
+    assert float((norms - norms[0]).abs().max()) < 1e-9
+    # general (non-uniform) kernel on a few of the same times agrees with the uniform-grid 3M kernel
+    few = solver.evolve_position(c, times[:8].contiguous())
+    assert float((few - pos[:8]).abs().max()) < 1e-9
+    big = cfg.supercell
+    length = float(np.linalg.norm(cfg.vectors()[0])) * cfg.repeat[0]
+    mom = kernels.measure_moments(pos, big, 0, length / big[0], length)
+    assert float((mom[:, 0] - norms**2).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize(("name", "count"), [("cfg4", 96), ("cfg5", 160)])
+def test_sharded_config_block_range_properties(cuda, name, count):
+    """cfg4 (hexagonal, N=512) / cfg5 (cubic, N=343) need k-sharding over GPUs: a contiguous block range (what one
+    rank owns) is built and diagonalised at full block size and checked through trace, ordering, residual and
+    orthogonality, and against numpy on three of its blocks."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.configs import CONFIGS
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    cfg = CONFIGS[name]
+    n = cfg.n
+    begin = cfg.n_k // 3
+    solver = BlochSolver(cfg.shape, cfg.repeat, cfg.dk(), cfg.mass(), HBAR, block_begin=begin, block_count=count)
+    h = solver.build(kernels.to_device(cfg.potential_table().ravel(), torch.complex128)).clone()
+    w, v = solver.diagonalise()
+    assert int(solver.info.abs().sum()) == 0
+    h_norm = torch.linalg.matrix_norm(h)
+    trace = torch.diagonal(h, dim1=1, dim2=2).real.sum(dim=1)
+    assert bool((w[:, 1:] >= w[:, :-1]).all())
+    assert float(((w.sum(dim=1) - trace).abs() / h_norm).max()) < 1e-12
+    vcols = v.transpose(1, 2)
+    resid = torch.linalg.matrix_norm(h @ vcols - vcols * w[:, None, :]) / h_norm
+    assert float(resid.max()) < 1e-10
+    eye = torch.eye(n, dtype=torch.complex128, device="cuda")
+    assert float(torch.linalg.matrix_norm(v.conj() @ vcols - eye).max()) < 1e-10
+    for b in (0, count // 2, count - 1):
+        w_ref = np.linalg.eigvalsh(h[b].cpu().numpy())
+        np.testing.assert_allclose(w[b].cpu().numpy(), w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
