@@ -11,7 +11,10 @@
  *    passed in as `workspace` with the size reported by the matching *_workspace_bytes function.
  *  - Return value: 0 = OK, < 0 = bad argument (SQB_E_*), > 0 = a cudaError_t from a launch.
  *    Numerical failures of the eigensolver are reported per matrix in `info[]`, not in the return value.
- *  - Re-entrant / thread-safe: no global mutable state.
+ *  - Re-entrant / thread-safe: no global mutable state.  Two environment variables are read once per process
+ *    (tuning / fallback switches, never needed for correctness): SQB_EIGH_TRIDIAG_SOLVER=ql selects the
+ *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_EVOLVE_TILES_PER_CTA=<k> sets how
+ *    many 64-row time tiles a CTA of the uniform-grid evolve kernel walks (default 8).
  *
  * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
  * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency

@@ -27,13 +27,6 @@ __device__ __forceinline__ void cfma(c128& acc, c128 a, c128 b) {
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(a.y, b.x, acc.y);
 }
-// acc -= a*b
-__device__ __forceinline__ void cfnma(c128& acc, c128 a, c128 b) {
-  acc.x = fma(-a.x, b.x, acc.x);
-  acc.x = fma(a.y, b.y, acc.x);
-  acc.y = fma(-a.x, b.y, acc.y);
-  acc.y = fma(-a.y, b.x, acc.y);
-}
 // acc += conj(a)*b
 __device__ __forceinline__ void cfmac(c128& acc, c128 a, c128 b) {
   acc.x = fma(a.x, b.x, acc.x);
