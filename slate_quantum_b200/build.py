@@ -37,6 +37,7 @@ def needs_build() -> bool:
     deps = [CSRC / s for s in SOURCES] + [
         CSRC / "sqb_common.cuh",
         CSRC / "eigh_dc.cuh",
+        CSRC / "eigh_wy.cuh",
         HERE.parent / "include" / "slate_b200.h",
     ]
     return any(d.stat().st_mtime > mtime for d in deps)

@@ -29,6 +29,7 @@
 
 #include "sqb_common.cuh"
 #include "eigh_dc.cuh"
+#include "eigh_wy.cuh"
 
 namespace {
 
@@ -49,7 +50,18 @@ struct EighWs {  // per-chunk workspace pointers (each array is [chunk, ...])
   c128* y;        // [chunk, n, n]  reflector i at y[i*n + r]
   double* qt;     // [chunk, n, n]  qt[e*n + k]
   DcWs dc;        // divide-and-conquer arrays (dc.q[0] == qt)
+  c128* wy_t;     // [chunk, wy_blocks(n), 32, 33] T factors of the blocked back-transformation (padded rows)
 };
+
+// blocked (compact WY, DMMA) back-transformation: 128 < n <= 256; SQB_BACKTRANSFORM=reflector disables it
+bool eigh_use_wy(int n) {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* v = getenv("SQB_BACKTRANSFORM");
+    cached = (v && strcmp(v, "reflector") == 0) ? 0 : 1;
+  }
+  return cached == 1 && n > 128 && n <= kWyMaxN;
+}
 
 // tridiagonal solver: 1 = divide and conquer (default), 0 = implicit QL + rotation replay
 int eigh_use_dc() {
@@ -777,6 +789,7 @@ size_t per_matrix_bytes(int n) {
   s += align_up((size_t)n * 16, 256);                          // tau
   s += align_up((size_t)n * n * 16, 256);                      // y
   s += align_up((size_t)n * n * 8, 256);                       // qt
+  if (eigh_use_wy(n)) s += align_up((size_t)wy_blocks(n) * kWyNb * kWyLdw * 16, 256);  // wy_t
   if (eigh_use_dc()) {
     s += dc_per_matrix_bytes(n);
   } else {
@@ -819,6 +832,7 @@ void carve(EighWs& ws, void* base, int n, int64_t chunk) {
   ws.tau = reinterpret_cast<c128*>(cv.take((size_t)n * 16, chunk));
   ws.y = reinterpret_cast<c128*>(cv.take((size_t)n * n * 16, chunk));
   ws.qt = reinterpret_cast<double*>(cv.take((size_t)n * n * 8, chunk));
+  ws.wy_t = eigh_use_wy(n) ? reinterpret_cast<c128*>(cv.take((size_t)wy_blocks(n) * kWyNb * kWyLdw * 16, chunk)) : nullptr;
   ws.rank = nullptr;
   ws.nsweeps = nullptr;
   ws.sweeps = nullptr;
@@ -940,7 +954,17 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
       if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
     }
 
-    if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
+    if (eigh_use_wy(n)) {
+      cudaError_t e = cudaFuncSetAttribute(backtransform_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kWySmem);
+      if (e != cudaSuccess) { status = (int)e; break; }
+      wy_tfactor_kernel<<<dim3((unsigned)wy_blocks(n), (unsigned)cnt), 256, 0, ls>>>(n, ws.y, ws.tau, ws.wy_t);
+      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
+      backtransform_wy_kernel<<<dim3((unsigned)((n + kWyEt - 1) / kWyEt), (unsigned)cnt), 32 * kWyWarps, kWySmem, ls>>>(
+          n, Ab, ws.qt, ws.y, ws.wy_t);
+      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
+      rc = SQB_OK;
+    } else if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 384) rc = launch_back<12, 32>(n, cnt, Ab, ws, ls);

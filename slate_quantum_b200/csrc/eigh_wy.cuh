@@ -1,0 +1,310 @@
+// K2, stage 3 for 128 < n <= 256: blocked (compact WY) Householder back-transformation on the FP64 tensor cores.
+// Included by eigh.cu (one translation unit).
+//
+// The reflectors H_i = I - tau_i v_i v_i^H of the tridiagonalisation are grouped in blocks of 32:
+//   H_{i0} ... H_{i0+31} = I - V T V^H        (LAPACK zlarft, forward / columnwise; T upper triangular)
+// and a block is applied to 16 eigenvectors at a time as three small complex GEMMs in the row layout
+// Z[e][k] (e = eigenvector, k = component):
+//   W  = Z conj(V)        [16 x 32]   (K = support of the block, split over the warps)
+//   W2 = W T^T            [16 x 32]
+//   Z -= W2 V^T           [16 x n]
+// The reflector-by-reflector kernel (backtransform_kernel) spends one shuffle reduction and two shared-memory
+// sweeps per (reflector, eigenvector pair); here V is read from shared memory once per GEMM for 16 eigenvectors
+// and all multiply-adds are DMMA.8x8x4 (8x fewer issue slots than DFMA for the same flops - on B200 the two
+// paths have the same FP64 peak, so the gain is in issue slots and dependent chains, not in flops).
+//
+// Z lives in registers for the whole kernel in the MMA accumulator layout: warp w owns the 8-column tiles
+// c = w, w+8, ... of all 16 eigenvectors.  The same registers are the A operand of W = Z conj(V): the k-slot q of
+// the MMA is mapped to component 8c + 2q (first k-step) / 8c + 2q + 1 (second k-step), which is exactly what lane
+// (row, q) holds, and the B fragments are loaded with the matching row order - no shuffles, no staging of Z.
+// The numpy model of the blocking is in tests/eigh_model.py::back_transform_wy.
+#pragma once
+
+namespace {
+
+constexpr int kWyNb = 32;          // reflectors per block
+constexpr int kWyEt = 16;          // eigenvectors per CTA
+constexpr int kWyWarps = 8;
+constexpr int kWyMaxN = 256;
+constexpr int kWyLc = kWyMaxN / 8 / kWyWarps;  // column tiles per warp (4)
+constexpr int kWyLdv = kWyMaxN + 1;  // c128 row stride of the V block Vt[j][k] in shared memory (== 1 mod 8: conflict free)
+constexpr int kWyLdw = kWyNb + 1;  // row stride of W / W2
+
+__host__ __device__ inline int wy_blocks(int n) { return (n - 1 + kWyNb - 1) / kWyNb; }
+
+// ------------------------------------------------------------------------------------------------
+// T factors: one CTA per (block, matrix).  G = V^H V (upper triangle) with a warp per entry, then the zlarft
+// recurrence T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j] by one warp.  Output [32][33] row major (row
+// stride kWyLdw), zero outside the upper triangle / beyond the block's reflector count.
+__global__ void __launch_bounds__(256)
+wy_tfactor_kernel(int n, const c128* __restrict__ y_all, const c128* __restrict__ tau_all, c128* __restrict__ t_all) {
+  __shared__ c128 g[kWyNb][kWyNb + 1];
+  __shared__ c128 t[kWyNb][kWyNb + 1];
+  const int blk = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int i0 = blk * kWyNb;
+  const int kb = min(kWyNb, n - 1 - i0);
+  const c128* y = y_all + b * (int64_t)n * n;
+  const c128* tau = tau_all + b * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int idx = threadIdx.x; idx < kWyNb * (kWyNb + 1); idx += blockDim.x) {
+    (&g[0][0])[idx] = make_double2(0.0, 0.0);
+    (&t[0][0])[idx] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  // entries (a, c), a < c < kb: sum_r conj(V[r][a]) V[r][c]; V[r][j] = y[i0+j][r] for r >= i0+j+1, else 0
+  for (int ent = warp; ent < kb * kb; ent += 8) {
+    const int a = ent / kb, c = ent - a * kb;
+    if (a >= c) continue;
+    const c128* ya = y + (int64_t)(i0 + a) * n;
+    const c128* yc = y + (int64_t)(i0 + c) * n;
+    c128 acc = make_double2(0.0, 0.0);
+    for (int r = i0 + c + 1 + lane; r < n; r += 32) cfmac(acc, ya[r], yc[r]);
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) g[a][c] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int j = 0; j < kb; ++j) {
+      const c128 tj = tau[i0 + j];
+      if (lane < j) {
+        c128 acc = make_double2(0.0, 0.0);
+        for (int l = lane; l < j; ++l) cfma(acc, t[lane][l], g[l][j]);
+        t[lane][j] = make_double2(-(tj.x * acc.x - tj.y * acc.y), -(tj.x * acc.y + tj.y * acc.x));
+      } else if (lane == j) {
+        t[j][j] = tj;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // padded [32][33] rows: the back-transformation copies a block's T with ONE bulk copy into the same layout
+  c128* out = t_all + (b * wy_blocks(n) + blk) * (int64_t)(kWyNb * kWyLdw);
+  for (int idx = threadIdx.x; idx < kWyNb * kWyLdw; idx += blockDim.x) out[idx] = (&t[0][0])[idx];
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wy_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+constexpr size_t kWySmemV = (size_t)kWyNb * kWyLdv * sizeof(c128);                 // V block   [32][257]
+constexpr size_t kWySmemW = (size_t)kWyWarps * kWyEt * kWyLdw * sizeof(c128);      // partials  [8][16][33]
+constexpr size_t kWySmemT = (size_t)kWyNb * kWyLdw * sizeof(c128);                 // T         [32][33]
+constexpr size_t kWySmem = kWySmemV + kWySmemW + kWySmemT + 64;
+
+__device__ __forceinline__ uint32_t wy_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wy_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wy_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void wy_mbar_arrive_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wy_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wy_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(wy_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void wy_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(wy_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(wy_smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kWyWarps, 1)
+backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restrict__ qt_all,
+                        const c128* __restrict__ y_all, const c128* __restrict__ t_all) {
+  extern __shared__ __align__(16) unsigned char wy_smem[];
+  c128* Vs = reinterpret_cast<c128*>(wy_smem);                          // [j][kWyLdv]    V[k][j] at Vs[j*ld + k]
+  c128* Wp = reinterpret_cast<c128*>(wy_smem + kWySmemV);               // [warp][e][kWyLdw] partial W
+  c128* Ts = reinterpret_cast<c128*>(wy_smem + kWySmemV + kWySmemW);    // [j][kWyLdw]
+  c128* Wf = Wp;                                                        // [e][kWyLdw] summed W   (after a sync)
+  c128* W2 = Wp + kWyEt * kWyLdw;                                       // [e][kWyLdw] W T^T
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wy_smem + kWySmemV + kWySmemW + kWySmemT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frow = lane >> 2, q = lane & 3;
+  const int64_t b = blockIdx.y;
+  const int e0 = blockIdx.x * kWyEt;
+  const double* qt = qt_all + b * (int64_t)n * n;
+  const c128* y = y_all + b * (int64_t)n * n;
+  const int nblk = wy_blocks(n);
+  const c128* tb = t_all + b * nblk * (int64_t)(kWyNb * kWyLdw);
+  const int ntiles = (n + 7) / 8;
+  if (tid == 0) {
+    wy_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Z in the accumulator layout: zr/zi[a][lc][h] = Z[e0 + 8a + frow][8c + 2q + h], c = warp + 8 lc
+  double zr[2][kWyLc][2], zi[2][kWyLc][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int lc = 0; lc < kWyLc; ++lc)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = e0 + 8 * a + frow, k = 8 * (warp + 8 * lc) + 2 * q + h;
+        zr[a][lc][h] = (e < n && k < n) ? qt[(int64_t)e * n + k] : 0.0;
+        zi[a][lc][h] = 0.0;
+      }
+
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int i0 = blk * kWyNb;
+    const int kb = min(kWyNb, n - 1 - i0);
+    const int c_first = (i0 + 1) / 8;  // tiles below hold no support row of this block
+    // ---- stage V and T: reflector j of the block is ONE bulk (TMA) copy of its support rows k >= i0+j+1 into
+    // Vs[j][k]; the few entries between the first active tile and the support (and the rows of a short last
+    // block) are zeroed by the threads meanwhile
+    if (warp == 0) {
+      // reflector j = lane: one bulk copy each, all issued at once; lane 0 registers the byte count first and
+      // also brings in the block's T.  Earlier generic-proxy stores (zero fills, W buffers) are ordered before
+      // the async-proxy writes by the fence.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) {
+        uint32_t bytes = (uint32_t)(kWyNb * kWyLdw * sizeof(c128));
+        for (int j = 0; j < kb; ++j) bytes += (uint32_t)((n - (i0 + j + 1)) * sizeof(c128));
+        wy_mbar_arrive_tx(bar, bytes);
+        wy_bulk_g2s(Ts, tb + (int64_t)blk * (kWyNb * kWyLdw), (uint32_t)(kWyNb * kWyLdw * sizeof(c128)), bar);
+      }
+      __syncwarp();
+      if (lane < kb) {
+        const int k0 = i0 + lane + 1;
+        wy_bulk_g2s(Vs + lane * kWyLdv + k0, y + (int64_t)(i0 + lane) * n + k0, (uint32_t)((n - k0) * sizeof(c128)), bar);
+      }
+    }
+    for (int idx = tid; idx < kWyNb * 48; idx += 32 * kWyWarps) {
+      const int j = idx / 48, k = c_first * 8 + (idx - j * 48);
+      if (j < kb && k < i0 + j + 1) Vs[j * kWyLdv + k] = make_double2(0.0, 0.0);
+    }
+    if (kb < kWyNb || n < ntiles * 8) {
+      for (int idx = tid; idx < kWyNb * ntiles * 8; idx += 32 * kWyWarps) {
+        const int j = idx / (ntiles * 8), k = idx - j * (ntiles * 8);
+        if (k >= c_first * 8 && (j >= kb || k >= n)) Vs[j * kWyLdv + k] = make_double2(0.0, 0.0);
+      }
+    }
+    wy_mbar_wait(bar, (uint32_t)((nblk - 1 - blk) & 1));
+    __syncthreads();
+
+    // ---- W partial = Z conj(V) over the warp's own column tiles
+    double wr[2][4][2], wi[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int jt = 0; jt < 4; ++jt) wr[a][jt][0] = wr[a][jt][1] = wi[a][jt][0] = wi[a][jt][1] = 0.0;
+#pragma unroll
+    for (int lc = 0; lc < kWyLc; ++lc) {
+      const int c = warp + 8 * lc;
+      if (c < c_first || c >= ntiles) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const c128* vcol = Vs + frow * kWyLdv + 8 * c + 2 * q + h;  // B[k-slot q][n = frow] of column tile jt
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) {
+          const c128 v = vcol[8 * jt * kWyLdv];
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            // W = Z conj(V): Wre += Zre Vre + Zim Vim ; Wim += Zim Vre - Zre Vim
+            wy_dmma(wr[a][jt][0], wr[a][jt][1], zr[a][lc][h], v.x);
+            wy_dmma(wr[a][jt][0], wr[a][jt][1], zi[a][lc][h], v.y);
+            wy_dmma(wi[a][jt][0], wi[a][jt][1], zi[a][lc][h], v.x);
+            wy_dmma(wi[a][jt][0], wi[a][jt][1], zr[a][lc][h], -v.y);
+          }
+        }
+      }
+    }
+    {
+      c128* mine = Wp + warp * (kWyEt * kWyLdw);
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            mine[(8 * a + frow) * kWyLdw + 8 * jt + 2 * q + h] = make_double2(wr[a][jt][h], wi[a][jt][h]);
+    }
+    __syncthreads();
+    // ---- W = sum of the partials (2 entries per thread), then W2 = W T^T
+    c128 s[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ent = tid + 256 * u, e = ent >> 5, j = ent & 31;
+      c128 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int w = 0; w < kWyWarps; ++w) acc = cadd(acc, Wp[w * (kWyEt * kWyLdw) + e * kWyLdw + j]);
+      s[u] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ent = tid + 256 * u;
+      Wf[(ent >> 5) * kWyLdw + (ent & 31)] = s[u];
+    }
+    __syncthreads();
+    {
+      // W2 = W T^T as one 8 x 8 complex tile per warp: rows a = warp / 4, columns jt = warp % 4, K = 32
+      const int a = warp >> 2, jt = warp & 3;
+      double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < kWyNb / 4; ++ks) {
+        const c128 wv = Wf[(8 * a + frow) * kWyLdw + 4 * ks + q];   // A[row = frow][slot q] = W[e][l = 4ks + q]
+        const c128 tv = Ts[(8 * jt + frow) * kWyLdw + 4 * ks + q];  // B[slot q][n = frow] = T[j = 8jt + frow][l]
+        wy_dmma(ar[0], ar[1], wv.x, tv.x);
+        wy_dmma(ar[0], ar[1], -wv.y, tv.y);
+        wy_dmma(ai[0], ai[1], wv.x, tv.y);
+        wy_dmma(ai[0], ai[1], wv.y, tv.x);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) W2[(8 * a + frow) * kWyLdw + 8 * jt + 2 * q + h] = make_double2(ar[h], ai[h]);
+    }
+    __syncthreads();
+    // ---- Z -= W2 V^T on the warp's own column tiles
+#pragma unroll
+    for (int js = 0; js < kWyNb / 4; ++js) {
+      c128 wa[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) wa[a] = W2[(8 * a + frow) * kWyLdw + 4 * js + q];  // A[row = frow][k-slot q]
+#pragma unroll
+      for (int lc = 0; lc < kWyLc; ++lc) {
+        const int c = warp + 8 * lc;
+        if (c < c_first || c >= ntiles) continue;
+        const c128 v = Vs[(4 * js + q) * kWyLdv + 8 * c + frow];  // B[k-slot q][n = frow] = V[k = 8c+frow][j]
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          // Zre -= W2re Vre - W2im Vim ; Zim -= W2re Vim + W2im Vre
+          wy_dmma(zr[a][lc][0], zr[a][lc][1], -wa[a].x, v.x);
+          wy_dmma(zr[a][lc][0], zr[a][lc][1], wa[a].y, v.y);
+          wy_dmma(zi[a][lc][0], zi[a][lc][1], -wa[a].x, v.y);
+          wy_dmma(zi[a][lc][0], zi[a][lc][1], -wa[a].y, v.x);
+        }
+      }
+    }
+    __syncthreads();  // Vs / W buffers are rewritten by the next block
+  }
+
+  // rows = eigenvectors of H: the conjugate undoes the conj(H) view of the tridiagonalisation
+  c128* out = A_all + b * (int64_t)n * n;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int lc = 0; lc < kWyLc; ++lc)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = e0 + 8 * a + frow, k = 8 * (warp + 8 * lc) + 2 * q + h;
+        if (e < n && k < n) out[(int64_t)e * n + k] = make_double2(zr[a][lc][h], -zi[a][lc][h]);
+      }
+}
+
+}  // namespace

@@ -136,6 +136,31 @@ def back_transform(z: np.ndarray, tau: np.ndarray, y: np.ndarray) -> np.ndarray:
     return u
 
 
+def wy_tfactor(v: np.ndarray, tau: np.ndarray) -> np.ndarray:
+    """T of H_0 ... H_{k-1} = I - V T V^H (LAPACK zlarft, forward / columnwise), as csrc/eigh_wy.cuh builds it."""
+    k = v.shape[1]
+    t = np.zeros((k, k), dtype=np.complex128)
+    g = v.conj().T @ v
+    for j in range(k):
+        t[j, j] = tau[j]
+        if j > 0:
+            t[:j, j] = -tau[j] * (t[:j, :j] @ g[:j, j])
+    return t
+
+
+def back_transform_wy(z: np.ndarray, tau: np.ndarray, y: np.ndarray, nb: int = 32) -> np.ndarray:
+    """Blocked back-transformation in the row layout of csrc/eigh_wy.cuh: W = Z conj(V), W2 = W T^T, Z -= W2 V^T."""
+    n = z.shape[0]
+    zr = z.T.astype(np.complex128)  # zr[e, k]
+    for i0 in reversed(range(0, n - 1, nb)):
+        i1 = min(i0 + nb, n - 1)
+        v = np.array([y[i] for i in range(i0, i1)]).T
+        t = wy_tfactor(v, tau[i0:i1])
+        w2 = (zr @ v.conj()) @ t.T
+        zr = zr - w2 @ v.T
+    return zr.T
+
+
 def eigh_model(h: np.ndarray):
     n = h.shape[0]
     d, e, tau, y = tridiagonalise(h)

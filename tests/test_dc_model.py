@@ -101,3 +101,13 @@ def test_secular_roots_interlace():
     assert np.all(lam[:-1] > dk[:-1]) and np.all(lam[:-1] < dk[1:]) and lam[-1] > dk[-1]
     ref = np.linalg.eigvalsh(np.diag(dk) + rho * np.outer(z, z))
     assert np.abs(lam - ref).max() < 1e-13
+
+
+def test_blocked_back_transform_model_equals_reflector_by_reflector():
+    """The compact-WY blocking of csrc/eigh_wy.cuh reproduces the reflector-by-reflector back-transformation."""
+    rng = np.random.default_rng(12)
+    for n in (5, 33, 100, 130):
+        g = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+        d, e, tau, y = em.tridiagonalise(g + g.conj().T)
+        z = rng.normal(size=(n, n))
+        np.testing.assert_allclose(em.back_transform_wy(z, tau, y), em.back_transform(z, tau, y), atol=1e-12)
