@@ -52,17 +52,47 @@ wy_tfactor_kernel(int n, const c128* __restrict__ y_all, const c128* __restrict_
     (&t[0][0])[idx] = make_double2(0.0, 0.0);
   }
   __syncthreads();
-  // entries (a, c), a < c < kb: sum_r conj(V[r][a]) V[r][c]; V[r][j] = y[i0+j][r] for r >= i0+j+1, else 0
-  for (int ent = warp; ent < kb * kb; ent += 8) {
-    const int a = ent / kb, c = ent - a * kb;
-    if (a >= c) continue;
-    const c128* ya = y + (int64_t)(i0 + a) * n;
-    const c128* yc = y + (int64_t)(i0 + c) * n;
-    c128 acc = make_double2(0.0, 0.0);
-    for (int r = i0 + c + 1 + lane; r < n; r += 32) cfmac(acc, ya[r], yc[r]);
-    acc.x = warp_sum(acc.x);
-    acc.y = warp_sum(acc.y);
-    if (lane == 0) g[a][c] = acc;
+  // G[a][c] = sum_r conj(V[r][a]) V[r][c] for a < c < kb, V[r][j] = y[i0+j][r] for r >= i0+j+1 (else 0).
+  // A warp computes a 4 x 4 tile of entries at a time: 8 row loads feed 16 products per 32 rows (entry by entry
+  // the kernel re-read the block 31 times through L1/L2)
+  for (int tile = warp; tile < 36; tile += 8) {
+    // upper-triangular 8 x 8 grid of 4 x 4 tiles, row-major enumeration
+    int ta = 0, rem = tile;
+    while (rem >= 8 - ta) {
+      rem -= 8 - ta;
+      ++ta;
+    }
+    const int tc = ta + rem;
+    const int a0 = 4 * ta, c0 = 4 * tc;
+    if (c0 >= kb) continue;
+    c128 acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = make_double2(0.0, 0.0);
+    for (int r = i0 + c0 + 1 + lane; r < n; r += 32) {
+      c128 xa[4], xc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // rows beyond the block's reflector count and entries above a reflector's support (never written by the
+        // tridiagonalisation: could be NaN bit patterns) are masked to zero
+        xa[u] = (a0 + u < kb && r >= i0 + a0 + u + 1) ? y[(int64_t)(i0 + a0 + u) * n + r] : make_double2(0.0, 0.0);
+        xc[u] = (c0 + u < kb && r >= i0 + c0 + u + 1) ? y[(int64_t)(i0 + c0 + u) * n + r] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cfmac(acc[u][v], xa[u], xc[v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        c128 z = acc[u][v];
+        z.x = warp_sum(z.x);
+        z.y = warp_sum(z.y);
+        if (lane == 0 && a0 + u < c0 + v && c0 + v < kb) g[a0 + u][c0 + v] = z;
+      }
   }
   __syncthreads();
   if (warp == 0) {
