@@ -22,7 +22,8 @@
 //
 // Stages (2)+(3) are the fallback (environment SQB_EIGH_TRIDIAG_SOLVER=ql); by default the tridiagonal
 // eigenproblem is solved by the divide-and-conquer kernels of eigh_dc.cuh (DMMA merge GEMMs), which write the
-// same Q_T layout.  The algorithms are modelled step by step in tests/eigh_model.py and tests/dc_model.py.
+// same Q_T layout.  For 128 < n <= 256 stage (4) is the blocked compact-WY back-transformation of eigh_wy.cuh
+// (three DMMA GEMMs per block of 32 reflectors) unless SQB_BACKTRANSFORM=reflector.  The algorithms are modelled step by step in tests/eigh_model.py and tests/dc_model.py.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
