@@ -16,7 +16,7 @@
  *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_EVOLVE_TILES_PER_CTA=<k> sets how
  *    many 64-row time tiles a CTA of the uniform-grid evolve kernel walks (default 8); SQB_BACKTRANSFORM=reflector
  *    selects the reflector-by-reflector back-transformation for every n (default: blocked compact-WY DMMA
- *    kernel for 128 < n <= 256).
+ *    kernel for 64 < n <= 512).
  *
  * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
  * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency
@@ -154,7 +154,7 @@ int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, in
  * n <= 512 (SQB_E_UNSUPPORTED above).  Algorithm: Householder tridiagonalisation; divide and conquer on the
  * real tridiagonal (QL leaves of <= 32 rows, dlaed2-style deflation, secular equation per root, Gu/Eisenstat
  * vectors, merge products on the FP64 tensor cores); Householder back-transformation (blocked compact WY on the
- * FP64 tensor cores for 128 < n <= 256, reflector by reflector otherwise).  With the environment
+ * FP64 tensor cores for 64 < n <= 512, reflector by reflector otherwise).  With the environment
  * variable SQB_EIGH_TRIDIAG_SOLVER=ql the tridiagonal stage is implicit-shift QL with recorded Givens
  * rotations replayed on shared-memory strips instead (info then also reports rotation-storage overflow).
  *

@@ -22,8 +22,8 @@
 //
 // Stages (2)+(3) are the fallback (environment SQB_EIGH_TRIDIAG_SOLVER=ql); by default the tridiagonal
 // eigenproblem is solved by the divide-and-conquer kernels of eigh_dc.cuh (DMMA merge GEMMs), which write the
-// same Q_T layout.  For 128 < n <= 256 stage (4) is the blocked compact-WY back-transformation of eigh_wy.cuh
-// (three DMMA GEMMs per block of 32 reflectors) unless SQB_BACKTRANSFORM=reflector.  The algorithms are modelled step by step in tests/eigh_model.py and tests/dc_model.py.
+// same Q_T layout.  For 64 < n <= 512 stage (4) is the blocked compact-WY back-transformation of eigh_wy.cuh
+// (three DMMA GEMMs per block of 32 / 16 reflectors) unless SQB_BACKTRANSFORM=reflector.  The algorithms are modelled step by step in tests/eigh_model.py and tests/dc_model.py.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,17 +51,17 @@ struct EighWs {  // per-chunk workspace pointers (each array is [chunk, ...])
   c128* y;        // [chunk, n, n]  reflector i at y[i*n + r]
   double* qt;     // [chunk, n, n]  qt[e*n + k]
   DcWs dc;        // divide-and-conquer arrays (dc.q[0] == qt)
-  c128* wy_t;     // [chunk, wy_blocks(n), 32, 33] T factors of the blocked back-transformation (padded rows)
+  c128* wy_t;     // [chunk, wy_blocks(n), NB, NB+1] T factors of the blocked back-transformation (padded rows)
 };
 
-// blocked (compact WY, DMMA) back-transformation: 128 < n <= 256; SQB_BACKTRANSFORM=reflector disables it
+// blocked (compact WY, DMMA) back-transformation: 64 < n <= 512; SQB_BACKTRANSFORM=reflector disables it
 bool eigh_use_wy(int n) {
   static int cached = -1;
   if (cached < 0) {
     const char* v = getenv("SQB_BACKTRANSFORM");
     cached = (v && strcmp(v, "reflector") == 0) ? 0 : 1;
   }
-  return cached == 1 && n > 128 && n <= kWyMaxN;
+  return cached == 1 && n > 64 && n <= 512;
 }
 
 // tridiagonal solver: 1 = divide and conquer (default), 0 = implicit QL + rotation replay
@@ -790,7 +790,7 @@ size_t per_matrix_bytes(int n) {
   s += align_up((size_t)n * 16, 256);                          // tau
   s += align_up((size_t)n * n * 16, 256);                      // y
   s += align_up((size_t)n * n * 8, 256);                       // qt
-  if (eigh_use_wy(n)) s += align_up((size_t)wy_blocks(n) * kWyNb * kWyLdw * 16, 256);  // wy_t
+  if (eigh_use_wy(n)) s += align_up(wy_t_elems(n) * 16, 256);  // wy_t
   if (eigh_use_dc()) {
     s += dc_per_matrix_bytes(n);
   } else {
@@ -833,7 +833,7 @@ void carve(EighWs& ws, void* base, int n, int64_t chunk) {
   ws.tau = reinterpret_cast<c128*>(cv.take((size_t)n * 16, chunk));
   ws.y = reinterpret_cast<c128*>(cv.take((size_t)n * n * 16, chunk));
   ws.qt = reinterpret_cast<double*>(cv.take((size_t)n * n * 8, chunk));
-  ws.wy_t = eigh_use_wy(n) ? reinterpret_cast<c128*>(cv.take((size_t)wy_blocks(n) * kWyNb * kWyLdw * 16, chunk)) : nullptr;
+  ws.wy_t = eigh_use_wy(n) ? reinterpret_cast<c128*>(cv.take(wy_t_elems(n) * 16, chunk)) : nullptr;
   ws.rank = nullptr;
   ws.nsweeps = nullptr;
   ws.sweeps = nullptr;
@@ -956,15 +956,9 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     }
 
     if (eigh_use_wy(n)) {
-      cudaError_t e = cudaFuncSetAttribute(backtransform_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kWySmem);
-      if (e != cudaSuccess) { status = (int)e; break; }
-      wy_tfactor_kernel<<<dim3((unsigned)wy_blocks(n), (unsigned)cnt), 256, 0, ls>>>(n, ws.y, ws.tau, ws.wy_t);
-      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
-      backtransform_wy_kernel<<<dim3((unsigned)((n + kWyEt - 1) / kWyEt), (unsigned)cnt), 32 * kWyWarps, kWySmem, ls>>>(
-          n, Ab, ws.qt, ws.y, ws.wy_t);
-      if (cudaGetLastError() != cudaSuccess) { status = (int)cudaErrorLaunchFailure; break; }
-      rc = SQB_OK;
+      if (n <= 128) rc = launch_back_wy<32, 2>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else if (n <= 256) rc = launch_back_wy<32, 4>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else rc = launch_back_wy<16, 8>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
     } else if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, ls);

@@ -1,12 +1,13 @@
-// K2, stage 3 for 128 < n <= 256: blocked (compact WY) Householder back-transformation on the FP64 tensor cores.
+// K2, stage 3 for 64 < n <= 512: blocked (compact WY) Householder back-transformation on the FP64 tensor cores.
 // Included by eigh.cu (one translation unit).
 //
-// The reflectors H_i = I - tau_i v_i v_i^H of the tridiagonalisation are grouped in blocks of 32:
-//   H_{i0} ... H_{i0+31} = I - V T V^H        (LAPACK zlarft, forward / columnwise; T upper triangular)
+// The reflectors H_i = I - tau_i v_i v_i^H of the tridiagonalisation are grouped in blocks of NB (32 for n <= 256,
+// 16 for n <= 512 where a 32-reflector block would not fit in shared memory):
+//   H_{i0} ... H_{i0+NB-1} = I - V T V^H      (LAPACK zlarft, forward / columnwise; T upper triangular)
 // and a block is applied to 16 eigenvectors at a time as three small complex GEMMs in the row layout
 // Z[e][k] (e = eigenvector, k = component):
-//   W  = Z conj(V)        [16 x 32]   (K = support of the block, split over the warps)
-//   W2 = W T^T            [16 x 32]
+//   W  = Z conj(V)        [16 x NB]   (K = support of the block, split over the warps)
+//   W2 = W T^T            [16 x NB]
 //   Z -= W2 V^T           [16 x n]
 // The reflector-by-reflector kernel (backtransform_kernel) spends one shuffle reduction and two shared-memory
 // sweeps per (reflector, eigenvector pair); here V is read from shared memory once per GEMM for 16 eigenvectors
@@ -22,44 +23,56 @@
 
 namespace {
 
-constexpr int kWyNb = 32;          // reflectors per block
 constexpr int kWyEt = 16;          // eigenvectors per CTA
 constexpr int kWyWarps = 8;
-constexpr int kWyMaxN = 256;
-constexpr int kWyLc = kWyMaxN / 8 / kWyWarps;  // column tiles per warp (4)
-constexpr int kWyLdv = kWyMaxN + 1;  // c128 row stride of the V block Vt[j][k] in shared memory (== 1 mod 8: conflict free)
-constexpr int kWyLdw = kWyNb + 1;  // row stride of W / W2
 
-__host__ __device__ inline int wy_blocks(int n) { return (n - 1 + kWyNb - 1) / kWyNb; }
+// NB = reflectors per block, LC = 8-column tiles per warp (the kernel covers n <= 64 LC)
+template <int NB, int LC>
+struct WyCfg {
+  static constexpr int kMaxN = 64 * LC;
+  static constexpr int kLdv = kMaxN + 1;  // c128 row stride of Vs[j][k] (== 1 mod 8: conflict-free fragment loads)
+  static constexpr int kLdw = NB + 1;     // row stride of W / W2 / T (== 1 mod 8)
+  static constexpr size_t kSmemV = (size_t)NB * kLdv * sizeof(c128);
+  static constexpr size_t kSmemW = (size_t)kWyWarps * kWyEt * kLdw * sizeof(c128);  // per-warp partial W
+  static constexpr size_t kSmemT = (size_t)NB * kLdw * sizeof(c128);
+  static constexpr size_t kSmem = kSmemV + kSmemW + kSmemT + 64;
+};
+
+__host__ __device__ inline int wy_nb(int n) { return n <= 256 ? 32 : 16; }
+__host__ __device__ inline int wy_blocks(int n) { return (n - 1 + wy_nb(n) - 1) / wy_nb(n); }
+// c128 elements of the T factors of one matrix: wy_blocks(n) padded [NB][NB+1] blocks
+__host__ __device__ inline size_t wy_t_elems(int n) { return (size_t)wy_blocks(n) * wy_nb(n) * (wy_nb(n) + 1); }
 
 // ------------------------------------------------------------------------------------------------
-// T factors: one CTA per (block, matrix).  G = V^H V (upper triangle) with a warp per entry, then the zlarft
-// recurrence T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j] by one warp.  Output [32][33] row major (row
-// stride kWyLdw), zero outside the upper triangle / beyond the block's reflector count.
+// T factors: one CTA per (block, matrix).  G = V^H V (upper triangle) in 4 x 4 register tiles per warp, then the
+// zlarft recurrence T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j] by one warp.  Output [NB][NB+1] row
+// major, zero outside the upper triangle / beyond the block's reflector count.
+template <int NB>
 __global__ void __launch_bounds__(256)
 wy_tfactor_kernel(int n, const c128* __restrict__ y_all, const c128* __restrict__ tau_all, c128* __restrict__ t_all) {
-  __shared__ c128 g[kWyNb][kWyNb + 1];
-  __shared__ c128 t[kWyNb][kWyNb + 1];
+  __shared__ c128 g[NB][NB + 1];
+  __shared__ c128 t[NB][NB + 1];
   const int blk = blockIdx.x;
   const int64_t b = blockIdx.y;
-  const int i0 = blk * kWyNb;
-  const int kb = min(kWyNb, n - 1 - i0);
+  const int i0 = blk * NB;
+  const int kb = min(NB, n - 1 - i0);
   const c128* y = y_all + b * (int64_t)n * n;
   const c128* tau = tau_all + b * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int idx = threadIdx.x; idx < kWyNb * (kWyNb + 1); idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < NB * (NB + 1); idx += blockDim.x) {
     (&g[0][0])[idx] = make_double2(0.0, 0.0);
     (&t[0][0])[idx] = make_double2(0.0, 0.0);
   }
   __syncthreads();
   // G[a][c] = sum_r conj(V[r][a]) V[r][c] for a < c < kb, V[r][j] = y[i0+j][r] for r >= i0+j+1 (else 0).
   // A warp computes a 4 x 4 tile of entries at a time: 8 row loads feed 16 products per 32 rows (entry by entry
-  // the kernel re-read the block 31 times through L1/L2)
-  for (int tile = warp; tile < 36; tile += 8) {
-    // upper-triangular 8 x 8 grid of 4 x 4 tiles, row-major enumeration
+  // the kernel re-read the block NB-1 times through L1/L2)
+  constexpr int kT = NB / 4;
+  for (int tile = warp; tile < kT * (kT + 1) / 2; tile += 8) {
+    // upper-triangular kT x kT grid of 4 x 4 tiles, row-major enumeration
     int ta = 0, rem = tile;
-    while (rem >= 8 - ta) {
-      rem -= 8 - ta;
+    while (rem >= kT - ta) {
+      rem -= kT - ta;
       ++ta;
     }
     const int tc = ta + rem;
@@ -109,9 +122,9 @@ wy_tfactor_kernel(int n, const c128* __restrict__ y_all, const c128* __restrict_
     }
   }
   __syncthreads();
-  // padded [32][33] rows: the back-transformation copies a block's T with ONE bulk copy into the same layout
-  c128* out = t_all + (b * wy_blocks(n) + blk) * (int64_t)(kWyNb * kWyLdw);
-  for (int idx = threadIdx.x; idx < kWyNb * kWyLdw; idx += blockDim.x) out[idx] = (&t[0][0])[idx];
+  // padded [NB][NB+1] rows: the back-transformation copies a block's T with ONE bulk copy into the same layout
+  c128* out = t_all + b * wy_t_elems(n) + (int64_t)blk * (NB * (NB + 1));
+  for (int idx = threadIdx.x; idx < NB * (NB + 1); idx += blockDim.x) out[idx] = (&t[0][0])[idx];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,12 +133,6 @@ __device__ __forceinline__ void wy_dmma(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
-
-constexpr size_t kWySmemV = (size_t)kWyNb * kWyLdv * sizeof(c128);                 // V block   [32][257]
-constexpr size_t kWySmemW = (size_t)kWyWarps * kWyEt * kWyLdw * sizeof(c128);      // partials  [8][16][33]
-constexpr size_t kWySmemT = (size_t)kWyNb * kWyLdw * sizeof(c128);                 // T         [32][33]
-constexpr size_t kWySmem = kWySmemV + kWySmemW + kWySmemT + 64;
-
 __device__ __forceinline__ uint32_t wy_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void wy_mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wy_smem_u32(bar)), "r"(count));
@@ -153,16 +160,20 @@ __device__ __forceinline__ void wy_bulk_g2s(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+template <int NB, int LC>
 __global__ void __launch_bounds__(32 * kWyWarps, 1)
 backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restrict__ qt_all,
                         const c128* __restrict__ y_all, const c128* __restrict__ t_all) {
+  using Cfg = WyCfg<NB, LC>;
+  constexpr int kLdv = Cfg::kLdv, kLdw = Cfg::kLdw;
+  constexpr int kJt = NB / 8;  // 8-column tiles of W
   extern __shared__ __align__(16) unsigned char wy_smem[];
-  c128* Vs = reinterpret_cast<c128*>(wy_smem);                          // [j][kWyLdv]    V[k][j] at Vs[j*ld + k]
-  c128* Wp = reinterpret_cast<c128*>(wy_smem + kWySmemV);               // [warp][e][kWyLdw] partial W
-  c128* Ts = reinterpret_cast<c128*>(wy_smem + kWySmemV + kWySmemW);    // [j][kWyLdw]
-  c128* Wf = Wp;                                                        // [e][kWyLdw] summed W   (after a sync)
-  c128* W2 = Wp + kWyEt * kWyLdw;                                       // [e][kWyLdw] W T^T
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wy_smem + kWySmemV + kWySmemW + kWySmemT);
+  c128* Vs = reinterpret_cast<c128*>(wy_smem);                              // [j][kLdv]  V[k][j] at Vs[j*ld + k]
+  c128* Wp = reinterpret_cast<c128*>(wy_smem + Cfg::kSmemV);                // [warp][e][kLdw] partial W
+  c128* Ts = reinterpret_cast<c128*>(wy_smem + Cfg::kSmemV + Cfg::kSmemW);  // [j][kLdw]
+  c128* Wf = Wp;                                                            // [e][kLdw] summed W (after a sync)
+  c128* W2 = Wp + kWyEt * kLdw;                                             // [e][kLdw] W T^T
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wy_smem + Cfg::kSmemV + Cfg::kSmemW + Cfg::kSmemT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frow = lane >> 2, q = lane & 3;
   const int64_t b = blockIdx.y;
@@ -170,7 +181,7 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
   const double* qt = qt_all + b * (int64_t)n * n;
   const c128* y = y_all + b * (int64_t)n * n;
   const int nblk = wy_blocks(n);
-  const c128* tb = t_all + b * nblk * (int64_t)(kWyNb * kWyLdw);
+  const c128* tb = t_all + b * wy_t_elems(n);
   const int ntiles = (n + 7) / 8;
   if (tid == 0) {
     wy_mbar_init(bar, 1);
@@ -179,11 +190,11 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
   __syncthreads();
 
   // Z in the accumulator layout: zr/zi[a][lc][h] = Z[e0 + 8a + frow][8c + 2q + h], c = warp + 8 lc
-  double zr[2][kWyLc][2], zi[2][kWyLc][2];
+  double zr[2][LC][2], zi[2][LC][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int lc = 0; lc < kWyLc; ++lc)
+    for (int lc = 0; lc < LC; ++lc)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int e = e0 + 8 * a + frow, k = 8 * (warp + 8 * lc) + 2 * q + h;
@@ -192,8 +203,8 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
       }
 
   for (int blk = nblk - 1; blk >= 0; --blk) {
-    const int i0 = blk * kWyNb;
-    const int kb = min(kWyNb, n - 1 - i0);
+    const int i0 = blk * NB;
+    const int kb = min(NB, n - 1 - i0);
     const int c_first = (i0 + 1) / 8;  // tiles below hold no support row of this block
     // ---- stage V and T: reflector j of the block is ONE bulk (TMA) copy of its support rows k >= i0+j+1 into
     // Vs[j][k]; the few entries between the first active tile and the support (and the rows of a short last
@@ -204,46 +215,47 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
       // the async-proxy writes by the fence.
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (lane == 0) {
-        uint32_t bytes = (uint32_t)(kWyNb * kWyLdw * sizeof(c128));
+        uint32_t bytes = (uint32_t)(NB * kLdw * sizeof(c128));
         for (int j = 0; j < kb; ++j) bytes += (uint32_t)((n - (i0 + j + 1)) * sizeof(c128));
         wy_mbar_arrive_tx(bar, bytes);
-        wy_bulk_g2s(Ts, tb + (int64_t)blk * (kWyNb * kWyLdw), (uint32_t)(kWyNb * kWyLdw * sizeof(c128)), bar);
+        wy_bulk_g2s(Ts, tb + (int64_t)blk * (NB * kLdw), (uint32_t)(NB * kLdw * sizeof(c128)), bar);
       }
       __syncwarp();
       if (lane < kb) {
         const int k0 = i0 + lane + 1;
-        wy_bulk_g2s(Vs + lane * kWyLdv + k0, y + (int64_t)(i0 + lane) * n + k0, (uint32_t)((n - k0) * sizeof(c128)), bar);
+        wy_bulk_g2s(Vs + lane * kLdv + k0, y + (int64_t)(i0 + lane) * n + k0, (uint32_t)((n - k0) * sizeof(c128)), bar);
       }
     }
-    for (int idx = tid; idx < kWyNb * 48; idx += 32 * kWyWarps) {
-      const int j = idx / 48, k = c_first * 8 + (idx - j * 48);
-      if (j < kb && k < i0 + j + 1) Vs[j * kWyLdv + k] = make_double2(0.0, 0.0);
+    constexpr int kGap = NB + 16;  // >= (i0 + NB) - 8 c_first: entries between the first active tile and a support
+    for (int idx = tid; idx < NB * kGap; idx += 32 * kWyWarps) {
+      const int j = idx / kGap, k = c_first * 8 + (idx - j * kGap);
+      if (j < kb && k < i0 + j + 1) Vs[j * kLdv + k] = make_double2(0.0, 0.0);
     }
-    if (kb < kWyNb || n < ntiles * 8) {
-      for (int idx = tid; idx < kWyNb * ntiles * 8; idx += 32 * kWyWarps) {
+    if (kb < NB || n < ntiles * 8) {
+      for (int idx = tid; idx < NB * ntiles * 8; idx += 32 * kWyWarps) {
         const int j = idx / (ntiles * 8), k = idx - j * (ntiles * 8);
-        if (k >= c_first * 8 && (j >= kb || k >= n)) Vs[j * kWyLdv + k] = make_double2(0.0, 0.0);
+        if (k >= c_first * 8 && (j >= kb || k >= n)) Vs[j * kLdv + k] = make_double2(0.0, 0.0);
       }
     }
     wy_mbar_wait(bar, (uint32_t)((nblk - 1 - blk) & 1));
     __syncthreads();
 
     // ---- W partial = Z conj(V) over the warp's own column tiles
-    double wr[2][4][2], wi[2][4][2];
+    double wr[2][kJt][2], wi[2][kJt][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int jt = 0; jt < 4; ++jt) wr[a][jt][0] = wr[a][jt][1] = wi[a][jt][0] = wi[a][jt][1] = 0.0;
+      for (int jt = 0; jt < kJt; ++jt) wr[a][jt][0] = wr[a][jt][1] = wi[a][jt][0] = wi[a][jt][1] = 0.0;
 #pragma unroll
-    for (int lc = 0; lc < kWyLc; ++lc) {
+    for (int lc = 0; lc < LC; ++lc) {
       const int c = warp + 8 * lc;
       if (c < c_first || c >= ntiles) continue;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const c128* vcol = Vs + frow * kWyLdv + 8 * c + 2 * q + h;  // B[k-slot q][n = frow] of column tile jt
+        const c128* vcol = Vs + frow * kLdv + 8 * c + 2 * q + h;  // B[k-slot q][n = frow] of column tile jt
 #pragma unroll
-        for (int jt = 0; jt < 4; ++jt) {
-          const c128 v = vcol[8 * jt * kWyLdv];
+        for (int jt = 0; jt < kJt; ++jt) {
+          const c128 v = vcol[8 * jt * kLdv];
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
             // W = Z conj(V): Wre += Zre Vre + Zim Vim ; Wim += Zim Vre - Zre Vim
@@ -256,61 +268,62 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
       }
     }
     {
-      c128* mine = Wp + warp * (kWyEt * kWyLdw);
+      c128* mine = Wp + warp * (kWyEt * kLdw);
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int jt = 0; jt < 4; ++jt)
+        for (int jt = 0; jt < kJt; ++jt)
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            mine[(8 * a + frow) * kWyLdw + 8 * jt + 2 * q + h] = make_double2(wr[a][jt][h], wi[a][jt][h]);
+            mine[(8 * a + frow) * kLdw + 8 * jt + 2 * q + h] = make_double2(wr[a][jt][h], wi[a][jt][h]);
     }
     __syncthreads();
-    // ---- W = sum of the partials (2 entries per thread), then W2 = W T^T
-    c128 s[2];
+    // ---- W = sum of the partials (kWyEt * NB entries over 256 threads), then W2 = W T^T
+    constexpr int kEnt = kWyEt * NB / (32 * kWyWarps);  // 2 (NB = 32) or 1 (NB = 16)
+    c128 s[kEnt];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int ent = tid + 256 * u, e = ent >> 5, j = ent & 31;
+    for (int u = 0; u < kEnt; ++u) {
+      const int ent = tid + 256 * u, e = ent / NB, j = ent % NB;
       c128 acc = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int w = 0; w < kWyWarps; ++w) acc = cadd(acc, Wp[w * (kWyEt * kWyLdw) + e * kWyLdw + j]);
+      for (int w = 0; w < kWyWarps; ++w) acc = cadd(acc, Wp[w * (kWyEt * kLdw) + e * kLdw + j]);
       s[u] = acc;
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kEnt; ++u) {
       const int ent = tid + 256 * u;
-      Wf[(ent >> 5) * kWyLdw + (ent & 31)] = s[u];
+      Wf[(ent / NB) * kLdw + (ent % NB)] = s[u];
     }
     __syncthreads();
-    {
-      // W2 = W T^T as one 8 x 8 complex tile per warp: rows a = warp / 4, columns jt = warp % 4, K = 32
-      const int a = warp >> 2, jt = warp & 3;
+    if (warp < 2 * kJt) {
+      // W2 = W T^T as one 8 x 8 complex tile per warp: rows a = warp / kJt, columns jt = warp % kJt, K = NB
+      const int a = warp / kJt, jt = warp % kJt;
       double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};
 #pragma unroll
-      for (int ks = 0; ks < kWyNb / 4; ++ks) {
-        const c128 wv = Wf[(8 * a + frow) * kWyLdw + 4 * ks + q];   // A[row = frow][slot q] = W[e][l = 4ks + q]
-        const c128 tv = Ts[(8 * jt + frow) * kWyLdw + 4 * ks + q];  // B[slot q][n = frow] = T[j = 8jt + frow][l]
+      for (int ks = 0; ks < NB / 4; ++ks) {
+        const c128 wv = Wf[(8 * a + frow) * kLdw + 4 * ks + q];   // A[row = frow][slot q] = W[e][l = 4ks + q]
+        const c128 tv = Ts[(8 * jt + frow) * kLdw + 4 * ks + q];  // B[slot q][n = frow] = T[j = 8jt + frow][l]
         wy_dmma(ar[0], ar[1], wv.x, tv.x);
         wy_dmma(ar[0], ar[1], -wv.y, tv.y);
         wy_dmma(ai[0], ai[1], wv.x, tv.y);
         wy_dmma(ai[0], ai[1], wv.y, tv.x);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) W2[(8 * a + frow) * kWyLdw + 8 * jt + 2 * q + h] = make_double2(ar[h], ai[h]);
+      for (int h = 0; h < 2; ++h) W2[(8 * a + frow) * kLdw + 8 * jt + 2 * q + h] = make_double2(ar[h], ai[h]);
     }
     __syncthreads();
     // ---- Z -= W2 V^T on the warp's own column tiles
 #pragma unroll
-    for (int js = 0; js < kWyNb / 4; ++js) {
+    for (int js = 0; js < NB / 4; ++js) {
       c128 wa[2];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) wa[a] = W2[(8 * a + frow) * kWyLdw + 4 * js + q];  // A[row = frow][k-slot q]
+      for (int a = 0; a < 2; ++a) wa[a] = W2[(8 * a + frow) * kLdw + 4 * js + q];  // A[row = frow][k-slot q]
 #pragma unroll
-      for (int lc = 0; lc < kWyLc; ++lc) {
+      for (int lc = 0; lc < LC; ++lc) {
         const int c = warp + 8 * lc;
         if (c < c_first || c >= ntiles) continue;
-        const c128 v = Vs[(4 * js + q) * kWyLdv + 8 * c + frow];  // B[k-slot q][n = frow] = V[k = 8c+frow][j]
+        const c128 v = Vs[(4 * js + q) * kLdv + 8 * c + frow];  // B[k-slot q][n = frow] = V[k = 8c+frow][j]
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           // Zre -= W2re Vre - W2im Vim ; Zim -= W2re Vim + W2im Vre
@@ -329,12 +342,27 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int lc = 0; lc < kWyLc; ++lc)
+    for (int lc = 0; lc < LC; ++lc)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int e = e0 + 8 * a + frow, k = 8 * (warp + 8 * lc) + 2 * q + h;
         if (e < n && k < n) out[(int64_t)e * n + k] = make_double2(zr[a][lc][h], -zi[a][lc][h]);
       }
+}
+
+template <int NB, int LC>
+int launch_back_wy(int n, int64_t count, c128* A, const double* qt, const c128* y, const c128* tau, c128* wy_t,
+                   cudaStream_t st) {
+  using Cfg = WyCfg<NB, LC>;
+  cudaError_t e = cudaFuncSetAttribute(backtransform_wy_kernel<NB, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::kSmem);
+  if (e != cudaSuccess) return (int)e;
+  wy_tfactor_kernel<NB><<<dim3((unsigned)wy_blocks(n), (unsigned)count), 256, 0, st>>>(n, y, tau, wy_t);
+  SQB_LAUNCH_CHECK();
+  backtransform_wy_kernel<NB, LC><<<dim3((unsigned)((n + kWyEt - 1) / kWyEt), (unsigned)count), 32 * kWyWarps, Cfg::kSmem,
+                                    st>>>(n, A, qt, y, wy_t);
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
 }
 
 }  // namespace

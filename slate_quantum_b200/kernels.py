@@ -284,7 +284,7 @@ def _eigh_launches_per_chunk(n: int) -> int:
 
     if os.environ.get("SQB_EIGH_TRIDIAG_SOLVER") == "ql":
         return 4  # ql + replay
-    wy = 1 if (128 < n <= 256 and os.environ.get("SQB_BACKTRANSFORM") != "reflector") else 0  # T-factor kernel
+    wy = 1 if (64 < n <= 512 and os.environ.get("SQB_BACKTRANSFORM") != "reflector") else 0  # T-factor kernel
     return 2 + wy + 1 + 2 * _dc_depth(n)  # leaves + (set-up, GEMM) per merge level
 
 
