@@ -956,9 +956,14 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     }
 
     if (eigh_use_wy(n)) {
-      if (n <= 128) rc = launch_back_wy<32, 2>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
-      else if (n <= 256) rc = launch_back_wy<32, 4>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
-      else rc = launch_back_wy<16, 8>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      // n <= 256: 16-reflector blocks and 8 eigenvectors per CTA keep the CTA below half an SM (two CTAs overlap
+      // each other's staging / reduction phases: 132.4 vs 135.0 ms at cfg3); n <= 512: 16 eigenvectors per CTA
+      static const int wy_variant = getenv("SQB_WY_VARIANT") ? atoi(getenv("SQB_WY_VARIANT")) : 1;
+      if (n <= 128 && wy_variant == 1) rc = launch_back_wy<16, 2, 1>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else if (n <= 128) rc = launch_back_wy<32, 2, 2>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else if (n <= 256 && wy_variant == 1) rc = launch_back_wy<16, 4, 1>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else if (n <= 256) rc = launch_back_wy<32, 4, 2>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
+      else rc = launch_back_wy<16, 8, 2>(n, cnt, Ab, ws.qt, ws.y, ws.tau, ws.wy_t, ls);
     } else if (n <= 64) rc = launch_back<4, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_back<8, 16>(n, cnt, Ab, ws, ls);
     else if (n <= 256) rc = launch_back<16, 16>(n, cnt, Ab, ws, ls);

@@ -23,25 +23,24 @@
 
 namespace {
 
-constexpr int kWyEt = 16;          // eigenvectors per CTA
 constexpr int kWyWarps = 8;
 
-// NB = reflectors per block, LC = 8-column tiles per warp (the kernel covers n <= 64 LC)
-template <int NB, int LC>
+// NB = reflectors per block, LC = 8-column tiles per warp (the kernel covers n <= 64 LC), ETT = 8-row tiles of
+// eigenvectors per CTA
+template <int NB, int LC, int ETT>
 struct WyCfg {
+  static constexpr int kEt = 8 * ETT;
   static constexpr int kMaxN = 64 * LC;
   static constexpr int kLdv = kMaxN + 1;  // c128 row stride of Vs[j][k] (== 1 mod 8: conflict-free fragment loads)
   static constexpr int kLdw = NB + 1;     // row stride of W / W2 / T (== 1 mod 8)
   static constexpr size_t kSmemV = (size_t)NB * kLdv * sizeof(c128);
-  static constexpr size_t kSmemW = (size_t)kWyWarps * kWyEt * kLdw * sizeof(c128);  // per-warp partial W
+  static constexpr size_t kSmemW = (size_t)kWyWarps * kEt * kLdw * sizeof(c128);  // per-warp partial W
   static constexpr size_t kSmemT = (size_t)NB * kLdw * sizeof(c128);
   static constexpr size_t kSmem = kSmemV + kSmemW + kSmemT + 64;
 };
 
-__host__ __device__ inline int wy_nb(int n) { return n <= 256 ? 32 : 16; }
-__host__ __device__ inline int wy_blocks(int n) { return (n - 1 + wy_nb(n) - 1) / wy_nb(n); }
-// c128 elements of the T factors of one matrix: wy_blocks(n) padded [NB][NB+1] blocks
-__host__ __device__ inline size_t wy_t_elems(int n) { return (size_t)wy_blocks(n) * wy_nb(n) * (wy_nb(n) + 1); }
+// c128 elements reserved per matrix for the T factors: ceil((n-1)/NB) padded [NB][NB+1] blocks, NB <= 32
+__host__ __device__ inline size_t wy_t_elems(int n) { return (size_t)((n - 1 + 31) / 32 + 1) * 32 * 33; }
 
 // ------------------------------------------------------------------------------------------------
 // T factors: one CTA per (block, matrix).  G = V^H V (upper triangle) in 4 x 4 register tiles per warp, then the
@@ -123,7 +122,8 @@ wy_tfactor_kernel(int n, const c128* __restrict__ y_all, const c128* __restrict_
   }
   __syncthreads();
   // padded [NB][NB+1] rows: the back-transformation copies a block's T with ONE bulk copy into the same layout
-  c128* out = t_all + b * wy_t_elems(n) + (int64_t)blk * (NB * (NB + 1));
+  const int nblk_all = (n - 1 + NB - 1) / NB;
+  c128* out = t_all + (b * nblk_all + blk) * (int64_t)(NB * (NB + 1));
   for (int idx = threadIdx.x; idx < NB * (NB + 1); idx += blockDim.x) out[idx] = (&t[0][0])[idx];
 }
 
@@ -160,12 +160,12 @@ __device__ __forceinline__ void wy_bulk_g2s(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-template <int NB, int LC>
-__global__ void __launch_bounds__(32 * kWyWarps, 1)
+template <int NB, int LC, int ETT>
+__global__ void __launch_bounds__(32 * kWyWarps, ETT == 1 ? 2 : 1)
 backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restrict__ qt_all,
                         const c128* __restrict__ y_all, const c128* __restrict__ t_all) {
-  using Cfg = WyCfg<NB, LC>;
-  constexpr int kLdv = Cfg::kLdv, kLdw = Cfg::kLdw;
+  using Cfg = WyCfg<NB, LC, ETT>;
+  constexpr int kLdv = Cfg::kLdv, kLdw = Cfg::kLdw, kWyEt = Cfg::kEt;
   constexpr int kJt = NB / 8;  // 8-column tiles of W
   extern __shared__ __align__(16) unsigned char wy_smem[];
   c128* Vs = reinterpret_cast<c128*>(wy_smem);                              // [j][kLdv]  V[k][j] at Vs[j*ld + k]
@@ -180,8 +180,8 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
   const int e0 = blockIdx.x * kWyEt;
   const double* qt = qt_all + b * (int64_t)n * n;
   const c128* y = y_all + b * (int64_t)n * n;
-  const int nblk = wy_blocks(n);
-  const c128* tb = t_all + b * wy_t_elems(n);
+  const int nblk = (n - 1 + NB - 1) / NB;
+  const c128* tb = t_all + b * nblk * (int64_t)(NB * kLdw);
   const int ntiles = (n + 7) / 8;
   if (tid == 0) {
     wy_mbar_init(bar, 1);
@@ -190,9 +190,9 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
   __syncthreads();
 
   // Z in the accumulator layout: zr/zi[a][lc][h] = Z[e0 + 8a + frow][8c + 2q + h], c = warp + 8 lc
-  double zr[2][LC][2], zi[2][LC][2];
+  double zr[ETT][LC][2], zi[ETT][LC][2];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < ETT; ++a)
 #pragma unroll
     for (int lc = 0; lc < LC; ++lc)
 #pragma unroll
@@ -241,9 +241,9 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
     __syncthreads();
 
     // ---- W partial = Z conj(V) over the warp's own column tiles
-    double wr[2][kJt][2], wi[2][kJt][2];
+    double wr[ETT][kJt][2], wi[ETT][kJt][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < ETT; ++a)
 #pragma unroll
       for (int jt = 0; jt < kJt; ++jt) wr[a][jt][0] = wr[a][jt][1] = wi[a][jt][0] = wi[a][jt][1] = 0.0;
 #pragma unroll
@@ -257,7 +257,7 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
         for (int jt = 0; jt < kJt; ++jt) {
           const c128 v = vcol[8 * jt * kLdv];
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
+          for (int a = 0; a < ETT; ++a) {
             // W = Z conj(V): Wre += Zre Vre + Zim Vim ; Wim += Zim Vre - Zre Vim
             wy_dmma(wr[a][jt][0], wr[a][jt][1], zr[a][lc][h], v.x);
             wy_dmma(wr[a][jt][0], wr[a][jt][1], zi[a][lc][h], v.y);
@@ -270,7 +270,7 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
     {
       c128* mine = Wp + warp * (kWyEt * kLdw);
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < ETT; ++a)
 #pragma unroll
         for (int jt = 0; jt < kJt; ++jt)
 #pragma unroll
@@ -279,24 +279,27 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
     }
     __syncthreads();
     // ---- W = sum of the partials (kWyEt * NB entries over 256 threads), then W2 = W T^T
-    constexpr int kEnt = kWyEt * NB / (32 * kWyWarps);  // 2 (NB = 32) or 1 (NB = 16)
+    constexpr int kTotal = kWyEt * NB;
+    constexpr int kEnt = (kTotal + 32 * kWyWarps - 1) / (32 * kWyWarps);
     c128 s[kEnt];
 #pragma unroll
     for (int u = 0; u < kEnt; ++u) {
       const int ent = tid + 256 * u, e = ent / NB, j = ent % NB;
       c128 acc = make_double2(0.0, 0.0);
+      if (ent < kTotal) {
 #pragma unroll
-      for (int w = 0; w < kWyWarps; ++w) acc = cadd(acc, Wp[w * (kWyEt * kLdw) + e * kLdw + j]);
+        for (int w = 0; w < kWyWarps; ++w) acc = cadd(acc, Wp[w * (kWyEt * kLdw) + e * kLdw + j]);
+      }
       s[u] = acc;
     }
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kEnt; ++u) {
       const int ent = tid + 256 * u;
-      Wf[(ent / NB) * kLdw + (ent % NB)] = s[u];
+      if (ent < kTotal) Wf[(ent / NB) * kLdw + (ent % NB)] = s[u];
     }
     __syncthreads();
-    if (warp < 2 * kJt) {
+    if (warp < ETT * kJt) {
       // W2 = W T^T as one 8 x 8 complex tile per warp: rows a = warp / kJt, columns jt = warp % kJt, K = NB
       const int a = warp / kJt, jt = warp % kJt;
       double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};
@@ -316,16 +319,16 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
     // ---- Z -= W2 V^T on the warp's own column tiles
 #pragma unroll
     for (int js = 0; js < NB / 4; ++js) {
-      c128 wa[2];
+      c128 wa[ETT];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) wa[a] = W2[(8 * a + frow) * kLdw + 4 * js + q];  // A[row = frow][k-slot q]
+      for (int a = 0; a < ETT; ++a) wa[a] = W2[(8 * a + frow) * kLdw + 4 * js + q];  // A[row = frow][k-slot q]
 #pragma unroll
       for (int lc = 0; lc < LC; ++lc) {
         const int c = warp + 8 * lc;
         if (c < c_first || c >= ntiles) continue;
         const c128 v = Vs[(4 * js + q) * kLdv + 8 * c + frow];  // B[k-slot q][n = frow] = V[k = 8c+frow][j]
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < ETT; ++a) {
           // Zre -= W2re Vre - W2im Vim ; Zim -= W2re Vim + W2im Vre
           wy_dmma(zr[a][lc][0], zr[a][lc][1], -wa[a].x, v.x);
           wy_dmma(zr[a][lc][0], zr[a][lc][1], wa[a].y, v.y);
@@ -340,7 +343,7 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
   // rows = eigenvectors of H: the conjugate undoes the conj(H) view of the tridiagonalisation
   c128* out = A_all + b * (int64_t)n * n;
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < ETT; ++a)
 #pragma unroll
     for (int lc = 0; lc < LC; ++lc)
 #pragma unroll
@@ -350,17 +353,17 @@ backtransform_wy_kernel(int n, c128* __restrict__ A_all, const double* __restric
       }
 }
 
-template <int NB, int LC>
+template <int NB, int LC, int ETT>
 int launch_back_wy(int n, int64_t count, c128* A, const double* qt, const c128* y, const c128* tau, c128* wy_t,
                    cudaStream_t st) {
-  using Cfg = WyCfg<NB, LC>;
-  cudaError_t e = cudaFuncSetAttribute(backtransform_wy_kernel<NB, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  using Cfg = WyCfg<NB, LC, ETT>;
+  cudaError_t e = cudaFuncSetAttribute(backtransform_wy_kernel<NB, LC, ETT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::kSmem);
   if (e != cudaSuccess) return (int)e;
-  wy_tfactor_kernel<NB><<<dim3((unsigned)wy_blocks(n), (unsigned)count), 256, 0, st>>>(n, y, tau, wy_t);
+  wy_tfactor_kernel<NB><<<dim3((unsigned)((n - 1 + NB - 1) / NB), (unsigned)count), 256, 0, st>>>(n, y, tau, wy_t);
   SQB_LAUNCH_CHECK();
-  backtransform_wy_kernel<NB, LC><<<dim3((unsigned)((n + kWyEt - 1) / kWyEt), (unsigned)count), 32 * kWyWarps, Cfg::kSmem,
-                                    st>>>(n, A, qt, y, wy_t);
+  backtransform_wy_kernel<NB, LC, ETT><<<dim3((unsigned)((n + Cfg::kEt - 1) / Cfg::kEt), (unsigned)count),
+                                         32 * kWyWarps, Cfg::kSmem, st>>>(n, A, qt, y, wy_t);
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }
