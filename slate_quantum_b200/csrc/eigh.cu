@@ -91,6 +91,30 @@ __device__ __forceinline__ double block_sum(double v, double* scratch, int nwarp
   return scratch[32];
 }
 
+// two sums at once (one barrier pair instead of two); scratch: >= 66 doubles
+__device__ __forceinline__ double2 block_sum2(double a, double b, double* scratch, int nwarps) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    scratch[w] = a;
+    scratch[32 + w] = b;
+  }
+  __syncthreads();
+  if (w == 0) {
+    double ta = lane < nwarps ? scratch[lane] : 0.0;
+    double tb = lane < nwarps ? scratch[32 + lane] : 0.0;
+    ta = warp_sum(ta);
+    tb = warp_sum(tb);
+    if (lane == 0) {
+      scratch[64] = ta;
+      scratch[65] = tb;
+    }
+  }
+  __syncthreads();
+  return make_double2(scratch[64], scratch[65]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // (1) Householder tridiagonalisation.  Threads = 256*RG; warp w: row group rg = w % RG, column group
 // cg = w / RG (8 column groups).  Lane rows: r = (c*RG + rg)*32 + lane, c < NR.
@@ -116,7 +140,8 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
   c128* red = vn + n;                           // [8][n] partial A22*v sums per column group (rows >= column)
   c128* redc = red + 8 * n;                     // [RG][n] mirrored (upper triangle) contributions per column
   double* scratch = reinterpret_cast<double*>(redc + RG * n);  // [40]
-  c128* res = reinterpret_cast<c128*>(scratch + 40);            // packed lower triangle of columns >= jres
+  double* scratch2 = scratch + 40;                              // [72] block_sum2
+  c128* res = reinterpret_cast<c128*>(scratch + 112);           // packed lower triangle of columns >= jres
   // scalars: scratch[34..39]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rg = warp % RG, cg = warp / RG;
@@ -294,8 +319,8 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
       dr = p.x * v.x + p.y * v.y;
       di = p.x * v.y - p.y * v.x;
     }
-    const double dot_r = block_sum(dr, scratch, kWarps);
-    const double dot_i = block_sum(di, scratch, kWarps);
+    const double2 dot_ri = block_sum2(dr, di, scratch2, kWarps);
+    const double dot_r = dot_ri.x, dot_i = dot_ri.y;
     if (r < n) {
       // alpha2 = -0.5 * tau * dot
       const c128 al = cscale(cmul(tau, make_double2(dot_r, dot_i)), -0.5);
@@ -850,7 +875,7 @@ void carve(EighWs& ws, void* base, int n, int64_t chunk) {
 
 template <int NR, int RG>
 int launch_tridiag(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st) {
-  const size_t vec = (size_t)(3 + 8 + RG) * n * sizeof(c128) + 40 * sizeof(double);
+  const size_t vec = (size_t)(3 + 8 + RG) * n * sizeof(c128) + 112 * sizeof(double);
   // resident columns: as many trailing columns as fit in the 227 KB opt-in limit next to the vectors; small
   // matrices take only what they need so that several CTAs share an SM
   const size_t budget = 232448 - 1024;
