@@ -270,13 +270,17 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
     // (B2) resident columns: the same update out of shared memory; the lane's rows of vo / wo / vn are hoisted
     // into registers so that an element costs one 16 B shared load and one 16 B shared store
     if (j < n) {
-      c128 vor[NR], wor[NR], vnr[NR];
+      // NR <= 4: hoisted (48 registers); NR = 8 (n > 256) would spill, it reads the vectors from shared memory
+      constexpr bool kHoist = NR <= 4;
+      c128 vor[kHoist ? NR : 1], wor[kHoist ? NR : 1], vnr[kHoist ? NR : 1];
+      if (kHoist) {
 #pragma unroll
-      for (int c = 0; c < NR; ++c) {
-        const bool in = rows[c] < n;
-        vor[c] = in ? vo[rows[c]] : make_double2(0.0, 0.0);
-        wor[c] = in ? wo[rows[c]] : make_double2(0.0, 0.0);
-        vnr[c] = in ? vn[rows[c]] : make_double2(0.0, 0.0);
+        for (int c = 0; c < NR; ++c) {
+          const bool in = rows[c] < n;
+          vor[kHoist ? c : 0] = in ? vo[rows[c]] : make_double2(0.0, 0.0);
+          wor[kHoist ? c : 0] = in ? wo[rows[c]] : make_double2(0.0, 0.0);
+          vnr[kHoist ? c : 0] = in ? vn[rows[c]] : make_double2(0.0, 0.0);
+        }
       }
       for (; j < n; j += 8) {
         c128* col = res + tri_off(n, jres, j);
@@ -286,12 +290,12 @@ tridiag_kernel(int n, int jres, c128* __restrict__ A_all, EighWs ws) {
         for (int c = 0; c < NR; ++c) {
           if (rows[c] >= j && rows[c] < n) {
             c128 a = col[rows[c]];
-            c128 t = cmul(vor[c], cw);
-            cfma(t, wor[c], cv);
+            c128 t = cmul(kHoist ? vor[kHoist ? c : 0] : vo[rows[c]], cw);
+            cfma(t, kHoist ? wor[kHoist ? c : 0] : wo[rows[c]], cv);
             a = csub(a, t);
             col[rows[c]] = a;
             cfma(acc[c], a, vj);
-            if (rows[c] > j) cfmac(dotj, a, vnr[c]);
+            if (rows[c] > j) cfmac(dotj, a, kHoist ? vnr[kHoist ? c : 0] : vn[rows[c]]);
           }
         }
         dotj.x = warp_sum(dotj.x);
