@@ -526,6 +526,49 @@ def run_ours(args) -> None:
             "evolved state copied back to pinned host staging buffers (PCIe-bound: the state list is "
             f"{T * row_e / 1e9:.1f} GB per rank)",
         }
+        if e2e_position:
+            # Same step when the caller wants OBSERVABLES of the evolved states instead of the states (what the
+            # reference's examples plot): operator.measure's moments (K6) are reduced on the GPU and [T, 5]
+            # doubles per axis come back instead of the state list.  Extra figure, not the contract's `e2e`.
+            big = cfg.supercell
+            lengths = [float(np.linalg.norm(cfg.vectors()[a])) * cfg.repeat[a] for a in range(cfg.nd)]
+            mom_host = torch.empty((cfg.nd, T, 5), dtype=torch.float64).pin_memory()
+
+            def e2e_observables_step() -> None:
+                tb = table_h.cuda(non_blocking=True)
+                ps = psi_h.cuda(non_blocking=True)
+                tm = times_h.cuda(non_blocking=True)
+                solver.build(tb, out=h_buf)
+                solver.diagonalise()
+                eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
+                solver.fold(out=folded_buf)
+                c = solver.project(ps)
+                for t0 in range(0, T, e_tile):
+                    tt = min(e_tile, T - t0)
+                    solver.evolve_cell(c, tm[t0 : t0 + tt], out=pos_tmp[:tt], uniform_dt=dt_uniform)
+                    pos = solver.cell_to_position(pos_tmp[:tt], out=e_src[:tt])
+                    for a in range(cfg.nd):
+                        mom = kernels.measure_moments(pos, big, a, lengths[a] / big[a], lengths[a])
+                        mom_host[a, t0 : t0 + tt].copy_(mom, non_blocking=True)
+
+            e2e_observables_step()
+            sync_all()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(n_e2e):
+                e2e_observables_step()
+            b.record()
+            sync_all()
+            obs_ms = a.elapsed_time(b) / n_e2e
+            e2e["observables_only"] = {
+                "value": n_k_global / (obs_ms * 1e-3),
+                "unit": UNIT,
+                "ms_per_step": obs_ms,
+                "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(eig_host.numel() * 8 + mom_host.numel() * 8),
+                "note": "same host-buffer step, but norm / <x> / <x^2> / scattering phase of every evolved state along "
+                "every axis (operator.measure, K6) are returned instead of the states",
+            }
 
     if rank == 0:
         flops_evolve = 8.0 * n * n * T * n_k_local
