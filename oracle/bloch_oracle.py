@@ -629,3 +629,46 @@ def coherent_state(
     phi = np.einsum("ij,i->j", disp, np.asarray(k_0, dtype=np.float64)[:nd])
     data = np.exp(1j * phi - np.square(distance) / 2)
     return data / np.sqrt(np.sum(np.square(np.abs(data))))
+
+
+# momentum-space observables (operator/_measure.py:307-420).  The k points are the FFT-ordered integer frequencies
+# times dk (pinned: the k-operator literal of tests/test_operator.py:184-196); only orthogonal axes are restated.
+def stacked_k_points(
+    delta_x: np.ndarray, shape: Sequence[int], offset: Sequence[float] | None = None, wrapped: bool = False
+) -> np.ndarray:
+    """Cartesian k of every momentum-basis index [nd, prod(shape)] (fundamental_stacked_k_points), optionally
+    displaced by ``offset`` and folded into the first Brillouin zone [-K/2, K/2) of the grid, K_a = N_a dk_a."""
+    nd = len(shape)
+    dk = stacked_dk(np.asarray(delta_x, dtype=np.float64)[:nd, :nd])
+    points = np.einsum("ij,ik->jk", dk, stacked_nk(shape).astype(np.float64))
+    if offset is not None:
+        points = points + np.asarray(offset, dtype=np.float64)[:nd, None]
+    if wrapped:
+        big = dk * np.asarray(shape, dtype=np.float64)[:, None]  # rows = delta_k vectors
+        frac = np.linalg.solve(big.T, points)
+        points = points - np.einsum("ij,ik->jk", big, np.floor(frac + 0.5))
+    return points
+
+
+def measure_all_k(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_k (operator/_measure.py:323-336): <k_axis> of every normalised position-basis state."""
+    momentum = position_to_momentum(np.atleast_2d(states), shape)
+    return _normalised_density(momentum) @ stacked_k_points(delta_x, shape)[axis]
+
+
+def measure_all_variance_k(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_variance_k (operator/_measure.py:361-378, variance_k :338-358): <(k - <k>)^2> with the
+    difference folded into the first Brillouin zone."""
+    momentum = position_to_momentum(np.atleast_2d(states), shape)
+    density = _normalised_density(momentum)
+    centre = density @ stacked_k_points(delta_x, shape)[axis]
+    out = np.empty(len(density))
+    for i, k0 in enumerate(centre):
+        offset = [-k0 if a == axis else 0.0 for a in range(len(shape))]
+        out[i] = density[i] @ np.square(stacked_k_points(delta_x, shape, offset, True)[axis])
+    return out
+
+
+def measure_all_uncertainty(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
+    """operator.measure.all_uncertainty (operator/_measure.py:381-420): sqrt(var_x var_k)."""
+    return np.sqrt(measure_all_variance_x(states, delta_x, shape, axis) * measure_all_variance_k(states, delta_x, shape, axis))

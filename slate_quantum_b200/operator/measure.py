@@ -1,4 +1,4 @@
-"""Observables on states / state lists (reference: slate_quantum/operator/_measure.py:105-305).
+"""Observables on states / state lists (reference: slate_quantum/operator/_measure.py:105-420).
 
 Every quantity here is a diagonal expectation in the position basis, ``sum_x f(x) |psi(x)|^2 / sum_x |psi(x)|^2``
 (the reference normalises with ``state.normalize_each`` and contracts a dense diagonal operator).  One CUDA
@@ -79,6 +79,76 @@ def _all_variance_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch
     return mom[:, 2] / mom[:, 0]
 
 
+def _momentum_data(states: Array, space: TupleMetadata) -> torch.Tensor:
+    """[lead, M] device tensor of the states in the transformed (momentum) basis of ``space`` (K4 on the GPU)."""
+    momentum = _basis.transformed_from_metadata(space).upcast()
+    if isinstance(states, StateList):
+        converted = states.with_state_basis(momentum)
+    else:
+        converted = states.with_basis(momentum)
+    data = converted.device_data
+    if not data.is_complex():
+        data = data.to(torch.complex128)
+    return data.reshape(-1, space.fundamental_size).contiguous()
+
+
+def _k_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
+    grid, spacing, _ = _axis_geometry(space, axis)  # also checks orthogonality
+    dk = 2 * np.pi / (spacing * grid[axis])
+    return grid, dk, dk * grid[axis]
+
+
+def _all_k(mom_data: torch.Tensor, space: TupleMetadata, axis: int) -> torch.Tensor:
+    # index i <-> k = i dk folded into [-K/2, K/2): the FFT order of the reference's k points
+    grid, dk, big_k = _k_geometry(space, axis)
+    mom = kernels.measure_moments(mom_data, grid, axis, dk, big_k, None, True)
+    return mom[:, 1] / mom[:, 0]
+
+
+def _all_variance_k(mom_data: torch.Tensor, space: TupleMetadata, axis: int) -> torch.Tensor:
+    grid, dk, big_k = _k_geometry(space, axis)
+    centre = _all_k(mom_data, space, axis)
+    mom = kernels.measure_moments(mom_data, grid, axis, dk, big_k, (-centre).contiguous(), True)
+    return mom[:, 2] / mom[:, 0]
+
+
+def all_k(states: StateList, *, axis: int) -> Array:
+    """Momentum of all states (reference operator/_measure.py:323-336)."""
+    space = states.basis.metadata().children[1]
+    return _list_array(states, _all_k(_momentum_data(states, space), space, axis))
+
+
+def all_variance_k(states: StateList, *, axis: int) -> Array:
+    """<(K - <K>)^2> of all states (reference operator/_measure.py:361-378)."""
+    space = states.basis.metadata().children[1]
+    return _list_array(states, _all_variance_k(_momentum_data(states, space), space, axis))
+
+
+def all_uncertainty(states: StateList, *, axis: int) -> Array:
+    """sqrt(var_x var_k) of all states (reference operator/_measure.py:400-420)."""
+    space = states.basis.metadata().children[1]
+    var_x = _all_variance_x(_position_data(states, space), space, axis)
+    var_k = _all_variance_k(_momentum_data(states, space), space, axis)
+    return _list_array(states, torch.sqrt(var_x * var_k))
+
+
+def k(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:307-320."""
+    space = state.basis.metadata()
+    return float(_all_k(_momentum_data(state, space), space, axis)[0])
+
+
+def variance_k(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:338-358."""
+    space = state.basis.metadata()
+    return float(_all_variance_k(_momentum_data(state, space), space, axis)[0])
+
+
+def uncertainty(state: State, *, axis: int) -> float:
+    """reference operator/_measure.py:381-397."""
+    return float(np.sqrt(variance_x(state, axis=axis) * variance_k(state, axis=axis)))
+
+
 def all_x(states: StateList, *, axis: int, offset: float = 0, wrapped: bool = False) -> Array:
     """Position of all states (reference operator/_measure.py:191-210)."""
     space = states.basis.metadata().children[1]
@@ -129,11 +199,17 @@ def coherent_width(state: State, *, axis: int) -> float:
 
 __all__: list[Any] = [
     "all_coherent_width",
+    "all_k",
+    "all_uncertainty",
+    "all_variance_k",
     "all_periodic_x",
     "all_variance_x",
     "all_x",
     "coherent_width",
+    "k",
     "periodic_x",
+    "uncertainty",
+    "variance_k",
     "variance_x",
     "x",
 ]

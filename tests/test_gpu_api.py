@@ -333,3 +333,35 @@ def test_dense_hamiltonian_schrodinger_evolution_and_observables(cuda, shape):
         np.testing.assert_allclose(got, o.measure_all_periodic_x(ref, vectors, shape, axis), atol=1e-8)
         got_w = operator.measure.all_coherent_width(in_position_list, axis=axis).raw_data
         np.testing.assert_allclose(got_w, o.measure_all_coherent_width(ref, vectors, shape, axis), atol=1e-8)
+
+
+def test_measure_api_momentum_observables(cuda):
+    """operator.measure.{k, all_k, all_variance_k, all_uncertainty} (reference operator/_measure.py:307-420) against
+    the oracle and the analytic values of a minimum-uncertainty wavepacket."""
+    from slate_quantum_b200 import operator, state
+    from slate_quantum_b200.core.metadata import spaced_volume_metadata_from_stacked_delta_x
+
+    shape = (48, 40)
+    lengths = (30.0, 24.0)
+    metadata = spaced_volume_metadata_from_stacked_delta_x(
+        (np.array([lengths[0], 0.0]), np.array([0.0, lengths[1]])), shape
+    )
+    delta_x = np.diag(lengths)
+    k0 = (2 * np.pi * 5 / lengths[0], -2 * np.pi * 3 / lengths[1])
+    sigmas = [(1.1, 1.4), (0.9, 1.2), (1.5, 1.0)]
+    states = state.StateList.from_states(
+        [state.build.coherent(metadata, (11.0, 9.0), k0, sg) for sg in sigmas]
+    )
+    raw = np.array([s.raw_data for s in states])
+    for axis in (0, 1):
+        got_k = operator.measure.all_k(states, axis=axis).raw_data
+        np.testing.assert_allclose(got_k, o.measure_all_k(raw, delta_x, shape, axis), atol=1e-10)
+        np.testing.assert_allclose(got_k, k0[axis], atol=1e-4)  # analytic value, up to the grid's aliasing
+        got_v = operator.measure.all_variance_k(states, axis=axis).raw_data
+        np.testing.assert_allclose(got_v, o.measure_all_variance_k(raw, delta_x, shape, axis), rtol=1e-9)
+        np.testing.assert_allclose(got_v, [1 / (2 * sg[axis] ** 2) for sg in sigmas], rtol=1e-3)
+        got_u = operator.measure.all_uncertainty(states, axis=axis).raw_data
+        np.testing.assert_allclose(got_u, o.measure_all_uncertainty(raw, delta_x, shape, axis), rtol=1e-9)
+        np.testing.assert_allclose(got_u, 0.5, rtol=1e-3)
+    np.testing.assert_allclose(operator.measure.k(states[1], axis=0), k0[0], atol=1e-4)
+    np.testing.assert_allclose(operator.measure.uncertainty(states[2], axis=1), 0.5, rtol=1e-3)

@@ -57,3 +57,18 @@ def test_measure_two_axes_are_independent():
                                o.measure_all_periodic_x(s0, dxm[:1, :1], shape[:1], 0), atol=1e-12)
     np.testing.assert_allclose(o.measure_all_variance_x(prod, dxm, shape, 1),
                                o.measure_all_variance_x(s1, dxm[1:, 1:], shape[1:], 0), atol=1e-12)
+
+
+def test_measure_k_and_uncertainty_of_a_gaussian():
+    """Momentum observables (reference operator/_measure.py:307-420) on a wavepacket with known answers:
+    <k> = k0, var_k = 1 / (2 sigma^2), sigma_x sigma_k = 1/2 (minimum-uncertainty state)."""
+    n = 400
+    length = 40.0
+    dxm = np.array([[length]])
+    sigma, k0 = 1.3, 2 * np.pi * 12 / length
+    s = o.coherent_state(dxm, (n,), (17.0,), (k0,), (sigma,))
+    np.testing.assert_allclose(o.measure_all_k(s, dxm, (n,), 0), k0, atol=1e-9)
+    np.testing.assert_allclose(o.measure_all_variance_k(s, dxm, (n,), 0), 1 / (2 * sigma**2), rtol=1e-8)
+    np.testing.assert_allclose(o.measure_all_uncertainty(s, dxm, (n,), 0), 0.5, rtol=1e-8)
+    # the k points are the FFT-ordered literal of tests/test_operator.py:184-196
+    np.testing.assert_allclose(o.stacked_k_points(np.array([[2 * np.pi]]), (5,))[0], [0, 1, 2, -2, -1])
