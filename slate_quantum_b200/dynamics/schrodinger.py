@@ -29,7 +29,8 @@ class EvolvedStateList(StateList):
     """StateList over (times, eigenbasis) whose [T, M] data is generated on demand."""
 
     def __init__(
-        self, basis: Basis, coefficients: torch.Tensor, eigenvalues: torch.Tensor, times: torch.Tensor, hbar: float
+        self, basis: Basis, coefficients: torch.Tensor, eigenvalues: torch.Tensor, times: torch.Tensor, hbar: float,
+        uniform_dt: float | None = None,
     ) -> None:
         self._basis = basis
         self._host = None
@@ -38,6 +39,7 @@ class EvolvedStateList(StateList):
         self._eigenvalues = eigenvalues  # [n_blocks, n] float64
         self._times = times
         self._hbar = hbar
+        self._uniform_dt = uniform_dt  # spacing of a uniform time grid: enables the table-driven 3M GEMM
 
     @property
     def device_data(self) -> torch.Tensor:
@@ -67,7 +69,7 @@ class EvolvedStateList(StateList):
             return super().with_state_basis(basis)
         states = kernels.evolve_bloch(blocks, self._eigenvalues.reshape(blocks.shape[0], -1).contiguous(),
                                       self._coefficients.reshape(blocks.shape[0], -1).contiguous(),
-                                      self._times, self._hbar)
+                                      self._times, self._hbar, uniform_dt=self._uniform_dt)
         data = inner.convert_vector_into(states, basis, -1) if inner != basis else states
         return StateList(out_basis, data.reshape(-1))
 
@@ -97,9 +99,10 @@ def _solve_schrodinger_equation_diagonal(
         eig_real = hamiltonian.device_data.real.contiguous()
     blocks = _strip(eigenbasis)._blocks()  # noqa: SLF001
     eig_real = eig_real.reshape(blocks.shape[0], n_total // blocks.shape[0]).contiguous()
-    time_values = kernels.to_device(_time_values(times).astype(np.float64), torch.float64)
+    host_times = _time_values(times).astype(np.float64)
+    time_values = kernels.to_device(host_times, torch.float64)
     out_basis = TupleBasis((times, eigenbasis)).upcast()
-    return EvolvedStateList(out_basis, coefficients, eig_real, time_values, hbar)
+    return EvolvedStateList(out_basis, coefficients, eig_real, time_values, hbar, kernels.uniform_step(host_times))
 
 
 def solve_schrodinger_equation_decomposition(
