@@ -202,7 +202,7 @@ def run_ours(args) -> None:
     import torch.distributed as dist
 
     from slate_quantum_b200 import _lib, kernels
-    from slate_quantum_b200.pipeline import BlochSolver, exchange_k_to_time
+    from slate_quantum_b200.pipeline import BlochSolver, TimeShardedEvolver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,20 +266,9 @@ def run_ours(args) -> None:
     free, _ = torch.cuda.mem_get_info()
     row_bytes = n_k_local * n * 16
     t_tile = T
-    # buffers of one time tile: states (+ position output; + all-to-all receive/transposed copies at N > 1)
-    gathered = world > 1 and with_position  # time-sharded evolve over all-gathered eigenvectors
-    w_all = torch.empty((n_k_global, n, n), dtype=torch.complex128, device="cuda") if gathered else None
-    c_all = torch.empty((n_k_global * n,), dtype=torch.complex128, device="cuda") if gathered else None
-    # block segments of the time-sharded evolve: this rank's own blocks first (local eigenvectors, no exchange
-    # needed), then the other ranks' blocks in the order their eigenvectors arrive (ring: rank-1, rank-2, ...);
-    # one 3M workspace per segment
-    seg_src = [(rank - k) % world for k in range(world)] if gathered else []
-    seg_ranges = [(src * n_k_local, n_k_local) for src in seg_src]
-    seg_ws = [
-        torch.empty(kernels.evolve_uniform_workspace_bytes(n, cnt, T // world), dtype=torch.uint8, device="cuda")
-        for _, cnt in seg_ranges
-    ]
-    comm_stream = torch.cuda.Stream() if gathered else None
+    # buffers of one time tile: states (+ position output)
+    gathered = world > 1 and with_position  # time-sharded evolve over ring-exchanged eigenvectors
+    sharded = TimeShardedEvolver(solver, T) if gathered else None  # pipeline.py; DESIGN.md section 6
     free, _ = torch.cuda.mem_get_info()
     if gathered:
         row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
@@ -289,7 +278,7 @@ def run_ours(args) -> None:
         t_tile //= 2
     states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
     pos_out = torch.empty_like(states) if with_position else None
-    eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 else None
+    eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 and not gathered else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     stage_names = ["build", "eigh", "fold", "project", "evolve", "exchange", "position"]
@@ -311,7 +300,9 @@ def run_ours(args) -> None:
 
         def eigh():
             solver.diagonalise()
-            if world > 1:
+            if sharded is not None:
+                sharded.gather_eigenvalues()
+            elif world > 1:
                 dist.all_gather_into_tensor(eig_all, solver.eigenvalues.reshape(-1))
 
         timed("eigh", eigh)
@@ -320,56 +311,11 @@ def run_ours(args) -> None:
             timed("fold", lambda: solver.fold(out=folded_buf))
         c = timed("project", lambda: solver.project(psi0))
         if world > 1 and with_position:
-            # Position output at N > 1: the across-block cell FFT needs every block of a time sample on one GPU.
-            # Instead of re-sharding the evolved STATES (all-to-all of T*M*16 B per step) the ranks all-gather the
-            # folded EIGENVECTORS (+ eigenvalues, coefficients) once per eigensolve - (G-1)/G * n_k*N^2*16 B received
-            # per rank, 2x less than the states at cfg3 and NVLS-friendly - and then evolve their own T/G time
-            # samples for ALL blocks locally (same flops per rank), followed by the local cell FFT.
-            # The exchange runs on a side stream, enqueued BEFORE the evolve of this rank's own blocks (which needs
-            # only local eigenvectors): the NCCL CTAs take their SMs first (an evolve CTA owns a whole SM's register
-            # file, so the two cannot share one).  It is a ring of G-1 send/recv steps (step k: receive rank-k's
-            # eigenvectors, send ours to rank+k) with one event per step, so the evolve of a peer's blocks starts
-            # as soon as THAT peer's eigenvectors are in: after the first step everything hides behind the GEMMs.
-            w_all_r = torch.view_as_real(w_all)
-            folded_r = torch.view_as_real(folded_buf)
-            arrived: list = [None] * world
-
-            def exchange():
-                dist.all_gather_into_tensor(torch.view_as_real(c_all), torch.view_as_real(c.reshape(-1)))
-                for k in range(1, world):
-                    src, dst = (rank - k) % world, (rank + k) % world
-                    ops = [
-                        dist.P2POp(dist.isend, folded_r, dst),
-                        dist.P2POp(dist.irecv, w_all_r[src * n_k_local : (src + 1) * n_k_local], src),
-                    ]
-                    for req in dist.batch_isend_irecv(ops):
-                        req.wait()
-                    arrived[k] = torch.cuda.Event()
-                    arrived[k].record(comm_stream)
-
-            cur = torch.cuda.current_stream()
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            comm_stream.wait_event(ready)
-            with torch.cuda.stream(comm_stream):
-                timed("exchange", exchange)
-            eig_g = eig_all.reshape(n_k_global, n)
-            c_g = c_all.reshape(n_k_global, n)
-            t_lo = rank * (T // world)
-            for i_tile, t0 in enumerate(range(0, T // world, t_tile)):
-                tt = min(t_tile, T // world - t0)
-                tsl = times[t_lo + t0 : t_lo + t0 + tt]
-                for i_seg, (b0, cnt) in enumerate(seg_ranges):
-                    if i_seg == 0:
-                        tr, ww, cc = folded_buf, solver.eigenvalues, c
-                    else:
-                        if i_tile == 0:
-                            cur.wait_event(arrived[i_seg])  # that rank's eigenvectors (and c_all) have arrived
-                        tr, ww, cc = w_all[b0 : b0 + cnt], eig_g[b0 : b0 + cnt], c_g[b0 : b0 + cnt]
-                    timed("evolve", lambda: kernels.evolve_bloch(
-                        tr, ww, cc, tsl, HBAR, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=dt_uniform,
-                        workspace=seg_ws[i_seg], reuse_plane=i_tile > 0))
-                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
+            # Position output at N > 1 (pipeline.TimeShardedEvolver): the ranks ring-exchange the folded eigenvectors
+            # on a side stream and each evolves its own T/G time samples of EVERY block, then runs the local cell FFT.
+            sharded.start_exchange(c, wrap=timed)
+            t_lo = sharded.time_begin
+            sharded.evolve_position(times[t_lo : t_lo + sharded.rows], states, pos_out, dt_uniform, wrap=timed)
             return
         for t0 in range(0, T, t_tile):
             tt = min(t_tile, T - t0)

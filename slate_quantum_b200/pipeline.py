@@ -278,3 +278,155 @@ def exchange_k_to_time(states: torch.Tensor, group=None, *, transpose: bool = Tr
     # [src rank, rows, width] -> [rows, src rank * width]
     out = torch.view_as_complex(recv.permute(1, 0, 2, 3).contiguous())
     return out.reshape(rows, world * width)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Position-basis output on G > 1 GPUs: time-sharded evolve over ring-exchanged eigenvectors
+# ---------------------------------------------------------------------------------------------------------------
+def ring_segments(rank: int, world: int, blocks_per_rank: int) -> list[tuple[int, int, int]]:
+    """(source rank, first global block, block count) in the order rank `rank` evolves them.
+
+    Segment 0 is the rank's own block range (its eigenvectors are local); segment k >= 1 is the range whose
+    eigenvectors arrive in step k of ring_exchange, i.e. rank - k (mod world).
+    """
+    if not 0 <= rank < world:
+        msg = f"rank {rank} outside world of {world}"
+        raise ValueError(msg)
+    return [(((rank - k) % world), ((rank - k) % world) * blocks_per_rank, blocks_per_rank) for k in range(world)]
+
+
+def ring_exchange(local: torch.Tensor, gathered: torch.Tensor, group=None, on_arrival=None) -> None:
+    """gathered[src] <- rank src's `local` for every src != rank, as world-1 paired send/recv steps.
+
+    `gathered` is [world, *local.shape]; row `rank` is NOT written (the caller keeps using `local`).  Step k sends
+    `local` to rank + k and receives rank - k's, then calls on_arrival(k) - the GPU path records an event there so
+    the evolve of that peer's blocks can start while later steps are still in flight.  Complex tensors travel as
+    their real views (NCCL has no complex dtype).
+    """
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if gathered.shape[0] != world or tuple(gathered.shape[1:]) != tuple(local.shape):
+        msg = f"gathered must be [{world}, {', '.join(map(str, local.shape))}], got {tuple(gathered.shape)}"
+        raise ValueError(msg)
+    if local.is_complex():
+        local, gathered = torch.view_as_real(local), torch.view_as_real(gathered)
+    for k in range(1, world):
+        src, dst = (rank - k) % world, (rank + k) % world
+        ops = [
+            dist.P2POp(dist.isend, local, dst if group is None else dist.get_global_rank(group, dst), group),
+            dist.P2POp(dist.irecv, gathered[src], src if group is None else dist.get_global_rank(group, src), group),
+        ]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if on_arrival is not None:
+            on_arrival(k)
+
+
+class TimeShardedEvolver:
+    """Position-basis states at G > 1: every rank evolves T/G time samples of EVERY k-block.
+
+    The across-block cell FFT (K4) needs all blocks of a time sample on one GPU.  Re-sharding the evolved states
+    would move T*M*16 B per step; instead the ranks exchange what the states are made FROM - the folded
+    eigenvectors (n_k*N^2*16 B, 2x less at cfg3), eigenvalues and coefficients - once per eigensolve, and each
+    evolves its own time range for all blocks (same flops per rank).  The exchange runs on a side stream as a
+    ring, enqueued before the evolve of the rank's own blocks, and each peer's segment waits only for that
+    peer's eigenvectors, so from the second segment on the transfer hides behind the GEMMs.
+
+    `solver` must own block range [rank*c, (rank+1)*c) with c = n_k / world (the weak- and strong-scaling layouts
+    of bench.py); `n_times` must be a multiple of world.
+    """
+
+    def __init__(self, solver: BlochSolver, n_times: int, group=None) -> None:
+        import torch.distributed as dist
+
+        self.solver, self.group = solver, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        c, n = solver.block_count, solver.n
+        if c * self.world != solver.n_k or solver.block_begin != self.rank * c:
+            msg = "TimeShardedEvolver needs equal contiguous block ranges in rank order"
+            raise ValueError(msg)
+        if n_times % self.world:
+            msg = f"the number of time samples ({n_times}) must be divisible by the number of ranks ({self.world})"
+            raise ValueError(msg)
+        self.rows = n_times // self.world
+        self.time_begin = self.rank * self.rows
+        self.segments = ring_segments(self.rank, self.world, c)
+        self.transforms = torch.empty((self.world, c, n, n), dtype=torch.complex128, device="cuda")
+        self.coefficients = torch.empty((self.world, c, n), dtype=torch.complex128, device="cuda")
+        self.eigenvalues = torch.empty((self.world, c, n), dtype=torch.float64, device="cuda")
+        self._ws = [
+            torch.empty(kernels.evolve_uniform_workspace_bytes(n, c, self.rows), dtype=torch.uint8, device="cuda")
+            for _ in self.segments
+        ]
+        self.comm_stream = torch.cuda.Stream()
+        self._arrived: list = [None] * self.world
+        self._local: tuple | None = None
+
+    def gather_eigenvalues(self) -> torch.Tensor:
+        """All-gather of the eigenvalues ([n_k, N], global block order); part of the eigensolve stage."""
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(self.eigenvalues, self.solver.eigenvalues.contiguous(), group=self.group)
+        return self.eigenvalues.reshape(-1, self.solver.n)
+
+    def start_exchange(self, coefficients: torch.Tensor, wrap=None) -> None:
+        """Enqueue the coefficient all-gather and the eigenvector ring on the side stream (after everything
+        already enqueued on the current stream).  `wrap(name, fn)` lets a caller time the enqueue."""
+        import torch.distributed as dist
+
+        folded = self.solver.fold()
+        self._local = (folded, coefficients)
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm_stream.wait_event(ready)
+
+        def arrived(k: int) -> None:
+            self._arrived[k] = torch.cuda.Event()
+            self._arrived[k].record(self.comm_stream)
+
+        def run() -> None:
+            dist.all_gather_into_tensor(
+                torch.view_as_real(self.coefficients), torch.view_as_real(coefficients.contiguous()), group=self.group
+            )
+            ring_exchange(folded, self.transforms, self.group, arrived)
+
+        with torch.cuda.stream(self.comm_stream):
+            run() if wrap is None else wrap("exchange", run)
+
+    def evolve_position(
+        self, times_local: torch.Tensor, states: torch.Tensor, out: torch.Tensor, uniform_dt: float | None,
+        on_tile=None, wrap=None,
+    ) -> None:
+        """Evolve this rank's time samples `times_local` ([rows], = times[time_begin : time_begin + rows]) for all
+        blocks, tile by tile: `states` / `out` are [t_tile, M] buffers (states in the cell layout is scratch);
+        on_tile(t0, tt, out[:tt]) is called after each tile's position-basis states have been enqueued."""
+        if self._local is None:
+            msg = "start_exchange() first"
+            raise RuntimeError(msg)
+        s, n = self.solver, self.solver.n
+        folded, c_local = self._local
+        cur = torch.cuda.current_stream()
+        call = (lambda _name, fn: fn()) if wrap is None else wrap
+        t_tile = states.shape[0]
+        for i_tile, t0 in enumerate(range(0, times_local.numel(), t_tile)):
+            tt = min(t_tile, times_local.numel() - t0)
+            tsl = times_local[t0 : t0 + tt]
+            for i_seg, (src, b0, cnt) in enumerate(self.segments):
+                if i_seg == 0:
+                    tr, ww, cc = folded, s.eigenvalues, c_local
+                else:
+                    if i_tile == 0:
+                        cur.wait_event(self._arrived[i_seg])  # that rank's eigenvectors (and coefficients) are in
+                    tr, ww, cc = self.transforms[src], self.eigenvalues[src], self.coefficients[src]
+                if uniform_dt is None:
+                    call("evolve", lambda: kernels.evolve_bloch(
+                        tr, ww, cc, tsl, s.hbar, out=states[:tt, b0 * n : (b0 + cnt) * n]))
+                else:
+                    call("evolve", lambda: kernels.evolve_bloch(
+                        tr, ww, cc, tsl, s.hbar, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=uniform_dt,
+                        workspace=self._ws[i_seg], reuse_plane=i_tile > 0))
+            call("position", lambda: s.cell_to_position(states[:tt], out=out[:tt]))
+            if on_tile is not None:
+                on_tile(t0, tt, out[:tt])

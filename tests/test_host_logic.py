@@ -147,3 +147,70 @@ def test_block_sharding_and_eigenvalue_gather_world_size_2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+_RING_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SQB_ROOT"])
+from slate_quantum_b200.pipeline import ring_exchange, ring_segments
+world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["SQB_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=world)
+rank = dist.get_rank()
+blocks, n = 3, 4
+def transform_of(r):  # what rank r's folded eigenvectors look like
+    return torch.from_numpy((np.arange(blocks * n * n).reshape(blocks, n, n) + 1000 * r) * (1 - 2j))
+local = transform_of(rank)
+gathered = torch.full((world, blocks, n, n), np.nan + 0j, dtype=torch.complex128)
+order = []
+ring_exchange(local, gathered, on_arrival=order.append)
+assert order == list(range(1, world)), order
+segs = ring_segments(rank, world, blocks)
+assert [s[0] for s in segs] == [(rank - k) % world for k in range(world)]
+assert sorted(s[1] for s in segs) == [r * blocks for r in range(world)] and all(s[2] == blocks for s in segs)
+for k, (src, b0, cnt) in enumerate(segs):
+    if k == 0:
+        assert src == rank and torch.isnan(gathered[src].real).all()  # own slot untouched
+    else:  # the segment visited k-th is the one that arrived in ring step k
+        assert torch.equal(gathered[src], transform_of(src)), (rank, src)
+# real tensors travel as they are
+gr = torch.zeros((world, 5), dtype=torch.float64)
+ring_exchange(torch.full((5,), float(rank), dtype=torch.float64), gr)
+assert all(torch.equal(gr[r], torch.full((5,), float(r), dtype=torch.float64)) for r in range(world) if r != rank)
+try:
+    ring_exchange(local, gathered[:, :1])
+except ValueError:
+    pass
+else:
+    raise AssertionError("shape mismatch not caught")
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_exchange_of_eigenvectors_gloo(tmp_path, world):
+    """The eigenvector exchange of the time-sharded evolve (pipeline.TimeShardedEvolver) over gloo on CPU."""
+    script = tmp_path / "ring_worker.py"
+    script.write_text(_RING_WORKER)
+    port = str(31600 + os.getpid() % 2000 + world)
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), SQB_ROOT=str(ROOT), SQB_PORT=port,
+                   MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+
+
+def test_ring_segments_validation():
+    from slate_quantum_b200.pipeline import ring_segments
+
+    assert ring_segments(0, 1, 7) == [(0, 0, 7)]
+    assert ring_segments(1, 4, 2) == [(1, 2, 2), (0, 0, 2), (3, 6, 2), (2, 4, 2)]
+    with pytest.raises(ValueError):
+        ring_segments(4, 4, 2)
