@@ -245,6 +245,37 @@ int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c1
                         double spacing, double length, const double* offsets, int wrapped, double* out,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K7  Operator / state algebra ("next" rows of the scope table).
+ * sqb_zgemm_batched replaces the dense einsum contractions of slate_quantum.operator.matmul / commute
+ * (operator/_linalg.py:108-137), matmul_list_operator / matmul_operator_list / get_commutator_operator_list
+ * (:172-215), operator.apply / expectation / expectation_of_each (operator/_operator.py:165-215):
+ *
+ *     C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b]         b in [0, batch)
+ *
+ * A(i, k) = a[b*a_batch_stride + i*a_row_stride + k*a_col_stride] (complex conjugated when conj_a != 0), i < m,
+ * k < k; B(k, j) likewise, j < n; strides in ELEMENTS, any sign-free combination (row-major, transposed,
+ * batch stride 0 = the same operator for every list entry), so a transpose or dagger is a stride swap and never
+ * a copy.  C is row-major with leading dimension ldc >= n; it may not overlap A or B.  alpha / beta point to
+ * {re, im} on the HOST.  FP64 tensor cores (DMMA.8x8x4), 4 real products per complex MAC; 8 m n k real flop per
+ * batch entry.
+ *
+ * sqb_rowwise_vdot    out[r] = sum_i conj(x[r, i]) y[r, i]      (state.inner_product_each, state/_state.py:208-228;
+ *                     the last step of expectation_of_each)
+ * sqb_abs2            out[i] = |x[i]|^2                          (state.get_all_occupations, state/_state.py:265-308)
+ * sqb_normalize_rows  out[r, :] = x[r, :] / sqrt(|norm2[r]|)     (state.normalize_each, state/_state.py:242-262)
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_zgemm_batched(int m, int n, int k, int64_t batch, const sqb_c128* a, int64_t a_row_stride,
+                      int64_t a_col_stride, int64_t a_batch_stride, int conj_a, const sqb_c128* b,
+                      int64_t b_row_stride, int64_t b_col_stride, int64_t b_batch_stride, int conj_b,
+                      const double* alpha, const double* beta, sqb_c128* c, int64_t ldc, int64_t c_batch_stride,
+                      void* stream);
+int sqb_rowwise_vdot(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride, const sqb_c128* y,
+                     int64_t y_row_stride, sqb_c128* out, void* stream);
+int sqb_abs2(int64_t count, const sqb_c128* x, double* out, void* stream);
+int sqb_normalize_rows(int64_t rows, int64_t len, const sqb_c128* x, const sqb_c128* norm2, sqb_c128* out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

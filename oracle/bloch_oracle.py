@@ -672,3 +672,71 @@ def measure_all_variance_k(states: np.ndarray, delta_x: np.ndarray, shape: Seque
 def measure_all_uncertainty(states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], axis: int) -> np.ndarray:
     """operator.measure.all_uncertainty (operator/_measure.py:381-420): sqrt(var_x var_k)."""
     return np.sqrt(measure_all_variance_x(states, delta_x, shape, axis) * measure_all_variance_k(states, delta_x, shape, axis))
+
+
+# --------------------------------------------------------------------------------------
+# K7: operator / state algebra (SURVEY §8f ranks 1 and 4) - dense numpy restatements
+# --------------------------------------------------------------------------------------
+def x_operator_array(
+    delta_x: np.ndarray, shape: Sequence[int], axis: int, offset: float = 0.0, wrapped: bool = False
+) -> np.ndarray:
+    """operator.build.x(...).as_array() (operator/_build/_position.py:228-242): diagonal in the position basis."""
+    off = [offset if i == axis else 0.0 for i in range(len(shape))]
+    return np.diag(stacked_x_points(delta_x, shape, off, wrapped)[axis]).astype(np.complex128)
+
+
+def k_operator_array(delta_x: np.ndarray, shape: Sequence[int], axis: int, power: int = 1) -> np.ndarray:
+    """operator.build.k / k_squared(...).as_array() (operator/_build/_momentum.py:37-62): diagonal in the momentum
+    basis, written in the position basis with the convention pinned by tests/test_operator.py:197-204."""
+    diag = np.diag(stacked_k_points(delta_x, shape)[axis].astype(np.complex128) ** power)
+    return momentum_matrix_to_position(diag, shape)
+
+
+def operator_matmul(lhs: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+    """operator.matmul: A_ik B_kj (operator/_linalg.py:108-119); also matmul_list_operator / matmul_operator_list
+    (:172-196) when one operand carries a leading list axis."""
+    return np.matmul(lhs, rhs)
+
+
+def operator_commutator(lhs: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+    """operator.commute / get_commutator_operator_list: lhs rhs - rhs lhs (operator/_linalg.py:122-137, :199-215)."""
+    return np.matmul(lhs, rhs) - np.matmul(rhs, lhs)
+
+
+def operator_dagger(op: np.ndarray) -> np.ndarray:
+    """operator.dagger / dagger_each (operator/_linalg.py:140-169)."""
+    return np.conj(np.swapaxes(op, -1, -2))
+
+
+def operator_apply(op: np.ndarray, state: np.ndarray) -> np.ndarray:
+    """operator.apply: (O psi)_i = O_ij psi_j (operator/_operator.py:210-218)."""
+    return op @ state
+
+
+def expectation_of_each(op: np.ndarray, states: np.ndarray) -> np.ndarray:
+    """operator.expectation_of_each: conj(psi_ai) O_ij psi_aj for every a (operator/_operator.py:196-207);
+    NOT divided by the norm (the reference does not normalise here)."""
+    states = np.atleast_2d(states)
+    return np.einsum("ai,ij,aj->a", states.conj(), op, states)
+
+
+def inner_product_each(states_0: np.ndarray, states_1: np.ndarray) -> np.ndarray:
+    """state.inner_product_each (state/_state.py:208-218)."""
+    return np.einsum("ji,ji->j", np.conj(states_0), states_1)
+
+
+def all_inner_product(states_0: np.ndarray, states_1: np.ndarray) -> np.ndarray:
+    """state.all_inner_product (state/_state.py:221-232)."""
+    return np.conj(states_0) @ states_1.T
+
+
+def occupations(states: np.ndarray) -> np.ndarray:
+    """state.get_occupations / get_all_occupations: abs(conj(a) a) of the stored coefficients
+    (state/_state.py:71-87, :265-308)."""
+    return np.abs(np.conj(states) * states)
+
+
+def normalize_each(states: np.ndarray) -> np.ndarray:
+    """state.normalize_each: every row divided by sqrt(<psi|psi>) (state/_state.py:249-262)."""
+    states = np.atleast_2d(states)
+    return states / np.sqrt(inner_product_each(states, states))[:, np.newaxis]

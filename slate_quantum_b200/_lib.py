@@ -39,6 +39,10 @@ EXPORTED_SYMBOLS = (
     "sqb_evolve_uniform_workspace_bytes",
     "sqb_evolve_bloch_uniform",
     "sqb_measure_moments",
+    "sqb_zgemm_batched",
+    "sqb_rowwise_vdot",
+    "sqb_abs2",
+    "sqb_normalize_rows",
     "sqb_peak_dmma",
     "sqb_peak_dfma",
 )
@@ -99,6 +103,17 @@ def load() -> ctypes.CDLL:
     lib.sqb_measure_moments.argtypes = [
         c_int, c_void_p, c_int64, c_void_p, c_int, c_double, c_double, c_void_p, c_int, c_void_p, c_void_p,
     ]
+    lib.sqb_zgemm_batched.restype = c_int
+    lib.sqb_zgemm_batched.argtypes = [
+        c_int, c_int, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64,
+        c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+    ]
+    lib.sqb_rowwise_vdot.restype = c_int
+    lib.sqb_rowwise_vdot.argtypes = [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.sqb_abs2.restype = c_int
+    lib.sqb_abs2.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
+    lib.sqb_normalize_rows.restype = c_int
+    lib.sqb_normalize_rows.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sqb_tridiag_eigh_workspace_bytes.restype = c_size_t
     lib.sqb_tridiag_eigh_workspace_bytes.argtypes = [c_int, c_int64]
     lib.sqb_tridiag_eigh_batched.restype = c_int

@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libslate_b200.so"
-SOURCES = ["abi.cu", "bloch_build.cu", "fft.cu", "eigh.cu", "evolve.cu", "measure.cu", "peaks.cu"]
+SOURCES = ["abi.cu", "bloch_build.cu", "fft.cu", "eigh.cu", "evolve.cu", "measure.cu", "zgemm.cu", "peaks.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

@@ -270,6 +270,16 @@ class volume:  # noqa: N801 - mirrors the module name slate_core.metadata.volume
             points = points - np.einsum("ij,ik->jk", a, np.floor(frac + 0.5))
         return tuple(points)
 
+    @staticmethod
+    def fundamental_stacked_k_points(metadata: TupleMetadata) -> tuple[np.ndarray, ...]:
+        """Cartesian wavevector of every momentum-basis index (FFT order per axis), C-order ravel."""
+        dk = volume.fundamental_stacked_dk(metadata)
+        nk = np.array(
+            [g.ravel() for g in np.meshgrid(*(fundamental_nk_points(c) for c in metadata.children), indexing="ij")],
+            dtype=np.float64,
+        )
+        return tuple(np.einsum("ij,ik->jk", dk, nk))
+
 
 fundamental_stacked_dk = volume.fundamental_stacked_dk
 fundamental_stacked_delta_k = volume.fundamental_stacked_delta_k

@@ -458,3 +458,104 @@ def measure_moments(
     _lib.check(rc, "sqb_measure_moments")
     _count(1)
     return out
+
+
+def _gemm_operand(t: torch.Tensor, name: str) -> tuple[torch.Tensor, int, int, int, int]:
+    """(tensor, row stride, col stride, batch stride, conj) of a [m, k] or [batch, m, k] complex128 CUDA view.
+    Transposed (`.mT`), daggered (`.mH`), conjugated and broadcast (`expand`) views are passed as they are."""
+    if not (t.is_cuda and t.dtype == torch.complex128 and t.dim() in (2, 3)):
+        msg = f"{name} must be a 2-d or 3-d CUDA complex128 tensor"
+        raise TypeError(msg)
+    if t.is_neg() or any(s < 0 for s in t.stride()):
+        t = t.resolve_neg().contiguous()
+    bs = t.stride(0) if t.dim() == 3 else 0
+    return t, t.stride(-2), t.stride(-1), bs, int(t.is_conj())
+
+
+def zgemm(
+    a: torch.Tensor, b: torch.Tensor, *, alpha: complex = 1.0, beta: complex = 0.0, out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """K7: out[..] = alpha * a @ b + beta * out for complex128 [m, k] @ [k, n] or batched [batch, m, k] @ [batch, k, n]
+    (a 2-d operand is shared by every batch entry).  Operands may be any strided / conjugated torch views."""
+    _require_cuda()
+    lib = _lib.load()
+    a, a_rs, a_cs, a_bs, a_cj = _gemm_operand(a, "a")
+    b, b_rs, b_cs, b_bs, b_cj = _gemm_operand(b, "b")
+    m, k = a.shape[-2:]
+    k2, n = b.shape[-2:]
+    if k != k2:
+        msg = f"inner dimensions differ: {tuple(a.shape)} @ {tuple(b.shape)}"
+        raise ValueError(msg)
+    batched = a.dim() == 3 or b.dim() == 3
+    batch = 1
+    if batched:
+        sizes = {t.shape[0] for t in (a, b) if t.dim() == 3}
+        if len(sizes) != 1:
+            msg = f"batch sizes differ: {tuple(a.shape)} @ {tuple(b.shape)}"
+            raise ValueError(msg)
+        batch = sizes.pop()
+    shape = (batch, m, n) if batched else (m, n)
+    if out is None:
+        if beta != 0:
+            msg = "beta != 0 needs `out`"
+            raise ValueError(msg)
+        out = torch.empty(shape, dtype=torch.complex128, device="cuda")
+    elif tuple(out.shape) != shape or not (out.is_cuda and out.dtype == torch.complex128 and out.is_contiguous()):
+        msg = f"out must be a contiguous CUDA complex128 tensor of shape {shape}"
+        raise TypeError(msg)
+    al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+    rc = lib.sqb_zgemm_batched(
+        m, n, k, batch, _ptr(a), a_rs, a_cs, a_bs, a_cj, _ptr(b), b_rs, b_cs, b_bs, b_cj, al, be, _ptr(out), n, m * n,
+        _stream(),
+    )
+    _lib.check(rc, "sqb_zgemm_batched")
+    _count(-(-batch // 65535) if m and n else 0)
+    return out
+
+
+def rowwise_vdot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """out[r] = sum_i conj(x[r, i]) * y[r, i] for [rows, len] complex128 tensors (unit stride along i)."""
+    _require_cuda()
+    for t, nm in ((x, "x"), (y, "y")):
+        if not (t.is_cuda and t.dtype == torch.complex128 and t.dim() == 2 and (t.shape[1] <= 1 or t.stride(1) == 1)):
+            msg = f"{nm} must be a [rows, len] CUDA complex128 tensor with unit stride along len"
+            raise TypeError(msg)
+    if x.shape != y.shape:
+        msg = "x and y must have the same shape"
+        raise ValueError(msg)
+    x, y = x.resolve_conj(), y.resolve_conj()
+    rows, length = x.shape
+    out = torch.empty((rows,), dtype=torch.complex128, device="cuda")
+    rc = _lib.load().sqb_rowwise_vdot(rows, length, _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(out), _stream())
+    _lib.check(rc, "sqb_rowwise_vdot")
+    _count(1 if rows else 0)
+    return out
+
+
+def abs2(x: torch.Tensor) -> torch.Tensor:
+    """|x|^2 elementwise (float64, same shape)."""
+    _require_cuda()
+    _c128(x, "x")
+    out = torch.empty(x.shape, dtype=torch.float64, device="cuda")
+    rc = _lib.load().sqb_abs2(x.numel(), _ptr(x), _ptr(out), _stream())
+    _lib.check(rc, "sqb_abs2")
+    _count(1 if x.numel() else 0)
+    return out
+
+
+def normalize_rows(x: torch.Tensor, norm2: torch.Tensor | None = None) -> torch.Tensor:
+    """x[r, :] / sqrt(|norm2[r]|) with norm2 = <x_r|x_r> unless given."""
+    _require_cuda()
+    _c128(x, "x")
+    if x.dim() != 2:
+        msg = "x must be [rows, len]"
+        raise TypeError(msg)
+    if norm2 is None:
+        norm2 = rowwise_vdot(x, x)
+    _c128(norm2, "norm2")
+    out = torch.empty_like(x)
+    rc = _lib.load().sqb_normalize_rows(x.shape[0], x.shape[1], _ptr(x), _ptr(norm2), _ptr(out), _stream())
+    _lib.check(rc, "sqb_normalize_rows")
+    _count(1 if x.numel() else 0)
+    return out

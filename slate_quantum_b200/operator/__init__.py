@@ -7,16 +7,44 @@ from slate_quantum_b200.operator._diagonal import (
     recast_diagonal_basis,
     with_outer_basis,
 )
-from slate_quantum_b200.operator._linalg import get_eigenstates_hermitian, into_diagonal, into_diagonal_hermitian
-from slate_quantum_b200.operator._operator import Operator, OperatorList, operator_basis
+from slate_quantum_b200.operator._linalg import (
+    commute,
+    dagger,
+    dagger_each,
+    get_commutator_operator_list,
+    get_eigenstates_hermitian,
+    into_diagonal,
+    into_diagonal_hermitian,
+    matmul,
+    matmul_list_operator,
+    matmul_operator_list,
+)
+from slate_quantum_b200.operator._operator import (
+    Operator,
+    OperatorList,
+    apply,
+    expectation,
+    expectation_of_each,
+    operator_basis,
+)
 
 __all__ = [
     "Operator",
     "OperatorList",
+    "apply",
     "build",
+    "commute",
+    "dagger",
+    "dagger_each",
+    "expectation",
+    "expectation_of_each",
+    "get_commutator_operator_list",
     "get_eigenstates_hermitian",
     "into_diagonal",
     "into_diagonal_hermitian",
+    "matmul",
+    "matmul_list_operator",
+    "matmul_operator_list",
     "measure",
     "momentum_operator_basis",
     "operator_basis",

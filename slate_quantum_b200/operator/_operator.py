@@ -33,7 +33,7 @@ class Operator(Array):
 
     def with_basis(self, basis: Basis) -> "Operator":
         assert basis.metadata() == self.basis.metadata()
-        data = self.basis.convert_vector_into(self.device_data.reshape(-1), basis, 0)
+        data = self.basis.convert_vector_into(self.device_data.to(dtype=_c128()).reshape(-1), basis, 0)
         return Operator(basis, data)
 
     def as_array(self) -> np.ndarray:
@@ -92,3 +92,56 @@ class OperatorList(Array):
         assert all(x.basis == ops[0].basis for x in ops)
         list_basis = FundamentalBasis.from_size(len(ops))
         return OperatorList(TupleBasis((list_basis, ops[0].basis)).upcast(), np.array([x.raw_data for x in ops]))
+
+
+# ------------------------------------------------------------------------------------------------ K7 contractions
+def dense_operator(operator: Operator):
+    """(TupleBasis((ket basis, bra basis)), [n0, n1] device matrix).  An operator that is not stored over a tuple
+    basis (diagonal, recast, block-diagonal ...) is expanded into the dense fundamental operator basis."""
+    from slate_quantum_b200.core.array import _complex
+
+    tup = _basis._strip(operator.basis)  # noqa: SLF001
+    if not isinstance(tup, TupleBasis):
+        tup = _basis.from_metadata(operator.basis.metadata(), is_dual=(False, True))
+        operator = operator.with_basis(tup)
+    return tup, _complex(operator.device_data).reshape(tup.shape).contiguous()
+
+
+_dense_operator = dense_operator
+
+
+def apply(operator: Operator, state: Any) -> Any:
+    """O|psi> in the operator's ket basis (reference operator/_operator.py:210-218)."""
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.core.array import _complex
+    from slate_quantum_b200.state._state import State
+
+    tup, o = _dense_operator(operator)
+    psi = _complex(state.with_basis(tup.children[1].dual_basis()).device_data).reshape(-1, 1)
+    return State(tup.children[0], kernels.zgemm(o, psi).reshape(-1))
+
+
+def expectation(operator: Operator, state: Any) -> complex:
+    """<psi|O|psi> (reference operator/_operator.py:178-193)."""
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.core.array import _complex
+
+    applied = apply(operator, state)
+    lhs = _complex(state.with_basis(applied.basis).device_data).reshape(1, -1)
+    return complex(kernels.rowwise_vdot(lhs, applied.device_data.reshape(1, -1)).cpu().numpy()[0])
+
+
+def expectation_of_each(operator: Operator, states: Any) -> Array:
+    """<psi_a|O|psi_a> for every state of a list (reference operator/_operator.py:196-207): Phi = Psi O^T as one
+    complex GEMM over the whole list (the operator is read through swapped strides), then a row-wise <Psi|Phi>."""
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.core.array import _complex
+
+    tup, o = _dense_operator(operator)
+    list_basis = _basis.as_tuple(states.basis).children[0]
+    rhs = states.with_state_basis(tup.children[1].dual_basis())
+    psi1 = _complex(rhs.device_data).reshape(list_basis.size, -1)
+    phi = kernels.zgemm(psi1, o.mT)
+    lhs = states.with_state_basis(tup.children[0])
+    psi0 = _complex(lhs.device_data).reshape(list_basis.size, -1)
+    return Array(list_basis, kernels.rowwise_vdot(psi0, phi))

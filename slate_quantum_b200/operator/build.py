@@ -154,3 +154,37 @@ def repeat_potential(potential_: Operator, shape: tuple[int, ...]) -> Operator:
         lambda i, y: TruncatedBasis(Truncation(transformed_basis.children[i].size, shape[i], 0), y).upcast(),
     ).upcast()
     return _build_potential(repeat_basis, as_transformed.raw_data * np.sqrt(np.prod(shape)))
+
+
+# --------------------------------------------------------------------------------- x / k / p operators
+def momentum(outer_basis: Basis, data: np.ndarray) -> Operator:
+    """Operator diagonal in the momentum basis (reference _build/_momentum.py:30-34)."""
+    return Operator(momentum_operator_basis(outer_basis), np.asarray(data).ravel())
+
+
+def x(metadata: TupleMetadata, *, axis: int, offset: float = 0, wrapped: bool = False) -> Operator:
+    """Cartesian position along `axis`, diagonal in the position basis (reference _build/_position.py:228-242)."""
+    inner_offset = tuple(offset if i == axis else 0 for i in range(len(metadata.children)))
+    points = volume.fundamental_stacked_x_points(metadata, offset=inner_offset, wrapped=wrapped)[axis]
+    return potential(basis.from_metadata(metadata).upcast(), points.astype(np.complex128))
+
+
+def k(metadata: TupleMetadata, *, axis: int) -> Operator:
+    """Cartesian wavevector along `axis`, diagonal in the momentum basis (reference _build/_momentum.py:37-48)."""
+    _require_periodic(metadata)
+    points = volume.fundamental_stacked_k_points(metadata)[axis].astype(np.complex128)
+    return momentum(basis.transformed_from_metadata(metadata).upcast(), points)
+
+
+def k_squared(metadata: TupleMetadata, *, axis: int) -> Operator:
+    """reference _build/_momentum.py:51-62."""
+    _require_periodic(metadata)
+    points = volume.fundamental_stacked_k_points(metadata)[axis].astype(np.complex128)
+    return momentum(basis.transformed_from_metadata(metadata).upcast(), points**2)
+
+
+def p(metadata: TupleMetadata, *, axis: int, hbar: float = hbar_si) -> Operator:
+    """hbar k (reference _build/_momentum.py:65-79)."""
+    _require_periodic(metadata)
+    points = volume.fundamental_stacked_k_points(metadata)[axis].astype(np.complex128)
+    return momentum(basis.transformed_from_metadata(metadata).upcast(), (hbar * points).astype(np.complex128))

@@ -6,9 +6,10 @@ from typing import Any
 
 import numpy as np
 
+from slate_quantum_b200 import kernels
 from slate_quantum_b200.core import basis as _basis
-from slate_quantum_b200.core.array import Array
-from slate_quantum_b200.core.basis import Basis, TupleBasis
+from slate_quantum_b200.core.array import Array, _complex
+from slate_quantum_b200.core.basis import BasisStateMetadata, Basis, FundamentalBasis, TupleBasis
 
 
 class State(Array):
@@ -22,16 +23,26 @@ class State(Array):
 
 def inner_product(state_0: State, state_1: State) -> complex:
     """<state_0|state_1> (reference state/_state.py:49-55)."""
-    rhs = state_1.with_basis(state_0.basis).raw_data
-    return complex(np.vdot(state_0.raw_data, rhs))
+    rhs = _complex(state_1.with_basis(state_0.basis).device_data).reshape(1, -1)
+    lhs = _complex(state_0.device_data).reshape(1, -1)
+    return complex(kernels.rowwise_vdot(lhs, rhs).cpu().numpy()[0])
 
 
 def normalization(state: State) -> float:
-    return float(np.real(inner_product(state, state)))
+    """abs(<state|state>) (reference state/_state.py:58-62)."""
+    return float(abs(inner_product(state, state)))
 
 
 def normalize(state: State) -> State:
-    return State(state.basis, state.raw_data / np.sqrt(normalization(state)))
+    """state / sqrt(<state|state>) (reference state/_state.py:65-68)."""
+    data = _complex(state.device_data).reshape(1, -1).contiguous()
+    return State(state.basis, kernels.normalize_rows(data).reshape(-1))
+
+
+def get_occupations(state: State) -> Array:
+    """abs(a_n)^2 of the state's own basis coefficients (reference state/_state.py:71-87)."""
+    basis = FundamentalBasis(BasisStateMetadata(state.basis))
+    return Array(basis, kernels.abs2(_complex(state.device_data).reshape(-1).contiguous()))
 
 
 class StateList(Array):
@@ -80,3 +91,45 @@ class StateList(Array):
         assert all(s.basis == states[0].basis for s in states)
         list_basis = _basis.FundamentalBasis.from_size(len(states))
         return StateList(TupleBasis((list_basis, states[0].basis)).upcast(), np.array([s.raw_data for s in states]))
+
+
+def _list_data(states: StateList) -> tuple[TupleBasis, Any]:
+    """(tuple basis, [len(list), state size] device data) of a state list."""
+    from slate_quantum_b200.core.array import as_tuple_basis
+
+    as_tuple = as_tuple_basis(states)
+    tup = _basis.as_tuple(as_tuple.basis)
+    return tup, _complex(as_tuple.device_data).reshape(tup.shape).contiguous()
+
+
+def inner_product_each(state_0: StateList, state_1: StateList) -> Array:
+    """<state_0[j]|state_1[j]> for every j (reference state/_state.py:208-218)."""
+    tup, lhs = _list_data(state_0)
+    _, rhs = _list_data(state_1.with_basis(tup.upcast()))
+    return Array(tup.children[0], kernels.rowwise_vdot(lhs, rhs))
+
+
+def all_inner_product(state_0: StateList, state_1: StateList) -> Array:
+    """<state_0[j]|state_1[k]> for every pair (reference state/_state.py:221-232): one complex GEMM (K7)."""
+    tup0, lhs = _list_data(state_0)
+    tup1, rhs = _list_data(state_1.with_state_basis(tup0.children[1]))
+    return Array(TupleBasis((tup0.children[0], tup1.children[0])), kernels.zgemm(lhs.conj(), rhs.mT).reshape(-1))
+
+
+def normalization_each(states: StateList) -> Array:
+    """abs(<state[j]|state[j]>) (reference state/_state.py:235-246)."""
+    product = inner_product_each(states, states)
+    return Array(product.basis, product.device_data.abs())
+
+
+def normalize_each(states: StateList) -> StateList:
+    """Every state divided by sqrt(<state|state>) (reference state/_state.py:249-262)."""
+    tup, data = _list_data(states)
+    return StateList(tup.upcast(), kernels.normalize_rows(data).reshape(-1))
+
+
+def get_all_occupations(states: StateList) -> Array:
+    """abs(a_n(t))^2 for every state of the list, in the list's own state basis (reference state/_state.py:265-308)."""
+    tup, data = _list_data(states)
+    basis = TupleBasis((tup.children[0], FundamentalBasis(BasisStateMetadata(tup.children[1]))))
+    return Array(basis, kernels.abs2(data).reshape(-1))

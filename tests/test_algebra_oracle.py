@@ -1,0 +1,89 @@
+"""CPU: the oracle's operator / state algebra (K7) pinned by the reference's own tests
+(tests/test_operator.py:180-260, :455-540; tests/test_state.py:20-75)."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import bloch_oracle as o
+
+DX = np.array([[2 * np.pi]])
+HBAR = o.HBAR_SI
+
+
+def test_k_operator_literal():
+    """tests/test_operator.py:184-210: diag([0,1,2,-2,-1]) in the momentum basis, ifft on kets / fft on bras."""
+    want = np.fft.fft(np.fft.ifft(np.diag([0, 1, 2, -2, -1]), norm="ortho", axis=0), norm="ortho", axis=1)
+    np.testing.assert_allclose(o.k_operator_array(DX, (5,), 0), want, atol=1e-15)
+    assert np.allclose(o.k_operator_array(DX, (5,), 0), o.operator_dagger(o.k_operator_array(DX, (5,), 0)))
+
+
+def test_x_operator_literal():
+    """tests/test_operator.py:170-181: diag(linspace(0, 2 pi, 5, endpoint=False))."""
+    np.testing.assert_allclose(o.x_operator_array(DX, (5,), 0), np.diag(np.linspace(0, 2 * np.pi, 5, endpoint=False)))
+
+
+def test_x_k_commutator():
+    """tests/test_operator.py:213-245."""
+    x, k = o.x_operator_array(DX, (5,), 0), o.k_operator_array(DX, (5,), 0)
+    np.testing.assert_allclose(o.operator_matmul(x, k), x @ k, atol=1e-15)
+    np.testing.assert_allclose(o.operator_commutator(x, k), x @ k - k @ x, atol=1e-15)
+    # tests/test_operator.py:248-259: an operator commutes with itself, exactly
+    np.testing.assert_array_equal(o.operator_commutator(x, x), np.zeros((5, 5)))
+    np.testing.assert_array_equal(o.operator_commutator(k, k), np.zeros((5, 5)))
+
+
+def test_canonical_commutator_on_a_smooth_state():
+    """[x, k] psi = i psi for a wavepacket well inside the cell (the continuum identity the reference's
+    tests/test_operator.py:471-476 quotes as [x, p] = i hbar)."""
+    n, length = 300, 2 * np.pi * 10
+    dxm = np.array([[length]])
+    psi = o.coherent_state(dxm, (n,), (length / 2,), (0.0,), (1.5,))
+    comm = o.operator_commutator(o.x_operator_array(dxm, (n,), 0), o.k_operator_array(dxm, (n,), 0))
+    np.testing.assert_allclose(o.operator_apply(comm, psi), 1j * psi, atol=1e-9)
+    np.testing.assert_allclose(o.expectation_of_each(comm, psi), [1j], atol=1e-9)
+
+
+def test_commutator_list_and_dagger():
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6))
+    ops = rng.normal(size=(3, 6, 6)) + 1j * rng.normal(size=(3, 6, 6))
+    got = o.operator_commutator(a, ops)
+    for m in range(3):
+        np.testing.assert_allclose(got[m], a @ ops[m] - ops[m] @ a, atol=1e-14)
+    np.testing.assert_allclose(o.operator_dagger(ops)[1], ops[1].conj().T)
+    # (AB)^dagger = B^dagger A^dagger
+    np.testing.assert_allclose(o.operator_dagger(o.operator_matmul(a, ops[0])),
+                               o.operator_matmul(o.operator_dagger(ops[0]), o.operator_dagger(a)), atol=1e-14)
+
+
+def test_occupations_literal():
+    """tests/test_state.py:50-74: two amplitudes (1-1j)/sqrt(2) -> occupations [1, 1, 0, 0, 0]."""
+    data = np.zeros(5, dtype=np.complex128)
+    data[:2] = (1 - 1j) / np.sqrt(2)
+    np.testing.assert_allclose(o.occupations(data), [1, 1, 0, 0, 0], atol=1e-15)
+
+
+def test_inner_products_literal():
+    """tests/test_state.py:20-47: orthogonal and parallel position states."""
+    s0 = np.zeros(5, dtype=np.complex128)
+    s0[:2] = (1 - 1j) / np.sqrt(2)
+    s1 = np.zeros(5, dtype=np.complex128)
+    s1[0], s1[1] = (1 - 1j) / np.sqrt(2), -(1 - 1j) / np.sqrt(2)
+    both = np.array([s0, s1])
+    np.testing.assert_allclose(o.inner_product_each(both, both), [2, 2], atol=1e-15)
+    np.testing.assert_allclose(o.all_inner_product(both, both), [[2, 0], [0, 2]], atol=1e-15)
+    normed = o.normalize_each(both)
+    np.testing.assert_allclose(o.inner_product_each(normed, normed), [1, 1], atol=1e-15)
+
+
+def test_expectation_matches_measure():
+    """<x> through the dense operator equals the K6 observable on a normalised state."""
+    n, length = 200, 30.0
+    dxm = np.array([[length]])
+    psi = o.coherent_state(dxm, (n,), (11.0,), (0.8,), (1.1,))
+    psi = o.normalize_each(psi)[0]
+    ex = o.expectation_of_each(o.x_operator_array(dxm, (n,), 0), psi)
+    np.testing.assert_allclose(ex.real, o.measure_all_x(psi, dxm, (n,), 0), atol=1e-12)
+    ek = o.expectation_of_each(o.k_operator_array(dxm, (n,), 0), psi)
+    np.testing.assert_allclose(ek.real, o.measure_all_k(psi, dxm, (n,), 0), atol=1e-10)

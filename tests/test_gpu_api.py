@@ -365,3 +365,194 @@ def test_measure_api_momentum_observables(cuda):
         np.testing.assert_allclose(got_u, 0.5, rtol=1e-3)
     np.testing.assert_allclose(operator.measure.k(states[1], axis=0), k0[0], atol=1e-4)
     np.testing.assert_allclose(operator.measure.uncertainty(states[2], axis=1), 0.5, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------- K7 operator algebra
+def _meta_1d(length, n):
+    _, _, _, _, _, _, metadata = _api()
+    return metadata.volume.spaced_volume_metadata_from_stacked_delta_x((np.array([length]),), (n,))
+
+
+def test_x_and_k_operators(cuda):
+    """reference tests/test_operator.py:170-210."""
+    _, _, operator, _, TupleBasis, basis, _ = _api()
+    meta = _meta_1d(2 * np.pi, 5)
+    x = operator.build.x(meta, axis=0)
+    np.testing.assert_allclose(x.as_array(), np.diag(np.linspace(0, 2 * np.pi, 5, endpoint=False)), atol=1e-15)
+    k = operator.build.k(meta, axis=0)
+    basis_k = basis.transformed_from_metadata(meta)
+    np.testing.assert_allclose(
+        k.with_basis(TupleBasis((basis_k, basis_k.dual_basis())).upcast()).raw_data.reshape(5, 5),
+        np.diag([0, 1, 2, -2, -1]), atol=1e-15,
+    )
+    np.testing.assert_allclose(k.as_array(), o.k_operator_array(np.array([[2 * np.pi]]), (5,), 0), atol=1e-15)
+    np.testing.assert_allclose((k * hbar).as_array(), operator.build.p(meta, axis=0).as_array(), atol=1e-15)
+    np.testing.assert_allclose(operator.build.k_squared(meta, axis=0).as_array(),
+                               o.k_operator_array(np.array([[2 * np.pi]]), (5,), 0, power=2), atol=1e-14)
+
+
+def test_x_k_commutator(cuda):
+    """reference tests/test_operator.py:213-245."""
+    _, _, operator, _, _, _, _ = _api()
+    meta = _meta_1d(2 * np.pi, 5)
+    x, k = operator.build.x(meta, axis=0), operator.build.k(meta, axis=0)
+    matmul_0 = operator.matmul(x, k)
+    np.testing.assert_allclose(matmul_0.as_array(), x.as_array() @ k.as_array(), atol=1e-15)
+    matmul_1 = operator.matmul(k, x)
+    np.testing.assert_allclose(matmul_1.as_array(), k.as_array() @ x.as_array(), atol=1e-15)
+    manual = matmul_0 - matmul_1
+    np.testing.assert_allclose(manual.as_array(), x.as_array() @ k.as_array() - k.as_array() @ x.as_array(), atol=1e-15)
+    commutator = operator.commute(x, k)
+    np.testing.assert_allclose(commutator.as_array(), manual.as_array(), atol=1e-15)
+    np.testing.assert_allclose(commutator.as_array(),
+                               o.operator_commutator(o.x_operator_array(np.array([[2 * np.pi]]), (5,), 0),
+                                                     o.k_operator_array(np.array([[2 * np.pi]]), (5,), 0)), atol=1e-14)
+
+
+def test_trivial_commutator(cuda):
+    """reference tests/test_operator.py:248-259: exactly zero."""
+    _, _, operator, _, _, _, _ = _api()
+    meta = _meta_1d(2 * np.pi, 5)
+    x, k = operator.build.x(meta, axis=0), operator.build.k(meta, axis=0)
+    np.testing.assert_array_equal(operator.commute(x, x).as_array(), np.zeros((5, 5)))
+    np.testing.assert_array_equal(operator.commute(k, k).as_array(), np.zeros((5, 5)))
+
+
+def test_dagger(cuda):
+    """reference tests/test_operator.py:479-499 (x and a non-hermitian operator)."""
+    _, _, operator, _, _, _, _ = _api()
+    meta = _meta_1d(2 * np.pi, 5)
+    x = operator.build.x(meta, axis=0)
+    np.testing.assert_allclose(operator.dagger(x).as_array(), x.as_array().T.conj())
+    xk = operator.matmul(x, operator.build.k(meta, axis=0))  # not hermitian
+    np.testing.assert_allclose(operator.dagger(xk).as_array(), xk.as_array().T.conj(), atol=1e-15)
+    assert operator.dagger(xk).basis.is_dual == xk.basis.is_dual
+
+
+def test_commute(cuda):
+    """reference tests/test_operator.py:509-540 (300 points; tolerances are the reference's)."""
+    _, _, operator, _, _, _, _ = _api()
+    meta = _meta_1d(2 * np.pi * 10, 300)
+
+    def commutator_numpy(a, b):
+        return a @ b - b @ a
+
+    x, k = operator.build.x(meta, axis=0), operator.build.k(meta, axis=0)
+    np.testing.assert_allclose(operator.commute(x, k).as_array(), commutator_numpy(x.as_array(), k.as_array()),
+                               atol=1e-13)
+    mass = hbar**2
+    kinetic = operator.build.kinetic_energy(meta, mass)
+    np.testing.assert_allclose(operator.commute(kinetic, x).as_array(),
+                               commutator_numpy(kinetic.as_array(), x.as_array()), atol=2e-12)
+    hamiltonian = operator.build.kinetic_hamiltonian(operator.build.cos_potential(meta, 0), mass)
+    np.testing.assert_allclose(operator.commute(hamiltonian, x).as_array(),
+                               commutator_numpy(hamiltonian.as_array(), x.as_array()), atol=2e-12)
+    # the canonical commutator on a smooth state (oracle: tests/test_algebra_oracle.py)
+    _, _, _, state, _, basis, _ = _api()
+    psi = o.coherent_state(np.array([[2 * np.pi * 10]]), (300,), (np.pi * 10,), (0.0,), (1.5,))
+    s = state.State(basis.from_metadata(meta).upcast(), psi)
+    got = operator.apply(operator.commute(x, k), s)
+    np.testing.assert_allclose(got.with_basis(s.basis).raw_data, 1j * psi, atol=1e-9)
+    np.testing.assert_allclose(operator.expectation(operator.commute(x, k), s), 1j * np.vdot(psi, psi), atol=1e-9)
+
+
+def test_operator_list_products_and_commutators(cuda):
+    """matmul_list_operator / matmul_operator_list / get_commutator_operator_list / dagger_each
+    (reference operator/_linalg.py:150-215) against the oracle, on a list [x, k, x k]."""
+    _, _, operator, _, _, _, _ = _api()
+    n, length = 48, 7.0
+    meta = _meta_1d(length, n)
+    dxm = np.array([[length]])
+    x, k = operator.build.x(meta, axis=0), operator.build.k(meta, axis=0)
+    fund = x.with_basis(operator.matmul(x, k).basis)  # dense (fundamental, fundamental.dual) operator basis
+    ops = operator.OperatorList.from_operators([fund, k.with_basis(fund.basis), operator.matmul(x, k)])
+    xa, ka = o.x_operator_array(dxm, (n,), 0), o.k_operator_array(dxm, (n,), 0)
+    ops_np = np.array([xa, ka, xa @ ka])
+    h = operator.build.kinetic_hamiltonian(operator.build.cos_potential(meta, 3.0), 1.0, hbar=1.0)
+    ha = h.as_array()
+    scale = np.abs(ha).max() * np.abs(ops_np).max() * n
+
+    def arr(lst):
+        return np.array([op.as_array() for op in lst])
+
+    np.testing.assert_allclose(arr(operator.matmul_operator_list(h, ops)), o.operator_matmul(ha, ops_np),
+                               rtol=0, atol=1e-14 * scale)
+    np.testing.assert_allclose(arr(operator.matmul_list_operator(ops, h)), o.operator_matmul(ops_np, ha),
+                               rtol=0, atol=1e-14 * scale)
+    np.testing.assert_allclose(arr(operator.get_commutator_operator_list(h, ops)), o.operator_commutator(ha, ops_np),
+                               rtol=0, atol=1e-14 * scale)
+    np.testing.assert_allclose(arr(operator.dagger_each(ops)), o.operator_dagger(ops_np), rtol=0,
+                               atol=1e-14 * np.abs(ops_np).max())
+    assert len(operator.get_commutator_operator_list(h, ops)) == 3
+
+
+def test_state_occupations_and_inner_products(cuda):
+    """reference tests/test_state.py:20-74 + the list forms (state/_state.py:208-308)."""
+    _, _, _, state, TupleBasis, basis, _ = _api()
+    meta = _meta_1d(2 * np.pi, 5)
+    state_basis = basis.from_metadata(meta)
+    data = np.zeros(5, dtype=np.complex128)
+    data[0] = data[1] = (1 - 1j) / np.sqrt(2)
+    s0 = state.State(state_basis, data)
+    occ = state.get_occupations(s0)
+    np.testing.assert_allclose(occ.raw_data, [1, 1, 0, 0, 0], atol=1e-15)
+    assert occ.basis.metadata().basis == state_basis
+    momentum_basis = basis.TransformedBasis(state_basis)
+    occ = state.get_occupations(state.State(momentum_basis, data))
+    np.testing.assert_allclose(occ.raw_data, [1, 1, 0, 0, 0], atol=1e-15)
+    assert occ.basis.metadata().basis == momentum_basis
+    data1 = data.copy()
+    data1[1] = -data[1]
+    s1 = state.State(state_basis, data1)
+    np.testing.assert_allclose(state.inner_product(s1, s0), 0, atol=1e-15)
+    np.testing.assert_allclose(state.normalization(s0), 2, atol=1e-15)
+    np.testing.assert_allclose(state.normalization(state.normalize(s0)), 1, atol=1e-15)
+    both = state.StateList.from_states([s0, s1])
+    both_np = np.array([data, data1])
+    np.testing.assert_allclose(state.inner_product_each(both, both).raw_data, o.inner_product_each(both_np, both_np),
+                               atol=1e-15)
+    np.testing.assert_allclose(state.all_inner_product(both, both).raw_data.reshape(2, 2),
+                               o.all_inner_product(both_np, both_np), atol=1e-15)
+    np.testing.assert_allclose(state.normalization_each(both).raw_data, [2, 2], atol=1e-15)
+    np.testing.assert_allclose(state.normalize_each(both).raw_data.reshape(2, 5), o.normalize_each(both_np), atol=1e-15)
+    np.testing.assert_allclose(state.get_all_occupations(both).raw_data.reshape(2, 5), o.occupations(both_np), atol=1e-15)
+    # a list held in the momentum basis is compared in the first list's basis
+    both_k = both.with_state_basis(momentum_basis)
+    np.testing.assert_allclose(state.inner_product_each(both, both_k).raw_data, [2, 2], atol=1e-14)
+    np.testing.assert_allclose(state.all_inner_product(both_k, both).raw_data.reshape(2, 2), [[2, 0], [0, 2]], atol=1e-14)
+
+
+def test_expectation_of_each_on_evolved_states(cuda):
+    """expectation_of_each (reference operator/_operator.py:196-207) of x, k and H over a Schrodinger-evolved list:
+    equals the K6 observables for x and k, and <H> is conserved."""
+    _, dynamics, operator, state, TupleBasis, basis, metadata = _api()
+    n, length = 128, 16.0
+    meta = _meta_1d(length, n)
+    dxm = np.array([[length]])
+    mass, hb = 1.0, 1.0
+    h = operator.build.kinetic_hamiltonian(operator.build.cos_potential(meta, 2.0), mass, hbar=hb)
+    psi = o.coherent_state(dxm, (n,), (6.0,), (1.2,), (0.9,))
+    psi /= np.linalg.norm(psi)
+    s = state.State(basis.from_metadata(meta).upcast(), psi)
+    from slate_quantum_b200.core import FundamentalBasis
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata
+
+    times = FundamentalBasis(SpacedTimeMetadata(9, domain=Domain(delta=0.45)))
+    evolved = dynamics.solve_schrodinger_equation_decomposition(s, times, h, hbar=hb)
+    pos = evolved.with_state_basis(basis.from_metadata(meta).upcast()).raw_data.reshape(9, n)
+    x, k = operator.build.x(meta, axis=0), operator.build.k(meta, axis=0)
+    np.testing.assert_allclose(operator.expectation_of_each(x, evolved).raw_data,
+                               o.expectation_of_each(o.x_operator_array(dxm, (n,), 0), pos), atol=1e-10)
+    np.testing.assert_allclose(operator.expectation_of_each(x, evolved).raw_data.real,
+                               operator.measure.all_x(evolved, axis=0).raw_data, atol=1e-10)
+    np.testing.assert_allclose(operator.expectation_of_each(k, evolved).raw_data,
+                               o.expectation_of_each(o.k_operator_array(dxm, (n,), 0), pos), atol=1e-10)
+    np.testing.assert_allclose(operator.expectation_of_each(k, evolved).raw_data.real,
+                               operator.measure.all_k(evolved, axis=0).raw_data, atol=1e-10)
+    energy = operator.expectation_of_each(h, evolved).raw_data
+    np.testing.assert_allclose(energy, energy[0], atol=1e-10)
+    np.testing.assert_allclose(energy.imag, 0, atol=1e-12)
+    occ = state.get_all_occupations(evolved)  # eigenbasis occupations are constants of the motion
+    occ = occ.raw_data.reshape(9, n)
+    np.testing.assert_allclose(occ, np.broadcast_to(occ[0], occ.shape), atol=1e-13)

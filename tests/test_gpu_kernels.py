@@ -657,3 +657,88 @@ def test_sharded_config_block_range_properties(cuda, name, count):
     for b in (0, count // 2, count - 1):
         w_ref = np.linalg.eigvalsh(h[b].cpu().numpy())
         np.testing.assert_allclose(w[b].cpu().numpy(), w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
+
+
+# ---------------------------------------------------------------------------------------- K7
+def _rand_c(rng, *shape):
+    return rng.normal(size=shape) + 1j * rng.normal(size=shape)
+
+
+@pytest.mark.parametrize(("m", "n", "k"), [(1, 1, 1), (5, 5, 5), (64, 64, 64), (70, 33, 129), (1, 257, 64),
+                                            (130, 1, 9), (300, 300, 300), (96, 200, 7)])
+@pytest.mark.parametrize("batch", [None, 3])
+def test_zgemm_against_numpy(cuda, m, n, k, batch):
+    """sqb_zgemm_batched against the oracle's operator_matmul on ragged sizes (tile edges in m, n and k)."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(m * 1000 + n * 10 + k)
+    lead = () if batch is None else (batch,)
+    a, b = _rand_c(rng, *lead, m, k), _rand_c(rng, *lead, k, n)
+    want = o.operator_matmul(a, b)
+    got = kernels.zgemm(kernels.to_device(a, torch.complex128), kernels.to_device(b, torch.complex128))
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-13 * max(1, k))
+
+
+def test_zgemm_strided_conjugated_and_broadcast_operands(cuda):
+    """Transposes / daggers / conjugates are stride swaps + a flag, a 2-d operand is shared by the batch, and
+    alpha / beta accumulate in place: out = alpha * op(A) op(B) + beta * out."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(77)
+    m, n, k, batch = 75, 50, 91, 4
+    a, b = _rand_c(rng, batch, k, m), _rand_c(rng, n, k)  # stored transposed
+    c0 = _rand_c(rng, batch, m, n)
+    ad, bd = kernels.to_device(a, torch.complex128), kernels.to_device(b, torch.complex128)
+    alpha, beta = 0.3 - 1.1j, -0.5 + 0.25j
+    cases = {
+        "T,T": (ad.mT, bd.mT, np.swapaxes(a, 1, 2), b.T),
+        "H,T": (ad.mH, bd.mT, np.conj(np.swapaxes(a, 1, 2)), b.T),
+        "T,H": (ad.mT, bd.mH, np.swapaxes(a, 1, 2), b.conj().T),
+        "H,H": (ad.mH, bd.mH, np.conj(np.swapaxes(a, 1, 2)), b.conj().T),
+    }
+    for name, (xa, xb, na, nb) in cases.items():
+        out = kernels.to_device(c0, torch.complex128)
+        kernels.zgemm(xa, xb, alpha=alpha, beta=beta, out=out)
+        want = alpha * (na @ nb) + beta * c0
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=2e-12, err_msg=name)
+    # sliced (non-compact) operands: a column block of a wider matrix
+    wide = _rand_c(rng, 40, 200)
+    wd = kernels.to_device(wide, torch.complex128)
+    got = kernels.zgemm(wd[:, 30:101], wd[:, 90:161].mH)
+    np.testing.assert_allclose(got.cpu().numpy(), wide[:, 30:101] @ wide[:, 90:161].conj().T, rtol=0, atol=1e-11)
+    # k = 0: out = beta * out
+    out = kernels.to_device(c0[0], torch.complex128)
+    kernels.zgemm(ad[0, :0].mT, bd[:, :0].mT, alpha=1.0, beta=2.0, out=out)
+    np.testing.assert_allclose(out.cpu().numpy(), 2 * c0[0], rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        kernels.zgemm(ad[0], bd)  # inner dimensions differ
+
+
+def test_zgemm_commutator_is_exactly_zero_for_equal_operands(cuda):
+    """reference tests/test_operator.py:248-259 asserts array_equal(commute(A, A), 0): AB and BA must be
+    accumulated in the same order so that the in-place subtraction cancels bit for bit."""
+    torch, kernels = _gpu()
+    a = kernels.to_device(_rand_c(np.random.default_rng(3), 150, 150), torch.complex128)
+    out = kernels.zgemm(a, a)
+    kernels.zgemm(a, a, alpha=-1.0, beta=1.0, out=out)
+    assert float(out.abs().max().item()) == 0.0
+
+
+def test_rowwise_reductions_against_oracle(cuda):
+    """sqb_rowwise_vdot / sqb_abs2 / sqb_normalize_rows vs the oracle's inner_product_each, occupations,
+    normalize_each (state/_state.py:208-308)."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(5)
+    for rows, length in [(1, 1), (3, 5), (7, 1000), (2, 70001)]:
+        x, y = _rand_c(rng, rows, length), _rand_c(rng, rows, length)
+        xd, yd = kernels.to_device(x, torch.complex128), kernels.to_device(y, torch.complex128)
+        scale = np.sqrt(length)
+        np.testing.assert_allclose(kernels.rowwise_vdot(xd, yd).cpu().numpy(), o.inner_product_each(x, y),
+                                   rtol=0, atol=1e-13 * length)
+        np.testing.assert_allclose(kernels.abs2(xd).cpu().numpy(), o.occupations(x), rtol=1e-15, atol=0)
+        np.testing.assert_allclose(kernels.normalize_rows(xd).cpu().numpy(), o.normalize_each(x), rtol=0,
+                                   atol=1e-15 * scale)
+    # strided rows (a column block)
+    wide = _rand_c(rng, 6, 300)
+    wd = kernels.to_device(wide, torch.complex128)
+    np.testing.assert_allclose(kernels.rowwise_vdot(wd[:, 10:150], wd[:, 150:290]).cpu().numpy(),
+                               o.inner_product_each(wide[:, 10:150], wide[:, 150:290]), rtol=0, atol=1e-12)
