@@ -740,3 +740,21 @@ def normalize_each(states: np.ndarray) -> np.ndarray:
     """state.normalize_each: every row divided by sqrt(<psi|psi>) (state/_state.py:249-262)."""
     states = np.atleast_2d(states)
     return states / np.sqrt(inner_product_each(states, states))[:, np.newaxis]
+
+
+BOLTZMANN_SI = 1.380649e-23
+
+
+def temperature_corrected_operators(
+    hamiltonian: np.ndarray, operators: np.ndarray, temperature: float, eta: float = 1.0, hbar: float = HBAR_SI
+) -> np.ndarray:
+    """noise.build.temperature_corrected_operators (noise/build/_build.py:141-155) on dense arrays [L, n, n]."""
+    kb_t = BOLTZMANN_SI * temperature
+    correction = operator_commutator(hamiltonian, operators) * (-1 * np.sqrt(eta / (8 * kb_t * hbar**2)))
+    return correction + operators * np.sqrt(2 * eta * kb_t / hbar**2)
+
+
+def hamiltonian_shift(hamiltonian: np.ndarray, operators: np.ndarray, eta: float, hbar: float = HBAR_SI) -> np.ndarray:
+    """noise.build.hamiltonian_shift (noise/build/_build.py:158-172): i eta / (4 hbar) [H, sum_m L_m^dagger L_m]."""
+    shift_product = np.einsum("ikj,ikl->jl", np.conj(operators), operators)
+    return operator_commutator(hamiltonian, shift_product) * (1j * eta / (4 * hbar))

@@ -85,6 +85,16 @@ class OperatorList(Array):
     def __len__(self) -> int:
         return _basis.as_tuple(self.basis).children[0].size
 
+    def __getitem__(self, index: Any) -> Operator:
+        """list[i] / list[i, :] -> the i-th operator (reference :329-375, integer index only)."""
+        tup = _basis.as_tuple(self.basis)
+        if isinstance(index, tuple) and len(index) == 2 and index[1] == slice(None):  # noqa: PLR2004
+            index = index[0]
+        if not isinstance(index, (int, np.integer)):
+            msg = "only list[i] / list[i, :] indexing is implemented"
+            raise NotImplementedError(msg)
+        return Operator(tup.children[1], self.raw_data.reshape(tup.shape)[index])
+
     @staticmethod
     def from_operators(iter_: Iterable[Operator]) -> "OperatorList":
         """reference :377-395."""

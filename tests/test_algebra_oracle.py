@@ -87,3 +87,23 @@ def test_expectation_matches_measure():
     np.testing.assert_allclose(ex.real, o.measure_all_x(psi, dxm, (n,), 0), atol=1e-12)
     ek = o.expectation_of_each(o.k_operator_array(dxm, (n,), 0), psi)
     np.testing.assert_allclose(ek.real, o.measure_all_k(psi, dxm, (n,), 0), atol=1e-10)
+
+
+def test_temperature_corrected_operators_and_shift():
+    """noise/build/_build.py:141-172 on dense arrays: hermitian L and H give an anti-hermitian correction term,
+    and the shift vanishes when sum L^dagger L commutes with H (e.g. a single unitary L)."""
+    rng = np.random.default_rng(1)
+    n = 7
+    g = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    h = g + g.conj().T
+    ops = np.array([np.diag(rng.normal(size=n)).astype(complex), o.k_operator_array(DX, (n,), 0)])
+    t, eta = 150.0, 0.3
+    got = o.temperature_corrected_operators(h, ops, t, eta, hbar=1.0)
+    kb_t = o.BOLTZMANN_SI * t
+    for m in range(2):
+        want = np.sqrt(2 * eta * kb_t) * ops[m] - np.sqrt(eta / (8 * kb_t)) * (h @ ops[m] - ops[m] @ h)
+        np.testing.assert_allclose(got[m], want, rtol=1e-13)
+    q, _ = np.linalg.qr(g)
+    np.testing.assert_allclose(o.hamiltonian_shift(h, q[np.newaxis], eta, hbar=1.0), np.zeros((n, n)), atol=1e-13)
+    shift = o.hamiltonian_shift(h, ops, eta, hbar=1.0)
+    np.testing.assert_allclose(shift, o.operator_dagger(shift), atol=1e-12)  # i [H, hermitian] is hermitian

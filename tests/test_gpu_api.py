@@ -556,3 +556,48 @@ def test_expectation_of_each_on_evolved_states(cuda):
     occ = state.get_all_occupations(evolved)  # eigenbasis occupations are constants of the motion
     occ = occ.raw_data.reshape(9, n)
     np.testing.assert_allclose(occ, np.broadcast_to(occ[0], occ.shape), atol=1e-13)
+
+
+def test_build_cl_operator(cuda):
+    """reference tests/test_operator.py:451-476, plus parity of the temperature correction and the Hamiltonian
+    shift (noise/build/_build.py:141-172) with the oracle."""
+    _, _, operator, _, _, _, _ = _api()
+    from slate_quantum_b200 import noise
+
+    n = 160
+    meta = _meta_1d(2 * np.pi, n)
+    dxm = np.array([[2 * np.pi]])
+    temperature, mass = 1, 1
+    operators = noise.build.caldeira_leggett_operators(meta)
+    assert len(operators) == 1  # one operator for a 1-d system
+    x_operator = operator.build.x(meta, axis=0)
+    np.testing.assert_allclose(operators[0, :].as_array(), x_operator.as_array(), atol=1e-15)
+    hamiltonian = operator.build.kinetic_energy(meta, mass)
+    corrected = noise.build.temperature_corrected_operators(hamiltonian, operators, temperature)
+    assert len(corrected) == 1
+    commutator = operator.commute(operator.build.x(meta, axis=0), operator.build.p(meta, axis=0))
+    np.testing.assert_allclose(commutator.as_array(), (1j * hbar), atol=1e-15)
+    # parity with the oracle on the same dense arrays
+    h_np, x_np = hamiltonian.as_array(), o.x_operator_array(dxm, (n,), 0)
+    want = o.temperature_corrected_operators(h_np, x_np[np.newaxis], temperature)
+    got = corrected[0].as_array()
+    np.testing.assert_allclose(got, want[0], rtol=0, atol=1e-12 * np.abs(want).max())
+    eta = 0.7
+    shift = noise.build.hamiltonian_shift(hamiltonian, operators, eta)
+    want_shift = o.hamiltonian_shift(h_np, x_np[np.newaxis], eta)
+    np.testing.assert_allclose(shift.as_array(), want_shift, rtol=0, atol=1e-12 * np.abs(want_shift).max())
+    # a longer list: [x, k, x k + k x]
+    k_op = operator.build.k(meta, axis=0)
+    xk = operator.matmul(x_operator, k_op)
+    sym = xk + operator.dagger(xk)
+    ops = operator.OperatorList.from_operators(
+        [x_operator.with_basis(xk.basis), k_op.with_basis(xk.basis), sym.with_basis(xk.basis)]
+    )
+    ops_np = np.array([op.as_array() for op in ops])
+    got = noise.build.temperature_corrected_operators(hamiltonian, ops, 300.0, eta)
+    want = o.temperature_corrected_operators(h_np, ops_np, 300.0, eta)
+    for m in range(3):
+        np.testing.assert_allclose(got[m].as_array(), want[m], rtol=0, atol=1e-12 * np.abs(want[m]).max())
+    got_shift = noise.build.hamiltonian_shift(hamiltonian, ops, eta).as_array()
+    want_shift = o.hamiltonian_shift(h_np, ops_np, eta)
+    np.testing.assert_allclose(got_shift, want_shift, rtol=0, atol=1e-11 * np.abs(want_shift).max())
