@@ -262,13 +262,13 @@ def run_ours(args) -> None:
     h_buf = torch.empty((n_k_local, n, n), dtype=torch.complex128, device="cuda")
     ws_bytes = lib.sqb_eigh_workspace_bytes(n, n_k_local)
     solver._eigh_ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")  # noqa: SLF001
-    folded_buf = torch.empty_like(h_buf) if with_position else None
     free, _ = torch.cuda.mem_get_info()
     row_bytes = n_k_local * n * 16
     t_tile = T
     # buffers of one time tile: states (+ position output)
     gathered = world > 1 and with_position  # time-sharded evolve over ring-exchanged eigenvectors
     sharded = TimeShardedEvolver(solver, T) if gathered else None  # pipeline.py; DESIGN.md section 6
+    folded_buf = torch.empty_like(h_buf) if with_position and not gathered else None
     free, _ = torch.cuda.mem_get_info()
     if gathered:
         row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
@@ -308,7 +308,7 @@ def run_ours(args) -> None:
         timed("eigh", eigh)
         if with_position:
             # eigenvectors -> in-cell position basis + Bloch twiddle, once per eigensolve (K4 on N-point cells)
-            timed("fold", lambda: solver.fold(out=folded_buf))
+            timed("fold", (lambda: sharded.fold()) if sharded is not None else (lambda: solver.fold(out=folded_buf)))
         c = timed("project", lambda: solver.project(psi0))
         if world > 1 and with_position:
             # Position output at N > 1 (pipeline.TimeShardedEvolver): the ranks ring-exchange the folded eigenvectors
@@ -546,8 +546,11 @@ def run_ours(args) -> None:
                 "l2_policy": "inputs larger than L2: every step rebuilds and re-reads the "
                 f"{n_k_local * n * n * 16 / 1e9:.2f} GB block array (L2 = 126 MB)",
                 "parallelism": f"k-block sharding x{world}"
-                + (", NCCL all-gather of eigenvalues, NCCL all-to-all (k-shards -> time-shards) before the cell FFT"
-                   if world > 1 else ""),
+                + (", NCCL all-gather of eigenvalues" if world > 1 else "")
+                + (f", eigenvector exchange ({sharded.exchange_mode}: "
+                   + ("peer copies over NVLink from symmetric memory" if sharded.exchange_mode == "p2p"
+                      else "ring of NCCL send/recv")
+                   + ") + time-sharded evolve before the local cell FFT" if sharded is not None else ""),
             },
             "blocks_diagonalised_per_s": n_k_global / ((stage_ms["build"] + stage_ms["eigh"]) * 1e-3),
             "state_time_evolutions_per_s": T

@@ -337,7 +337,7 @@ class TimeShardedEvolver:
     of bench.py); `n_times` must be a multiple of world.
     """
 
-    def __init__(self, solver: BlochSolver, n_times: int, group=None) -> None:
+    def __init__(self, solver: BlochSolver, n_times: int, group=None, exchange: str | None = None) -> None:
         import torch.distributed as dist
 
         self.solver, self.group = solver, group
@@ -359,9 +359,42 @@ class TimeShardedEvolver:
             torch.empty(kernels.evolve_uniform_workspace_bytes(n, c, self.rows), dtype=torch.uint8, device="cuda")
             for _ in self.segments
         ]
-        self.comm_stream = torch.cuda.Stream()
+        self.comm_stream = torch.cuda.Stream(priority=-1)
         self._arrived: list = [None] * self.world
         self._local: tuple | None = None
+        # Where fold() writes the rank's own folded eigenvectors.  exchange="p2p" (default; env SQB_EXCHANGE): two
+        # symmetric-memory buffers (torch.distributed._symmetric_memory: cuMemCreate allocations mapped into every
+        # peer's address space over NVLink), so a peer's eigenvectors are fetched with a plain device-to-device copy
+        # on the copy engines - no communication kernel competes with the evolve CTAs for SMs.  Two buffers,
+        # alternating per eigensolve: the barrier that opens exchange s+1 proves every rank has finished reading
+        # the buffers of exchange s, and buffer s%2 is not written again before fold s+2.
+        # exchange="nccl": ring of NCCL send/recv pairs (ring_exchange) from an ordinary buffer.
+        import os
+
+        want = exchange or os.environ.get("SQB_EXCHANGE", "p2p")
+        if want not in ("p2p", "nccl"):
+            msg = f"exchange must be 'p2p' or 'nccl', got {want!r}"
+            raise ValueError(msg)
+        self._symm = None
+        self._generation = 0
+        if want == "p2p" and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                dev = torch.device("cuda", torch.cuda.current_device())
+                flat = symm.empty((2 * c * n * n * 2,), dtype=torch.float64, device=dev)
+                handle = symm.rendezvous(flat, dist.group.WORLD if group is None else group)
+                self._symm = (flat, handle)
+            except (RuntimeError, ImportError, AttributeError) as err:
+                if exchange == "p2p":
+                    raise
+                self._symm_error = repr(err)  # symmetric memory unavailable on this box: NCCL ring instead
+        self.exchange_mode = "p2p" if self._symm is not None else "nccl"
+        if self._symm is not None:
+            both = torch.view_as_complex(self._symm[0].view(2, c, n, n, 2))
+            self._fold_buffers = [both[0], both[1]]
+        else:
+            self._fold_buffers = [torch.empty((c, n, n), dtype=torch.complex128, device="cuda")]
 
     def gather_eigenvalues(self) -> torch.Tensor:
         """All-gather of the eigenvalues ([n_k, N], global block order); part of the eigensolve stage."""
@@ -370,12 +403,22 @@ class TimeShardedEvolver:
         dist.all_gather_into_tensor(self.eigenvalues, self.solver.eigenvalues.contiguous(), group=self.group)
         return self.eigenvalues.reshape(-1, self.solver.n)
 
+    def fold(self) -> torch.Tensor:
+        """solver.fold() into the buffer the exchange reads from (call once per eigensolve, before
+        start_exchange)."""
+        self._generation += 1
+        return self.solver.fold(out=self._fold_buffers[self._generation % len(self._fold_buffers)])
+
     def start_exchange(self, coefficients: torch.Tensor, wrap=None) -> None:
-        """Enqueue the coefficient all-gather and the eigenvector ring on the side stream (after everything
+        """Enqueue the coefficient all-gather and the eigenvector exchange on the side stream (after everything
         already enqueued on the current stream).  `wrap(name, fn)` lets a caller time the enqueue."""
         import torch.distributed as dist
 
-        folded = self.solver.fold()
+        mine = self._fold_buffers[self._generation % len(self._fold_buffers)]
+        folded = self.solver.transform_folded
+        if folded is None or folded.data_ptr() != mine.data_ptr():
+            msg = "TimeShardedEvolver.fold() first (the exchange reads the evolver's own buffer)"
+            raise RuntimeError(msg)
         self._local = (folded, coefficients)
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
@@ -390,7 +433,18 @@ class TimeShardedEvolver:
             dist.all_gather_into_tensor(
                 torch.view_as_real(self.coefficients), torch.view_as_real(coefficients.contiguous()), group=self.group
             )
-            ring_exchange(folded, self.transforms, self.group, arrived)
+            if self._symm is None:
+                ring_exchange(folded, self.transforms, self.group, arrived)
+                return
+            _, handle = self._symm
+            handle.barrier(channel=0)  # every rank's fold of this generation is complete
+            count = folded.numel() * 2
+            offset = (self._generation % 2) * count
+            for k in range(1, self.world):
+                src = (self.rank - k) % self.world
+                peer = handle.get_buffer(src, (count,), torch.float64, offset)
+                torch.view_as_real(self.transforms[src]).reshape(-1).copy_(peer, non_blocking=True)
+                arrived(k)
 
         with torch.cuda.stream(self.comm_stream):
             run() if wrap is None else wrap("exchange", run)

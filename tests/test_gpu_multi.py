@@ -40,28 +40,38 @@ T = 24 * world
 blocks = o.bloch_blocks(dx, shape, comps, HBAR**2, repeat)
 w_ref, t_ref = o.eigh_blocks(blocks)
 c = solver.project(kernels.to_device(psi, torch.complex128))
-sharded = TimeShardedEvolver(solver, T)
-assert sharded.rows == 24 and sharded.time_begin == 24 * rank
-eig = sharded.gather_eigenvalues().cpu().numpy()
-assert np.abs(eig - w_ref).max() <= 1e-10 * np.abs(w_ref).max()
-for uniform in (True, False):
-    times = np.linspace(0, 5 * HBAR, T) if uniform else np.sort(rng.uniform(0, 5 * HBAR, T))
-    dt = kernels.uniform_step(times) if uniform else None
-    assert (dt is not None) == uniform
-    want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
-    lo = sharded.time_begin
-    t_dev = kernels.to_device(times[lo:lo + sharded.rows], torch.float64)
-    for t_tile in (sharded.rows, 10):  # one tile / ragged tiles reusing the Re+Im plane
+for mode in ("p2p", "nccl"):
+    sharded = TimeShardedEvolver(solver, T, exchange=mode)
+    assert sharded.exchange_mode == mode
+    assert sharded.rows == 24 and sharded.time_begin == 24 * rank
+    eig = sharded.gather_eigenvalues().cpu().numpy()
+    assert np.abs(eig - w_ref).max() <= 1e-10 * np.abs(w_ref).max()
+    try:
         sharded.start_exchange(c)
-        states = torch.empty((t_tile, solver.m), dtype=torch.complex128, device="cuda")
-        out = torch.empty_like(states)
-        got = np.empty((sharded.rows, solver.m), dtype=np.complex128)
-        def keep(t0, tt, tile):
-            got[t0:t0 + tt] = tile.cpu().numpy()
-        sharded.evolve_position(t_dev, states, out, dt, on_tile=keep)
-        torch.cuda.synchronize()
-        err = np.abs(got - want[lo:lo + sharded.rows]).max()
-        assert err < 1e-9, (rank, uniform, t_tile, err)
+    except RuntimeError:
+        pass
+    else:
+        raise AssertionError("start_exchange before fold() must fail")
+    for uniform in (True, False):
+        times = np.linspace(0, 5 * HBAR, T) if uniform else np.sort(rng.uniform(0, 5 * HBAR, T))
+        dt = kernels.uniform_step(times) if uniform else None
+        assert (dt is not None) == uniform
+        want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
+        lo = sharded.time_begin
+        t_dev = kernels.to_device(times[lo:lo + sharded.rows], torch.float64)
+        for t_tile in (sharded.rows, 10):  # one tile / ragged tiles reusing the Re+Im plane
+            sharded.fold()  # a new generation each time: alternates the two symmetric buffers
+            sharded.start_exchange(c)
+            states = torch.empty((t_tile, solver.m), dtype=torch.complex128, device="cuda")
+            out = torch.empty_like(states)
+            got = np.empty((sharded.rows, solver.m), dtype=np.complex128)
+            def keep(t0, tt, tile):
+                got[t0:t0 + tt] = tile.cpu().numpy()
+            sharded.evolve_position(t_dev, states, out, dt, on_tile=keep)
+            torch.cuda.synchronize()
+            err = np.abs(got - want[lo:lo + sharded.rows]).max()
+            assert err < 1e-9, (rank, mode, uniform, t_tile, err)
+    dist.barrier()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
