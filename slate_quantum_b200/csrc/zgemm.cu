@@ -21,6 +21,7 @@ constexpr int kZgTile = 64;
 constexpr int kZgKc = 8;
 constexpr int kZgLd = kZgTile + 8;
 constexpr int kZgThreads = 128;
+constexpr int kZgGroup = 8;  // tile rows per L2 group
 
 __device__ __forceinline__ void zg_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -53,7 +54,14 @@ zgemm_kernel(int m, int n, int k, ZgOperand A, ZgOperand B, c128* __restrict__ c
   __shared__ double Br[2][kZgKc * kZgLd], Bi[2][kZgKc * kZgLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = batch0 + blockIdx.z;
-  const int i0 = blockIdx.y * kZgTile, j0 = blockIdx.x * kZgTile;
+  // grouped tile order: consecutive CTAs walk kZgGroup tile rows column by column, so the CTAs resident at the same
+  // time share a few A panels and a few B panels in L2 instead of streaming all of B once per tile row
+  const int tiles_m = (m + kZgTile - 1) / kZgTile, tiles_n = (n + kZgTile - 1) / kZgTile;
+  const int width = kZgGroup * tiles_n;
+  const int first_m = ((int)blockIdx.x / width) * kZgGroup;
+  const int gsize = min(tiles_m - first_m, kZgGroup);
+  const int i0 = (first_m + ((int)blockIdx.x % width) % gsize) * kZgTile;
+  const int j0 = (((int)blockIdx.x % width) / gsize) * kZgTile;
   const c128* a = A.p + b * A.bs;
   const c128* bb = B.p + b * B.bs;
   const bool a_kfast = A.cs == 1, b_kfast = B.rs == 1 && B.cs != 1;
@@ -218,11 +226,11 @@ extern "C" int sqb_zgemm_batched(int m, int n, int k, int64_t batch, const sqb_c
   ZgOperand A{reinterpret_cast<const c128*>(a), a_row_stride, a_col_stride, a_batch_stride, conj_a != 0};
   ZgOperand B{reinterpret_cast<const c128*>(b), b_row_stride, b_col_stride, b_batch_stride, conj_b != 0};
   const c128 al = make_double2(alpha[0], alpha[1]), be = make_double2(beta[0], beta[1]);
-  const unsigned gx = (unsigned)((n + kZgTile - 1) / kZgTile), gy = (unsigned)((m + kZgTile - 1) / kZgTile);
-  if (gy > 65535u) return SQB_E_BADARG;
+  const int64_t tiles = (int64_t)((n + kZgTile - 1) / kZgTile) * ((m + kZgTile - 1) / kZgTile);
+  if (tiles > 0x7fffffff) return SQB_E_UNSUPPORTED;
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const unsigned gz = (unsigned)sqb_min64(65535, batch - b0);
-    zgemm_kernel<<<dim3(gx, gy, gz), kZgThreads, 0, sqb_stream(stream)>>>(
+    zgemm_kernel<<<dim3((unsigned)tiles, 1, gz), kZgThreads, 0, sqb_stream(stream)>>>(
         m, n, k, A, B, reinterpret_cast<c128*>(c), ldc, c_batch_stride, al, be, b0);
     SQB_LAUNCH_CHECK();
   }

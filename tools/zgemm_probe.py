@@ -14,6 +14,7 @@ def timeit(fn, reps=5, warm=2):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return min(ts)
 
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 res = {}
 g = torch.Generator(device="cuda").manual_seed(0)
 def rnd(*s):
@@ -26,6 +27,8 @@ for name, (batch, m, n, k, tb) in {
     "blocks_4096x256": (4096, 256, 256, 256, False),
     "states_4096xM4096": (None, 4096, 4096, 4096, True),
 }.items():
+    if only and name != only:
+        continue
     lead = () if batch is None else (batch,)
     a = rnd(*lead, m, k)
     b = rnd(*lead, n, k).mT if tb else rnd(*lead, k, n)
