@@ -262,6 +262,9 @@ int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c1
  *
  * sqb_rowwise_vdot    out[r] = sum_i conj(x[r, i]) y[r, i]      (state.inner_product_each, state/_state.py:208-228;
  *                     the last step of expectation_of_each)
+ * sqb_rowwise_weighted_abs2  out[r] = sum_i weights[i] |x[r, i]|^2: expectation_of_each of an operator that is
+ *                     DIAGONAL in the basis the states are written in (potentials, x, kinetic energy, k): one pass over
+ *                     the state list instead of a dense [M, M] operator
  * sqb_abs2            out[i] = |x[i]|^2                          (state.get_all_occupations, state/_state.py:265-308)
  * sqb_normalize_rows  out[r, :] = x[r, :] / sqrt(|norm2[r]|)     (state.normalize_each, state/_state.py:242-262)
  * ---------------------------------------------------------------------------------------------- */
@@ -272,6 +275,8 @@ int sqb_zgemm_batched(int m, int n, int k, int64_t batch, const sqb_c128* a, int
                       void* stream);
 int sqb_rowwise_vdot(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride, const sqb_c128* y,
                      int64_t y_row_stride, sqb_c128* out, void* stream);
+int sqb_rowwise_weighted_abs2(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride,
+                              const sqb_c128* weights, sqb_c128* out, void* stream);
 int sqb_abs2(int64_t count, const sqb_c128* x, double* out, void* stream);
 int sqb_normalize_rows(int64_t rows, int64_t len, const sqb_c128* x, const sqb_c128* norm2, sqb_c128* out,
                        void* stream);

@@ -192,6 +192,37 @@ rowwise_vdot_kernel(int64_t len, const c128* __restrict__ x, int64_t x_rs, const
   }
 }
 
+// out[r] = sum_i w[i] |x[r, i]|^2: the expectation of an operator that is diagonal in the basis x is written in
+__global__ void __launch_bounds__(kRowThreads)
+rowwise_weighted_abs2_kernel(int64_t len, const c128* __restrict__ x, int64_t x_rs, const c128* __restrict__ w,
+                             c128* __restrict__ out) {
+  __shared__ double red[2][kRowThreads / 32];
+  const int64_t r = blockIdx.x;
+  const c128* xr = x + r * x_rs;
+  double ax = 0.0, ay = 0.0;
+  for (int64_t i = threadIdx.x; i < len; i += kRowThreads) {
+    const c128 z = xr[i], wi = w[i];
+    const double p = fma(z.x, z.x, z.y * z.y);
+    ax = fma(wi.x, p, ax);
+    ay = fma(wi.y, p, ay);
+  }
+  ax = warp_sum(ax);
+  ay = warp_sum(ay);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = ax;
+    red[1][threadIdx.x >> 5] = ay;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sx = 0.0, sy = 0.0;
+    for (int k = 0; k < kRowThreads / 32; ++k) {
+      sx += red[0][k];
+      sy += red[1][k];
+    }
+    out[r] = make_double2(sx, sy);
+  }
+}
+
 // out[i] = |x[i]|^2
 __global__ void __launch_bounds__(kRowThreads)
 abs2_kernel(int64_t count, const c128* __restrict__ x, double* __restrict__ out) {
@@ -247,6 +278,21 @@ extern "C" int sqb_rowwise_vdot(int64_t rows, int64_t len, const sqb_c128* x, in
     rowwise_vdot_kernel<<<g, kRowThreads, 0, sqb_stream(stream)>>>(
         len, reinterpret_cast<const c128*>(x) + r0 * x_row_stride, x_row_stride,
         reinterpret_cast<const c128*>(y) + r0 * y_row_stride, y_row_stride, reinterpret_cast<c128*>(out) + r0);
+    SQB_LAUNCH_CHECK();
+  }
+  return SQB_OK;
+}
+
+extern "C" int sqb_rowwise_weighted_abs2(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride,
+                                        const sqb_c128* weights, sqb_c128* out, void* stream) {
+  if (rows < 0 || len < 0) return SQB_E_BADARG;
+  if (rows == 0) return SQB_OK;
+  if (!out || (len > 0 && (!x || !weights))) return SQB_E_BADARG;
+  for (int64_t r0 = 0; r0 < rows; r0 += 0x7fffffff) {
+    const unsigned g = (unsigned)sqb_min64(0x7fffffff, rows - r0);
+    rowwise_weighted_abs2_kernel<<<g, kRowThreads, 0, sqb_stream(stream)>>>(
+        len, reinterpret_cast<const c128*>(x) + r0 * x_row_stride, x_row_stride,
+        reinterpret_cast<const c128*>(weights), reinterpret_cast<c128*>(out) + r0);
     SQB_LAUNCH_CHECK();
   }
   return SQB_OK;

@@ -533,6 +533,26 @@ def rowwise_vdot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rowwise_weighted_abs2(x: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """out[r] = sum_i weights[i] * |x[r, i]|^2 for [rows, len] complex128 states and [len] complex128 weights."""
+    _require_cuda()
+    if not (x.is_cuda and x.dtype == torch.complex128 and x.dim() == 2 and (x.shape[1] <= 1 or x.stride(1) == 1)):
+        msg = "x must be a [rows, len] CUDA complex128 tensor with unit stride along len"
+        raise TypeError(msg)
+    _c128(weights, "weights")
+    if weights.numel() != x.shape[1]:
+        msg = "one weight per column"
+        raise ValueError(msg)
+    x = x.resolve_conj()
+    out = torch.empty((x.shape[0],), dtype=torch.complex128, device="cuda")
+    rc = _lib.load().sqb_rowwise_weighted_abs2(
+        x.shape[0], x.shape[1], _ptr(x), x.stride(0), _ptr(weights), _ptr(out), _stream()
+    )
+    _lib.check(rc, "sqb_rowwise_weighted_abs2")
+    _count(1 if x.shape[0] else 0)
+    return out
+
+
 def abs2(x: torch.Tensor) -> torch.Tensor:
     """|x|^2 elementwise (float64, same shape)."""
     _require_cuda()

@@ -141,14 +141,55 @@ def expectation(operator: Operator, state: Any) -> complex:
     return complex(kernels.rowwise_vdot(lhs, applied.device_data.reshape(1, -1)).cpu().numpy()[0])
 
 
+def _diagonal_form(operator: Operator):
+    """(ket basis, diagonal) when the operator is stored as a diagonal over (b, b.dual) - potentials, x
+    (position basis), kinetic energy, k, p (momentum basis), the output of into_diagonal_hermitian (eigenbasis) -
+    else None."""
+    from slate_quantum_b200.core.array import _complex
+    from slate_quantum_b200.core.basis import DiagonalBasis, RecastBasis
+
+    stored = _basis._strip(operator.basis)  # noqa: SLF001
+    data = _complex(operator.device_data).reshape(-1)
+    if isinstance(stored, RecastBasis):
+        inner = _basis._strip(stored.inner)  # noqa: SLF001
+        if not isinstance(inner, DiagonalBasis):
+            return None
+        data = stored.into_inner(data, 0)
+        stored = inner
+    if not isinstance(stored, DiagonalBasis):
+        return None
+    ket, bra = _basis.as_tuple(stored.inner).children
+    if bra != ket.dual_basis():
+        return None
+    return ket, data.contiguous()
+
+
 def expectation_of_each(operator: Operator, states: Any) -> Array:
-    """<psi_a|O|psi_a> for every state of a list (reference operator/_operator.py:196-207): Phi = Psi O^T as one
-    complex GEMM over the whole list (the operator is read through swapped strides), then a row-wise <Psi|Phi>."""
+    """<psi_a|O|psi_a> for every state of a list (reference operator/_operator.py:196-207).
+
+    Diagonal operators (potential, x: position basis; kinetic energy, k, p: momentum basis; a diagonalised
+    Hamiltonian: its eigenbasis) take ONE pass over the states written in that basis, sum_i d_i |psi_ai|^2
+    (sqb_rowwise_weighted_abs2) - the only form that scales to the Bloch supercells, where a dense [M, M] operator
+    cannot exist; a SplitBasis Hamiltonian (potential + kinetic) is the sum of its two diagonal parts.  Anything
+    else: Phi = Psi O^T as one complex GEMM over the whole list (the operator is read through swapped strides),
+    then a row-wise <Psi|Phi>."""
     from slate_quantum_b200 import kernels
     from slate_quantum_b200.core.array import _complex
+    from slate_quantum_b200.core.basis import SplitBasis
 
-    tup, o = _dense_operator(operator)
     list_basis = _basis.as_tuple(states.basis).children[0]
+    stored = _basis._strip(operator.basis)  # noqa: SLF001
+    if isinstance(stored, SplitBasis):
+        data = operator.device_data.reshape(-1)
+        lhs = expectation_of_each(Operator(stored.lhs, data[: stored.lhs.size]), states)
+        rhs = expectation_of_each(Operator(stored.rhs, data[stored.lhs.size :]), states)
+        return Array(list_basis, lhs.device_data + rhs.device_data)
+    diagonal = _diagonal_form(operator)
+    if diagonal is not None:
+        ket, diag = diagonal
+        psi = _complex(states.with_state_basis(ket).device_data).reshape(list_basis.size, -1)
+        return Array(list_basis, kernels.rowwise_weighted_abs2(psi, diag))
+    tup, o = _dense_operator(operator)
     rhs = states.with_state_basis(tup.children[1].dual_basis())
     psi1 = _complex(rhs.device_data).reshape(list_basis.size, -1)
     phi = kernels.zgemm(psi1, o.mT)

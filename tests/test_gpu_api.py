@@ -553,6 +553,17 @@ def test_expectation_of_each_on_evolved_states(cuda):
     energy = operator.expectation_of_each(h, evolved).raw_data
     np.testing.assert_allclose(energy, energy[0], atol=1e-10)
     np.testing.assert_allclose(energy.imag, 0, atol=1e-12)
+    # the same three through the dense-operator GEMM path (the diagonal forms above take the one-pass reduction)
+    fund = basis.from_metadata(meta)
+    dense_basis = TupleBasis((fund, fund.dual_basis()))
+    for op in (x, k, h):
+        dense = op.with_basis(dense_basis)
+        np.testing.assert_allclose(operator.expectation_of_each(dense, evolved).raw_data,
+                                   operator.expectation_of_each(op, evolved).raw_data, rtol=0,
+                                   atol=1e-11 * max(1.0, np.abs(dense.raw_data).max()))
+    # a diagonalised Hamiltonian is diagonal in its own eigenbasis: no basis change of the evolved list at all
+    diagonal = operator.into_diagonal_hermitian(h)
+    np.testing.assert_allclose(operator.expectation_of_each(diagonal, evolved).raw_data, energy, atol=1e-10)
     occ = state.get_all_occupations(evolved)  # eigenbasis occupations are constants of the motion
     occ = occ.raw_data.reshape(9, n)
     np.testing.assert_allclose(occ, np.broadcast_to(occ[0], occ.shape), atol=1e-13)
@@ -601,3 +612,42 @@ def test_build_cl_operator(cuda):
     got_shift = noise.build.hamiltonian_shift(hamiltonian, ops, eta).as_array()
     want_shift = o.hamiltonian_shift(h_np, ops_np, eta)
     np.testing.assert_allclose(got_shift, want_shift, rtol=0, atol=1e-11 * np.abs(want_shift).max())
+
+
+def test_expectation_of_each_bloch_hamiltonian(cuda):
+    """<H>, <V>, <T> of Bloch-evolved states through the diagonal one-pass path (no dense supercell operator):
+    the sparse Bloch Hamiltonian's expectation equals the oracle's dense supercell one and is conserved."""
+    bloch, dynamics, operator, state, TupleBasis, basis, metadata = _api()
+    from slate_quantum_b200.core import FundamentalBasis
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata, repeat_volume_metadata
+
+    shape, repeat = (6, 4), (3, 4)
+    vectors = 2 * np.pi * np.eye(2)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(tuple(vectors), shape)
+    potential = operator.build.cos_potential(meta, 3.0)
+    mass = hbar**2
+    full_meta = repeat_volume_metadata(meta, repeat)
+    big = tuple(a * b for a, b in zip(shape, repeat))
+    rng = np.random.default_rng(21)
+    psi = rng.normal(size=int(np.prod(big))) + 1j * rng.normal(size=int(np.prod(big)))
+    psi /= np.linalg.norm(psi)
+    initial = state.State(basis.from_metadata(full_meta).upcast(), psi)
+    times = FundamentalBasis(SpacedTimeMetadata(7, domain=Domain(delta=3 * hbar)))
+    hamiltonian = bloch.build.kinetic_hamiltonian(potential, mass, repeat)
+    evolved = dynamics.solve_schrodinger_equation_decomposition(initial, times, hamiltonian)
+    pos = evolved.with_state_basis(basis.from_metadata(full_meta).upcast()).raw_data.reshape(7, -1)
+    comps = o.cos_potential_components(shape, 3.0)
+    h_x = o.momentum_matrix_to_position(o.supercell_hamiltonian(vectors, shape, comps, mass, repeat), big)
+    want = o.expectation_of_each(h_x, pos)
+    np.testing.assert_allclose(want, want[0], atol=1e-10 * abs(want[0]))
+    # the repeated potential + kinetic split Hamiltonian on the supercell: two diagonal passes
+    split = operator.build.kinetic_hamiltonian(operator.build.repeat_potential(potential, repeat), mass)
+    got = operator.expectation_of_each(split, evolved).raw_data
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * abs(want[0]))
+    v_part = operator.expectation_of_each(operator.build.repeat_potential(potential, repeat), evolved).raw_data
+    t_part = operator.expectation_of_each(operator.build.kinetic_energy(full_meta, mass), evolved).raw_data
+    np.testing.assert_allclose(v_part + t_part, want, rtol=0, atol=1e-10 * abs(want[0]))
+    # in the position basis the kinetic term has a constant diagonal (its mean), the rest of diag(H) is V(x)
+    v_x = np.diag(h_x).real - o.kinetic_energy(vectors * np.array(repeat)[:, None], big, mass).real.mean()
+    np.testing.assert_allclose(v_part.real, (np.abs(pos) ** 2) @ v_x, rtol=0, atol=1e-10 * abs(want[0]))

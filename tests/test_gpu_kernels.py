@@ -742,3 +742,15 @@ def test_rowwise_reductions_against_oracle(cuda):
     wd = kernels.to_device(wide, torch.complex128)
     np.testing.assert_allclose(kernels.rowwise_vdot(wd[:, 10:150], wd[:, 150:290]).cpu().numpy(),
                                o.inner_product_each(wide[:, 10:150], wide[:, 150:290]), rtol=0, atol=1e-12)
+
+
+def test_rowwise_weighted_abs2(cuda):
+    """sqb_rowwise_weighted_abs2 = the oracle's expectation_of_each of a diagonal operator."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(6)
+    for rows, length in [(1, 1), (4, 37), (3, 5000)]:
+        x, w = _rand_c(rng, rows, length), _rand_c(rng, length)
+        got = kernels.rowwise_weighted_abs2(kernels.to_device(x, torch.complex128), kernels.to_device(w, torch.complex128))
+        np.testing.assert_allclose(got.cpu().numpy(), o.expectation_of_each(np.diag(w), x), rtol=0, atol=1e-13 * length)
+    with pytest.raises(ValueError):
+        kernels.rowwise_weighted_abs2(kernels.to_device(x, torch.complex128), kernels.to_device(w[:-1], torch.complex128))
