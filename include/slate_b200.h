@@ -265,6 +265,7 @@ int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c1
  * sqb_rowwise_weighted_abs2  out[r] = sum_i weights[i] |x[r, i]|^2: expectation_of_each of an operator that is
  *                     DIAGONAL in the basis the states are written in (potentials, x, kinetic energy, k): one pass over
  *                     the state list instead of a dense [M, M] operator
+ * sqb_scale_columns   out[r, i] = weights[i] x[r, i]: apply_to_each of a diagonal operator (operator/_operator.py:219-226)
  * sqb_abs2            out[i] = |x[i]|^2                          (state.get_all_occupations, state/_state.py:265-308)
  * sqb_normalize_rows  out[r, :] = x[r, :] / sqrt(|norm2[r]|)     (state.normalize_each, state/_state.py:242-262)
  * ---------------------------------------------------------------------------------------------- */
@@ -277,6 +278,8 @@ int sqb_rowwise_vdot(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row
                      int64_t y_row_stride, sqb_c128* out, void* stream);
 int sqb_rowwise_weighted_abs2(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride,
                               const sqb_c128* weights, sqb_c128* out, void* stream);
+int sqb_scale_columns(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride, const sqb_c128* weights,
+                      sqb_c128* out, void* stream);
 int sqb_abs2(int64_t count, const sqb_c128* x, double* out, void* stream);
 int sqb_normalize_rows(int64_t rows, int64_t len, const sqb_c128* x, const sqb_c128* norm2, sqb_c128* out,
                        void* stream);

@@ -758,3 +758,20 @@ def hamiltonian_shift(hamiltonian: np.ndarray, operators: np.ndarray, eta: float
     """noise.build.hamiltonian_shift (noise/build/_build.py:158-172): i eta / (4 hbar) [H, sum_m L_m^dagger L_m]."""
     shift_product = np.einsum("ikj,ikl->jl", np.conj(operators), operators)
     return operator_commutator(hamiltonian, shift_product) * (1j * eta / (4 * hbar))
+
+
+def measure_all_potential_from_function(
+    states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], fn, offset=None, wrapped: bool = False
+) -> np.ndarray:
+    """operator.measure.all_potential_from_function (operator/_measure.py:41-61): <f(x)> of the normalised states."""
+    weights = np.asarray(fn(tuple(stacked_x_points(delta_x, shape, offset, wrapped)))).ravel()
+    return np.real(_normalised_density(np.atleast_2d(states)) @ weights)
+
+
+def measure_all_momentum_from_function(
+    states: np.ndarray, delta_x: np.ndarray, shape: Sequence[int], fn, offset=None, wrapped: bool = False
+) -> np.ndarray:
+    """operator.measure.momentum_from_function (operator/_measure.py:64-83) for every state: <f(k)>."""
+    weights = np.asarray(fn(tuple(stacked_k_points(delta_x, shape, offset, wrapped)))).ravel()
+    momentum = position_to_momentum(np.atleast_2d(states), shape)
+    return np.real(_normalised_density(momentum) @ weights)

@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "sqb_zgemm_batched",
     "sqb_rowwise_vdot",
     "sqb_rowwise_weighted_abs2",
+    "sqb_scale_columns",
     "sqb_abs2",
     "sqb_normalize_rows",
     "sqb_peak_dmma",
@@ -113,6 +114,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_rowwise_vdot.argtypes = [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
     lib.sqb_rowwise_weighted_abs2.restype = c_int
     lib.sqb_rowwise_weighted_abs2.argtypes = [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.sqb_scale_columns.restype = c_int
+    lib.sqb_scale_columns.argtypes = [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.sqb_abs2.restype = c_int
     lib.sqb_abs2.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
     lib.sqb_normalize_rows.restype = c_int

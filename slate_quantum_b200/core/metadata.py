@@ -271,14 +271,25 @@ class volume:  # noqa: N801 - mirrors the module name slate_core.metadata.volume
         return tuple(points)
 
     @staticmethod
-    def fundamental_stacked_k_points(metadata: TupleMetadata) -> tuple[np.ndarray, ...]:
-        """Cartesian wavevector of every momentum-basis index (FFT order per axis), C-order ravel."""
+    def fundamental_stacked_k_points(
+        metadata: TupleMetadata, *, offset: Sequence[float] | None = None, wrapped: bool = False
+    ) -> tuple[np.ndarray, ...]:
+        """Cartesian wavevector of every momentum-basis index (FFT order per axis), C-order ravel; ``offset`` is a
+        Cartesian displacement, ``wrapped`` folds the points into the first zone [-K/2, K/2), K_a = N_a dk_a."""
         dk = volume.fundamental_stacked_dk(metadata)
+        nd = len(metadata.children)
         nk = np.array(
             [g.ravel() for g in np.meshgrid(*(fundamental_nk_points(c) for c in metadata.children), indexing="ij")],
             dtype=np.float64,
         )
-        return tuple(np.einsum("ij,ik->jk", dk, nk))
+        points = np.einsum("ij,ik->jk", dk, nk)
+        if offset is not None:
+            points = points + np.asarray(offset, dtype=np.float64)[:nd, None]
+        if wrapped:
+            big = volume.fundamental_stacked_delta_k(metadata)
+            frac = np.linalg.solve(big.T, points)
+            points = points - np.einsum("ij,ik->jk", big, np.floor(frac + 0.5))
+        return tuple(points)
 
 
 fundamental_stacked_dk = volume.fundamental_stacked_dk

@@ -223,6 +223,16 @@ rowwise_weighted_abs2_kernel(int64_t len, const c128* __restrict__ x, int64_t x_
   }
 }
 
+// out[r, i] = w[i] * x[r, i]: a diagonal operator applied to every state of a list
+__global__ void __launch_bounds__(kRowThreads)
+scale_columns_kernel(int64_t rows, int64_t len, const c128* __restrict__ x, int64_t x_rs, const c128* __restrict__ w,
+                     c128* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kRowThreads;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y)
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < len; i += stride)
+      out[r * len + i] = cmul(w[i], x[r * x_rs + i]);
+}
+
 // out[i] = |x[i]|^2
 __global__ void __launch_bounds__(kRowThreads)
 abs2_kernel(int64_t count, const c128* __restrict__ x, double* __restrict__ out) {
@@ -295,6 +305,19 @@ extern "C" int sqb_rowwise_weighted_abs2(int64_t rows, int64_t len, const sqb_c1
         reinterpret_cast<const c128*>(weights), reinterpret_cast<c128*>(out) + r0);
     SQB_LAUNCH_CHECK();
   }
+  return SQB_OK;
+}
+
+extern "C" int sqb_scale_columns(int64_t rows, int64_t len, const sqb_c128* x, int64_t x_row_stride,
+                                const sqb_c128* weights, sqb_c128* out, void* stream) {
+  if (rows < 0 || len < 0) return SQB_E_BADARG;
+  if (rows == 0 || len == 0) return SQB_OK;
+  if (!x || !weights || !out) return SQB_E_BADARG;
+  const unsigned gx = (unsigned)sqb_min64((len + kRowThreads - 1) / kRowThreads, 148 * 8);
+  scale_columns_kernel<<<dim3(gx, (unsigned)sqb_min64(rows, 65535)), kRowThreads, 0, sqb_stream(stream)>>>(
+      rows, len, reinterpret_cast<const c128*>(x), x_row_stride, reinterpret_cast<const c128*>(weights),
+      reinterpret_cast<c128*>(out));
+  SQB_LAUNCH_CHECK();
   return SQB_OK;
 }
 

@@ -553,6 +553,24 @@ def rowwise_weighted_abs2(x: torch.Tensor, weights: torch.Tensor) -> torch.Tenso
     return out
 
 
+def scale_columns(x: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """out[r, i] = weights[i] * x[r, i] (a diagonal operator applied to every state of a list)."""
+    _require_cuda()
+    if not (x.is_cuda and x.dtype == torch.complex128 and x.dim() == 2 and (x.shape[1] <= 1 or x.stride(1) == 1)):
+        msg = "x must be a [rows, len] CUDA complex128 tensor with unit stride along len"
+        raise TypeError(msg)
+    _c128(weights, "weights")
+    if weights.numel() != x.shape[1]:
+        msg = "one weight per column"
+        raise ValueError(msg)
+    x = x.resolve_conj()
+    out = torch.empty(tuple(x.shape), dtype=torch.complex128, device="cuda")
+    rc = _lib.load().sqb_scale_columns(x.shape[0], x.shape[1], _ptr(x), x.stride(0), _ptr(weights), _ptr(out), _stream())
+    _lib.check(rc, "sqb_scale_columns")
+    _count(1 if x.numel() else 0)
+    return out
+
+
 def abs2(x: torch.Tensor) -> torch.Tensor:
     """|x|^2 elementwise (float64, same shape)."""
     _require_cuda()

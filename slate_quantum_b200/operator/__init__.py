@@ -23,6 +23,7 @@ from slate_quantum_b200.operator._operator import (
     Operator,
     OperatorList,
     apply,
+    apply_to_each,
     expectation,
     expectation_of_each,
     operator_basis,
@@ -32,6 +33,7 @@ __all__ = [
     "Operator",
     "OperatorList",
     "apply",
+    "apply_to_each",
     "build",
     "commute",
     "dagger",

@@ -196,3 +196,21 @@ def expectation_of_each(operator: Operator, states: Any) -> Array:
     lhs = states.with_state_basis(tup.children[0])
     psi0 = _complex(lhs.device_data).reshape(list_basis.size, -1)
     return Array(list_basis, kernels.rowwise_vdot(psi0, phi))
+
+
+def apply_to_each(operator: Operator, states: Any) -> Any:
+    """O|psi_a> for every state of a list, in the operator's ket basis (reference operator/_operator.py:219-226):
+    a column scaling for operators stored as diagonals, else Psi O^T as one complex GEMM."""
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.core.array import _complex
+    from slate_quantum_b200.state._state import StateList
+
+    list_basis = _basis.as_tuple(states.basis).children[0]
+    diagonal = _diagonal_form(operator)
+    if diagonal is not None:
+        ket, diag = diagonal
+        psi = _complex(states.with_state_basis(ket).device_data).reshape(list_basis.size, -1)
+        return StateList(TupleBasis((list_basis, ket)).upcast(), kernels.scale_columns(psi, diag).reshape(-1))
+    tup, o = dense_operator(operator)
+    psi = _complex(states.with_state_basis(tup.children[1].dual_basis()).device_data).reshape(list_basis.size, -1)
+    return StateList(TupleBasis((list_basis, tup.children[0])).upcast(), kernels.zgemm(psi, o.mT).reshape(-1))

@@ -188,3 +188,17 @@ def p(metadata: TupleMetadata, *, axis: int, hbar: float = hbar_si) -> Operator:
     _require_periodic(metadata)
     points = volume.fundamental_stacked_k_points(metadata)[axis].astype(np.complex128)
     return momentum(basis.transformed_from_metadata(metadata).upcast(), (hbar * points).astype(np.complex128))
+
+
+def momentum_from_function(
+    metadata: TupleMetadata,
+    fn: Callable[[tuple[np.ndarray, ...]], np.ndarray],
+    *,
+    wrapped: bool = False,
+    offset: tuple[float, ...] | None = None,
+) -> Operator:
+    """f(k) as an operator diagonal in the momentum basis (reference _build/_momentum.py:82-98)."""
+    _require_periodic(metadata)
+    positions = volume.fundamental_stacked_k_points(metadata, offset=offset, wrapped=wrapped)
+    points = np.asarray(fn(positions)).ravel().astype(np.complex128)
+    return momentum(basis.transformed_from_metadata(metadata).upcast(), points)

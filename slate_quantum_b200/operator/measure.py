@@ -213,3 +213,57 @@ __all__: list[Any] = [
     "variance_x",
     "x",
 ]
+
+
+# ---------------------------------------------------------------------------------------- generic f(x) / f(k)
+def _expectation_over_norm(operator: Any, states: StateList) -> torch.Tensor:
+    """real(<psi|O|psi> / <psi|psi>) per state: the reference normalises the states first (state.normalize_each),
+    which for a linear expectation is a division of the two one-pass reductions."""
+    from slate_quantum_b200.operator._operator import expectation_of_each
+    from slate_quantum_b200.state._state import inner_product_each
+
+    value = expectation_of_each(operator, states).device_data
+    norm = inner_product_each(states, states).device_data
+    return (value / norm).real.contiguous()
+
+
+def _as_list(state: State) -> StateList:
+    return StateList.from_states([state])
+
+
+def all_potential_from_function(
+    states: StateList, fn: Any, *, wrapped: bool = False, offset: tuple[float, ...] | None = None
+) -> Array:
+    """<f(x)> of every (normalised) state for a generic function of the Cartesian position
+    (reference operator/_measure.py:41-61); one weighted pass over the position-basis states."""
+    from slate_quantum_b200.operator import build as _build
+
+    space = states.basis.metadata().children[1]
+    operator = _build.potential_from_function(space, fn=fn, wrapped=wrapped, offset=offset)
+    return _list_array(states, _expectation_over_norm(operator, states))
+
+
+def potential_from_function(
+    state: State, fn: Any, *, wrapped: bool = False, offset: tuple[float, ...] | None = None
+) -> float:
+    """reference operator/_measure.py:19-38."""
+    return float(all_potential_from_function(_as_list(state), fn, wrapped=wrapped, offset=offset).raw_data[0])
+
+
+def all_momentum_from_function(
+    states: StateList, fn: Any, *, wrapped: bool = False, offset: tuple[float, ...] | None = None
+) -> Array:
+    """<f(k)> of every (normalised) state for a generic function of the Cartesian wavevector (the list form of
+    reference operator/_measure.py:64-83); one weighted pass over the momentum-basis states."""
+    from slate_quantum_b200.operator import build as _build
+
+    space = states.basis.metadata().children[1]
+    operator = _build.momentum_from_function(space, fn=fn, wrapped=wrapped, offset=offset)
+    return _list_array(states, _expectation_over_norm(operator, states))
+
+
+def momentum_from_function(
+    state: State, fn: Any, *, wrapped: bool = False, offset: tuple[float, ...] | None = None
+) -> float:
+    """reference operator/_measure.py:64-83."""
+    return float(all_momentum_from_function(_as_list(state), fn, wrapped=wrapped, offset=offset).raw_data[0])

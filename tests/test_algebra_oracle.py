@@ -107,3 +107,21 @@ def test_temperature_corrected_operators_and_shift():
     np.testing.assert_allclose(o.hamiltonian_shift(h, q[np.newaxis], eta, hbar=1.0), np.zeros((n, n)), atol=1e-13)
     shift = o.hamiltonian_shift(h, ops, eta, hbar=1.0)
     np.testing.assert_allclose(shift, o.operator_dagger(shift), atol=1e-12)  # i [H, hermitian] is hermitian
+
+
+def test_measure_from_function_reduces_to_named_observables():
+    """f(x) = x_axis and f(k) = k_axis reproduce all_x / all_k (pinned in tests/test_measure_oracle.py), f = x^2 the
+    second moment; an unnormalised state gives the same values (the reference normalises first)."""
+    shape = (24, 18)
+    dxm = np.diag([2 * np.pi, 5.0])
+    s = np.outer(o.coherent_state(dxm[:1, :1], (24,), (2.0,), (1.0,), (0.5,)),
+                 o.coherent_state(dxm[1:, 1:], (18,), (1.7,), (-2 * np.pi / 5, ), (0.6,))).ravel()
+    states = np.array([s, 3.0j * np.roll(s, 5)])
+    for axis in range(2):
+        np.testing.assert_allclose(o.measure_all_potential_from_function(states, dxm, shape, lambda x, a=axis: x[a]),
+                                   o.measure_all_x(states, dxm, shape, axis), atol=1e-12)
+        np.testing.assert_allclose(o.measure_all_momentum_from_function(states, dxm, shape, lambda k, a=axis: k[a]),
+                                   o.measure_all_k(states, dxm, shape, axis), atol=1e-12)
+    np.testing.assert_allclose(
+        o.measure_all_potential_from_function(states, dxm, shape, lambda x: x[0] ** 2 + 0 * x[1]),
+        o._normalised_density(states) @ (o.stacked_x_points(dxm, shape)[0] ** 2), atol=1e-12)

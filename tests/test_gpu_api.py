@@ -651,3 +651,57 @@ def test_expectation_of_each_bloch_hamiltonian(cuda):
     # in the position basis the kinetic term has a constant diagonal (its mean), the rest of diag(H) is V(x)
     v_x = np.diag(h_x).real - o.kinetic_energy(vectors * np.array(repeat)[:, None], big, mass).real.mean()
     np.testing.assert_allclose(v_part.real, (np.abs(pos) ** 2) @ v_x, rtol=0, atol=1e-10 * abs(want[0]))
+
+
+def test_measure_from_function_and_apply_to_each(cuda):
+    """operator.measure.{potential_from_function, all_potential_from_function, momentum_from_function}
+    (reference operator/_measure.py:19-83) and operator.apply_to_each (operator/_operator.py:219-226), for diagonal
+    and dense operators, against the oracle."""
+    _, _, operator, state, TupleBasis, basis, metadata = _api()
+    shape = (24, 18)
+    dxm = np.diag([2 * np.pi, 5.0])
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(tuple(dxm), shape)
+    s = np.outer(o.coherent_state(dxm[:1, :1], (24,), (2.0,), (1.0,), (0.5,)),
+                 o.coherent_state(dxm[1:, 1:], (18,), (1.7,), (-2 * np.pi / 5,), (0.6,))).ravel()
+    states_np = np.array([s, 3.0j * np.roll(s, 5), s + 0.5 * np.roll(s, 40)])
+    fund = basis.from_metadata(meta)
+    states = state.StateList.from_states([state.State(fund.upcast(), row) for row in states_np])
+
+    def f_x(x):
+        return np.cos(x[0]) + 0.1 * x[1] ** 2
+
+    def f_k(k):
+        return k[0] ** 2 + 0.5 * k[1]
+
+    np.testing.assert_allclose(operator.measure.all_potential_from_function(states, f_x).raw_data,
+                               o.measure_all_potential_from_function(states_np, dxm, shape, f_x), atol=1e-12)
+    np.testing.assert_allclose(
+        operator.measure.all_potential_from_function(states, f_x, wrapped=True, offset=(0.3, -1.0)).raw_data,
+        o.measure_all_potential_from_function(states_np, dxm, shape, f_x, (0.3, -1.0), True), atol=1e-12)
+    np.testing.assert_allclose(operator.measure.all_momentum_from_function(states, f_k).raw_data,
+                               o.measure_all_momentum_from_function(states_np, dxm, shape, f_k), atol=1e-10)
+    np.testing.assert_allclose(operator.measure.potential_from_function(states[1], f_x),
+                               o.measure_all_potential_from_function(states_np[1], dxm, shape, f_x)[0], atol=1e-12)
+    np.testing.assert_allclose(operator.measure.momentum_from_function(states[2], f_k),
+                               o.measure_all_momentum_from_function(states_np[2], dxm, shape, f_k)[0], atol=1e-10)
+    # f = the coordinate itself reproduces the named observables
+    np.testing.assert_allclose(operator.measure.all_potential_from_function(states, lambda x: x[1]).raw_data,
+                               operator.measure.all_x(states, axis=1).raw_data, atol=1e-12)
+    np.testing.assert_allclose(operator.measure.all_momentum_from_function(states, lambda k: k[0]).raw_data,
+                               operator.measure.all_k(states, axis=0).raw_data, atol=1e-10)
+
+    # apply_to_each: diagonal (column scaling) and dense (GEMM) forms agree with O @ psi
+    v_op = operator.build.potential_from_function(meta, f_x)
+    k_op = operator.build.momentum_from_function(meta, f_k)
+    dense_basis = TupleBasis((fund, fund.dual_basis()))
+    for op in (v_op, k_op):
+        o_np = op.as_array()
+        want = states_np @ o_np.T
+        scale = np.abs(want).max()
+        got = operator.apply_to_each(op, states).with_state_basis(fund.upcast()).raw_data.reshape(3, -1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * scale)
+        got_dense = operator.apply_to_each(op.with_basis(dense_basis), states)
+        np.testing.assert_allclose(got_dense.with_state_basis(fund.upcast()).raw_data.reshape(3, -1), want, rtol=0,
+                                   atol=1e-12 * scale)
+        np.testing.assert_allclose(operator.apply(op, states[0]).with_basis(fund.upcast()).raw_data, want[0], rtol=0,
+                                   atol=1e-12 * scale)
