@@ -388,7 +388,13 @@ class TimeShardedEvolver:
             except (RuntimeError, ImportError, AttributeError) as err:
                 if exchange == "p2p":
                     raise
-                self._symm_error = repr(err)  # symmetric memory unavailable on this box: NCCL ring instead
+                import warnings
+
+                self._symm_error = repr(err)
+                warnings.warn(  # both transports are GPU paths; say which one runs
+                    f"symmetric memory unavailable ({err!r}); TimeShardedEvolver uses the NCCL ring exchange",
+                    RuntimeWarning, stacklevel=2,
+                )
         self.exchange_mode = "p2p" if self._symm is not None else "nccl"
         if self._symm is not None:
             both = torch.view_as_complex(self._symm[0].view(2, c, n, n, 2))
