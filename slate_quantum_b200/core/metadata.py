@@ -233,6 +233,12 @@ class volume:  # noqa: N801 - mirrors the module name slate_core.metadata.volume
         return np.array([c.domain.delta * d for c, d in zip(metadata.children, dirs, strict=True)])
 
     @staticmethod
+    def fundamental_stacked_dx(metadata: TupleMetadata) -> np.ndarray:
+        """Row i = grid step along axis i, a_i / N_i."""
+        shape = np.asarray(metadata.shape, dtype=np.float64)
+        return volume.fundamental_stacked_delta_x(metadata) / shape[:, np.newaxis]
+
+    @staticmethod
     def fundamental_stacked_delta_k(metadata: TupleMetadata) -> np.ndarray:
         """Row i = N_i * dk_i."""
         dk = volume.fundamental_stacked_dk(metadata)
