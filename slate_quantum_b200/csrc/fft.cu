@@ -20,12 +20,14 @@
 // Convention (reference): position -> momentum on a ket index = np.fft.fft(norm="ortho"),
 // momentum -> position = np.fft.ifft(norm="ortho")  (tests/test_operator.py:197-204).
 #include <math.h>
+#include <stdlib.h>
 
 #include "sqb_common.cuh"
 
 namespace {
 
 constexpr int kFftThreads = 256;
+constexpr int kFftThreadsWide = 512;  // in-place variant: one butterfly per thread and stage
 constexpr int kMaxSmemLen = 4096;   // complex elements of one ping-pong buffer
 constexpr int kMaxStages = 24;
 constexpr int kMaxRadix = 31;
@@ -67,6 +69,7 @@ struct FftPass {
   double scale;            // multiplied into every output
   int64_t tw_len;          // 0 = none; else multiply output (pos k, inner i) by exp(sign*2*pi*i*k*(i/tw_div)/tw_len)
   int64_t tw_div;          // divisor applied to the inner index before the twiddle (>= 1)
+  int inplace_mid;         // 1 = the middle stages run in place (one shared buffer; needs work <= threads, see launch_pass)
 };
 
 __device__ __forceinline__ c128 tw_lookup(const c128* tab, int idx, int sign) {
@@ -207,7 +210,7 @@ struct StageIo {
 // One Stockham stage of radix R over `lines` lines held by the CTA.  The first stage reads its butterfly
 // inputs straight from global memory and the last one writes straight to global memory, so an FFT of S
 // stages makes S-1 round trips through shared memory instead of S+1.
-template <int R>
+template <int R, int kThreads>
 __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io, int ns, int lines, const c128* tab) {
   const int len = P.len, sign = P.sign, lpc = P.lines_per_cta;
   const int per_line = len / R;
@@ -219,7 +222,7 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
   // position touches 32 consecutive elements (conflict free); [line][pos] would be a 32-way bank conflict there
   const int s_line = io.line_major ? 1 : len;
   const int s_pos = io.line_major ? lpc : 1;
-  for (int w = threadIdx.x; w < work; w += kFftThreads) {
+  for (int w = threadIdx.x; w < work; w += kThreads) {
     int line, j, jq, k;
     if (io.line_fastest) {
       line = w & (lpc - 1);
@@ -265,6 +268,40 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
   }
 }
 
+// Middle stage IN PLACE on one shared buffer ([pos][line] layout): every thread owns at most one butterfly, reads
+// its R inputs, the CTA synchronises, then the outputs go back into the same buffer.  Halves the shared memory
+// of a three-stage pass, which doubles the adjacent lines a CTA can take (longer coalesced runs).
+template <int R, int kThreads>
+__device__ __forceinline__ void stage_fixed_inplace(const FftPass& P, c128* buf, int ns, int lines, const c128* tab) {
+  const int len = P.len, sign = P.sign, lpc = P.lines_per_cta;
+  const int per_line = len / R;
+  const int tw_step = len / (ns * R);
+  const int ns_shift = pow2_shift(ns);
+  const int lshift = 31 - __clz(lpc);
+  const int w = threadIdx.x;
+  const int line = w & (lpc - 1);
+  const int j = w >> lshift;
+  const bool active = w < per_line * lpc && line < lines;
+  int jq, k;
+  fast_divmod(j, ns, ns_shift, jq, k);
+  c128 x[R];
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[t] = buf[line + (j + t * per_line) * lpc];
+    if (ns > 1) {
+#pragma unroll
+      for (int t = 1; t < R; ++t) x[t] = cmul(x[t], tw_lookup(tab, t * k * tw_step, sign));
+    }
+    dft_small<R>(x, sign, tab, len / R);
+  }
+  __syncthreads();
+  if (active) {
+    const int pos0 = (j - k) * R + k;
+#pragma unroll
+    for (int t = 0; t < R; ++t) buf[line + (pos0 + t * ns) * lpc] = x[t];
+  }
+}
+
 // Any radix (primes 11..31): shared memory on both sides (the caller brackets it with copy stages).
 __device__ __forceinline__ void stage_generic(const c128* src, c128* dst, int len, int ns, int r, int lines,
                                               const c128* tab, int sign) {
@@ -293,8 +330,8 @@ __device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 
 // compiled in, which keeps the register count down for 4 CTAs / SM)
 // kVariant 0: radices {2,4,8} only (power-of-two lengths, the hot cell-FFT passes); 1: {2,3,4,5,7,8};
 // 2: any radix <= 31 (local-memory arrays).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
-template <int kVariant>
-__global__ void __launch_bounds__(kFftThreads, kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))
+template <int kVariant, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2)))
 fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
   extern __shared__ c128 smem[];
   __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
@@ -316,7 +353,7 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
     s_out_base[threadIdx.x] = digits_offset(P.out_outer, o) + digits_offset(P.out_inner, i);
     s_inner_idx[threadIdx.x] = i;
   }
-  for (int j = threadIdx.x; j < len; j += kFftThreads) tab[j] = tab_g[j];
+  for (int j = threadIdx.x; j < len; j += kThreads) tab[j] = tab_g[j];
   __syncthreads();
 
   const int lshift = 31 - __clz(lpc);
@@ -335,10 +372,10 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
     if (P.inner_fastest) {
       const int l = threadIdx.x & (lpc - 1);
       if (l < lines)
-        for (int pos = threadIdx.x >> lshift; pos < len; pos += kFftThreads >> lshift)
+        for (int pos = threadIdx.x >> lshift; pos < len; pos += kThreads >> lshift)
           buf0[l * len + pos] = in[s_in_base[l] + pos_offset(pos, P.in_split, P.in_sl_hi, P.in_sl)];
     } else {
-      for (int e = threadIdx.x; e < lines * len; e += kFftThreads) {
+      for (int e = threadIdx.x; e < lines * len; e += kThreads) {
         const int l = e / len, pos = e - l * len;
         buf0[l * len + pos] = in[s_in_base[l] + pos_offset(pos, P.in_split, P.in_sl_hi, P.in_sl)];
       }
@@ -361,13 +398,24 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
     io.inner_idx = s_inner_idx;
     io.line_major = line_major;
     io.line_fastest = line_major || (io.first && P.inner_fastest) || (io.last && P.out_inner_fastest);
+    const bool mid_inplace = P.inplace_mid && !io.first && !io.last;
+    if (mid_inplace) {
+      switch (r) {
+        case 8: stage_fixed_inplace<8, kThreads>(P, src, ns, lines, tab); break;
+        case 4: stage_fixed_inplace<4, kThreads>(P, src, ns, lines, tab); break;
+        default: stage_fixed_inplace<2, kThreads>(P, src, ns, lines, tab); break;
+      }
+      __syncthreads();
+      ns *= r;
+      continue;
+    }
     switch (r) {
-      case 8: stage_fixed<8>(P, io, ns, lines, tab); break;
-      case 4: stage_fixed<4>(P, io, ns, lines, tab); break;
-      case 2: stage_fixed<2>(P, io, ns, lines, tab); break;
-      case 3: if constexpr (kVariant >= 1) stage_fixed<3>(P, io, ns, lines, tab); break;
-      case 5: if constexpr (kVariant >= 1) stage_fixed<5>(P, io, ns, lines, tab); break;
-      case 7: if constexpr (kVariant >= 1) stage_fixed<7>(P, io, ns, lines, tab); break;
+      case 8: stage_fixed<8, kThreads>(P, io, ns, lines, tab); break;
+      case 4: stage_fixed<4, kThreads>(P, io, ns, lines, tab); break;
+      case 2: stage_fixed<2, kThreads>(P, io, ns, lines, tab); break;
+      case 3: if constexpr (kVariant >= 1) stage_fixed<3, kThreads>(P, io, ns, lines, tab); break;
+      case 5: if constexpr (kVariant >= 1) stage_fixed<5, kThreads>(P, io, ns, lines, tab); break;
+      case 7: if constexpr (kVariant >= 1) stage_fixed<7, kThreads>(P, io, ns, lines, tab); break;
       default:
         if constexpr (kVariant == 2) stage_generic(src, dst, len, ns, r, lines, tab, P.sign);
         break;
@@ -397,9 +445,9 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
   if (P.out_inner_fastest) {
     const int l = threadIdx.x & (lpc - 1);
     if (l < lines)
-      for (int pos = threadIdx.x >> lshift; pos < len; pos += kFftThreads >> lshift) emit(l, pos);
+      for (int pos = threadIdx.x >> lshift; pos < len; pos += kThreads >> lshift) emit(l, pos);
   } else {
-    for (int e = threadIdx.x; e < lines * len; e += kFftThreads) {
+    for (int e = threadIdx.x; e < lines * len; e += kThreads) {
       const int l = e / len;
       emit(l, e - l * len);
     }
@@ -488,6 +536,15 @@ bool smooth(int len) {
   return factorize(len, radix, &ns);
 }
 
+bool fft_inplace_on() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* v = getenv("SQB_FFT_INPLACE");
+    cached = (v && v[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t st) {
   if (!factorize(P.len, P.radix, &P.n_stages)) return SQB_E_UNSUPPORTED;
   if (P.len > kMaxSmemLen) return SQB_E_UNSUPPORTED;
@@ -497,6 +554,7 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   const bool copy_out = P.n_stages == 0 || !fixed(P.radix[P.n_stages - 1]);
   const int smem_writes = P.n_stages - 1 + (copy_in ? 1 : 0) + (copy_out ? 1 : 0);  // stages writing shared
   const int n_buf = smem_writes >= 2 ? 2 : 1;
+  int n_buf_used = n_buf;
   // lines per CTA (power of two): enough for 128..256 B coalesced runs across lines and >= 1024 elements of
   // work per CTA, small enough for several CTAs per SM (<= ~72 KB of shared memory when possible)
   int lpc = 1;
@@ -510,21 +568,40 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   }
   const int64_t n_lines = P.n_outer * P.n_inner;
   while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
-  P.lines_per_cta = lpc;
-  const size_t smem = ((size_t)n_buf * lpc * P.len + P.len) * sizeof(c128);
   int variant = 0;
   for (int q = 0; q < P.n_stages; ++q) {
     const int r = P.radix[q];
     if (!fixed(r)) variant = 2;
     else if ((r == 3 || r == 5 || r == 7) && variant < 1) variant = 1;
   }
-  auto* kern = variant == 0 ? fft_pass_kernel<0> : (variant == 1 ? fft_pass_kernel<1> : fft_pass_kernel<2>);
+  // Long strided power-of-two lines with three stages (256, 512 points: the across-block cell FFT of an enlarged
+  // k-grid): the two-buffer version can only take 8 / 4 adjacent lines (128 / 64 B runs).  Running the middle stage
+  // in place on ONE buffer, with 512 threads so that every thread owns exactly one butterfly per stage, doubles
+  // the lines per CTA in the same shared memory.  SQB_FFT_INPLACE=0 switches it off.
+  P.inplace_mid = 0;
+  int threads = kFftThreads;
+  if (variant == 0 && P.n_stages == 3 && P.len >= 256 && P.inner_fastest && P.out_inner_fastest && fft_inplace_on()) {
+    const int per_line_mid = P.len / P.radix[1];
+    int wide = kFftThreadsWide / per_line_mid;  // lines such that the middle stage has one butterfly per thread
+    while (wide > 1 && wide / 2 >= n_lines) wide /= 2;
+    if (wide > lpc && wide <= kMaxLines && (size_t)(wide + 1) * P.len * sizeof(c128) <= 100 * 1024) {
+      lpc = wide;
+      n_buf_used = 1;
+      P.inplace_mid = 1;
+      threads = kFftThreadsWide;
+    }
+  }
+  P.lines_per_cta = lpc;
+  const size_t smem = ((size_t)n_buf_used * lpc * P.len + P.len) * sizeof(c128);
+  auto* kern = P.inplace_mid ? fft_pass_kernel<0, kFftThreadsWide>
+                             : (variant == 0 ? fft_pass_kernel<0, kFftThreads>
+                                             : (variant == 1 ? fft_pass_kernel<1, kFftThreads> : fft_pass_kernel<2, kFftThreads>));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   fft_table_kernel<<<(P.len + 255) / 256, 256, 0, st>>>(tab, P.len);
   const int64_t grid = (n_lines + lpc - 1) / lpc;
   if (grid > 2147483647LL) return SQB_E_UNSUPPORTED;
-  kern<<<(unsigned)grid, kFftThreads, smem, st>>>(P, in, out, tab);
+  kern<<<(unsigned)grid, threads, smem, st>>>(P, in, out, tab);
   SQB_LAUNCH_CHECK();
   return SQB_OK;
 }

@@ -754,3 +754,34 @@ def test_rowwise_weighted_abs2(cuda):
         np.testing.assert_allclose(got.cpu().numpy(), o.expectation_of_each(np.diag(w), x), rtol=0, atol=1e-13 * length)
     with pytest.raises(ValueError):
         kernels.rowwise_weighted_abs2(kernels.to_device(x, torch.complex128), kernels.to_device(w[:-1], torch.complex128))
+
+
+@pytest.mark.parametrize("length", [256, 512])
+@pytest.mark.parametrize(("outer", "inner"), [(1, 3), (2, 24), (3, 16), (1, 37), (2, 1)])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_fft_axis_long_strided_lines(cuda, length, outer, inner, sign):
+    """Three-stage power-of-two lines with adjacent lines in memory (the across-block cell FFT of a 256- or
+    512-wide k-grid) take the one-buffer variant with an in-place middle stage; ragged line counts included."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(length + 7 * outer + inner)
+    x = _rand_c(rng, outer, length, inner)
+    got = kernels.fft_axis(kernels.to_device(x, torch.complex128), outer, length, inner, sign).cpu().numpy()
+    want = (np.fft.fft if sign < 0 else np.fft.ifft)(x, axis=1, norm="ortho")
+    np.testing.assert_allclose(got.reshape(x.shape), want, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize(("shape", "repeat"), [((2, 2), (512, 3)), ((3,), (256,)), ((2, 2), (4, 512))])
+def test_cell_fft_long_block_axis(cuda, shape, repeat):
+    """cell FFT across 256 / 512 blocks (8-GPU weak-scaling k-grids) against the literal supercell chain."""
+    torch, kernels = _gpu()
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    big = tuple(a * b for a, b in zip(shape, repeat))
+    rng = np.random.default_rng(12)
+    v = _rand_c(rng, n_k, n, n)
+    a = _rand_c(rng, 2, n_k, n)
+    bloch = np.einsum("tbe,bek->tbk", a, v).reshape(2, -1)
+    want = o.momentum_to_position(o.bloch_into_supercell(bloch, shape, repeat), big)
+    folded = kernels.fold_transform(shape, repeat, kernels.to_device(v, torch.complex128))
+    cell = kernels.apply_transform(folded, kernels.to_device(a.reshape(2, -1), torch.complex128), 0)
+    got = kernels.cell_fft(shape, repeat, cell, 1).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
