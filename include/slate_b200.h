@@ -11,7 +11,7 @@
  *    passed in as `workspace` with the size reported by the matching *_workspace_bytes function.
  *  - Return value: 0 = OK, < 0 = bad argument (SQB_E_*), > 0 = a cudaError_t from a launch.
  *    Numerical failures of the eigensolver are reported per matrix in `info[]`, not in the return value.
- *  - Re-entrant / thread-safe: no global mutable state.  Two environment variables are read once per process
+ *  - Re-entrant / thread-safe: no global mutable state.  A few environment variables are read once per process
  *    (tuning / fallback switches, never needed for correctness): SQB_EIGH_TRIDIAG_SOLVER=ql selects the
  *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_FFT_INPLACE=0 uses the two-buffer FFT pass for 256/512-point strided lines; SQB_EVOLVE_TILES_PER_CTA=<k> sets how
  *    many 64-row time tiles a CTA of the uniform-grid evolve kernel walks (default 8); SQB_BACKTRANSFORM=reflector
