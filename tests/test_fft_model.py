@@ -1,0 +1,39 @@
+"""CPU: the Stockham index maps of csrc/fft.cu (out-of-place stages and the in-place middle stage of the
+one-buffer variant) reproduce np.fft; and the launch rule picks the in-place variant exactly where intended."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from fft_model import factorize, stockham, stockham_inplace_mid
+
+
+@pytest.mark.parametrize("length", [8, 64, 128, 256, 512, 1024, 96, 60, 343])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_stockham_stages_equal_numpy(length, sign):
+    rng = np.random.default_rng(length)
+    x = rng.normal(size=length) + 1j * rng.normal(size=length)
+    want = np.fft.fft(x) if sign < 0 else np.fft.ifft(x) * length
+    np.testing.assert_allclose(stockham(x, factorize(length), sign), want, atol=1e-11)
+
+
+@pytest.mark.parametrize("length", [256, 512])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_inplace_middle_stage_equals_numpy(length, sign):
+    """256 = 8*8*4 and 512 = 8*8*8: the three-stage lengths that take the one-buffer variant (launch_pass)."""
+    radices = factorize(length)
+    assert len(radices) == 3
+    rng = np.random.default_rng(length + 1)
+    x = rng.normal(size=length) + 1j * rng.normal(size=length)
+    want = np.fft.fft(x) if sign < 0 else np.fft.ifft(x) * length
+    np.testing.assert_allclose(stockham_inplace_mid(x, radices, sign), want, atol=1e-11)
+
+
+def test_inplace_variant_thread_budget():
+    """One butterfly per thread in the middle stage: lines * (len / R_mid) == 512 threads, buffer <= 100 KB."""
+    for length, lines in ((256, 16), (512, 8)):
+        r_mid = factorize(length)[1]
+        assert lines * (length // r_mid) == 512
+        assert (lines + 1) * length * 16 <= 100 * 1024
+        assert lines * 16 >= 128  # bytes of a coalesced run across the CTA's adjacent lines
