@@ -214,3 +214,20 @@ def test_ring_segments_validation():
     assert ring_segments(1, 4, 2) == [(1, 2, 2), (0, 0, 2), (3, 6, 2), (2, 4, 2)]
     with pytest.raises(ValueError):
         ring_segments(4, 4, 2)
+
+
+@pytest.mark.parametrize(("tiles_m", "tiles_n"), [(1, 1), (3, 5), (8, 8), (9, 2), (64, 64), (17, 33), (1, 40)])
+def test_zgemm_grouped_tile_order_is_a_bijection(tiles_m, tiles_n):
+    """csrc/zgemm.cu maps the linear CTA index to (tile row, tile column) in groups of kZgGroup = 8 tile rows walked
+    column by column; every tile must be visited exactly once, and a group's CTAs must be contiguous."""
+    group = 8
+    seen = []
+    for bid in range(tiles_m * tiles_n):
+        width = group * tiles_n
+        first = (bid // width) * group
+        gsize = min(tiles_m - first, group)
+        seen.append((first + (bid % width) % gsize, (bid % width) // gsize))
+    assert sorted(seen) == [(i, j) for i in range(tiles_m) for j in range(tiles_n)]
+    # the first min(8, tiles_m) CTAs share one B panel (same tile column)
+    head = seen[: min(group, tiles_m)]
+    assert len({j for _, j in head}) == 1
