@@ -645,6 +645,13 @@ def test_expectation_of_each_bloch_hamiltonian(cuda):
     split = operator.build.kinetic_hamiltonian(operator.build.repeat_potential(potential, repeat), mass)
     got = operator.expectation_of_each(split, evolved).raw_data
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * abs(want[0]))
+    # the diagonalised Bloch Hamiltonian is diagonal in the evolved list's own (eigen)basis: one pass, no transform
+    from slate_quantum_b200.operator._operator import _diagonal_form
+
+    diagonal = bloch.into_diagonal(hamiltonian)
+    assert _diagonal_form(diagonal) is not None
+    np.testing.assert_allclose(operator.expectation_of_each(diagonal, evolved).raw_data, want, rtol=0,
+                               atol=1e-10 * abs(want[0]))
     v_part = operator.expectation_of_each(operator.build.repeat_potential(potential, repeat), evolved).raw_data
     t_part = operator.expectation_of_each(operator.build.kinetic_energy(full_meta, mass), evolved).raw_data
     np.testing.assert_allclose(v_part + t_part, want, rtol=0, atol=1e-10 * abs(want[0]))
