@@ -52,6 +52,63 @@ def tridiagonalise(h: np.ndarray):
     return d, e, tau, y
 
 
+def tridiagonalise_blocked(h: np.ndarray, nb: int = 16):
+    """Panel-blocked variant of `tridiagonalise` (LAPACK zhetrd / zlatrd, lower triangle), the design candidate for
+    the next version of tridiag_kernel.
+
+    Inside a panel of `nb` columns the trailing matrix is only READ: column i is materialised from the panel's
+    pending rank-2j update, the matrix-vector product uses the matrix as it was at the panel start and is
+    corrected with the panel's V and W (two thin products), and the rank-2nb update A -= V W^H + W V^H is applied
+    once per panel (GEMM shaped: the DMMA path).  Same conventions and outputs as `tridiagonalise`.
+    Returns (d, e, tau, y, sweeps) with sweeps = (read sweeps, read+write sweeps) over the trailing matrix.
+    """
+    n = h.shape[0]
+    a = np.array(h.T, dtype=np.complex128)
+    d = np.zeros(n)
+    e = np.zeros(n)
+    tau = np.zeros(n, dtype=np.complex128)
+    y = np.zeros((n, n), dtype=np.complex128)
+    reads = writes = 0
+    i0 = 0
+    while i0 < n - 1:
+        width = min(nb, n - 1 - i0)
+        v_panel = np.zeros((n, width), dtype=np.complex128)
+        w_panel = np.zeros((n, width), dtype=np.complex128)
+        for j in range(width):
+            i = i0 + j
+            col = a[i:, i] - v_panel[i:, :j] @ np.conj(w_panel[i, :j]) - w_panel[i:, :j] @ np.conj(v_panel[i, :j])
+            d[i] = col[0].real
+            alpha = col[1]
+            x = col[2:]
+            xnorm = np.linalg.norm(x)
+            v = np.zeros(n, dtype=np.complex128)
+            v[i + 1] = 1
+            if xnorm == 0 and alpha.imag == 0:
+                t = 0.0
+                beta = alpha.real
+            else:
+                beta = -np.copysign(np.sqrt(alpha.real**2 + alpha.imag**2 + xnorm**2), alpha.real)
+                t = complex((beta - alpha.real) / beta, -alpha.imag / beta)
+                v[i + 2 :] = x / (alpha - beta)
+            e[i] = beta
+            tau[i] = t
+            y[i] = v
+            vt, lo = v[i + 1 :], i + 1
+            p = a[lo:, lo:] @ vt  # the matrix of the panel start: read only
+            reads += 1
+            p -= v_panel[lo:, :j] @ (np.conj(w_panel[lo:, :j]).T @ vt) + w_panel[lo:, :j] @ (np.conj(v_panel[lo:, :j]).T @ vt)
+            p *= t
+            w = p + (-0.5 * t * np.vdot(p, vt)) * vt
+            v_panel[:, j] = v
+            w_panel[lo:, j] = w
+        lo = i0 + width
+        a[lo:, lo:] -= v_panel[lo:] @ np.conj(w_panel[lo:]).T + w_panel[lo:] @ np.conj(v_panel[lo:]).T
+        writes += 1
+        i0 += width
+    d[n - 1] = a[n - 1, n - 1].real
+    return d, e, tau, y, (reads, writes)
+
+
 def ql_record(d: np.ndarray, e: np.ndarray, max_iter: int = 60):
     """Implicit QL (EISPACK imtql2 / NR tqli); returns eigenvalues (unsorted), sweeps [(l, m, [(c,s)...])], fails."""
     n = len(d)
