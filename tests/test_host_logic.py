@@ -231,3 +231,34 @@ def test_zgemm_grouped_tile_order_is_a_bijection(tiles_m, tiles_n):
     # the first min(8, tiles_m) CTAs share one B panel (same tile column)
     head = seen[: min(group, tiles_m)]
     assert len({j for _, j in head}) == 1
+
+
+def test_x_k_p_builders_bookkeeping_on_cpu():
+    """operator.build.{x, k, k_squared, p, momentum_from_function} and noise.build.caldeira_leggett_operators are
+    host-side constructors: their stored diagonals and bases can be checked without a GPU (reference
+    tests/test_operator.py:170-210, :451-462)."""
+    from slate_quantum_b200 import noise, operator
+    from slate_quantum_b200.configs import HBAR
+    from slate_quantum_b200.core.basis import DiagonalBasis, RecastBasis, _strip
+    from slate_quantum_b200.core.metadata import spaced_volume_metadata_from_stacked_delta_x, volume
+
+    meta = spaced_volume_metadata_from_stacked_delta_x((np.array([2 * np.pi]),), (5,))
+    x = operator.build.x(meta, axis=0)
+    np.testing.assert_allclose(x.raw_data, np.linspace(0, 2 * np.pi, 5, endpoint=False))
+    k = operator.build.k(meta, axis=0)
+    np.testing.assert_array_equal(k.raw_data, [0, 1, 2, -2, -1])
+    np.testing.assert_array_equal(operator.build.k_squared(meta, axis=0).raw_data, [0, 1, 4, 4, 1])
+    np.testing.assert_allclose(operator.build.p(meta, axis=0).raw_data, HBAR * np.array([0, 1, 2, -2, -1]))
+    for op in (x, k):
+        stored = _strip(op.basis)
+        assert isinstance(stored, RecastBasis) and isinstance(_strip(stored.inner), DiagonalBasis)
+        assert op.basis.metadata().children[0] == meta
+    shifted = operator.build.x(meta, axis=0, offset=-np.pi, wrapped=True)
+    np.testing.assert_allclose(shifted.raw_data, o.stacked_x_points(np.array([[2 * np.pi]]), (5,), (-np.pi,), True)[0])
+    f_k = operator.build.momentum_from_function(meta, lambda kk: kk[0] ** 3, wrapped=True, offset=(0.25,))
+    np.testing.assert_allclose(f_k.raw_data, o.stacked_k_points(np.array([[2 * np.pi]]), (5,), (0.25,), True)[0] ** 3)
+    np.testing.assert_allclose(volume.fundamental_stacked_dx(meta), [[2 * np.pi / 5]])
+    cl = noise.build.caldeira_leggett_operators(meta)
+    assert len(cl) == 1
+    np.testing.assert_allclose(cl.raw_data.ravel(), x.raw_data)
+    np.testing.assert_array_equal(cl.basis.metadata().children[0].values, [1])
