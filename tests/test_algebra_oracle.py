@@ -125,3 +125,21 @@ def test_measure_from_function_reduces_to_named_observables():
     np.testing.assert_allclose(
         o.measure_all_potential_from_function(states, dxm, shape, lambda x: x[0] ** 2 + 0 * x[1]),
         o._normalised_density(states) @ (o.stacked_x_points(dxm, shape)[0] ** 2), atol=1e-12)
+
+
+def test_oracle_against_the_golden_literals_file():
+    """tests/golden/reference_literals.json carries the K6 / K7 literals transcribed from the reference's tests."""
+    import json
+    from pathlib import Path
+
+    lit = json.loads((Path(__file__).parent / "golden" / "reference_literals.json").read_text())
+    np.testing.assert_allclose(np.diag(o.x_operator_array(DX, (5,), 0)).real,
+                               lit["x_operator_diagonal_2pi_cell_5_points"]["value"], atol=1e-15)
+    np.testing.assert_allclose(o.stacked_k_points(DX, (5,))[0], lit["k_operator_fft_order_5"]["value"], atol=1e-15)
+    occ = lit["occupations_two_equal_amplitudes"]
+    amp = np.array(occ["amplitudes_re_im"]) @ np.array([1, 1j])
+    np.testing.assert_allclose(o.occupations(amp), occ["value"], atol=1e-15)
+    ip = lit["inner_product_orthogonal_position_states"]
+    s0 = np.array(ip["state_0_re_im"]) @ np.array([1, 1j])
+    s1 = np.array(ip["state_1_re_im"]) @ np.array([1, 1j])
+    np.testing.assert_allclose(o.inner_product_each(s1[None], s0[None]), [ip["value"]], atol=1e-15)
