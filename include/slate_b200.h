@@ -139,6 +139,18 @@ int sqb_fold_transform(int nd, const int* shape_host, const int* repeat_host, in
                        int64_t batch, const sqb_c128* transform, sqb_c128* folded, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* sqb_bloch_cell_vectors: the in-cell half of the same factorisation for VECTORS in Bloch order (what
+ * BlochTransposedBasis.__into_fundamental__ / __from_fundamental__ walk for a state or a StateList,
+ * bloch/_transposed_basis.py:102-167 + _shifted_basis.py:62-111 + the TransformedBasis leaves):
+ *   direction 1: [lead, n_k, N] Bloch momentum order -> cell layout [lead, n_k, N(j)]
+ *                (in-cell FFT of every block with direction `sign`, then the twiddle exp(sign 2 pi i q j / L))
+ *   direction 0: the inverse.  sqb_cell_fft finishes (or starts) the job with the R-point passes.
+ * sign = +1 for ket indices (momentum -> position is ifft), -1 for bra (dual) indices.  in == out allowed.
+ * workspace: sqb_fft_workspace_bytes(nd, shape, lead * n_k). */
+int sqb_bloch_cell_vectors(int nd, const int* shape_host, const int* repeat_host, int direction, int sign,
+                           int64_t lead, const sqb_c128* in, sqb_c128* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2  Batched Hermitian eigensolver, complex128, one problem per k-block.
  * Replaces: slate_core.linalg.into_diagonal_hermitian (np.linalg.eigh / LAPACK zheevd per block),

@@ -94,16 +94,30 @@ class BlochTransposedBasis(WrappedBasis):
         n_states, n_repeats = self._dims()
         return _moved(t, axis, lambda v: kernels.bloch_permute(n_states, n_repeats, v, 0))
 
+    def _cell_path(self) -> bool:
+        """The factorised route (in-cell FFT + twiddle + R-point FFTs across blocks) needs
+        every repeat to be a smooth length the shared-memory FFT takes in one pass."""
+        _, n_repeats = self._dims()
+        return all(r <= 4096 and kernels.is_smooth(r) for r in n_repeats)
+
     def into_fundamental(self, t: torch.Tensor, axis: int = -1) -> torch.Tensor:
+        """Bloch order -> supercell position basis (reference chain :102-133 + _shifted_basis.py:62-84 + the
+        TransformedBasis leaves): N-point FFTs inside the blocks, the Bloch twiddle, R-point FFTs across blocks -
+        no K5 gather and no supercell-sized FFT lines.  Bra (dual) indices use the conjugate transform."""
         if not self._standard_children():
             return super().into_fundamental(t, axis)
         n_states, n_repeats = self._dims()
         big = tuple(n * r for n, r in zip(n_states, n_repeats, strict=True))
-        sign = -1 if self._is_dual_any() else +1
+        dual = self._is_dual_any()
 
         def fn(v: torch.Tensor) -> torch.Tensor:
-            vk = kernels.bloch_permute(n_states, n_repeats, v, 1)
-            return kernels.fft_c2c(vk, big, sign, out=vk)
+            if not self._cell_path():
+                vk = kernels.bloch_permute(n_states, n_repeats, v, 1)
+                return kernels.fft_c2c(vk, big, -1 if dual else +1, out=vk)
+            x = torch.conj_physical(v) if dual else v
+            cell = kernels.bloch_cell_vectors(n_states, n_repeats, x, 1)
+            pos = kernels.cell_fft(n_states, n_repeats, cell, 1, out=cell if len(n_states) == 1 else None)
+            return torch.conj_physical(pos).reshape(v.shape) if dual else pos.reshape(v.shape)
 
         return _moved(t, axis, fn)
 
@@ -112,11 +126,16 @@ class BlochTransposedBasis(WrappedBasis):
             return super().from_fundamental(t, axis)
         n_states, n_repeats = self._dims()
         big = tuple(n * r for n, r in zip(n_states, n_repeats, strict=True))
-        sign = +1 if self._is_dual_any() else -1
+        dual = self._is_dual_any()
 
         def fn(v: torch.Tensor) -> torch.Tensor:
-            vk = kernels.fft_c2c(v, big, sign)
-            return kernels.bloch_permute(n_states, n_repeats, vk, 0)
+            if not self._cell_path():
+                vk = kernels.fft_c2c(v, big, +1 if dual else -1)
+                return kernels.bloch_permute(n_states, n_repeats, vk, 0)
+            x = torch.conj_physical(v) if dual else v
+            cell = kernels.cell_fft(n_states, n_repeats, x, 0)
+            out = kernels.bloch_cell_vectors(n_states, n_repeats, cell, 0, out=cell)
+            return torch.conj_physical(out).reshape(v.shape) if dual else out.reshape(v.shape)
 
         return _moved(t, axis, fn)
 

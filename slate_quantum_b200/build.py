@@ -62,7 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         log.append(f"== {src}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    # --cudart=shared: the process already holds torch's libcudart.so.12; a second, statically linked runtime would
+    # only duplicate state (and drags the whole runtime's symbol table into the shipped artefact)
+    cmd = [_nvcc(), "-shared", "--cudart=shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

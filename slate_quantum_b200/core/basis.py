@@ -47,6 +47,7 @@ def as_device(vectors: Any) -> torch.Tensor:
 def _moved(t: torch.Tensor, axis: int, fn: Callable[[torch.Tensor], torch.Tensor]) -> torch.Tensor:
     """Apply `fn` (acting on the LAST axis of a contiguous tensor) along `axis`."""
     axis %= t.ndim
+    t = t.resolve_conj().resolve_neg()  # the C ABI reads raw memory: lazy conj / neg view bits must be materialised
     if axis == t.ndim - 1:
         return fn(t.contiguous())
     return fn(t.movedim(axis, -1).contiguous()).movedim(-1, axis).contiguous()
@@ -699,6 +700,8 @@ class ExplicitUnitaryBasis(WrappedBasis):
     def dual_basis(self) -> "ExplicitUnitaryBasis":
         out = type(self)(self._matrix, direction=self._direction, data_id=self._data_id)
         out._dual = not self._dual
+        # a bra index converts through the DUAL of the inner basis (opposite FFT direction further down the chain)
+        out._inner = self._inner.dual_basis()
         return out
 
     def _blocks(self) -> torch.Tensor:
@@ -713,13 +716,15 @@ class ExplicitUnitaryBasis(WrappedBasis):
     def into_inner(self, t: torch.Tensor, axis: int = -1) -> torch.Tensor:
         v = self._blocks()
         if self._dual:
-            return _moved(t, axis, lambda x: kernels.apply_transform(v, x.conj().contiguous(), 0).conj())
+            # bra index: conj(V) acts, i.e. conj(apply(V, conj(x))).  conj_physical MATERIALISES the conjugate - a lazy
+            # .conj() only sets a view bit that the raw-pointer C ABI cannot see
+            return _moved(t, axis, lambda x: torch.conj_physical(kernels.apply_transform(v, torch.conj_physical(x), 0)))
         return _moved(t, axis, lambda x: kernels.apply_transform(v, x, 0))
 
     def from_inner(self, t: torch.Tensor, axis: int = -1) -> torch.Tensor:
         v = self._blocks()
         if self._dual:
-            return _moved(t, axis, lambda x: kernels.apply_transform(v, x.conj().contiguous(), 1).conj())
+            return _moved(t, axis, lambda x: torch.conj_physical(kernels.apply_transform(v, torch.conj_physical(x), 1)))
         return _moved(t, axis, lambda x: kernels.apply_transform(v, x, 1))
 
     def eigenvectors(self) -> Any:

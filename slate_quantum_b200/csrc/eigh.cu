@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "sqb_common.cuh"
 #include "eigh_dc.cuh"
 #include "eigh_wy.cuh"
@@ -909,6 +911,46 @@ int launch_back(int n, int64_t count, c128* A, const EighWs& ws, cudaStream_t st
   return SQB_OK;
 }
 
+// Two internal streams + fork / join events per device, created lazily ONCE (not per call) and kept for the
+// life of the process.  nullptr when any creation fails: the caller then runs single-lane on its own stream.
+struct LanePool {
+  cudaStream_t lane[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ok = false;
+  std::mutex use;  // held while one call enqueues on the lanes (fork / join events are shared)
+};
+
+LanePool* lane_pool() {
+  static std::mutex mu;
+  static LanePool pools[64];
+  static bool tried[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  LanePool& p = pools[dev];
+  if (!tried[dev]) {
+    tried[dev] = true;
+    bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < 2 && ok; ++l) {
+      ok = cudaStreamCreateWithFlags(&p.lane[l], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p.join[l], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+      for (int l = 0; l < 2; ++l) {
+        if (p.lane[l]) cudaStreamDestroy(p.lane[l]);
+        if (p.join[l]) cudaEventDestroy(p.join[l]);
+        p.lane[l] = nullptr;
+        p.join[l] = nullptr;
+      }
+      if (p.fork) cudaEventDestroy(p.fork);
+      p.fork = nullptr;
+      (void)cudaGetLastError();
+    }
+    p.ok = ok;
+  }
+  return p.ok ? &p : nullptr;
+}
+
 }  // namespace
 
 extern "C" size_t sqb_eigh_workspace_bytes(int n, int64_t batch) {
@@ -940,19 +982,24 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
   }
   // Two chunks are kept in flight on two internal streams (each with its own half of the workspace): the
   // latency-bound QL stage of one chunk then overlaps the bandwidth / FP64-bound stages of the other.
-  const bool two_lanes = batch >= 512 && chunk >= 256;
+  bool two_lanes = batch >= 512 && chunk >= 256;
+  cudaStream_t lanes[2] = {st, st};
+  LanePool* pool = two_lanes ? lane_pool() : nullptr;  // created once per device; nullptr = creation failed
+  if (!pool) two_lanes = false;                        // clean single-lane fallback on the caller's stream
+  std::unique_lock<std::mutex> pool_lock;
+  if (two_lanes) pool_lock = std::unique_lock<std::mutex>(pool->use);
   const int n_lanes = two_lanes ? 2 : 1;
+  (void)n_lanes;
   if (two_lanes) chunk = sqb_min64(chunk / 2, (batch + 1) / 2);
   const size_t lane_bytes = align_up(per * (size_t)chunk, 256);
-  cudaStream_t lanes[2] = {st, st};
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   if (two_lanes) {
-    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
-    cudaEventRecord(fork, st);
-    for (int l = 0; l < 2; ++l) {
-      if (cudaStreamCreateWithFlags(&lanes[l], cudaStreamNonBlocking) != cudaSuccess) return (int)cudaGetLastError();
-      cudaStreamWaitEvent(lanes[l], fork, 0);
+    // fork: both lanes start after everything already enqueued on the caller's stream
+    cudaError_t e = cudaEventRecord(pool->fork, st);
+    for (int l = 0; l < 2 && e == cudaSuccess; ++l) {
+      lanes[l] = pool->lane[l];
+      e = cudaStreamWaitEvent(lanes[l], pool->fork, 0);
     }
+    if (e != cudaSuccess) return (int)e;
   }
   int status = SQB_OK;
   int which = 0;
@@ -1001,15 +1048,16 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     if (rc) { status = rc; break; }
   }
   if (two_lanes) {
+    // join: the caller's stream continues only after both lanes have drained (also on an error path, so that
+    // the caller's workspace cannot be reused while a lane still runs)
     for (int l = 0; l < 2; ++l) {
-      if (cudaEventCreateWithFlags(&join[l], cudaEventDisableTiming) == cudaSuccess) {
-        cudaEventRecord(join[l], lanes[l]);
-        cudaStreamWaitEvent(st, join[l], 0);
-        cudaEventDestroy(join[l]);
+      cudaError_t e = cudaEventRecord(pool->join[l], lanes[l]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, pool->join[l], 0);
+      if (e != cudaSuccess) {
+        cudaStreamSynchronize(lanes[l]);  // last resort: order by blocking the host
+        if (status == SQB_OK) status = (int)e;
       }
-      cudaStreamDestroy(lanes[l]);  // deferred by the runtime until the enqueued work has drained
     }
-    cudaEventDestroy(fork);
   }
   return status;
 }

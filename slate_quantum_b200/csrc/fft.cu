@@ -459,8 +459,12 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
 // The twiddle depends on (block, j) only: a CTA computes the n factors of its block once into shared memory
 // (one sincospi per j instead of per element) and streams kFoldRows eigenvector rows through them.
 constexpr int kFoldRows = 32;
+// Rows of one block are `rows` vectors of n entries, row r of block bl at W[bl * block_stride + r * row_stride]:
+//   eigenvector blocks [batch, n, n]:           rows = n,    row_stride = n,       block_stride = n * n
+//   state lists in block order [lead, n_k, n]:  rows = lead, row_stride = n_k * n, block_stride = n
 __global__ void __launch_bounds__(256)
-fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int sign, c128* __restrict__ W) {
+fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int sign, int64_t rows,
+                    int64_t row_stride, int64_t block_stride, const c128* __restrict__ in, c128* __restrict__ W) {
   extern __shared__ __align__(16) unsigned char fold_smem[];
   c128* tw = reinterpret_cast<c128*>(fold_smem);  // [n]
   const int64_t bl = blockIdx.y;                   // block inside the batch
@@ -484,12 +488,14 @@ fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int si
     tw[j] = make_double2(cs, sn);
   }
   __syncthreads();
-  const int r0 = blockIdx.x * kFoldRows;
-  const int r1 = min(n, r0 + kFoldRows);
-  c128* Wb = W + bl * (int64_t)n * n;
-  for (int r = r0; r < r1; ++r) {
-    c128* row = Wb + (int64_t)r * n;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) row[j] = cmul(row[j], tw[j]);
+  const int64_t r0 = (int64_t)blockIdx.x * kFoldRows;
+  const int64_t r1 = sqb_min64(rows, r0 + kFoldRows);
+  const c128* Ib = in + bl * block_stride;
+  c128* Wb = W + bl * block_stride;
+  for (int64_t r = r0; r < r1; ++r) {
+    const c128* src = Ib + r * row_stride;
+    c128* row = Wb + r * row_stride;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) row[j] = cmul(src[j], tw[j]);
   }
 }
 
@@ -917,9 +923,46 @@ extern "C" int sqb_fold_transform(int nd, const int* shape_host, const int* repe
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int64_t cnt = sqb_min64(65535, batch - b0);
     const dim3 grid((unsigned)((n + kFoldRows - 1) / kFoldRows), (unsigned)cnt);
+    c128* fb = reinterpret_cast<c128*>(folded) + b0 * n * n;
     fold_twiddle_kernel<<<grid, 256, (size_t)n * sizeof(c128), sqb_stream(stream)>>>(
-        d, (int)n, block_begin + b0, cnt, +1, reinterpret_cast<c128*>(folded) + b0 * n * n);
+        d, (int)n, block_begin + b0, cnt, +1, n, n, n * n, fb, fb);
     SQB_LAUNCH_CHECK();
   }
   return SQB_OK;
+}
+
+// The same factorisation for VECTORS (state lists) in Bloch order [lead, n_k, N]:
+//   direction 1: Bloch momentum order -> cell layout  = in-cell FFT (sign) of every block, then the twiddle
+//   direction 0: cell layout -> Bloch momentum order  = conjugate twiddle, then the in-cell FFT (-sign)
+// `sign` is the direction of the ket transform momentum -> position (+1); bra (dual) indices pass -1.
+extern "C" int sqb_bloch_cell_vectors(int nd, const int* shape_host, const int* repeat_host, int direction, int sign,
+                                      int64_t lead, const sqb_c128* in, sqb_c128* out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  SqbDims d;
+  int64_t n, nk;
+  int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
+  if (rc) return rc;
+  if (!in || !out || lead < 0 || (direction != 0 && direction != 1) || (sign != 1 && sign != -1)) return SQB_E_BADARG;
+  if (lead == 0) return SQB_OK;
+  if (nk > 65535 * (int64_t)65535) return SQB_E_UNSUPPORTED;
+  const c128* src = reinterpret_cast<const c128*>(in);
+  c128* dst = reinterpret_cast<c128*>(out);
+  auto twiddle = [&](const c128* pin, c128* pout, int sg) -> int {
+    for (int64_t b0 = 0; b0 < nk; b0 += 65535) {
+      const int64_t cnt = sqb_min64(65535, nk - b0);
+      const dim3 grid((unsigned)((lead + kFoldRows - 1) / kFoldRows), (unsigned)cnt);
+      fold_twiddle_kernel<<<grid, 256, (size_t)n * sizeof(c128), sqb_stream(stream)>>>(
+          d, (int)n, b0, cnt, sg, lead, nk * n, n, pin + b0 * n, pout + b0 * n);
+      SQB_LAUNCH_CHECK();
+    }
+    return SQB_OK;
+  };
+  if (direction == 1) {
+    rc = sqb_fft_c2c(nd, shape_host, lead * nk, sign, in, out, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return twiddle(dst, dst, sign);
+  }
+  rc = twiddle(src, dst, -sign);
+  if (rc) return rc;
+  return sqb_fft_c2c(nd, shape_host, lead * nk, -sign, out, out, workspace, workspace_bytes, stream);
 }

@@ -46,12 +46,19 @@ def _c128(t: torch.Tensor, name: str) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
         msg = f"{name} must be a contiguous CUDA complex128 tensor"
         raise TypeError(msg)
+    if t.is_conj() or t.is_neg():
+        # a lazy .conj() / negation is a view bit the raw pointer cannot carry: the kernel would read unconjugated data
+        msg = f"{name} carries a lazy conj/neg bit; materialise it first (torch.conj_physical / .resolve_conj())"
+        raise TypeError(msg)
     return t
 
 
 def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
         msg = f"{name} must be a contiguous CUDA float64 tensor"
+        raise TypeError(msg)
+    if t.is_neg():
+        msg = f"{name} carries a lazy neg bit; materialise it first (.resolve_neg())"
         raise TypeError(msg)
     return t
 
@@ -239,6 +246,47 @@ def fold_transform(
     )
     _lib.check(rc, "sqb_fold_transform")
     _count(_fft_launches(shape) + 1)
+    return out
+
+
+def is_smooth(length: int, max_prime: int = 31) -> bool:
+    """True when `length` factors into primes <= max_prime (what the shared-memory FFT passes implement)."""
+    rem = int(length)
+    if rem < 1:
+        return False
+    for p in range(2, max_prime + 1):
+        while rem % p == 0:
+            rem //= p
+    return rem == 1
+
+
+def bloch_cell_vectors(
+    shape: Sequence[int], repeat: Sequence[int], x: torch.Tensor, direction: int, out: torch.Tensor | None = None,
+    sign: int = 1,
+) -> torch.Tensor:
+    """In-cell half of the Bloch cell FFT for vectors: [lead, n_k, N] Bloch momentum order <-> cell layout.
+
+    direction 1: in-cell FFT of every block + Bloch twiddle (cell_fft(..., 1) then gives the position basis);
+    direction 0: the inverse (after cell_fft(..., 0)).  `out` may be `x`."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(x, "x")
+    n = int(np.prod(shape))
+    n_k = int(np.prod(repeat))
+    if x.numel() % (n * n_k):
+        msg = "vectors must hold whole supercell states"
+        raise ValueError(msg)
+    lead = x.numel() // (n * n_k)
+    out = torch.empty_like(x) if out is None else _c128(out, "out")
+    shape_c = _lib.int_array(shape)
+    ws_bytes = lib.sqb_fft_workspace_bytes(len(shape), shape_c, lead * n_k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_bloch_cell_vectors(
+        len(shape), shape_c, _lib.int_array(repeat), int(direction), int(sign), lead, _ptr(x), _ptr(out), _ptr(ws),
+        ws_bytes, _stream(),
+    )
+    _lib.check(rc, "sqb_bloch_cell_vectors")
+    _count(_fft_launches(shape) + -(-n_k // 65535))
     return out
 
 

@@ -186,9 +186,13 @@ def expectation_of_each(operator: Operator, states: Any) -> Array:
         return Array(list_basis, lhs.device_data + rhs.device_data)
     diagonal = _diagonal_form(operator)
     if diagonal is not None:
+        import torch
+
+        from slate_quantum_b200.state._state import iter_list_tiles
+
         ket, diag = diagonal
-        psi = _complex(states.with_state_basis(ket).device_data).reshape(list_basis.size, -1)
-        return Array(list_basis, kernels.rowwise_weighted_abs2(psi, diag))
+        parts = [kernels.rowwise_weighted_abs2(psi, diag) for psi in iter_list_tiles(states, ket)]
+        return Array(list_basis, parts[0] if len(parts) == 1 else torch.cat(parts))
     tup, o = _dense_operator(operator)
     rhs = states.with_state_basis(tup.children[1].dual_basis())
     psi1 = _complex(rhs.device_data).reshape(list_basis.size, -1)

@@ -23,17 +23,38 @@ from slate_quantum_b200.core.metadata import TupleMetadata, volume
 from slate_quantum_b200.state._state import State, StateList
 
 
-def _position_data(states: Array, space: TupleMetadata) -> torch.Tensor:
-    """[lead, M] device tensor of the states in the fundamental (position) basis of ``space``."""
-    position = _basis.from_metadata(space).upcast()
-    if isinstance(states, StateList):
-        converted = states.with_state_basis(position)
-    else:
-        converted = states.with_basis(position)
+def _tiles_in(states: Array, target: Any) -> Any:
+    """Device tensors [rows, M] covering the states in basis `target`, in list order.
+
+    An ordinary Array gives one tensor.  The lazy evolved lists of dynamics.schrodinger (anything with `tiles()`)
+    are walked one time tile at a time, so the observables of a list that does not fit in HBM (cfg3: 68.7 GB)
+    are reduced on the GPU without the list ever existing."""
+    converted = states.with_state_basis(target) if isinstance(states, StateList) else states.with_basis(target)
+    size = target.size
+    if hasattr(converted, "tiles") and getattr(converted, "_device", None) is None:
+        for _, tile in converted.tiles():
+            yield tile.reshape(-1, size)
+        return
     data = converted.device_data
     if not data.is_complex():
         data = data.to(torch.complex128)
-    return data.reshape(-1, space.fundamental_size).contiguous()
+    yield data.reshape(-1, size).contiguous()
+
+
+def _reduce_position(states: Array, space: TupleMetadata, fn: Any) -> torch.Tensor:
+    """cat(fn(tile)) over the position-basis tiles of `states` (fn: [rows, M] -> [rows])."""
+    position = _basis.from_metadata(space).upcast()
+    return torch.cat([fn(tile) for tile in _tiles_in(states, position)])
+
+
+def _reduce_momentum(states: Array, space: TupleMetadata, fn: Any) -> torch.Tensor:
+    momentum = _basis.transformed_from_metadata(space).upcast()
+    return torch.cat([fn(tile) for tile in _tiles_in(states, momentum)])
+
+
+def _position_data(states: Array, space: TupleMetadata) -> torch.Tensor:
+    """[lead, M] device tensor of the states in the fundamental (position) basis of ``space``."""
+    return torch.cat(list(_tiles_in(states, _basis.from_metadata(space).upcast())))
 
 
 def _axis_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
@@ -81,15 +102,7 @@ def _all_variance_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch
 
 def _momentum_data(states: Array, space: TupleMetadata) -> torch.Tensor:
     """[lead, M] device tensor of the states in the transformed (momentum) basis of ``space`` (K4 on the GPU)."""
-    momentum = _basis.transformed_from_metadata(space).upcast()
-    if isinstance(states, StateList):
-        converted = states.with_state_basis(momentum)
-    else:
-        converted = states.with_basis(momentum)
-    data = converted.device_data
-    if not data.is_complex():
-        data = data.to(torch.complex128)
-    return data.reshape(-1, space.fundamental_size).contiguous()
+    return torch.cat(list(_tiles_in(states, _basis.transformed_from_metadata(space).upcast())))
 
 
 def _k_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
@@ -115,20 +128,20 @@ def _all_variance_k(mom_data: torch.Tensor, space: TupleMetadata, axis: int) -> 
 def all_k(states: StateList, *, axis: int) -> Array:
     """Momentum of all states (reference operator/_measure.py:323-336)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _all_k(_momentum_data(states, space), space, axis))
+    return _list_array(states, _reduce_momentum(states, space, lambda mom: _all_k(mom, space, axis)))
 
 
 def all_variance_k(states: StateList, *, axis: int) -> Array:
     """<(K - <K>)^2> of all states (reference operator/_measure.py:361-378)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _all_variance_k(_momentum_data(states, space), space, axis))
+    return _list_array(states, _reduce_momentum(states, space, lambda mom: _all_variance_k(mom, space, axis)))
 
 
 def all_uncertainty(states: StateList, *, axis: int) -> Array:
     """sqrt(var_x var_k) of all states (reference operator/_measure.py:400-420)."""
     space = states.basis.metadata().children[1]
-    var_x = _all_variance_x(_position_data(states, space), space, axis)
-    var_k = _all_variance_k(_momentum_data(states, space), space, axis)
+    var_x = _reduce_position(states, space, lambda pos: _all_variance_x(pos, space, axis))
+    var_k = _reduce_momentum(states, space, lambda mom: _all_variance_k(mom, space, axis))
     return _list_array(states, torch.sqrt(var_x * var_k))
 
 
@@ -152,25 +165,25 @@ def uncertainty(state: State, *, axis: int) -> float:
 def all_x(states: StateList, *, axis: int, offset: float = 0, wrapped: bool = False) -> Array:
     """Position of all states (reference operator/_measure.py:191-210)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _all_x(_position_data(states, space), space, axis, offset, wrapped))
+    return _list_array(states, _reduce_position(states, space, lambda pos: _all_x(pos, space, axis, offset, wrapped)))
 
 
 def all_periodic_x(states: StateList, *, axis: int) -> Array:
     """Periodic position coordinate of all states (reference operator/_measure.py:242-268)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _all_periodic_x(_position_data(states, space), space, axis))
+    return _list_array(states, _reduce_position(states, space, lambda pos: _all_periodic_x(pos, space, axis)))
 
 
 def all_variance_x(states: StateList, *, axis: int) -> Array:
     """<x^2> around each state's periodic position (reference operator/_measure.py:271-292)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _all_variance_x(_position_data(states, space), space, axis))
+    return _list_array(states, _reduce_position(states, space, lambda pos: _all_variance_x(pos, space, axis)))
 
 
 def all_coherent_width(states: StateList, *, axis: int) -> Array:
     """Width of a Gaussian wavepacket, sqrt(2 variance) (reference operator/_measure.py:295-305)."""
     space = states.basis.metadata().children[1]
-    variance = _all_variance_x(_position_data(states, space), space, axis)
+    variance = _reduce_position(states, space, lambda pos: _all_variance_x(pos, space, axis))
     return _list_array(states, torch.sqrt(2.0 * variance))
 
 

@@ -93,6 +93,20 @@ class StateList(Array):
         return StateList(TupleBasis((list_basis, states[0].basis)).upcast(), np.array([s.raw_data for s in states]))
 
 
+def iter_list_tiles(states: "StateList", state_basis: Basis | None = None):
+    """[rows, size] device tensors covering the list in `state_basis` (default: its own), in list order.
+
+    Ordinary lists give one tensor; the lazy evolved lists of dynamics.schrodinger (anything with `tiles()`) are
+    walked one time tile at a time so that per-state reductions never need the whole list in HBM."""
+    converted = states if state_basis is None else states.with_state_basis(state_basis)
+    if hasattr(converted, "tiles") and getattr(converted, "_device", None) is None:
+        for _, tile in converted.tiles():
+            yield tile
+        return
+    tup = _basis.as_tuple(converted.basis)
+    yield _complex(converted.device_data).reshape(tup.children[0].size, -1).contiguous()
+
+
 def _list_data(states: StateList) -> tuple[TupleBasis, Any]:
     """(tuple basis, [len(list), state size] device data) of a state list."""
     from slate_quantum_b200.core.array import as_tuple_basis
@@ -104,6 +118,12 @@ def _list_data(states: StateList) -> tuple[TupleBasis, Any]:
 
 def inner_product_each(state_0: StateList, state_1: StateList) -> Array:
     """<state_0[j]|state_1[j]> for every j (reference state/_state.py:208-218)."""
+    if state_0 is state_1 and hasattr(state_0, "tiles"):
+        # <psi_j|psi_j> of a lazy evolved list: one pass per time tile
+        import torch
+
+        list_basis = _basis.as_tuple(state_0.basis).children[0]
+        return Array(list_basis, torch.cat([kernels.rowwise_vdot(t, t) for t in iter_list_tiles(state_0)]))
     tup, lhs = _list_data(state_0)
     _, rhs = _list_data(state_1.with_basis(tup.upcast()))
     return Array(tup.children[0], kernels.rowwise_vdot(lhs, rhs))
