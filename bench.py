@@ -2,18 +2,21 @@
 """bench.py -- one "step" = one pass of the hot path over one synthetic Bloch workload:
 
     K1 build every k-block  ->  K2 eigh of every block  ->  K4+K5+K3a project psi0  ->
-    K3c evolve over T times (fused phase x eigenvector DMMA GEMM)  ->  [N=1: K5+K4 to the position basis]
+    K3c evolve over T times (fused phase x eigenvector DMMA GEMM)  ->  K4b cell FFT to the position basis
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
 
-Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), k-blocks sharded in contiguous
-ranges, weak scaling (each rank owns prod(repeat) blocks of a k-grid enlarged along axis 0), the only
-collective is the NCCL all-gather of eigenvalues.  See DESIGN.md section "Measurement".
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), k-blocks sharded in contiguous ranges.
+`value` is the weak-scaling figure (each rank owns the config's k-grid, enlarged along axis 0); the same line carries
+`strong_scaling` (the config's own k-grid split over the ranks), `parity_check` (sampled blocks of the LAST time rows
+against the CPU oracle, every N), `e2e` (through the reference-shaped API at N=1; position-basis, time-sharded states
+to host at N>1), and short runs of the other BASELINE.json configs (`other_configs`).  See DESIGN.md "Measurement".
 """
 
 from __future__ import annotations
 
 import argparse
+import csv
 import ctypes
 import json
 import os
@@ -29,10 +32,11 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-from slate_quantum_b200.configs import CONFIGS, HBAR, BlochWorkload  # noqa: E402
+from slate_quantum_b200.configs import CONFIGS, HBAR, BlochWorkload, shard_blocks  # noqa: E402
 
 METRIC = "bloch_k_blocks_per_s"
 UNIT = "k-blocks/s (each block built, diagonalised and evolved over the config's time batch)"
+PARITY_TOL = 1e-9  # north_star: evolved states max-abs 1e-9
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -92,19 +96,47 @@ class ClockSampler:
         }
 
 
+def config_dict(cfg: BlochWorkload, world: int, strong: bool, with_position: bool, **extra) -> dict:
+    """The `config` object of the JSON line; the reference arm prints the SAME dict (same keys and values)."""
+    repeat_global = tuple(cfg.repeat) if strong else (cfg.repeat[0] * world, *cfg.repeat[1:])
+    n_k_local = cfg.n_k // world if strong else cfg.n_k
+    out = {
+        "workload": cfg.name,
+        "shape": list(cfg.shape),
+        "repeat_per_gpu": list(cfg.repeat),
+        "repeat_global": list(repeat_global),
+        "block_size_N": cfg.n,
+        "k_blocks_per_gpu": n_k_local,
+        "n_times": cfg.n_times,
+        "position_basis": bool(with_position),
+        "l2_policy": "inputs larger than L2: every step rebuilds and re-reads the "
+        f"{n_k_local * cfg.n * cfg.n * 16 / 1e9:.2f} GB block array (L2 = 126 MB)",
+        "parallelism": f"k-block sharding x{world}",
+    }
+    assert not extra
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy restatement of the reference; the reference itself cannot be imported here)
+def _blas_threads(want: int | None = None) -> int:
+    """Threads the BLAS / LAPACK pools will use; `want` raises the limit (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        if want is not None:
+            threadpool_limits(limits=want)
+        return max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+    except Exception:  # noqa: BLE001
+        return 1
+
+
 def cpu_sample(cfg: BlochWorkload, n_blocks: int, n_times: int, with_position: bool) -> dict:
     """Time the oracle on a bounded sample of `cfg`; extrapolate linearly to one full step."""
     from oracle import bloch_oracle as o
 
-    try:
-        from threadpoolctl import threadpool_info
-
-        blas_threads = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
-    except Exception:  # noqa: BLE001
-        blas_threads = 1
     cores = len(os.sched_getaffinity(0))
+    blas_threads = _blas_threads(cores)  # all host threads, whatever OMP_NUM_THREADS the launcher exported
     comps = cfg.potential_components()
     n_blocks = min(n_blocks, cfg.n_k)
     n_times = min(n_times, cfg.n_times)
@@ -163,7 +195,9 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cfg = CONFIGS[args.config]
+    strong = args.scaling == "strong"
     # bounded sample per step so that K+W steps end within a few minutes
     nb = 64 if cfg.n <= 256 else 16
     nt = 256
@@ -173,6 +207,8 @@ def run_reference(args) -> None:
     vals = [cpu_sample(cfg, nb, nt, args.position) for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     best = max(vals, key=lambda d: d["value"])
+    # the CPU arm has one set of host cores whatever N is: its per-block rate does not depend on the k-grid, so the
+    # weak-scaling workload of N GPUs (N x the blocks) takes N x the time at the same k-blocks/s
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -181,63 +217,679 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": best["step_s_extrapolated"] * 1e3,
+        "ms_per_step": best["step_s_extrapolated"] * 1e3 * (1 if strong else world),
+        "ms_per_step_is": "linear extrapolation of the timed sample to the full step (not a timed step); "
+        "`sample_wall_s` is what was timed",
         "higher_is_better": True,
         "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "c128 (f64)",
         "data": "synthetic",
-        "config": {"workload": cfg.name, "position_basis": bool(args.position)},
-        "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "blas_threads", "kind", "sample")},
+        "config": config_dict(cfg, world, strong, bool(args.position)),
+        "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "blas_threads", "kind", "sample", "sample_wall_s")},
         "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_wall_s": best["sample_wall_s"],
         "note": "numpy/LAPACK restatement of the reference (reference needs Python>=3.14 + un-vendored slate_core); "
-        f"sample wall {wall:.1f}s",
+        f"all {vals[0]['blas_threads']} BLAS threads of {vals[0]['cores']} cores; total wall {wall:.1f}s",
     }
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------
+def _hbm_peak() -> float:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"])
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0  # B200_PROFILING.md fallback
+
+
+_UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic(kernel: str, cfg_name: str, t_tile: int) -> tuple[float | None, str | None]:
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel`, read from the committed ncu
+    `--set full` raw page named in profiles/traffic_index.json for exactly this (config, time tile); else None."""
+    index = ROOT / "profiles" / "traffic_index.json"
+    try:
+        entry = json.loads(index.read_text()).get(kernel)
+        if not entry or not cfg_name.startswith(entry["config"]) or int(entry["t_tile"]) != int(t_tile):
+            return None, None
+        rows = list(csv.reader((ROOT / "profiles" / entry["csv"]).open()))
+        head, units = rows[0], rows[1]
+        k_col = head.index("Kernel Name")
+        total = 0.0
+        for row in rows[2:]:
+            if kernel in row[k_col]:
+                for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    c = head.index(name)
+                    total += float(row[c].replace(",", "")) * _UNIT_SCALE[units[c]]
+                return total, f"profiles/{entry['csv']}"
+    except Exception:  # noqa: BLE001
+        return None, None
+    return None, None
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> int | None:
+    """Pin this process (and so its first-touch pinned allocations) to the NUMA node of its GPU."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text().strip())
+        if node < 0:
+            return None
+        cpus: set[int] = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
+class Ctx:
+    def __init__(self) -> None:
+        import torch
+        import torch.distributed as dist
+
+        from slate_quantum_b200 import _lib
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device; slate_quantum_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.numa_node = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.lib = _lib.load()
+
+    def sync_all(self) -> None:
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values: list[float]) -> list[float]:
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def sample_blocks(n_k: int) -> list[int]:
+    """A few k-blocks spread over the whole grid (so at N > 1 they lie in several ranks' ranges)."""
+    return sorted({0, n_k // 3, min(n_k // 2 + 1, n_k - 1), n_k - 1})
+
+
+def oracle_gate(cfg: BlochWorkload, repeat_global, psi0: np.ndarray, times_sel: np.ndarray, rows: np.ndarray,
+                basis: str) -> tuple[float, list[int]]:
+    """max |device - oracle| over sampled blocks of the given evolved rows (the CPU oracle is the checker)."""
+    from oracle import bloch_oracle as o
+
+    n_k = int(np.prod(repeat_global))
+    blocks = sample_blocks(n_k)
+    err = o.sampled_block_parity(
+        cfg.vectors(), cfg.shape, cfg.potential_components(), cfg.mass(), repeat_global, psi0, times_sel, rows, blocks,
+        HBAR, basis=basis,
+    )
+    return err, blocks
+
+
+# ----------------------------------------------------------------------------------------------------
+class PositionRun:
+    """The measured step with position-basis output (pipeline.BlochSolver at N=1, + TimeShardedEvolver at N>1)."""
+
+    STAGES = ["build", "eigh", "fold", "project", "evolve", "exchange", "position"]
+
+    def __init__(self, ctx: Ctx, cfg: BlochWorkload, strong: bool, with_position: bool = True) -> None:
+        from slate_quantum_b200 import kernels
+        from slate_quantum_b200.pipeline import BlochSolver, TimeShardedEvolver
+
+        torch = ctx.torch
+        self.ctx, self.cfg, self.strong, self.with_position = ctx, cfg, strong, with_position
+        world, rank = ctx.world, ctx.rank
+        if strong and cfg.n_k % world:
+            raise SystemExit(f"strong scaling needs n_k={cfg.n_k} divisible by the number of GPUs")
+        self.repeat_global = tuple(cfg.repeat) if strong else (cfg.repeat[0] * world, *cfg.repeat[1:])
+        self.n, self.T = cfg.n, cfg.n_times
+        self.n_k_local = cfg.n_k // world if strong else cfg.n_k
+        self.n_k_global = self.n_k_local * world
+        n, T = self.n, self.T
+        self.solver = BlochSolver(cfg.shape, self.repeat_global, cfg.dk(), cfg.mass(), HBAR, rank * self.n_k_local,
+                                  self.n_k_local)
+        # ---- host inputs (pinned) -> device
+        self.table_h = torch.from_numpy(cfg.potential_table().ravel().copy()).pin_memory()
+        wl_global = BlochWorkload(cfg.name, cfg.delta_x, cfg.shape, self.repeat_global, cfg.potential, cfg.height, T,
+                                  cfg.t_max_over_hbar)
+        self.psi_np = wl_global.initial_state()
+        self.psi_h = torch.from_numpy(self.psi_np).pin_memory()
+        self.times_np = cfg.times()
+        self.times_h = torch.from_numpy(self.times_np).pin_memory()
+        self.table = self.table_h.cuda(non_blocking=True)
+        self.psi0 = self.psi_h.cuda(non_blocking=True)
+        self.times = self.times_h.cuda(non_blocking=True)
+        self.dt_uniform = kernels.uniform_step(self.times_np)  # uniform grid -> table-driven phases (3M kernel)
+        # ---- buffers
+        self.h_buf = torch.empty((self.n_k_local, n, n), dtype=torch.complex128, device="cuda")
+        ws_bytes = ctx.lib.sqb_eigh_workspace_bytes(n, self.n_k_local)
+        self.solver._eigh_ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")  # noqa: SLF001
+        self.gathered = world > 1 and with_position  # time-sharded evolve over exchanged eigenvectors
+        self.sharded = TimeShardedEvolver(self.solver, T) if self.gathered else None
+        self.folded_buf = torch.empty_like(self.h_buf) if with_position and not self.gathered else None
+        free, _ = torch.cuda.mem_get_info()
+        row_bytes = self.n_k_local * n * 16
+        t_tile = T
+        if self.gathered:
+            row_bytes = self.n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
+            t_tile = T // world
+        budget = int(free * 0.8 / (2 if with_position else 1))
+        while t_tile * row_bytes > budget and t_tile > 64:
+            t_tile //= 2
+        self.t_tile, self.row_bytes = t_tile, row_bytes
+        self.states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
+        self.pos_out = torch.empty_like(self.states) if with_position else None
+        self.eig_all = (
+            torch.empty((world, self.n_k_local * n), dtype=torch.float64, device="cuda")
+            if world > 1 and not self.gathered else None
+        )
+        self.last_tile: tuple[int, int] = (0, 0)  # (first global time index, rows) of what pos_out / states holds
+
+    def step(self, record: list | None = None) -> None:
+        """One pass of the hot path.  `record` collects (stage, start_event, end_event) triples."""
+        ctx, solver, sharded = self.ctx, self.solver, self.sharded
+        T, t_tile = self.T, self.t_tile
+
+        def timed(name, fn):
+            if record is None:
+                return fn()
+            a, b = ctx.ev(), ctx.ev()
+            a.record()
+            out = fn()
+            b.record()
+            record.append((name, a, b))
+            return out
+
+        timed("build", lambda: solver.build(self.table, out=self.h_buf))
+
+        def eigh():
+            solver.diagonalise()
+            if sharded is not None:
+                sharded.gather_eigenvalues()
+            elif ctx.world > 1:
+                ctx.dist.all_gather_into_tensor(self.eig_all, solver.eigenvalues.reshape(-1))
+
+        timed("eigh", eigh)
+        if self.with_position:
+            # eigenvectors -> in-cell position basis + Bloch twiddle, once per eigensolve (K4 on N-point cells)
+            timed("fold", (lambda: sharded.fold()) if sharded is not None else (lambda: solver.fold(out=self.folded_buf)))
+        c = timed("project", lambda: solver.project(self.psi0))
+        if sharded is not None:
+            # Position output at N > 1 (pipeline.TimeShardedEvolver): the ranks exchange the folded eigenvectors on a
+            # side stream and each evolves its own T/G time samples of EVERY block, then runs the local cell FFT.
+            sharded.start_exchange(c, wrap=timed)
+            t_lo = sharded.time_begin
+            sharded.evolve_position(self.times[t_lo : t_lo + sharded.rows], self.states, self.pos_out,
+                                    self.dt_uniform, wrap=timed)
+            last0 = (sharded.rows - 1) // t_tile * t_tile
+            self.last_tile = (t_lo + last0, sharded.rows - last0)
+            return
+        for t0 in range(0, T, t_tile):
+            tt = min(t_tile, T - t0)
+            if self.with_position:
+                timed("evolve", lambda: solver.evolve_cell(c, self.times[t0 : t0 + tt], out=self.states[:tt],
+                                                           uniform_dt=self.dt_uniform))
+                timed("position", lambda: solver.cell_to_position(self.states[:tt], out=self.pos_out[:tt]))
+            else:
+                timed("evolve", lambda: solver.evolve_bloch(c, self.times[t0 : t0 + tt], out=self.states[:tt],
+                                                            uniform_dt=self.dt_uniform))
+            self.last_tile = (t0, tt)
+
+    def measure(self, steps: int, warmup: int, clocks: bool = True) -> dict:
+        from slate_quantum_b200 import kernels
+
+        ctx, torch = self.ctx, self.ctx.torch
+        for _ in range(warmup):
+            self.step()
+        ctx.sync_all()
+        assert int(self.solver.info.abs().sum().item()) == 0, "eigensolver reported non-convergence"
+        records = [[] for _ in range(steps)]
+        launches_before = kernels.LAUNCHES
+        start, stop = ctx.ev(), ctx.ev()
+        sampler = ClockSampler(ctx.local_rank) if clocks else None
+        if sampler:
+            sampler.__enter__()
+        try:
+            ctx.sync_all()
+            start.record()
+            for k in range(steps):
+                self.step(records[k])
+            stop.record()
+            ctx.sync_all()
+        finally:
+            if sampler:
+                sampler.__exit__()
+        launches = (kernels.LAUNCHES - launches_before) // max(steps, 1)
+        stage_ms = {nm: 0.0 for nm in self.STAGES}
+        for rec in records:
+            for nm, a_ev, b_ev in rec:
+                stage_ms[nm] += a_ev.elapsed_time(b_ev) / steps
+        vals = ctx.max_over_ranks([start.elapsed_time(stop) / steps] + [stage_ms[nm] for nm in self.STAGES])
+        ms_per_step = vals[0]
+        stage_ms = dict(zip(self.STAGES, vals[1:]))
+        del torch
+        return {
+            "ms_per_step": ms_per_step,
+            "value": self.n_k_global / (ms_per_step * 1e-3),
+            "stage_ms": stage_ms,
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+        }
+
+    def parity_check(self) -> dict:
+        """Sampled blocks of the FIRST and LAST time row this rank holds (the last tile of the last step), against
+        the CPU oracle; max over ranks.  At N > 1 the sampled blocks lie in several ranks' k-ranges and every rank
+        checks its own time rows, so the eigenvector exchange and the time sharding are both covered."""
+        ctx = self.ctx
+        t0, tt = self.last_tile
+        buf = self.pos_out if self.with_position else self.states
+        pick = sorted({0, tt - 1})
+        rows = buf[pick].cpu().numpy()
+        t_idx = [t0 + r for r in pick]
+        if self.with_position:
+            err, blocks = oracle_gate(self.cfg, self.repeat_global, self.psi_np, self.times_np[t_idx], rows, "position")
+        else:
+            # k-sharded Bloch-order output: this rank's blocks only
+            from oracle import bloch_oracle as o
+
+            b0, cnt = self.solver.block_begin, self.solver.block_count
+            blocks = sorted({b0, b0 + cnt // 2, b0 + cnt - 1})
+            want = o.evolve_sampled_blocks(self.cfg.vectors(), self.cfg.shape, self.cfg.potential_components(),
+                                           self.cfg.mass(), self.repeat_global, self.psi_np, self.times_np[t_idx],
+                                           blocks, HBAR)
+            got = rows.reshape(len(pick), cnt, self.n)[:, [b - b0 for b in blocks], :]
+            err = float(np.abs(got - want).max())
+        err_all = ctx.max_over_ranks([err])[0]
+        return {
+            "max_err": err_all,
+            "tol": PARITY_TOL,
+            "ok": bool(err_all < PARITY_TOL),
+            "checked": "sampled k-blocks of the first and last time row of every rank's last time tile vs the CPU "
+            "oracle (np.linalg.eigh + np.exp + matmul per block; rows brought back through np.fft + the K5 permutation)",
+            "time_rows_rank0": t_idx,
+            "blocks_rank0": blocks,
+            "basis": "position" if self.with_position else "bloch momentum (k-sharded)",
+        }
+
+    def close(self) -> None:
+        torch = self.ctx.torch
+        for name in ("states", "pos_out", "h_buf", "folded_buf", "eig_all", "sharded", "solver"):
+            setattr(self, name, None)
+        torch.cuda.empty_cache()
+
+
+# ----------------------------------------------------------------------------------------------------
+def api_objects(cfg: BlochWorkload):
+    """Host-side objects of the reference-shaped API for `cfg` (metadata, potential builder, bases)."""
+    from slate_quantum_b200 import operator
+    from slate_quantum_b200.core import FundamentalBasis, basis, metadata
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata, repeat_volume_metadata
+
+    vectors = cfg.vectors()
+    cell_meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(
+        tuple(vectors[i] for i in range(cfg.nd)), cfg.shape
+    )
+    super_meta = repeat_volume_metadata(cell_meta, cfg.repeat)
+    position_basis = basis.from_metadata(super_meta).upcast()
+    # "Fourier" spacing = start + delta j / n, i.e. cfg.times() (linspace without the end point)
+    times = FundamentalBasis(SpacedTimeMetadata(cfg.n_times, domain=Domain(delta=cfg.t_max_over_hbar * HBAR),
+                                                interpolation="Fourier"))
+    build_potential = {"cos": operator.build.cos_potential, "fcc": operator.build.fcc_potential}[cfg.potential]
+    return cell_meta, super_meta, position_basis, times, build_potential
+
+
+def e2e_api(ctx: Ctx, cfg: BlochWorkload, steps: int) -> dict:
+    """End to end through the reference-shaped calls with HOST buffers, N = 1:
+
+        bloch.build.kinetic_hamiltonian -> dynamics.solve_schrodinger_equation_decomposition ->
+        StateList.with_state_basis(position basis)     (reference dynamics/schrodinger.py:59-73, state/_state.py:153-165)
+
+    psi0 comes from pinned host memory; every evolved position-basis state is copied back to pinned host staging
+    buffers (host_tiles) inside the timed region."""
+    from slate_quantum_b200 import bloch, dynamics, kernels
+    from slate_quantum_b200.state import State
+
+    torch = ctx.torch
+    cell_meta, _, position_basis, times, build_potential = api_objects(cfg)
+    psi_np = cfg.initial_state()
+    psi_h = torch.from_numpy(psi_np).pin_memory()
+    T, m = cfg.n_times, cfg.m
+    want_rows = sorted({0, T // 2 - 1, T - 1})
+    kept: dict[int, np.ndarray] = {}
+    n_tiles = [0]
+
+    def step(keep: bool) -> None:
+        potential = build_potential(cell_meta, cfg.height)
+        hamiltonian = bloch.build.kinetic_hamiltonian(potential, cfg.mass(), cfg.repeat)
+        psi0 = State(position_basis, psi_h)
+        evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
+        in_position = evolution.with_state_basis(position_basis)
+        n_tiles[0] = 0
+        for t0, rows in in_position.host_tiles():
+            n_tiles[0] += 1
+            if keep:
+                for r in want_rows:
+                    if t0 <= r < t0 + rows.shape[0]:
+                        kept[r] = rows[r - t0].numpy().copy()
+
+    step(False)
+    ctx.sync_all()
+    n_e2e = max(1, min(steps, 2))
+    launches_before = kernels.LAUNCHES
+    a, b = ctx.ev(), ctx.ev()
+    a.record()
+    for i in range(n_e2e):
+        step(i == n_e2e - 1)
+    b.record()
+    ctx.sync_all()
+    ms = a.elapsed_time(b) / n_e2e
+    launches = (kernels.LAUNCHES - launches_before) // n_e2e
+    rows = np.stack([kept[r] for r in want_rows])
+    err, blocks = oracle_gate(cfg, cfg.repeat, psi_np, cfg.times()[want_rows], rows, "position")
+    torch.cuda.empty_cache()
+    return {
+        "value": cfg.n_k / (ms * 1e-3),
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(psi_h.numel() * 16 + T * 8 + cfg.potential_components().size * 16),
+        "d2h_bytes_per_step": int(T * m * 16),
+        "ms_per_step": ms,
+        "steps": n_e2e,
+        "gpu_launches": int(launches),
+        "host_chunks_per_step": n_tiles[0],
+        "path": "slate_quantum_b200.bloch.build.kinetic_hamiltonian -> dynamics.solve_schrodinger_equation_decomposition"
+        " -> StateList.with_state_basis(position basis) -> host_tiles()",
+        "note": "host potential + pinned psi0 + times -> the reference-shaped API -> every evolved POSITION-basis state "
+        f"copied back to pinned host staging buffers (PCIe-bound: the state list is {T * m * 16 / 1e9:.1f} GB)",
+        "parity_check": {
+            "max_err": err, "tol": PARITY_TOL, "ok": bool(err < PARITY_TOL), "time_rows": want_rows, "blocks": blocks,
+            "checked": "host copies of the API's position-basis states vs the CPU oracle on sampled k-blocks",
+        },
+    }
+
+
+def e2e_api_observables(ctx: Ctx, cfg: BlochWorkload, steps: int) -> dict:
+    """The same API chain when the caller wants operator.measure observables of every evolved state instead of the
+    states: the lazy list is reduced tile by tile on the GPU (K6), [T] doubles per observable come back."""
+    from slate_quantum_b200 import bloch, dynamics
+    from slate_quantum_b200.operator import measure
+    from slate_quantum_b200.state import State
+
+    torch = ctx.torch
+    cell_meta, _, position_basis, times, build_potential = api_objects(cfg)
+    psi_h = torch.from_numpy(cfg.initial_state()).pin_memory()
+    out: dict[str, np.ndarray] = {}
+
+    def step() -> None:
+        potential = build_potential(cell_meta, cfg.height)
+        hamiltonian = bloch.build.kinetic_hamiltonian(potential, cfg.mass(), cfg.repeat)
+        evolution = dynamics.solve_schrodinger_equation_decomposition(State(position_basis, psi_h), times, hamiltonian)
+        # materialise the position-basis list once (it fits: 68.7 GB at cfg3); each observable is then one read pass.
+        # (measure.* on the lazy `evolution` itself also works - it re-evolves tile by tile per observable.)
+        in_position = evolution.with_state_basis(position_basis)
+        in_position.device_data  # noqa: B018
+        for axis in range(cfg.nd):
+            out[f"x{axis}"] = measure.all_x(in_position, axis=axis).raw_data
+            out[f"width{axis}"] = measure.all_coherent_width(in_position, axis=axis).raw_data
+
+    step()
+    ctx.sync_all()
+    n_e2e = max(1, min(steps, 2))
+    a, b = ctx.ev(), ctx.ev()
+    a.record()
+    for _ in range(n_e2e):
+        step()
+    b.record()
+    ctx.sync_all()
+    ms = a.elapsed_time(b) / n_e2e
+    torch.cuda.empty_cache()
+    return {
+        "value": cfg.n_k / (ms * 1e-3),
+        "unit": UNIT,
+        "ms_per_step": ms,
+        "d2h_bytes_per_step": int(sum(v.size for v in out.values()) * 8),
+        "note": "same API chain, but operator.measure.all_x / all_coherent_width of every evolved state along every "
+        "axis are returned instead of the states (the lazy list is reduced tile by tile, never materialised)",
+        "x0_first_last": [float(np.real(out["x0"][0])), float(np.real(out["x0"][-1]))],
+    }
+
+
+def e2e_sharded(ctx: Ctx, run: PositionRun, steps: int) -> dict:
+    """End to end at N > 1 with HOST buffers: the same deliverable as `value` - POSITION-basis states, time-sharded
+    (rank r returns time rows [r T/G, (r+1) T/G) of the whole supercell) - plus an observables-only leg."""
+    from slate_quantum_b200 import kernels
+
+    torch, cfg, solver, sharded = ctx.torch, run.cfg, run.solver, run.sharded
+    n, T = run.n, run.T
+    row_bytes = run.row_bytes
+    m_global = row_bytes // 16
+    rows_local = sharded.rows
+    t_tile = max(1, min(rows_local, (8 << 30) // row_bytes))
+    host_rows = max(1, min(t_tile, (1 << 30) // row_bytes))
+    n_stage = 4
+    run.states = run.pos_out = None
+    torch.cuda.empty_cache()
+    states = torch.empty((t_tile, m_global), dtype=torch.complex128, device="cuda")
+    outs = [torch.empty((t_tile, m_global), dtype=torch.complex128, device="cuda") for _ in range(2)]
+    stage = [torch.empty((host_rows, m_global), dtype=torch.complex128).pin_memory() for _ in range(n_stage)]
+    eig_host = torch.empty((run.n_k_local * n,), dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    big = solver.supercell
+    vec = cfg.vectors()
+    lengths = [float(np.linalg.norm(vec[a])) * run.repeat_global[a] for a in range(cfg.nd)]
+    mom_host = torch.empty((cfg.nd, rows_local, 5), dtype=torch.float64).pin_memory()
+    kept: dict[int, np.ndarray] = {}
+
+    def step(mode: str, keep: bool = False) -> None:
+        cur = torch.cuda.current_stream()
+        tb = run.table_h.cuda(non_blocking=True)
+        ps = run.psi_h.cuda(non_blocking=True)
+        tm = run.times_h.cuda(non_blocking=True)
+        solver.build(tb, out=run.h_buf)
+        solver.diagonalise()
+        sharded.gather_eigenvalues()
+        eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
+        sharded.fold()
+        c = solver.project(ps)
+        sharded.start_exchange(c)
+        k = [0]
+
+        def drain(t0: int, tt: int, tile):
+            if mode == "observables":
+                for a in range(cfg.nd):
+                    mom = kernels.measure_moments(tile, big, a, lengths[a] / big[a], lengths[a])
+                    mom_host[a, t0 : t0 + tt].copy_(mom, non_blocking=True)
+                return None
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                for r0 in range(0, tt, host_rows):
+                    rr = min(host_rows, tt - r0)
+                    stage[k[0] % n_stage][:rr].copy_(tile[r0 : r0 + rr], non_blocking=True)
+                    k[0] += 1
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            if keep and t0 + tt == rows_local:
+                done.synchronize()
+                last = (k[0] - 1) % n_stage
+                rr = tt - (tt - 1) // host_rows * host_rows
+                kept[sharded.time_begin + rows_local - 1] = stage[last][rr - 1].numpy().copy()
+            return done
+
+        t_lo = sharded.time_begin
+        sharded.evolve_position(tm[t_lo : t_lo + rows_local], states, outs, run.dt_uniform, on_tile=drain)
+        cur.wait_stream(copy_stream)
+
+    result = {}
+    for mode in ("states", "observables"):
+        step(mode)
+        ctx.sync_all()
+        n_e2e = max(1, min(steps, 2))
+        a, b = ctx.ev(), ctx.ev()
+        a.record()
+        for i in range(n_e2e):
+            step(mode, keep=(mode == "states" and i == n_e2e - 1))
+        b.record()
+        ctx.sync_all()
+        ms = ctx.max_over_ranks([a.elapsed_time(b) / n_e2e])[0]
+        result[mode] = ms
+    t_idx = sorted(kept)
+    err, blocks = oracle_gate(cfg, run.repeat_global, run.psi_np, run.times_np[t_idx], np.stack([kept[t] for t in t_idx]),
+                              "position")
+    err = ctx.max_over_ranks([err])[0]
+    h2d = run.table_h.numel() * 16 + run.psi_h.numel() * 16 + run.times_h.numel() * 8
+    return {
+        "value": run.n_k_global / (result["states"] * 1e-3),
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(h2d),
+        "d2h_bytes_per_step": int(eig_host.numel() * 8 + rows_local * row_bytes),
+        "ms_per_step": result["states"],
+        "basis": "position (supercell), time-sharded: rank r returns time rows [r T/G, (r+1) T/G) - the deliverable "
+        "`value` measures",
+        "numa_node_rank0": ctx.numa_node,
+        "note": "pinned host inputs -> C ABI (pipeline.TimeShardedEvolver) -> eigenvalues and this rank's evolved "
+        f"position-basis states copied back through {n_stage} x {host_rows * row_bytes / 2**30:.2f} GiB pinned staging "
+        f"buffers allocated on the GPU's NUMA node ({rows_local * row_bytes / 1e9:.1f} GB per rank)",
+        "parity_check": {"max_err": err, "tol": PARITY_TOL, "ok": bool(err < PARITY_TOL), "blocks": blocks,
+                         "checked": "every rank's LAST time row, read from its host staging buffer, vs the CPU oracle"},
+        "observables_only": {
+            "value": run.n_k_global / (result["observables"] * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": result["observables"],
+            "d2h_bytes_per_step": int(eig_host.numel() * 8 + mom_host.numel() * 8),
+            "note": "same host-buffer step, but norm / <x> / <x^2> / scattering phase (K6) of every evolved state "
+            "along every axis are returned instead of the states",
+        },
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_other_config(ctx: Ctx, cfg: BlochWorkload, steps: int = 1) -> dict:
+    """A short k-sharded run of another BASELINE.json config: build + eigh (+ evolution over the config's time batch
+    in the Bloch momentum basis), blocks split over the ranks, with the oracle gate on sampled blocks."""
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    torch = ctx.torch
+    begin, count = shard_blocks(cfg.n_k, ctx.rank, ctx.world)
+    n, T = cfg.n, cfg.n_times
+    solver = BlochSolver(cfg.shape, cfg.repeat, cfg.dk(), cfg.mass(), HBAR, begin, count)
+    table = kernels.to_device(cfg.potential_table().ravel().copy(), torch.complex128)
+    psi_np = cfg.initial_state()
+    psi0 = kernels.to_device(psi_np, torch.complex128)
+    times_np = cfg.times()
+    times = kernels.to_device(times_np, torch.float64)
+    dt = kernels.uniform_step(times_np)
+    h_buf = torch.empty((count, n, n), dtype=torch.complex128, device="cuda")
+    free, _ = torch.cuda.mem_get_info()
+    row_bytes = count * n * 16
+    t_tile = max(1, min(T, int(free * 0.25) // row_bytes))
+    if t_tile >= 512:
+        t_tile = t_tile // 512 * 512
+    states = torch.empty((t_tile, count * n), dtype=torch.complex128, device="cuda")
+    rec: dict[str, float] = {}
+
+    def step(record: bool) -> None:
+        evs = [ctx.ev() for _ in range(5)]
+        evs[0].record()
+        solver.build(table, out=h_buf)
+        evs[1].record()
+        solver.diagonalise()
+        evs[2].record()
+        c = solver.project(psi0)
+        evs[3].record()
+        for t0 in range(0, T, t_tile):
+            tt = min(t_tile, T - t0)
+            solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt)
+        evs[4].record()
+        if record:
+            torch.cuda.synchronize()
+            for i, nm in enumerate(("build", "eigh", "project", "evolve")):
+                rec[nm] = rec.get(nm, 0.0) + evs[i].elapsed_time(evs[i + 1]) / steps
+            rec["total"] = rec.get("total", 0.0) + evs[0].elapsed_time(evs[4]) / steps
+
+    step(False)
+    ctx.sync_all()
+    for _ in range(steps):
+        step(True)
+    ctx.sync_all()
+    assert int(solver.info.abs().sum().item()) == 0, "eigensolver reported non-convergence"
+    names = ("build", "eigh", "project", "evolve", "total")
+    vals = dict(zip(names, ctx.max_over_ranks([rec[k] for k in names])))
+    # oracle gate: this rank's first / middle / last block at the last tile's first and last time
+    from oracle import bloch_oracle as o
+
+    t0 = (T - 1) // t_tile * t_tile
+    tt = T - t0
+    pick = sorted({0, tt - 1})
+    rows = states[pick].cpu().numpy().reshape(len(pick), count, n)
+    blocks = sorted({begin, begin + count // 2, begin + count - 1})
+    want = o.evolve_sampled_blocks(cfg.vectors(), cfg.shape, cfg.potential_components(), cfg.mass(), cfg.repeat, psi_np,
+                                   times_np[[t0 + r for r in pick]], blocks, HBAR)
+    err = float(np.abs(rows[:, [b - begin for b in blocks], :] - want).max())
+    w_ref = np.linalg.eigvalsh(o.bloch_blocks(cfg.vectors(), cfg.shape, cfg.potential_components(), cfg.mass(),
+                                              cfg.repeat, hbar=HBAR, block_begin=blocks[-1], block_count=1))[0]
+    w_err = float(np.abs(solver.eigenvalues[blocks[-1] - begin].cpu().numpy() - w_ref).max() / np.abs(w_ref).max())
+    err, w_err = ctx.max_over_ranks([err, w_err])
+    flops_eigh = (68.0 / 3.0) * n**3 * count
+    flops_evolve = 8.0 * n * n * T * count
+    out = {
+        "workload": cfg.name,
+        "k_blocks": cfg.n_k,
+        "k_blocks_per_gpu": count,
+        "block_size_N": n,
+        "n_times": T,
+        "value": cfg.n_k / (vals["total"] * 1e-3),
+        "unit": UNIT,
+        "ms_per_step": vals["total"],
+        "stage_ms": {k: vals[k] for k in ("build", "eigh", "project", "evolve")},
+        "eigh_tflops": flops_eigh / (vals["eigh"] * 1e-3) / 1e12,
+        "evolve_tflops": flops_evolve / (vals["evolve"] * 1e-3) / 1e12,
+        "basis": "bloch momentum (k-sharded, no data-path collective)",
+        "parity_check": {"max_err": err, "tol": PARITY_TOL, "eigenvalue_rel_err": w_err,
+                         "ok": bool(err < PARITY_TOL and w_err < 1e-10), "blocks_rank0": blocks},
+    }
+    del states, h_buf, solver
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
 def run_ours(args) -> None:
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx()
+    torch, dist, lib = ctx.torch, ctx.dist, ctx.lib
+    from slate_quantum_b200 import kernels
 
-    from slate_quantum_b200 import _lib, kernels
-    from slate_quantum_b200.pipeline import BlochSolver, TimeShardedEvolver
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device; slate_quantum_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
+    world, rank = ctx.world, ctx.rank
     cfg = CONFIGS[args.config]
     with_position = bool(args.position)
-
-    # weak scaling (default): the k-grid grows along axis 0 with the number of GPUs, rank r owns n_k contiguous
-    # blocks.  strong scaling (--scaling strong): the config's own k-grid is split into `world` contiguous ranges.
     strong = args.scaling == "strong"
-    if strong and cfg.n_k % world:
-        raise SystemExit(f"--scaling strong needs n_k={cfg.n_k} divisible by the number of GPUs")
-    repeat_global = tuple(cfg.repeat) if strong else (cfg.repeat[0] * world, *cfg.repeat[1:])
     n, T = cfg.n, cfg.n_times
-    n_k_local = cfg.n_k // world if strong else cfg.n_k
-    n_k_global = n_k_local * world
-    solver = BlochSolver(cfg.shape, repeat_global, cfg.dk(), cfg.mass(), HBAR, rank * n_k_local, n_k_local)
-    supercell = solver.supercell
-    m_global = solver.m
-
-    # ---- host inputs (pinned) -> device
-    table_h = torch.from_numpy(cfg.potential_table().ravel().copy()).pin_memory()
-    wl_global = BlochWorkload(cfg.name, cfg.delta_x, cfg.shape, repeat_global, cfg.potential, cfg.height, T, cfg.t_max_over_hbar)
-    psi_h = torch.from_numpy(wl_global.initial_state()).pin_memory()
-    times_h = torch.from_numpy(cfg.times()).pin_memory()
-    table = table_h.cuda(non_blocking=True)
-    psi0 = psi_h.cuda(non_blocking=True)
-    times = times_h.cuda(non_blocking=True)
-    dt_uniform = kernels.uniform_step(cfg.times())  # SpacedTimeMetadata-style uniform grid -> phase recurrence
 
     # ---- measured FP64 tensor (DMMA) and FMA peaks for the roofline denominators
     sink = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -258,114 +910,17 @@ def run_ours(args) -> None:
             best = max(best, fl.value / a.elapsed_time(b) / 1e9)
         return best
 
-    # ---- buffers
-    h_buf = torch.empty((n_k_local, n, n), dtype=torch.complex128, device="cuda")
-    ws_bytes = lib.sqb_eigh_workspace_bytes(n, n_k_local)
-    solver._eigh_ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")  # noqa: SLF001
-    free, _ = torch.cuda.mem_get_info()
-    row_bytes = n_k_local * n * 16
-    t_tile = T
-    # buffers of one time tile: states (+ position output)
-    gathered = world > 1 and with_position  # time-sharded evolve over ring-exchanged eigenvectors
-    sharded = TimeShardedEvolver(solver, T) if gathered else None  # pipeline.py; DESIGN.md section 6
-    folded_buf = torch.empty_like(h_buf) if with_position and not gathered else None
-    free, _ = torch.cuda.mem_get_info()
-    if gathered:
-        row_bytes = n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
-        t_tile = T // world
-    budget = int(free * 0.8 / (2 if with_position else 1))
-    while t_tile * row_bytes > budget and t_tile > 64:
-        t_tile //= 2
-    states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
-    pos_out = torch.empty_like(states) if with_position else None
-    eig_all = torch.empty((world, n_k_local * n), dtype=torch.float64, device="cuda") if world > 1 and not gathered else None
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    stage_names = ["build", "eigh", "fold", "project", "evolve", "exchange", "position"]
-
-    def step(record: list | None = None) -> None:
-        """One pass of the hot path.  `record` collects (stage, start_event, end_event) triples."""
-
-        def timed(name, fn):
-            if record is None:
-                return fn()
-            a, b = ev(), ev()
-            a.record()
-            out = fn()
-            b.record()
-            record.append((name, a, b))
-            return out
-
-        timed("build", lambda: solver.build(table, out=h_buf))
-
-        def eigh():
-            solver.diagonalise()
-            if sharded is not None:
-                sharded.gather_eigenvalues()
-            elif world > 1:
-                dist.all_gather_into_tensor(eig_all, solver.eigenvalues.reshape(-1))
-
-        timed("eigh", eigh)
-        if with_position:
-            # eigenvectors -> in-cell position basis + Bloch twiddle, once per eigensolve (K4 on N-point cells)
-            timed("fold", (lambda: sharded.fold()) if sharded is not None else (lambda: solver.fold(out=folded_buf)))
-        c = timed("project", lambda: solver.project(psi0))
-        if world > 1 and with_position:
-            # Position output at N > 1 (pipeline.TimeShardedEvolver): the ranks ring-exchange the folded eigenvectors
-            # on a side stream and each evolves its own T/G time samples of EVERY block, then runs the local cell FFT.
-            sharded.start_exchange(c, wrap=timed)
-            t_lo = sharded.time_begin
-            sharded.evolve_position(times[t_lo : t_lo + sharded.rows], states, pos_out, dt_uniform, wrap=timed)
-            return
-        for t0 in range(0, T, t_tile):
-            tt = min(t_tile, T - t0)
-            if with_position:
-                timed("evolve", lambda: solver.evolve_cell(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
-                timed("position", lambda: solver.cell_to_position(states[:tt], out=pos_out[:tt]))
-            else:
-                timed("evolve", lambda: solver.evolve_bloch(c, times[t0 : t0 + tt], out=states[:tt], uniform_dt=dt_uniform))
-
-    def sync_all() -> None:
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    assert int(solver.info.abs().sum().item()) == 0, "eigensolver reported non-convergence"
-    # roofline denominators, measured now that the warm-up steps have brought the clocks up
+    run = PositionRun(ctx, cfg, strong, with_position)
+    main = run.measure(args.steps, args.warmup)
+    # roofline denominators, measured now that the steps have brought the clocks up
     dmma_variants = [peak(lib.sqb_peak_dmma, v) for v in range(3)]  # 4 / 8 / 16 chains per warp
     dmma_peak = max(dmma_variants)
     dfma_peak = peak(lib.sqb_peak_dfma)
-
-    # ---- device-resident timed region: exactly K steps
-    records = [[] for _ in range(args.steps)]
-    launches_before = kernels.LAUNCHES
-    start, stop = ev(), ev()
-    with ClockSampler(local_rank) as clocks:
-        sync_all()
-        start.record()
-        for k in range(args.steps):
-            step(records[k])
-        stop.record()
-        sync_all()
-    launches = (kernels.LAUNCHES - launches_before) // max(args.steps, 1)
-    total_ms = start.elapsed_time(stop)
-    stage_ms = {nm: 0.0 for nm in stage_names}
-    for rec in records:
-        for nm, a_ev, b_ev in rec:
-            stage_ms[nm] += a_ev.elapsed_time(b_ev) / args.steps
-    ms_per_step = total_ms / args.steps
-    if world > 1:
-        tmax = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_per_step = float(tmax.item())
-        st = torch.tensor([stage_ms[nm] for nm in stage_names], dtype=torch.float64, device="cuda")
-        dist.all_reduce(st, op=dist.ReduceOp.MAX)
-        stage_ms = dict(zip(stage_names, st.tolist()))
-    value = n_k_global / (ms_per_step * 1e-3)
+    parity = run.parity_check()
+    stage_ms, ms_per_step, value = main["stage_ms"], main["ms_per_step"], main["value"]
+    t_tile, n_k_local, n_k_global = run.t_tile, run.n_k_local, run.n_k_global
+    repeat_global = run.repeat_global
+    exchange_mode = run.sharded.exchange_mode if run.sharded is not None else None
 
     # ---- K6 (SURVEY 8f "next" row, outside the step): observables of the position-basis states of the last time
     # tile, one pass over the tile; reported beside the step, extrapolated to all T samples
@@ -374,11 +929,11 @@ def run_ours(args) -> None:
         big = cfg.supercell
         length0 = float(np.linalg.norm(cfg.vectors()[0])) * cfg.repeat[0]
         tt = min(t_tile, T)
-        kernels.measure_moments(pos_out[:tt], big, 0, length0 / big[0], length0)
+        kernels.measure_moments(run.pos_out[:tt], big, 0, length0 / big[0], length0)
         torch.cuda.synchronize()
-        a_ev, b_ev = ev(), ev()
+        a_ev, b_ev = ctx.ev(), ctx.ev()
         a_ev.record()
-        mom = kernels.measure_moments(pos_out[:tt], big, 0, length0 / big[0], length0)
+        mom = kernels.measure_moments(run.pos_out[:tt], big, 0, length0 / big[0], length0)
         b_ev.record()
         torch.cuda.synchronize()
         obs_ms = a_ev.elapsed_time(b_ev)
@@ -396,130 +951,58 @@ def run_ours(args) -> None:
             "norm_drift_max": float((mom[:, 0] - mom[0, 0]).abs().max().item()),
         }
 
-    # ---- end-to-end through the C ABI with HOST buffers (H2D of inputs, D2H of eigenvalues and states)
+    # ---- end to end with HOST buffers
     e2e = None
     if not args.no_e2e:
-        copy_stream = torch.cuda.Stream()
-        # self-contained buffers (the device-resident leg's big tiles are released first)
-        del states, pos_out
-        torch.cuda.empty_cache()
-        row_e = n_k_local * n * 16
-        e_tile = max(1, min(T // 2, (4 << 30) // row_e))          # two device tiles ping-pong
-        d2h_rows = max(1, min(e_tile, (1 << 30) // row_e))        # <= 1 GiB pinned staging buffers, ping-pong
-        e2e_position = with_position and world == 1  # at N > 1 the e2e leg returns k-sharded momentum-basis states
-        e_src = torch.empty((2 * e_tile, n_k_local * n), dtype=torch.complex128, device="cuda")
-        pos_tmp = torch.empty((e_tile, n_k_local * n), dtype=torch.complex128, device="cuda") if e2e_position else None
-        stage_buf = [torch.empty((d2h_rows, n_k_local * n), dtype=torch.complex128).pin_memory() for _ in range(2)]
-        eig_host = torch.empty((n_k_local * n,), dtype=torch.float64).pin_memory()
-        tile_free = [torch.cuda.Event(), torch.cuda.Event()]
-        h2d = table_h.numel() * 16 + psi_h.numel() * 16 + times_h.numel() * 8
-        d2h = eig_host.numel() * 8 + T * row_e
+        if world == 1:
+            run.close()
+            e2e = e2e_api(ctx, cfg, args.steps)
+            e2e["observables_only"] = e2e_api_observables(ctx, cfg, args.steps)
+        elif run.sharded is not None:
+            e2e = e2e_sharded(ctx, run, args.steps)
+    run.close()
 
-        def e2e_step() -> None:
-            cur = torch.cuda.current_stream()
-            tb = table_h.cuda(non_blocking=True)
-            ps = psi_h.cuda(non_blocking=True)
-            tm = times_h.cuda(non_blocking=True)
-            solver.build(tb, out=h_buf)
-            solver.diagonalise()
-            eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
-            if e2e_position:
-                solver.fold(out=folded_buf)
-            c = solver.project(ps)
-            k = 0
-            for i_tile, t0 in enumerate(range(0, T, e_tile)):
-                tt = min(e_tile, T - t0)
-                buf = e_src[(i_tile & 1) * e_tile : (i_tile & 1) * e_tile + tt]
-                cur.wait_event(tile_free[i_tile & 1])  # the D2H of the tile that used this buffer is done
-                if e2e_position:
-                    solver.evolve_cell(c, tm[t0 : t0 + tt], out=pos_tmp[:tt], uniform_dt=dt_uniform)
-                    solver.cell_to_position(pos_tmp[:tt], out=buf)
-                else:
-                    solver.evolve_bloch(c, tm[t0 : t0 + tt], out=buf, uniform_dt=dt_uniform)
-                ready = torch.cuda.Event()
-                ready.record(cur)
-                copy_stream.wait_event(ready)
-                with torch.cuda.stream(copy_stream):
-                    for r0 in range(0, tt, d2h_rows):
-                        rr = min(d2h_rows, tt - r0)
-                        stage_buf[k & 1][:rr].copy_(buf[r0 : r0 + rr], non_blocking=True)
-                        k += 1
-                    tile_free[i_tile & 1].record(copy_stream)
-            cur.wait_stream(copy_stream)
-
-        e2e_step()
-        sync_all()
-        a, b = ev(), ev()
-        a.record()
-        n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
-            e2e_step()
-        b.record()
-        sync_all()
-        e2e_ms = a.elapsed_time(b) / n_e2e
-        if world > 1:
-            tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            e2e_ms = float(tmax.item())
-        e2e = {
-            "value": n_k_global / (e2e_ms * 1e-3),
+    # ---- strong scaling of the SAME config in the same line (north_star: "cfg3 ... scales >= 7x at 8 GPUs")
+    strong_line = None
+    if world > 1 and not strong and not args.no_strong and cfg.n_k % world == 0 and T % world == 0:
+        srun = PositionRun(ctx, cfg, True, with_position)
+        sm = srun.measure(args.steps, args.warmup, clocks=False)
+        sp = srun.parity_check()
+        strong_line = {
+            "value": sm["value"],
             "unit": UNIT,
-            "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": e2e_ms,
-            "steps": n_e2e,
-            "note": "host potential table + psi0 + times in pinned memory -> C ABI -> eigenvalues and every "
-            "evolved state copied back to pinned host staging buffers (PCIe-bound: the state list is "
-            f"{T * row_e / 1e9:.1f} GB per rank)",
+            "ms_per_step": sm["ms_per_step"],
+            "stage_ms": sm["stage_ms"],
+            "gpu_launches": sm["gpu_launches"],
+            "k_blocks_total": srun.n_k_global,
+            "k_blocks_per_gpu": srun.n_k_local,
+            "time_rows_per_gpu": T // world,
+            "parity_check": sp,
+            "note": f"{cfg.name}'s own k-grid split over {world} GPUs (same kernels and exchange as the weak run); "
+            "speed-up = this value / the 1-GPU value of the same bench",
         }
-        if e2e_position:
-            # Same step when the caller wants OBSERVABLES of the evolved states instead of the states (what the
-            # reference's examples plot): operator.measure's moments (K6) are reduced on the GPU and [T, 5]
-            # doubles per axis come back instead of the state list.  Extra figure, not the contract's `e2e`.
-            big = cfg.supercell
-            lengths = [float(np.linalg.norm(cfg.vectors()[a])) * cfg.repeat[a] for a in range(cfg.nd)]
-            mom_host = torch.empty((cfg.nd, T, 5), dtype=torch.float64).pin_memory()
+        srun.close()
 
-            def e2e_observables_step() -> None:
-                tb = table_h.cuda(non_blocking=True)
-                ps = psi_h.cuda(non_blocking=True)
-                tm = times_h.cuda(non_blocking=True)
-                solver.build(tb, out=h_buf)
-                solver.diagonalise()
-                eig_host.copy_(solver.eigenvalues.reshape(-1), non_blocking=True)
-                solver.fold(out=folded_buf)
-                c = solver.project(ps)
-                for t0 in range(0, T, e_tile):
-                    tt = min(e_tile, T - t0)
-                    solver.evolve_cell(c, tm[t0 : t0 + tt], out=pos_tmp[:tt], uniform_dt=dt_uniform)
-                    pos = solver.cell_to_position(pos_tmp[:tt], out=e_src[:tt])
-                    for a in range(cfg.nd):
-                        mom = kernels.measure_moments(pos, big, a, lengths[a] / big[a], lengths[a])
-                        mom_host[a, t0 : t0 + tt].copy_(mom, non_blocking=True)
-
-            e2e_observables_step()
-            sync_all()
-            a, b = ev(), ev()
-            a.record()
-            for _ in range(n_e2e):
-                e2e_observables_step()
-            b.record()
-            sync_all()
-            obs_ms = a.elapsed_time(b) / n_e2e
-            e2e["observables_only"] = {
-                "value": n_k_global / (obs_ms * 1e-3),
-                "unit": UNIT,
-                "ms_per_step": obs_ms,
-                "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(eig_host.numel() * 8 + mom_host.numel() * 8),
-                "note": "same host-buffer step, but norm / <x> / <x^2> / scattering phase of every evolved state along "
-                "every axis (operator.measure, K6) are returned instead of the states",
-            }
+    # ---- the other BASELINE.json configs, short k-sharded runs with the oracle gate
+    others = None
+    if not args.no_others:
+        others = {}
+        for name in sorted(CONFIGS):
+            if name == args.config:
+                continue
+            try:
+                others[name] = run_other_config(ctx, CONFIGS[name])
+            except Exception as err:  # noqa: BLE001  (reported, never hidden: a failing config shows in the line)
+                others[name] = {"error": repr(err)}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         flops_evolve = 8.0 * n * n * T * n_k_local
         flops_eigh = (68.0 / 3.0) * n**3 * n_k_local
         ach = flops_evolve / (stage_ms["evolve"] * 1e-3) / 1e12
+        uniform = kernels.uniform_step(cfg.times()) is not None
+        kernel_name = "evolve_bloch_3m_kernel" if uniform else "evolve_bloch_kernel"
+        traffic, traffic_src = ncu_traffic(kernel_name, cfg.name, min(t_tile, T)) if world == 1 else (None, None)
         line = {
             "metric": METRIC,
             "value": value,
@@ -533,34 +1016,25 @@ def run_ours(args) -> None:
             "vs_baseline": None,
             "dtype": "c128 (f64)",
             "data": "synthetic",
-            "config": {
-                "workload": cfg.name,
-                "shape": list(cfg.shape),
-                "repeat_per_gpu": list(cfg.repeat),
-                "repeat_global": list(repeat_global),
-                "block_size_N": n,
-                "k_blocks_per_gpu": n_k_local,
-                "n_times": T,
-                "position_basis": with_position,
+            # identical (keys and values) to the `config` the reference arm prints for the same flags
+            "config": config_dict(cfg, world, strong, with_position),
+            "execution": {
                 "time_tile": t_tile,
-                "l2_policy": "inputs larger than L2: every step rebuilds and re-reads the "
-                f"{n_k_local * n * n * 16 / 1e9:.2f} GB block array (L2 = 126 MB)",
-                "parallelism": f"k-block sharding x{world}"
-                + (", NCCL all-gather of eigenvalues" if world > 1 else "")
-                + (f", eigenvector exchange ({sharded.exchange_mode}: "
-                   + ("peer copies over NVLink from symmetric memory" if sharded.exchange_mode == "p2p"
+                "collectives": ("NCCL all-gather of eigenvalues and coefficients" if world > 1 else "none")
+                + (f"; eigenvector exchange ({exchange_mode}: "
+                   + ("peer copies over NVLink from symmetric memory" if exchange_mode == "p2p"
                       else "ring of NCCL send/recv")
-                   + ") + time-sharded evolve before the local cell FFT" if sharded is not None else ""),
+                   + ") + time-sharded evolve before the local cell FFT" if exchange_mode is not None else ""),
             },
             "blocks_diagonalised_per_s": n_k_global / ((stage_ms["build"] + stage_ms["eigh"]) * 1e-3),
             "state_time_evolutions_per_s": T
             * world
             / ((stage_ms["fold"] + stage_ms["project"] + stage_ms["evolve"] + stage_ms["exchange"] + stage_ms["position"]) * 1e-3),
             "stage_ms": stage_ms,
+            "parity_check": parity,
             "roofline": {
-                "kernel": "evolve_bloch_3m_kernel (K3c fused phase x eigenvector complex GEMM, 3M product, DMMA.8x8x4)"
-                if dt_uniform is not None
-                else "evolve_bloch_kernel (K3c fused phase x eigenvector complex GEMM, DMMA.8x8x4)",
+                "kernel": f"{kernel_name} (K3c fused phase x eigenvector complex GEMM"
+                + (", 3M product" if uniform else "") + ", DMMA.8x8x4)",
                 "bound": "tensor",
                 "achieved": ach,
                 "peak": dmma_peak,
@@ -569,22 +1043,22 @@ def run_ours(args) -> None:
                 # the 3M complex product executes 6 N^2 T real flop for the 8 N^2 T algorithmic flop of the
                 # normalisation, so `frac` (algorithmic / peak) can exceed 1; the tensor-pipe utilisation is this:
                 "executed": {
-                    "flops_per_launch": (0.75 if dt_uniform is not None else 1.0) * flops_evolve * min(t_tile, T) / T,
-                    "achieved": (0.75 if dt_uniform is not None else 1.0) * ach,
-                    "frac": (0.75 if dt_uniform is not None else 1.0) * ach / dmma_peak,
+                    "flops_per_launch": (0.75 if uniform else 1.0) * flops_evolve * min(t_tile, T) / T,
+                    "achieved": (0.75 if uniform else 1.0) * ach,
+                    "frac": (0.75 if uniform else 1.0) * ach / dmma_peak,
                     "note": "3 real DMMA products per complex MAC (3M) instead of 4: executed = 0.75 x algorithmic flop",
                 },
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from profiles/r01_s2_evolve3m_cfg3_raw.csv
-                # (ncu --set full, cfg3, 2048-sample time tile); null for other shapes (not captured)
-                "traffic": 41.518867e9 if (cfg.name.startswith("cfg3") and min(t_tile, T) == 2048 and world == 1) else None,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic": traffic,
+                "traffic_source": traffic_src,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed "
+                "--set full capture of this kernel at this config and time tile; null when no capture matches)",
                 # states written + eigenvectors read once (+ their Re+Im plane for the 3M kernel)
-                "algorithmic_bytes_per_launch": (16.0 * n * min(t_tile, T) + (24.0 if dt_uniform is not None else 16.0) * n * n)
-                * n_k_local,
+                "algorithmic_bytes_per_launch": (16.0 * n * min(t_tile, T) + (24.0 if uniform else 16.0) * n * n) * n_k_local,
                 "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
                 f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
-                "warm-up (MEASURED_PEAKS.json carries only bf16 and HBM); plain DFMA peak measured "
-                f"{dfma_peak:.1f} TFLOP/s",
+                "the timed steps; MEASURED_PEAKS.json carries only bf16 and HBM - the FP64 tensor peak it lacks is "
+                "ncu's sm__ops_path_tensor_src_fp64.sum.peak_sustained (18 944 op/cycle x 1.965 GHz = 37.2 TFLOP/s, "
+                f"profiles/r01_s2_evolve3m_cfg3_raw.csv), which this micro-benchmark reproduces; plain DFMA {dfma_peak:.1f}",
                 "algorithmic_flops_per_launch": flops_evolve * min(t_tile, T) / T,
             },
             "roofline_stages": {
@@ -610,13 +1084,17 @@ def run_ours(args) -> None:
                     "frac": (flops_evolve + flops_eigh) / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
                 },
             },
-            "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "gpu_launches": main["gpu_launches"],
+            "clocks": main["clocks"],
         }
+        if strong_line is not None:
+            line["strong_scaling"] = strong_line
         if observables is not None:
             line["observables"] = observables
         if e2e is not None:
             line["e2e"] = e2e
+        if others is not None:
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu:
             nb = 64 if n <= 256 else 16
             line["cpu_baseline"] = dict(cpu_sample(cfg, nb, 256, with_position))
@@ -626,16 +1104,6 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def _hbm_peak() -> float:
-    p = ROOT / "MEASURED_PEAKS.json"
-    if p.exists():
-        try:
-            return float(json.loads(p.read_text())["hbm_gbs"])
-        except Exception:  # noqa: BLE001
-            pass
-    return 6650.0  # B200_PROFILING.md fallback
-
-
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -643,11 +1111,14 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--position", type=int, default=1, help="include K5+K4 to the position basis (N=1 only)")
+    ap.add_argument("--position", type=int, default=1, help="include the cell FFT to the position basis")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every GPU owns the config's k-grid (default); strong: the config is split over the GPUs")
+                    help="what `value` is.  weak (default): every GPU owns the config's k-grid; strong: the config is "
+                    "split over the GPUs.  The weak line also carries the strong figure (`strong_scaling`)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

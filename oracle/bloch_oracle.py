@@ -775,3 +775,76 @@ def measure_all_momentum_from_function(
     weights = np.asarray(fn(tuple(stacked_k_points(delta_x, shape, offset, wrapped)))).ravel()
     momentum = position_to_momentum(np.atleast_2d(states), shape)
     return np.real(_normalised_density(momentum) @ weights)
+
+
+# --------------------------------------------------------------------------------------
+# sampled-block parity at full size (checker for bench.py's parity gate and the full-size tests)
+# --------------------------------------------------------------------------------------
+def evolve_sampled_blocks(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    components: np.ndarray,
+    mass: float,
+    repeat: Sequence[int],
+    psi0_position: np.ndarray,
+    times: np.ndarray,
+    blocks: Sequence[int],
+    hbar: float = HBAR_SI,
+) -> np.ndarray:
+    """Bloch-ordered momentum components of the sampled k-blocks at `times`: [len(times), len(blocks), N].
+
+    The chain of :func:`evolve_pipeline` (K4 -> K5 -> K3a -> K3b -> K3c) restricted to a few blocks: every block
+    evolves on its own (the Hamiltonian is block diagonal, bloch/build.py:131-135), so the oracle can check
+    sampled blocks of a full-size configuration at ANY time row in milliseconds per block.
+    """
+    big = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    n_k, size = int(np.prod(repeat)), int(np.prod(shape))
+    psi_k = position_to_momentum(np.asarray(psi0_position, dtype=np.complex128).reshape(1, -1), big)
+    psi_b = bloch_from_supercell(psi_k, shape, repeat).reshape(n_k, size)
+    times = np.asarray(times, dtype=np.float64)
+    out = np.empty((times.size, len(blocks), size), dtype=np.complex128)
+    for i, b in enumerate(blocks):
+        h = bloch_blocks(delta_x, shape, components, mass, repeat, hbar=hbar, block_begin=int(b), block_count=1)
+        w, t = eigh_blocks(h)
+        c = project(t, psi_b[int(b)][None, :])
+        a = evolve_eigenbasis(c, w, times, hbar)
+        out[:, i, :] = back_transform(t, a).reshape(times.size, size)
+    return out
+
+
+def position_rows_to_blocks(
+    rows: np.ndarray, shape: Sequence[int], repeat: Sequence[int], blocks: Sequence[int]
+) -> np.ndarray:
+    """Position-basis supercell states [R, M] -> their Bloch-ordered momentum components in the sampled blocks
+    [R, len(blocks), N] (K4 forward + K5 from_inner, the inverse of the tail of :func:`evolve_pipeline`)."""
+    big = tuple(n * r for n, r in zip(shape, repeat, strict=True))
+    n_k, size = int(np.prod(repeat)), int(np.prod(shape))
+    rows = np.asarray(rows, dtype=np.complex128).reshape(-1, n_k * size)
+    psi_b = bloch_from_supercell(position_to_momentum(rows, big), shape, repeat).reshape(rows.shape[0], n_k, size)
+    return psi_b[:, [int(b) for b in blocks], :]
+
+
+def sampled_block_parity(
+    delta_x: np.ndarray,
+    shape: Sequence[int],
+    components: np.ndarray,
+    mass: float,
+    repeat: Sequence[int],
+    psi0_position: np.ndarray,
+    times: np.ndarray,
+    rows: np.ndarray,
+    blocks: Sequence[int],
+    hbar: float = HBAR_SI,
+    basis: str = "position",
+) -> float:
+    """max |device - oracle| over the sampled blocks of evolved states `rows` (one per entry of `times`).
+
+    basis "position": rows are supercell position-basis states [R, M]; "bloch": rows are Bloch-ordered
+    momentum states [R, M] (the k-sharded output)."""
+    want = evolve_sampled_blocks(delta_x, shape, components, mass, repeat, psi0_position, times, blocks, hbar)
+    n_k, size = int(np.prod(repeat)), int(np.prod(shape))
+    if basis == "position":
+        got = position_rows_to_blocks(rows, shape, repeat, blocks)
+    else:
+        got = np.asarray(rows).reshape(-1, n_k, size)[:, [int(b) for b in blocks], :]
+    return float(np.abs(got - want).max())

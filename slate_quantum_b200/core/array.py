@@ -22,7 +22,13 @@ class Array:
         self._basis = basis
         self._host: np.ndarray | None = None
         self._device: torch.Tensor | None = None
-        if isinstance(data, torch.Tensor):
+        self._host_tensor: torch.Tensor | None = None
+        if isinstance(data, torch.Tensor) and not data.is_cuda:
+            # a HOST torch tensor (e.g. pinned memory): kept as it is and uploaded asynchronously on first use
+            self._host_tensor = data
+            self._host = data.detach().numpy()
+            n = data.numel()
+        elif isinstance(data, torch.Tensor):
             self._device = data
             n = data.numel()
         else:
@@ -45,6 +51,9 @@ class Array:
     @property
     def device_data(self) -> torch.Tensor:
         """The data as a CUDA tensor (uploaded once if the array was created from numpy)."""
+        if self._device is None and self._host_tensor is not None:
+            dtype = torch.complex128 if self._host_tensor.is_complex() else torch.float64
+            self._device = self._host_tensor.to(device="cuda", dtype=dtype, non_blocking=True).contiguous()
         if self._device is None:
             dtype = torch.complex128 if np.iscomplexobj(self._host) else torch.float64
             self._device = kernels.to_device(np.ascontiguousarray(self._host).astype(

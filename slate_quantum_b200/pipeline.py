@@ -456,12 +456,17 @@ class TimeShardedEvolver:
             run() if wrap is None else wrap("exchange", run)
 
     def evolve_position(
-        self, times_local: torch.Tensor, states: torch.Tensor, out: torch.Tensor, uniform_dt: float | None,
+        self, times_local: torch.Tensor, states: torch.Tensor, out, uniform_dt: float | None,
         on_tile=None, wrap=None,
     ) -> None:
         """Evolve this rank's time samples `times_local` ([rows], = times[time_begin : time_begin + rows]) for all
         blocks, tile by tile: `states` / `out` are [t_tile, M] buffers (states in the cell layout is scratch);
-        on_tile(t0, tt, out[:tt]) is called after each tile's position-basis states have been enqueued."""
+        on_tile(t0, tt, out[:tt]) is called after each tile's position-basis states have been enqueued.
+
+        `out` may be a LIST of buffers used round-robin (a consumer that drains a tile asynchronously, e.g. a
+        device -> host copy on another stream): when on_tile returns a CUDA event, the buffer it was given is not
+        written again before that event has completed - only the cell FFT of the later tile waits, its evolve
+        (which writes `states`) overlaps the drain."""
         if self._local is None:
             msg = "start_exchange() first"
             raise RuntimeError(msg)
@@ -469,6 +474,8 @@ class TimeShardedEvolver:
         folded, c_local = self._local
         cur = torch.cuda.current_stream()
         call = (lambda _name, fn: fn()) if wrap is None else wrap
+        outs = list(out) if isinstance(out, (list, tuple)) else [out]
+        busy: list = [None] * len(outs)
         t_tile = states.shape[0]
         for i_tile, t0 in enumerate(range(0, times_local.numel(), t_tile)):
             tt = min(t_tile, times_local.numel() - t0)
@@ -487,6 +494,11 @@ class TimeShardedEvolver:
                     call("evolve", lambda: kernels.evolve_bloch(
                         tr, ww, cc, tsl, s.hbar, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=uniform_dt,
                         workspace=self._ws[i_seg], reuse_plane=i_tile > 0))
-            call("position", lambda: s.cell_to_position(states[:tt], out=out[:tt]))
+            slot = i_tile % len(outs)
+            if busy[slot] is not None:
+                cur.wait_event(busy[slot])
+                busy[slot] = None
+            dst = outs[slot]
+            call("position", lambda: s.cell_to_position(states[:tt], out=dst[:tt]))
             if on_tile is not None:
-                on_tile(t0, tt, out[:tt])
+                busy[slot] = on_tile(t0, tt, dst[:tt])

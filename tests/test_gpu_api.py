@@ -712,3 +712,241 @@ def test_measure_from_function_and_apply_to_each(cuda):
                                    atol=1e-12 * scale)
         np.testing.assert_allclose(operator.apply(op, states[0]).with_basis(fund.upcast()).raw_data, want[0], rtol=0,
                                    atol=1e-12 * scale)
+
+
+# ---------------------------------------------------------------------------------------- round 2 additions
+def test_build_square_operator(cuda):
+    """operator.build.square_potential (reference operator/_build/_potential.py:134-164): with every Fourier term
+    kept the potential is 0.5 * height * prod_a sign(cos(2 pi j_a / N_a)) on the grid (lanczos_factor = 0), and
+    cropping to n_terms keeps the lowest |frequency| components of that square wave."""
+    _, _, operator, _, _, _, metadata = _api()
+    shape = (12, 10)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(
+        (np.array([2 * np.pi, 0]), np.array([0, 2 * np.pi])), shape
+    )
+    wave = [np.sign(np.cos(np.linspace(0, 2 * np.pi, n, endpoint=False))) for n in shape]
+    expected = 0.5 * 3.0 * np.multiply.outer(wave[0], wave[1]).ravel()
+    actual = operator.build.square_potential(meta, 3.0)
+    np.testing.assert_allclose(actual.as_array(), np.diag(expected), atol=1e-13)
+    # cropped, with a Lanczos factor: the analytic truncated Fourier series
+    n_terms = (5, 3)
+    cropped = operator.build.square_potential(meta, 3.0, n_terms=n_terms, lanczos_factor=1.0)
+    series = []
+    for n_full, n_t in zip(shape, n_terms):
+        coeff = np.sinc(2 * np.fft.fftfreq(n_t)) ** 1.0 * np.fft.ifft(
+            np.sign(np.cos(np.linspace(0, 2 * np.pi, n_t, endpoint=False)))
+        )
+        freqs = np.fft.ifftshift(np.arange(-(n_t // 2), n_t - (n_t // 2)))
+        j = np.arange(n_full)
+        # V(x) = fft_ortho(V~) on the dual index: sum_k c_k exp(-2 pi i k j / N)
+        series.append(sum(c * np.exp(-2j * np.pi * k * j / n_full) for c, k in zip(coeff, freqs)))
+    expected = 0.5 * 3.0 * np.multiply.outer(series[0], series[1]).ravel()
+    np.testing.assert_allclose(np.diag(cropped.as_array()), expected, atol=1e-13)
+
+
+def test_diagonalised_operator_back_to_dense(cuda):
+    """A diagonalised Hamiltonian converted back to a dense basis equals the Hamiltonian, and products with it
+    equal products with the dense operator (the dual explicit basis conjugates MATERIALISED data)."""
+    bloch, _, operator, _, TupleBasis, basis, metadata = _api()
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x((np.array([2 * np.pi, 0]), np.array([0, 2 * np.pi])), (4, 3))
+    potential = operator.build.sin_potential(meta, 2.0, offset=0.3)
+    hamiltonian = operator.build.kinetic_hamiltonian(potential, hbar**2)
+    diagonal = operator.into_diagonal_hermitian(hamiltonian)
+    for dense_basis in (
+        basis.transformed_from_metadata(hamiltonian.basis.metadata(), is_dual=(False, True)).upcast(),
+        basis.from_metadata(hamiltonian.basis.metadata(), is_dual=(False, True)).upcast(),
+    ):
+        want = hamiltonian.with_basis(dense_basis).raw_data
+        got = diagonal.with_basis(dense_basis).raw_data
+        np.testing.assert_allclose(got, want, atol=1e-12)
+    np.testing.assert_allclose(diagonal.as_array(), hamiltonian.as_array(), atol=1e-12)
+    x = operator.build.x(meta, axis=0)
+    np.testing.assert_allclose(
+        operator.matmul(diagonal, x).as_array(), operator.matmul(hamiltonian, x).as_array(), atol=1e-12
+    )
+    np.testing.assert_allclose(
+        operator.commute(diagonal, x).as_array(), operator.commute(hamiltonian, x).as_array(), atol=1e-12
+    )
+    # the same through a Bloch (block diagonal) Hamiltonian
+    sparse = bloch.build.kinetic_hamiltonian(potential, hbar**2, (3, 2))
+    np.testing.assert_allclose(bloch.into_diagonal(sparse).as_array(), sparse.as_array(), atol=1e-12)
+
+
+@pytest.mark.parametrize(("shape", "repeat"), [((5,), (6,)), ((4, 3), (3, 4)), ((3, 2, 2), (2, 3, 2))])
+def test_bloch_basis_list_conversion_is_factorised_and_exact(cuda, shape, repeat):
+    """BlochTransposedBasis.__into_fundamental__ / __from_fundamental__ on state lists (the chain of reference
+    bloch/_transposed_basis.py:102-167 + _shifted_basis.py:62-111 + TransformedBasis): the factorised route
+    (in-cell FFT + twiddle + across-block FFT) equals the oracle's permute + supercell FFT, kets and bras."""
+    import torch
+
+    bloch, _, _, _, _, basis, metadata = _api()
+    from slate_quantum_b200.metadata import repeat_volume_metadata
+
+    nd = len(shape)
+    vectors = 2 * np.pi * np.eye(nd)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(tuple(vectors[i] for i in range(nd)), shape)
+    super_meta = repeat_volume_metadata(meta, repeat)
+    bloch_basis = bloch.build.basis_from_metadata(super_meta)
+    big = tuple(n * r for n, r in zip(shape, repeat))
+    rng = np.random.default_rng(5)
+    m = int(np.prod(big))
+    vecs = rng.normal(size=(7, m)) + 1j * rng.normal(size=(7, m))
+    want = o.momentum_to_position(o.bloch_into_supercell(vecs, shape, repeat), big)
+    got = bloch_basis.__into_fundamental__(vecs, axis=-1).ok().cpu().numpy()
+    np.testing.assert_allclose(got, want, atol=1e-12)
+    back = bloch_basis.__from_fundamental__(got, axis=-1).ok().cpu().numpy()
+    np.testing.assert_allclose(back, vecs, atol=1e-12)
+    # along axis 0 (vectors stored as columns) and on the dual basis (bra indices: the conjugate transform)
+    got0 = bloch_basis.__into_fundamental__(vecs.T.copy(), axis=0).ok().cpu().numpy()
+    np.testing.assert_allclose(got0, want.T, atol=1e-12)
+    dual = bloch_basis.dual_basis()
+    got_dual = dual.__into_fundamental__(vecs.conj(), axis=-1).ok().cpu().numpy()
+    np.testing.assert_allclose(got_dual, want.conj(), atol=1e-12)
+    back_dual = dual.__from_fundamental__(got_dual, axis=-1).ok().cpu().numpy()
+    np.testing.assert_allclose(back_dual, vecs.conj(), atol=1e-12)
+    del torch
+
+
+def _bloch_problem(cfg_shape, cfg_repeat, height, n_times, t_max):
+    """(hamiltonian, initial state, times basis, position basis, oracle pieces) of a square-lattice cos problem."""
+    bloch, _, operator, state, _, basis, metadata = _api()
+    from slate_quantum_b200.core import FundamentalBasis
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata, repeat_volume_metadata
+
+    nd = len(cfg_shape)
+    vectors = 2 * np.pi * np.eye(nd)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x(tuple(vectors[i] for i in range(nd)), cfg_shape)
+    potential = operator.build.cos_potential(meta, height)
+    hamiltonian = bloch.build.kinetic_hamiltonian(potential, hbar**2, cfg_repeat)
+    super_meta = repeat_volume_metadata(meta, cfg_repeat)
+    psi0 = state.build.coherent(super_meta, tuple(np.pi * r for r in cfg_repeat), (0.0,) * nd, (np.pi,) * nd)
+    times = FundamentalBasis(SpacedTimeMetadata(n_times, domain=Domain(delta=t_max), interpolation="Fourier"))
+    position_basis = basis.from_metadata(super_meta).upcast()
+    return hamiltonian, psi0, times, position_basis, vectors
+
+
+def test_lazy_tiled_evolution_access_paths(cuda):
+    """EvolvedStateList.with_state_basis returns a lazy, time-tiled list: tiles(), host_tiles(), copy_to_host(),
+    device_data, raw_data, indexing and iteration all give the oracle's states, for the position, momentum and
+    Bloch bases; operator.measure on the lazy list equals operator.measure on the materialised one."""
+    import torch
+
+    _, dynamics, operator, _, _, basis, _ = _api()
+    from slate_quantum_b200.dynamics.schrodinger import TiledEvolvedStates
+
+    shape, repeat, n_t = (4, 4), (4, 3), 50
+    hamiltonian, psi0, times, position_basis, vectors = _bloch_problem(shape, repeat, 4.0, n_t, 6 * hbar)
+    evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
+    comps = o.cos_potential_components(shape, 4.0)
+    w_ref, t_ref = o.eigh_blocks(o.bloch_blocks(vectors, shape, comps, hbar**2, repeat))
+    t_values = np.asarray(times.metadata().values)
+    want = o.evolve_pipeline(psi0.raw_data, shape, repeat, w_ref, t_ref, t_values, hbar)
+
+    lazy = evolution.with_state_basis(position_basis)
+    assert isinstance(lazy, TiledEvolvedStates) and lazy._kind == "position"  # noqa: SLF001
+    assert len(lazy) == n_t and lazy.basis.size == n_t * want["position"].shape[1]
+    got = np.concatenate([tile.cpu().numpy() for _, tile in lazy.tiles(rows=16)])  # ragged last tile
+    np.testing.assert_allclose(got, want["position"], atol=1e-9)
+    starts = [t0 for t0, _ in lazy.tiles(rows=16)]
+    assert starts == [0, 16, 32, 48]
+    host = np.concatenate([view.numpy().copy() for _, view in lazy.host_tiles(rows=16, chunk_bytes=7 * lazy.row_bytes)])
+    np.testing.assert_allclose(host, want["position"], atol=1e-9)
+    pageable = np.empty((n_t, lazy.state_size), dtype=np.complex128)
+    lazy.copy_to_host(pageable, rows=20)
+    np.testing.assert_allclose(pageable, want["position"], atol=1e-9)
+    pinned = torch.empty((n_t, lazy.state_size), dtype=torch.complex128).pin_memory()
+    lazy.copy_to_host(pinned, rows=20)
+    np.testing.assert_allclose(pinned.numpy(), want["position"], atol=1e-9)
+    np.testing.assert_allclose(lazy[7].raw_data, want["position"][7], atol=1e-9)
+    np.testing.assert_allclose(lazy[n_t - 1, :].raw_data, want["position"][-1], atol=1e-9)
+    # observables on the LAZY list (tile by tile) == on the materialised list == oracle
+    x_lazy = operator.measure.all_x(evolution, axis=0).raw_data
+    w_lazy = operator.measure.all_coherent_width(evolution, axis=1).raw_data
+    big = tuple(n * r for n, r in zip(shape, repeat))
+    super_dx = vectors * np.array(repeat)[:, None]
+    np.testing.assert_allclose(x_lazy, o.measure_all_x(want["position"], super_dx, big, 0), atol=1e-9)
+    np.testing.assert_allclose(w_lazy, o.measure_all_coherent_width(want["position"], super_dx, big, 1), atol=1e-8)
+    np.testing.assert_allclose(lazy.raw_data.reshape(n_t, -1), want["position"], atol=1e-9)  # materialises
+    np.testing.assert_allclose(operator.measure.all_x(lazy, axis=0).raw_data, x_lazy, atol=1e-12)
+    # momentum and Bloch bases
+    momentum_basis = basis.transformed_from_metadata(position_basis.metadata()).upcast()
+    in_k = evolution.with_state_basis(momentum_basis)
+    assert in_k._kind == "momentum"  # noqa: SLF001
+    np.testing.assert_allclose(in_k.raw_data.reshape(n_t, -1), want["momentum"], atol=1e-9)
+    bloch_basis = evolution.basis.inner.children[1].inner
+    in_b = evolution.with_state_basis(bloch_basis)
+    assert in_b._kind == "bloch"  # noqa: SLF001
+    np.testing.assert_allclose(in_b.raw_data.reshape(n_t, -1), want["bloch"], atol=1e-9)
+    states = list(in_b)
+    assert len(states) == n_t
+    np.testing.assert_allclose(states[3].raw_data, want["bloch"][3], atol=1e-9)
+    # <H> through the diagonal-form expectation, tile by tile on the lazy list
+    energy = operator.expectation_of_each(hamiltonian, evolution).raw_data
+    assert np.abs(energy - energy[0]).max() < 1e-9 * abs(energy[0])
+
+
+def test_cfg1_end_to_end_through_the_api(cuda):
+    """BASELINE.json configs[0] (examples/blochs_theorem.py-style: 1-D cosine, 3 Fourier components, 100 k-points,
+    64 states per block) through the drop-in API, against the oracle: blocks, every eigenvalue, degenerate-subspace
+    projectors, evolved states in the eigen- and position bases."""
+    _, dynamics, operator, _, _, _, _ = _api()
+    from slate_quantum_b200 import bloch
+    from slate_quantum_b200.configs import CONFIGS
+
+    cfg = CONFIGS["cfg1"]
+    hamiltonian, psi0, times, position_basis, vectors = _bloch_problem(cfg.shape, cfg.repeat, cfg.height, cfg.n_times,
+                                                                       cfg.t_max_over_hbar * hbar)
+    comps = cfg.potential_components()
+    blocks = o.bloch_blocks(vectors, cfg.shape, comps, hbar**2, cfg.repeat)
+    np.testing.assert_allclose(hamiltonian.raw_data.reshape(blocks.shape), blocks, atol=1e-13)
+    diagonal = bloch.into_diagonal(hamiltonian)
+    w_ref, t_ref = o.eigh_blocks(blocks)
+    w = diagonal.raw_data.real.reshape(w_ref.shape)
+    np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
+    transform = diagonal.basis.inner.inner.children[0].inner.transform().raw_data.reshape(t_ref.shape)
+    res, orth = o.eigh_residuals(blocks, w, transform)
+    assert res < 1e-10 and orth < 1e-10
+    for b in range(cfg.n_k):
+        assert o.subspace_projector_error(w_ref[b], t_ref[b], transform[b], float(np.linalg.norm(blocks[b]))) < 1e-6
+    evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
+    t_values = np.asarray(times.metadata().values)
+    want = o.evolve_pipeline(psi0.raw_data, cfg.shape, cfg.repeat, w_ref, t_ref, t_values, hbar)
+    np.testing.assert_allclose(np.abs(evolution.raw_data), np.abs(want["eigen"]), atol=1e-9)  # phases are gauge
+    in_position = evolution.with_state_basis(position_basis).raw_data.reshape(cfg.n_times, -1)
+    np.testing.assert_allclose(in_position, want["position"], atol=1e-9)
+    del operator
+
+
+def test_cfg2_full_size_through_the_api_against_the_oracle(cuda):
+    """BASELINE.json configs[1] at FULL size (1024 k-points, N = 128, 1024 times) through
+    bloch.build.kinetic_hamiltonian -> solve_schrodinger_equation_decomposition -> with_state_basis(position):
+    sampled k-blocks of the first, a middle and the last time row against the CPU oracle at 1e-9, eigenvalues of the
+    sampled blocks at rel 1e-10."""
+    _, dynamics, _, _, _, _, _ = _api()
+    from slate_quantum_b200.configs import CONFIGS
+
+    cfg = CONFIGS["cfg2"]
+    hamiltonian, psi0, times, position_basis, vectors = _bloch_problem(cfg.shape, cfg.repeat, cfg.height, cfg.n_times,
+                                                                       cfg.t_max_over_hbar * hbar)
+    evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
+    lazy = evolution.with_state_basis(position_basis)
+    rows_wanted = [0, cfg.n_times // 2 - 1, cfg.n_times - 1]
+    kept = {}
+    for t0, tile in lazy.tiles(rows=512):
+        for r in rows_wanted:
+            if t0 <= r < t0 + tile.shape[0]:
+                kept[r] = tile[r - t0].cpu().numpy()
+    t_values = np.asarray(times.metadata().values)
+    np.testing.assert_allclose(t_values, cfg.times(), rtol=1e-15)
+    blocks = [0, 341, 513, 1023]
+    err = o.sampled_block_parity(
+        vectors, cfg.shape, cfg.potential_components(), hbar**2, cfg.repeat, psi0.raw_data, t_values[rows_wanted],
+        np.stack([kept[r] for r in rows_wanted]), blocks, hbar,
+    )
+    assert err < 1e-9, err
+    w = evolution._eigenvalues.cpu().numpy()  # noqa: SLF001
+    for b in blocks:
+        w_ref = np.linalg.eigvalsh(o.bloch_blocks(vectors, cfg.shape, cfg.potential_components(), hbar**2, cfg.repeat,
+                                                  block_begin=b, block_count=1)[0])
+        np.testing.assert_allclose(w[b], w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
