@@ -391,7 +391,7 @@ class PositionRun:
         self.gathered = world > 1 and with_position  # time-sharded evolve over exchanged eigenvectors
         self.sharded = TimeShardedEvolver(self.solver, T) if self.gathered else None
         self.folded_buf = torch.empty_like(self.h_buf) if with_position and not self.gathered else None
-        free, _ = torch.cuda.mem_get_info()
+        free = kernels.free_bytes()
         row_bytes = self.n_k_local * n * 16
         t_tile = T
         if self.gathered:
@@ -806,7 +806,7 @@ def run_other_config(ctx: Ctx, cfg: BlochWorkload, steps: int = 1) -> dict:
     times = kernels.to_device(times_np, torch.float64)
     dt = kernels.uniform_step(times_np)
     h_buf = torch.empty((count, n, n), dtype=torch.complex128, device="cuda")
-    free, _ = torch.cuda.mem_get_info()
+    free = kernels.free_bytes()
     row_bytes = count * n * 16
     t_tile = max(1, min(T, int(free * 0.25) // row_bytes))
     if t_tile >= 512:

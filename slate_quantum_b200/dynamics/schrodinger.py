@@ -41,7 +41,7 @@ _TILE_QUANTUM = 512
 
 def _tile_rows(n_times: int, row_bytes: int, n_buffers: int, reserve_bytes: int = 0, fraction: float = 0.8) -> int:
     """Largest tile (rows) such that `n_buffers` [rows, M] buffers fit in `fraction` of the free HBM."""
-    free, _ = torch.cuda.mem_get_info()
+    free = kernels.free_bytes()
     budget = max(int(free * fraction) - reserve_bytes, 0)
     rows = budget // max(n_buffers * row_bytes, 1)
     if rows >= n_times:
@@ -55,6 +55,18 @@ def _tile_rows(n_times: int, row_bytes: int, n_buffers: int, reserve_bytes: int 
         )
         raise MemoryError(msg)
     return rows
+
+
+# Pinned host staging buffers are expensive to create (cudaHostAlloc of 1 GiB takes ~0.1 s): host_tiles() keeps the
+# ones it made, keyed by shape, and reuses them in later calls.
+_PINNED_POOL: dict[tuple[int, int], list[torch.Tensor]] = {}
+
+
+def _pinned_buffers(rows: int, width: int, count: int) -> list[torch.Tensor]:
+    pool = _PINNED_POOL.setdefault((rows, width), [])
+    while len(pool) < count:
+        pool.append(torch.empty((rows, width), dtype=torch.complex128).pin_memory())
+    return pool[:count]
 
 
 class TiledEvolvedStates(StateList):
@@ -180,7 +192,7 @@ class TiledEvolvedStates(StateList):
         host_rows = min(host_rows, rows)
         dev = [torch.empty((rows, m), dtype=torch.complex128, device="cuda") for _ in range(2)]
         scratch = torch.empty((rows, m), dtype=torch.complex128, device="cuda") if self._n_scratch() else None
-        stage = [torch.empty((host_rows, m), dtype=torch.complex128).pin_memory() for _ in range(n_host_buffers)]
+        stage = _pinned_buffers(host_rows, m, n_host_buffers)
         copy_stream = torch.cuda.Stream()
         cur = torch.cuda.current_stream()
         tile_free = [None, None]
@@ -241,13 +253,14 @@ class TiledEvolvedStates(StateList):
         if self._device is None:
             self._transform()
             total = self.n_times * self.row_bytes
-            free, _ = torch.cuda.mem_get_info()
+            free = kernels.free_bytes()
             if total + self._n_scratch() * self.row_bytes > free:
                 msg = (
                     f"the evolved state list needs {total / 1e9:.1f} GB but {free / 1e9:.1f} GB of HBM are free: "
                     "iterate tiles() / host_tiles() or copy_to_host() instead of materialising it"
                 )
                 raise MemoryError(msg)
+            torch.cuda.empty_cache()  # one big block: hand the allocator's cached pieces back first
             full = torch.empty((self.n_times, self.state_size), dtype=torch.complex128, device="cuda")
             rows = self.n_times
             scratch = None

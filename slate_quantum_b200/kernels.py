@@ -63,6 +63,13 @@ def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def free_bytes() -> int:
+    """HBM this process can still allocate: free device memory plus what torch's caching allocator holds unused."""
+    _require_cuda()
+    free, _ = torch.cuda.mem_get_info()
+    return int(free + torch.cuda.memory_reserved() - torch.cuda.memory_allocated())
+
+
 def to_device(a: np.ndarray | torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     _require_cuda()
     if isinstance(a, torch.Tensor):
@@ -306,7 +313,7 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
     info = torch.empty((batch,), dtype=torch.int32, device="cuda")
     if workspace is None:
         ws_bytes = lib.sqb_eigh_workspace_bytes(n, batch)
-        free, _ = torch.cuda.mem_get_info()
+        free = free_bytes()
         ws_bytes = min(ws_bytes, max(int(free * 0.6), lib.sqb_eigh_workspace_bytes(n, 1)))
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     rc = lib.sqb_eigh_batched(n, batch, _ptr(a), _ptr(w), _ptr(info), _ptr(workspace), workspace.numel(), _stream())

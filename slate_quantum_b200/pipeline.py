@@ -72,7 +72,7 @@ class BlochSolver:
             from slate_quantum_b200 import _lib
 
             want = _lib.load().sqb_eigh_workspace_bytes(self.n, h.shape[0])
-            free, _ = torch.cuda.mem_get_info()
+            free = kernels.free_bytes()
             floor = _lib.load().sqb_eigh_workspace_bytes(self.n, 1)
             self._eigh_ws = torch.empty(max(min(want, int(free * 0.5)), floor), dtype=torch.uint8, device="cuda")
         w, v, info = kernels.eigh_batched(h, workspace=self._eigh_ws)

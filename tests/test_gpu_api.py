@@ -874,7 +874,7 @@ def test_lazy_tiled_evolution_access_paths(cuda):
     in_k = evolution.with_state_basis(momentum_basis)
     assert in_k._kind == "momentum"  # noqa: SLF001
     np.testing.assert_allclose(in_k.raw_data.reshape(n_t, -1), want["momentum"], atol=1e-9)
-    bloch_basis = evolution.basis.inner.children[1].inner
+    bloch_basis = evolution._eigenbasis().inner  # noqa: SLF001  (the eigenbasis' inner = Bloch-ordered momentum basis)
     in_b = evolution.with_state_basis(bloch_basis)
     assert in_b._kind == "bloch"  # noqa: SLF001
     np.testing.assert_allclose(in_b.raw_data.reshape(n_t, -1), want["bloch"], atol=1e-9)
@@ -912,7 +912,9 @@ def test_cfg1_end_to_end_through_the_api(cuda):
     evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
     t_values = np.asarray(times.metadata().values)
     want = o.evolve_pipeline(psi0.raw_data, cfg.shape, cfg.repeat, w_ref, t_ref, t_values, hbar)
-    np.testing.assert_allclose(np.abs(evolution.raw_data), np.abs(want["eigen"]), atol=1e-9)  # phases are gauge
+    # eigenvector phases (and rotations inside degenerate pairs) are a gauge choice: compare each block's weight
+    got_w = np.linalg.norm(evolution.raw_data.reshape(cfg.n_times, cfg.n_k, cfg.n), axis=2)
+    np.testing.assert_allclose(got_w, np.linalg.norm(want["eigen"].reshape(cfg.n_times, cfg.n_k, cfg.n), axis=2), atol=1e-9)
     in_position = evolution.with_state_basis(position_basis).raw_data.reshape(cfg.n_times, -1)
     np.testing.assert_allclose(in_position, want["position"], atol=1e-9)
     del operator
