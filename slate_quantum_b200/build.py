@@ -34,12 +34,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     mtime = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [
-        CSRC / "sqb_common.cuh",
-        CSRC / "eigh_dc.cuh",
-        CSRC / "eigh_wy.cuh",
-        HERE.parent / "include" / "slate_b200.h",
-    ]
+    deps = [CSRC / s for s in SOURCES] + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "slate_b200.h"]
     return any(d.stat().st_mtime > mtime for d in deps)
 
 
@@ -53,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     build_dir.mkdir(exist_ok=True)
     for src in SOURCES:
         obj = build_dir / (src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        extra = os.environ.get("SQB_NVCC_EXTRA", "").split()  # developer switches, e.g. -DSQB_PANEL_PROFILE
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     log = []

@@ -33,6 +33,7 @@
 #include "sqb_common.cuh"
 #include "eigh_dc.cuh"
 #include "eigh_wy.cuh"
+#include "eigh_panel.cuh"
 
 namespace {
 
@@ -64,6 +65,19 @@ bool eigh_use_wy(int n) {
     cached = (v && strcmp(v, "reflector") == 0) ? 0 : 1;
   }
   return cached == 1 && n > 64 && n <= 512;
+}
+
+// tridiagonalisation: blocked panel kernel (eigh_panel.cuh) for 64 < n <= 256 unless SQB_TRIDIAG=column;
+// SQB_TRIDIAG_NB = 4 | 8 | 16 selects the panel width (default 8)
+int eigh_panel_nb(int n) {
+  static int cached = -2;
+  if (cached == -2) {
+    const char* v = getenv("SQB_TRIDIAG");
+    const char* nb = getenv("SQB_TRIDIAG_NB");
+    cached = (v && strcmp(v, "column") == 0) ? 0 : (nb ? atoi(nb) : 8);
+    if (cached != 0 && cached != 4 && cached != 8 && cached != 16) cached = 8;
+  }
+  return (n > 64 && n <= kPnMaxN) ? cached : 0;
 }
 
 // tridiagonal solver: 1 = divide and conquer (default), 0 = implicit QL + rotation replay
@@ -1011,7 +1025,11 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     carve(ws, reinterpret_cast<char*>(base) + (size_t)l * lane_bytes, n, chunk);
     c128* Ab = A + b0 * (int64_t)n * n;
     int rc;
-    if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, ls);
+    const int pnb = eigh_panel_nb(n);
+    if (pnb == 4) rc = launch_tridiag_panel<4>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb == 8) rc = launch_tridiag_panel<8>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb == 16) rc = launch_tridiag_panel<16>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, ls);
     else if (n <= 64) rc = launch_tridiag<2, 1>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_tridiag<2, 2>(n, cnt, Ab, ws, ls);
     else if (n <= 256) rc = launch_tridiag<4, 2>(n, cnt, Ab, ws, ls);
