@@ -50,7 +50,7 @@ __device__ unsigned long long pn_prof[16];
 constexpr int kPnThreads = 256;
 constexpr int kPnWarps = kPnThreads / 32;
 constexpr unsigned kPnFull = 0xffffffffu;
-constexpr int kPnMaxN = 256;
+constexpr int kPnMaxN = 512;
 
 __device__ __forceinline__ void pn_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -73,8 +73,8 @@ __host__ __device__ inline PanelLayout panel_layout(int n, int nb) {
   o += (size_t)nb * L.ldp * 16;
   L.wp = o;
   o += (size_t)nb * L.ldp * 16;
-  L.red = o;  // [rc + 1][n8]: partial sums of the matrix-vector product (last row: the diagonal segments' z)
-  o += (size_t)(L.rc + 1) * L.n8 * 16;
+  L.red = o;  // [kPnWarps][n8]: every warp's partial sums of the matrix-vector product (only that warp writes it)
+  o += (size_t)(kPnThreads / 32) * L.n8 * 16;
   L.tmp = o;  // [2][nb] W^H v, V^H v
   o += (size_t)2 * nb * 16;
   L.scal = o;  // 128 doubles: reduction scratch + scalars
@@ -216,7 +216,7 @@ __device__ __forceinline__ c128 pn_unit(int n, int lo, int r0, int c0, int lane,
   return y[0];
 }
 
-template <int NB>
+template <int NB, int NR>
 __global__ void __launch_bounds__(kPnThreads, 1)
 tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restrict__ d_all, double* __restrict__ e_all,
                      c128* __restrict__ tau_all, c128* __restrict__ Y_all) {
@@ -225,8 +225,8 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
   const int n8 = L.n8, ldp = L.ldp, RC = L.rc;
   c128* Vp = reinterpret_cast<c128*>(pn_smem + L.vp);   // [NB][ldp]  Vp[k][r]
   c128* Wp = reinterpret_cast<c128*>(pn_smem + L.wp);   // [NB][ldp]
-  c128* red = reinterpret_cast<c128*>(pn_smem + L.red); // [RC + 1][n8]
-  c128* zdiag = red + (size_t)RC * n8;
+  c128* part_w = reinterpret_cast<c128*>(pn_smem + L.red) + (size_t)(threadIdx.x >> 5) * n8;  // this warp's slot
+  const c128* part_all = reinterpret_cast<const c128*>(pn_smem + L.red);
   c128* tmp1 = reinterpret_cast<c128*>(pn_smem + L.tmp);  // W^H v
   c128* tmp2 = tmp1 + NB;                                  // V^H v
   double* scratch = reinterpret_cast<double*>(pn_smem + L.scal);  // [0..71] reductions, [80..] scalars
@@ -264,7 +264,10 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
   long long pn_t0__ = clock64();
 #endif
   PN_TICK(0);
-  const int r = tid;  // the row a thread owns in the column phases (n <= 256 < kPnThreads)
+  // column phases: thread t owns rows t + kPnThreads * s, s < NR  (n <= NR * kPnThreads)
+  c128 a_pref[NR];
+#pragma unroll
+  for (int s = 0; s < NR; ++s) a_pref[s] = make_double2(0.0, 0.0);
   for (int i0 = 0; i0 < n - 1; i0 += NB) {
     const int width = min(NB, n - 1 - i0);
     if (width < NB) {  // last, narrower panel: the unused panel rows must not carry the previous panel
@@ -279,23 +282,33 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
       const int lo = i + 1;
       c128* vn = Vp + jj * ldp;
       // ---------------- (a) column i with the panel's pending update; Householder reflector
-      c128 colv = make_double2(0.0, 0.0);
+      c128 colv[NR];
       double part = 0.0;
-      if (r >= i && r < n) {
-        c128 a = i >= jres ? res[cbase[i] + r] : A[(int64_t)i * n + r];
-        c128 t = make_double2(0.0, 0.0);
-        for (int k = 0; k < jj; ++k) {
-          const c128 cw = cconj(Wp[k * ldp + i]), cv = cconj(Vp[k * ldp + i]);
-          cfma(t, Vp[k * ldp + r], cw);
-          cfma(t, Wp[k * ldp + r], cv);
-        }
-        a = csub(a, t);
-        colv = a;
-        if (r >= i + 2) part = a.x * a.x + a.y * a.y;
-        if (r == i) dd[i] = a.x;
-        if (r == i + 1) {
-          scratch[80] = a.x;
-          scratch[81] = a.y;
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        const int r = tid + s * kPnThreads;
+        colv[s] = make_double2(0.0, 0.0);
+        if (r >= i && r < n) {
+          // column i was fetched during the previous step's matrix-vector product (the matrix is read-only inside
+          // a panel); the first column of a panel is fetched here, after the trailing update
+          c128 a = jj > 0 ? a_pref[s] : (i >= jres ? res[cbase[i] + r] : A[(int64_t)i * n + r]);
+          c128 t = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < NB - 1; ++k) {
+            if (k < jj) {
+              const c128 cw = cconj(Wp[k * ldp + i]), cv = cconj(Vp[k * ldp + i]);
+              cfma(t, Vp[k * ldp + r], cw);
+              cfma(t, Wp[k * ldp + r], cv);
+            }
+          }
+          a = csub(a, t);
+          colv[s] = a;
+          if (r >= i + 2) part += a.x * a.x + a.y * a.y;
+          if (r == i) dd[i] = a.x;
+          if (r == i + 1) {
+            scratch[80] = a.x;
+            scratch[81] = a.y;
+          }
         }
       }
       const double xnorm2 = pn_block_sum(part, scratch);  // scratch[0..15]; also publishes scratch[80..81]
@@ -316,12 +329,17 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
         scal = make_double2(pr / den, -pi / den);
       }
       const c128 tau = make_double2(tau_r, tau_i);
-      c128 myv = make_double2(0.0, 0.0);
-      if (r < n) {
-        if (r == i + 1) myv = make_double2(1.0, 0.0);
-        else if (r >= i + 2) myv = cmul(colv, scal);
-        vn[r] = myv;
-        if (r >= i + 1) Y[(int64_t)i * n + r] = myv;
+      c128 myv[NR];
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        const int r = tid + s * kPnThreads;
+        myv[s] = make_double2(0.0, 0.0);
+        if (r < n) {
+          if (r == i + 1) myv[s] = make_double2(1.0, 0.0);
+          else if (r >= i + 2) myv[s] = cmul(colv[s], scal);
+          vn[r] = myv[s];
+          if (r >= i + 1) Y[(int64_t)i * n + r] = myv[s];
+        }
       }
       if (tid == 0) {
         ee[i] = beta;
@@ -332,6 +350,17 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
 
       // ---------------- (b) p = A22 v from the panel-start matrix (read only) + the correction dot products
       {
+        // next column of the panel for phase (a) of the next step (rows >= lo; hidden behind the units below)
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+          const int r = tid + s * kPnThreads;
+          const bool want = jj + 1 < width && r >= lo && r < n;
+          if (lo >= jres) a_pref[s] = pn_lds(res + cbase[min(lo, n - 1)] + min(r, n - 1), want);
+          else a_pref[s] = pn_ldg(A + (int64_t)lo * n + min(r, n - 1), want);
+        }
+        // this warp's partial-sum slot, zeroed over the trailing range
+        for (int x = (lo & ~31) + lane; x < n8; x += 32) part_w[x] = make_double2(0.0, 0.0);
+        __syncwarp();
         const int X0 = lo >> 5;
         const int T = RC - X0;
         const int total = T * T;  // half-units: diagonal unit = 1, full unit = 2
@@ -346,21 +375,20 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
           }
           const int c0 = Cb * 32;
           bool open = false;
-          int seg_first = 0, seg_last = 0;
           c128 z[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) z[q] = make_double2(0.0, 0.0);
-          for (int Rc = Cb; Rc < RC; ++Rc) {
-            const bool mine = pos >= w_lo && pos < w_hi;
+          // first unit of the strip whose start position is >= w_lo: position of unit Rc = pos + (Rc == Cb ? 0 : 2 (Rc - Cb) - 1)
+          int Rc = Cb;
+          if (pos < w_lo) {
+            Rc = Cb + (w_lo - pos + 2) / 2;  // smallest Rc > Cb with pos + 2 (Rc - Cb) - 1 >= w_lo
+            pos += 2 * (Rc - Cb) - 1;
+          }
+          for (; Rc < RC && pos < w_hi; ++Rc) {
             pos += (Rc == Cb) ? 1 : 2;
-            if (!mine) continue;  // a warp's units are contiguous in this order
-            if (!open) {
-              open = true;
-              seg_first = Rc;
-            }
-            seg_last = Rc;
+            open = true;
             c128 y;
-#ifdef SQB_PANEL_PROFILE
+#if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
             const long long u0__ = clock64();
 #endif
             const int r0 = Rc * 32;
@@ -371,7 +399,7 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
               if (Rc == Cb) y = pn_unit<false, true>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
               else y = pn_unit<false, false>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
             }
-#ifdef SQB_PANEL_PROFILE
+#if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
             if (blockIdx.x == 0 && threadIdx.x == 0) {
               const int slot = (c0 >= jres ? 8 : 6) + (Rc == Cb ? 1 : 0);
               pn_prof[slot] += (unsigned long long)(clock64() - u0__);
@@ -379,7 +407,8 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
             }
 #endif
             const int rr = Rc * 32 + (lane & 7) + 8 * (((lane >> 3) & 1) * 2 + ((lane >> 4) & 1));
-            if (rr < n) red[(size_t)Cb * n8 + rr] = y;
+            if (rr < n) part_w[rr] = cadd(part_w[rr], y);
+            __syncwarp();
           }
           if (open) {
             // z: 8 values per lane, summed over the 8 row lanes li (lane bits 0, 1, 2) -> one column per lane
@@ -392,11 +421,8 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
             pn_xchg(z[1], z[3], b1, 2);
             pn_xchg(z[0], z[1], b2, 4);
             const int c = c0 + (lane >> 3) + 4 * ((b0 ? 4 : 0) + (b1 ? 2 : 0) + (b2 ? 1 : 0));
-            if (c < n) {
-              c128* dst = seg_first == Cb ? zdiag : red + (size_t)seg_first * n8;
-              dst[c] = z[0];
-              for (int k = seg_first + 1; k <= seg_last; ++k) red[(size_t)k * n8 + c] = make_double2(0.0, 0.0);
-            }
+            if (c < n) part_w[c] = cadd(part_w[c], z[0]);
+            __syncwarp();
           }
         }
         // correction dot products: tmp1[k] = W_k^H v, tmp2[k] = V_k^H v over rows >= lo
@@ -415,26 +441,39 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
       PN_TICK(3);
 
       // ---------------- (d) w = tau (p - V tmp1 - W tmp2) - (tau/2)(p^H v) v
-      c128 p = make_double2(0.0, 0.0);
+      c128 p[NR];
       double dr = 0.0, di = 0.0;
-      if (r >= lo && r < n) {
-        c128 s = zdiag[r];
-        for (int k = lo >> 5; k < RC; ++k) s = cadd(s, red[(size_t)k * n8 + r]);
-        c128 t = make_double2(0.0, 0.0);
-        for (int k = 0; k < jj; ++k) {
-          cfma(t, Vp[k * ldp + r], tmp1[k]);
-          cfma(t, Wp[k * ldp + r], tmp2[k]);
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        const int r = tid + s * kPnThreads;
+        p[s] = make_double2(0.0, 0.0);
+        if (r >= lo && r < n) {
+          c128 sum = part_all[r];
+#pragma unroll
+          for (int w = 1; w < kPnWarps; ++w) sum = cadd(sum, part_all[(size_t)w * n8 + r]);
+          c128 t = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < NB - 1; ++k) {
+            if (k < jj) {
+              cfma(t, Vp[k * ldp + r], tmp1[k]);
+              cfma(t, Wp[k * ldp + r], tmp2[k]);
+            }
+          }
+          p[s] = cmul(tau, csub(sum, t));
+          dr += p[s].x * myv[s].x + p[s].y * myv[s].y;  // conj(p) * v
+          di += p[s].x * myv[s].y - p[s].y * myv[s].x;
         }
-        p = cmul(tau, csub(s, t));
-        dr = p.x * myv.x + p.y * myv.y;  // conj(p) * v
-        di = p.x * myv.y - p.y * myv.x;
       }
       const double2 dot = pn_block_sum2(dr, di, scratch + 32);  // scratch[32..63]
-      if (r < n) {
-        const c128 al = cscale(cmul(tau, dot), -0.5);
-        c128 w = make_double2(0.0, 0.0);
-        if (r >= lo) w = cadd(p, cmul(al, myv));
-        Wp[jj * ldp + r] = w;
+      const c128 al = cscale(cmul(tau, dot), -0.5);
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        const int r = tid + s * kPnThreads;
+        if (r < n) {
+          c128 w = make_double2(0.0, 0.0);
+          if (r >= lo) w = cadd(p[s], cmul(al, myv[s]));
+          Wp[jj * ldp + r] = w;
+        }
       }
       __syncthreads();
       PN_TICK(4);
@@ -537,13 +576,14 @@ inline int panel_jres(int n, int nb, size_t budget, size_t* smem_out) {
   return jres;
 }
 
-template <int NB>
+template <int NB, int NR>
 int launch_tridiag_panel(int n, int64_t count, c128* A, double* d, double* e, c128* tau, c128* y, cudaStream_t st) {
   size_t smem = 0;
   const int jres = panel_jres(n, NB, 232448 - 1024, &smem);
-  cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err =
+      cudaFuncSetAttribute(tridiag_panel_kernel<NB, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  tridiag_panel_kernel<NB><<<(unsigned)count, kPnThreads, smem, st>>>(n, jres, A, d, e, tau, y);
+  tridiag_panel_kernel<NB, NR><<<(unsigned)count, kPnThreads, smem, st>>>(n, jres, A, d, e, tau, y);
   SQB_LAUNCH_CHECK();
 #ifdef SQB_PANEL_PROFILE
   {
