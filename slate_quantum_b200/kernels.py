@@ -297,6 +297,9 @@ def bloch_cell_vectors(
     return out
 
 
+EIGH_KERNEL_MAX_N = 512  # sqb_eigh_batched keeps a matrix on one SM (include/slate_b200.h); larger: core/jacobi.py
+
+
 def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """K2 IN PLACE: `a` [batch,n,n] is overwritten by the transform (rows = eigenvectors).
 
@@ -309,6 +312,16 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
     if n != n2:
         msg = "matrices must be square"
         raise ValueError(msg)
+    if n > EIGH_KERNEL_MAX_N:
+        # one SM cannot hold such a matrix: two-sided block Jacobi over batched K2 sub-problems + K7 GEMMs
+        from slate_quantum_b200.core.jacobi import eigh_block_jacobi
+
+        w = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+        for i in range(batch):
+            wi, vi, _ = eigh_block_jacobi(a[i])
+            w[i] = wi
+            a[i] = vi
+        return w, a, torch.zeros((batch,), dtype=torch.int32, device="cuda")
     w = torch.empty((batch, n), dtype=torch.float64, device="cuda")
     info = torch.empty((batch,), dtype=torch.int32, device="cuda")
     if workspace is None:

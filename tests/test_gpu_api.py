@@ -952,3 +952,37 @@ def test_cfg2_full_size_through_the_api_against_the_oracle(cuda):
         w_ref = np.linalg.eigvalsh(o.bloch_blocks(vectors, cfg.shape, cfg.potential_components(), hbar**2, cfg.repeat,
                                                   block_begin=b, block_count=1)[0])
         np.testing.assert_allclose(w[b], w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
+
+
+def test_dense_single_cell_eigenstates_above_512_states(cuda):
+    """examples/eigenstates.py:16-35 on a single large cell (N = 1536 > the 512-state single-SM limit):
+    operator.build.kinetic_hamiltonian + into_diagonal_hermitian against np.linalg.eigh at 1e-10, and a short
+    eigen-decomposition evolution of a coherent state against the oracle's dense propagation."""
+    _, dynamics, operator, state, _, basis, metadata = _api()
+    from slate_quantum_b200.core import FundamentalBasis
+    from slate_quantum_b200.core.metadata import Domain
+    from slate_quantum_b200.metadata import SpacedTimeMetadata
+
+    n = 1536
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x((np.array([2 * np.pi]),), (n,))
+    potential = operator.build.cos_potential(meta, 40.0)
+    hamiltonian = operator.build.kinetic_hamiltonian(potential, hbar**2)
+    dense = o.dense_hamiltonian(2 * np.pi * np.eye(1), (n,), o.pad_components((n,), o.cos_potential_components((n,), 40.0)),
+                                hbar**2, None)
+    w_ref, v_ref = np.linalg.eigh(dense)
+    diagonal = operator.into_diagonal_hermitian(hamiltonian)
+    w = diagonal.raw_data.real
+    np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
+    transform = diagonal.basis.inner.inner.children[0].inner.transform().raw_data.reshape(n, n)
+    res, orth = o.eigh_residuals(dense[None], w[None], transform[None])
+    assert res < 1e-10 and orth < 1e-10
+    initial = state.build.coherent(meta, (np.pi,), (0.0,), (0.4,))
+    times = FundamentalBasis(SpacedTimeMetadata(5, domain=Domain(delta=2 * hbar), interpolation="Fourier"))
+    evolution = dynamics.solve_schrodinger_equation_decomposition(initial, times, hamiltonian)
+    momentum = basis.transformed_from_metadata(meta).upcast()
+    got = evolution.with_state_basis(momentum).raw_data.reshape(5, n)
+    psi_k = np.fft.fft(initial.raw_data, norm="ortho")
+    c = v_ref.conj().T @ psi_k
+    t_values = np.asarray(times.metadata().values)
+    want = np.array([v_ref @ (c * np.exp(-1j * w_ref * t / hbar)) for t in t_values])
+    np.testing.assert_allclose(got, want, atol=1e-9)

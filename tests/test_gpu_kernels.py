@@ -905,3 +905,30 @@ def test_golden_fixtures_against_the_cuda_path(cuda, case):
     np.testing.assert_allclose(pos2, g[f"{case}/position"], atol=1e-9)
     perm = kernels.bloch_permute(shape, repeat, kernels.to_device(np.arange(solver.m).astype(np.complex128), torch.complex128), 0)
     np.testing.assert_array_equal(perm.cpu().numpy().real.astype(np.int64), g[f"{case}/permutation"])
+
+
+@pytest.mark.parametrize("n", [600, 1024])
+def test_eigh_dense_above_the_single_sm_limit(cuda, n):
+    """One dense Hermitian matrix with n > 512: two-sided block Jacobi over batched K2
+    sub-problems and K7 GEMMs (core/jacobi.py), same contract as the kernel path - ascending eigenvalues at rel
+    1e-10, residual and orthogonality below 1e-10, rows = eigenvectors."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(n)
+    g = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    h = g + g.conj().T
+    w, t, info = kernels.eigh_batched(kernels.to_device(h[None], torch.complex128))
+    assert int(info.abs().sum()) == 0
+    _check_eigh(h[None], w.cpu().numpy(), t.cpu().numpy(), info.cpu().numpy())
+
+
+def test_round_robin_pairs_cover_every_pair_once():
+    from slate_quantum_b200.core.jacobi import _round_robin
+
+    for nb in (2, 4, 6, 10):
+        rounds = _round_robin(nb)
+        assert len(rounds) == nb - 1
+        seen = [p for r in rounds for p in r]
+        assert len(seen) == len(set(seen)) == nb * (nb - 1) // 2
+        for r in rounds:  # disjoint within a round
+            flat = [x for p in r for x in p]
+            assert sorted(flat) == list(range(nb))
