@@ -257,6 +257,15 @@ int sqb_measure_moments(int nd, const int* grid_host, int64_t lead, const sqb_c1
                         double spacing, double length, const double* offsets, int wrapped, double* out,
                         void* stream);
 
+/* sqb_measure_moments_lattice: the same five sums for a GENERAL (non-orthogonal) cell, where the Cartesian
+ * component `axis` of the position mixes every lattice axis (operator/_build/_position.py:228-242 through
+ * slate_core fundamental_stacked_x_points): x = sum_a frac_a delta_x[a][axis], frac_a = n_a / N_a plus the
+ * fractional image of the per-state Cartesian offset along `axis`, folded into [-1/2, 1/2) when `wrapped`.
+ * delta_x_host: [nd * nd] row a = lattice vector a (Cartesian).  The scattering sums use the index along `axis`. */
+int sqb_measure_moments_lattice(int nd, const int* grid_host, int64_t lead, const sqb_c128* states, int axis,
+                                const double* delta_x_host, const double* offsets, int wrapped, double* out,
+                                void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K7  Operator / state algebra ("next" rows of the scope table).
  * sqb_zgemm_batched replaces the dense einsum contractions of slate_quantum.operator.matmul / commute

@@ -848,3 +848,34 @@ def sampled_block_parity(
     else:
         got = np.asarray(rows).reshape(-1, n_k, size)[:, [int(b) for b in blocks], :]
     return float(np.abs(got - want).max())
+
+
+# --------------------------------------------------------------------------------------
+# noise kernels and their eigenvalue diagonalisation
+# --------------------------------------------------------------------------------------
+def noise_kernel_from_operators(values: np.ndarray, operators: np.ndarray) -> np.ndarray:
+    """noise/_kernel.py:38-66: beta[i, j, k, l] = sum_a lambda_a conj(L_a[j, i]) L_a[k, l]."""
+    ops = np.asarray(operators, dtype=np.complex128)
+    return np.einsum("a,aji,akl->ijkl", np.asarray(values), np.conj(ops), ops)
+
+
+def diagonal_noise_kernel_from_operators(values: np.ndarray, diagonals: np.ndarray) -> np.ndarray:
+    """noise/_kernel.py:145-177: beta[i, j] = sum_a lambda_a conj(d_a[i]) d_a[j]."""
+    d = np.asarray(diagonals, dtype=np.complex128)
+    return np.einsum("a,ai,aj->ij", np.asarray(values), np.conj(d), d)
+
+
+def noise_operators_diagonal_eigenvalue(kernel: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """noise/diagonalize/_eigenvalue.py:80-131: (eigenvalues, conj(U^T)) of eigh(beta); row b = noise operator b."""
+    np.testing.assert_allclose(kernel, np.conj(kernel.T), atol=1e-10 * max(np.abs(kernel).max(), 1e-300))
+    res = np.linalg.eigh(kernel)
+    return res.eigenvalues, np.conj(res.eigenvectors.T)
+
+
+def noise_operators_eigenvalue(kernel: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """noise/diagonalize/_eigenvalue.py:22-77 for beta[i, j, k, l]: swap the first two indices, eigh of the
+    [n^2, n^2] matrix, operators = conj(U^T) reshaped [n^2, n, n]."""
+    n = kernel.shape[0]
+    data = kernel.swapaxes(0, 1).reshape(n * n, n * n)
+    w, ops = noise_operators_diagonal_eigenvalue(data)
+    return w, ops.reshape(n * n, n, n)

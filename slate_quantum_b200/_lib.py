@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "sqb_evolve_uniform_workspace_bytes",
     "sqb_evolve_bloch_uniform",
     "sqb_measure_moments",
+    "sqb_measure_moments_lattice",
     "sqb_zgemm_batched",
     "sqb_rowwise_vdot",
     "sqb_rowwise_weighted_abs2",
@@ -107,6 +108,10 @@ def load() -> ctypes.CDLL:
     lib.sqb_measure_moments.restype = c_int
     lib.sqb_measure_moments.argtypes = [
         c_int, c_void_p, c_int64, c_void_p, c_int, c_double, c_double, c_void_p, c_int, c_void_p, c_void_p,
+    ]
+    lib.sqb_measure_moments_lattice.restype = c_int
+    lib.sqb_measure_moments_lattice.argtypes = [
+        c_int, c_void_p, c_int64, c_void_p, c_int, dp, c_void_p, c_int, c_void_p, c_void_p,
     ]
     lib.sqb_zgemm_batched.restype = c_int
     lib.sqb_zgemm_batched.argtypes = [

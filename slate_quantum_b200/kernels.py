@@ -528,6 +528,37 @@ def measure_moments(
     return out
 
 
+def measure_moments_lattice(
+    states: torch.Tensor, grid: Sequence[int], axis: int, delta_x: np.ndarray, offsets: torch.Tensor | None = None,
+    wrapped: bool = False,
+) -> torch.Tensor:
+    """K6 for a general (non-orthogonal) cell: same five sums as `measure_moments`, x = Cartesian component `axis`
+    of the grid position for lattice vectors `delta_x` ([nd, nd], row a = vector a)."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(states, "states")
+    m = int(np.prod(grid))
+    if states.numel() % m:
+        msg = "states must hold whole vectors over the grid"
+        raise ValueError(msg)
+    lead = states.numel() // m
+    if offsets is not None:
+        _f64(offsets, "offsets")
+        if offsets.numel() != lead:
+            msg = "one offset per state"
+            raise ValueError(msg)
+    nd = len(grid)
+    out = torch.empty((lead, 5), dtype=torch.float64, device="cuda")
+    g = (ctypes.c_int * nd)(*[int(x) for x in grid])
+    rc = lib.sqb_measure_moments_lattice(
+        nd, g, lead, _ptr(states), int(axis), _lib.double_array(np.asarray(delta_x, dtype=np.float64)[:nd, :nd].ravel()),
+        _ptr(offsets) if offsets is not None else None, int(bool(wrapped)), _ptr(out), _stream(),
+    )
+    _lib.check(rc, "sqb_measure_moments_lattice")
+    _count(1)
+    return out
+
+
 def _gemm_operand(t: torch.Tensor, name: str) -> tuple[torch.Tensor, int, int, int, int]:
     """(tensor, row stride, col stride, batch stride, conj) of a [m, k] or [batch, m, k] complex128 CUDA view.
     Transposed (`.mT`), daggered (`.mH`), conjugated and broadcast (`expand`) views are passed as they are."""

@@ -6,7 +6,8 @@ kernel (``sqb_measure_moments``) reads the ``[T, M]`` state list ONCE and return
 fundamental scattering phase together; nothing is computed on the CPU and only ``[T]`` floats ever leave the
 GPU - which is what makes the observables of a 68.7 GB evolved state list cheap to bring back to the host.
 
-Orthogonal axes only (x along ``axis`` must depend on that axis' index alone).
+Position observables work on any cell (orthogonal axes: table-driven kernel; otherwise the lattice kernel that
+decodes every index); the momentum observables need an axis orthogonal to the others.
 """
 
 from __future__ import annotations
@@ -57,23 +58,37 @@ def _position_data(states: Array, space: TupleMetadata) -> torch.Tensor:
     return torch.cat(list(_tiles_in(states, _basis.from_metadata(space).upcast())))
 
 
-def _axis_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
-    delta_x = np.asarray(volume.fundamental_stacked_delta_x(space), dtype=np.float64)
+def _cell(space: TupleMetadata) -> tuple[np.ndarray, tuple[int, ...]]:
     nd = len(space.children)
-    a = delta_x[:nd, :nd]
+    delta_x = np.asarray(volume.fundamental_stacked_delta_x(space), dtype=np.float64)[:nd, :nd]
+    return delta_x, tuple(int(c.fundamental_size) for c in space.children)
+
+
+def _is_orthogonal_axis(space: TupleMetadata, axis: int) -> bool:
+    """x along `axis` depends on that axis' index alone (the table-driven kernel applies)."""
+    a, _ = _cell(space)
     off_axis = a[axis].copy()
     off_axis[axis] = 0.0
-    if np.abs(off_axis).max(initial=0.0) > 1e-12 * np.abs(a).max() or np.abs(a[:, axis]).sum() - abs(a[axis, axis]) > 1e-12 * np.abs(a).max():
-        msg = "operator.measure on the B200 path needs an axis orthogonal to the others"
+    tol = 1e-12 * np.abs(a).max()
+    return bool(np.abs(off_axis).max(initial=0.0) <= tol and np.abs(a[:, axis]).sum() - abs(a[axis, axis]) <= tol)
+
+
+def _axis_geometry(space: TupleMetadata, axis: int) -> tuple[tuple[int, ...], float, float]:
+    a, grid = _cell(space)
+    if not _is_orthogonal_axis(space, axis):
+        msg = "this observable needs an axis orthogonal to the others on the B200 path"
         raise NotImplementedError(msg)
-    grid = tuple(int(c.fundamental_size) for c in space.children)
-    length = float(np.linalg.norm(delta_x[axis]))
-    return grid, float(a[axis, axis]) / grid[axis], length
+    return grid, float(a[axis, axis]) / grid[axis], float(np.linalg.norm(a[axis]))
 
 
 def _moments(pos: torch.Tensor, space: TupleMetadata, axis: int, offsets: torch.Tensor | None, wrapped: bool) -> torch.Tensor:
-    grid, spacing, length = _axis_geometry(space, axis)
-    return kernels.measure_moments(pos, grid, axis, spacing, length, offsets, wrapped)
+    """[lead, 5] sums {|psi|^2, x |psi|^2, x^2 |psi|^2, cos, sin} of position-basis states; orthogonal axes use the
+    table-driven kernel, general cells (e.g. cfg4's hexagonal lattice) the lattice kernel."""
+    if _is_orthogonal_axis(space, axis):
+        grid, spacing, length = _axis_geometry(space, axis)
+        return kernels.measure_moments(pos, grid, axis, spacing, length, offsets, wrapped)
+    delta_x, grid = _cell(space)
+    return kernels.measure_moments_lattice(pos, grid, axis, delta_x, offsets, wrapped)
 
 
 def _list_array(states: StateList, values: torch.Tensor) -> Array:
@@ -88,7 +103,7 @@ def _all_x(pos: torch.Tensor, space: TupleMetadata, axis: int, offset: float, wr
 
 
 def _all_periodic_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch.Tensor:
-    _, _, length = _axis_geometry(space, axis)
+    length = float(np.linalg.norm(_cell(space)[0][axis]))
     mom = _moments(pos, space, axis, None, False)
     angle = torch.atan2(mom[:, 4], mom[:, 3])
     return torch.remainder(angle, 2 * np.pi) * (length / (2 * np.pi))

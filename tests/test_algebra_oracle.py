@@ -143,3 +143,30 @@ def test_oracle_against_the_golden_literals_file():
     s0 = np.array(ip["state_0_re_im"]) @ np.array([1, 1j])
     s1 = np.array(ip["state_1_re_im"]) @ np.array([1, 1j])
     np.testing.assert_allclose(o.inner_product_each(s1[None], s0[None]), [ip["value"]], atol=1e-15)
+
+
+def test_noise_kernel_eigenvalue_diagonalisation_round_trips():
+    """Oracle restatement of noise/_kernel.py:38-177 and noise/diagonalize/_eigenvalue.py:22-131: the operators
+    returned by the eigenvalue method rebuild the kernel they came from (the reference asserts exactly this
+    reconstruction at :55-64 and :105-115)."""
+    from oracle import bloch_oracle as o
+
+    rng = np.random.default_rng(8)
+    n, n_ops = 5, 3
+    values = np.array([0.7, 1.3, 2.0])
+    diag = rng.normal(size=(n_ops, n)) + 1j * rng.normal(size=(n_ops, n))
+    beta = o.diagonal_noise_kernel_from_operators(values, diag)
+    np.testing.assert_allclose(beta, beta.conj().T, atol=1e-14)
+    w, ops = o.noise_operators_diagonal_eigenvalue(beta)
+    assert np.all(w[:-n_ops] < 1e-12 * w[-1]) and np.all(w[-n_ops:] > 0)  # rank = number of independent operators
+    np.testing.assert_allclose(o.diagonal_noise_kernel_from_operators(w, ops), beta, atol=1e-12)
+    full_ops = rng.normal(size=(n_ops, n, n)) + 1j * rng.normal(size=(n_ops, n, n))
+    kernel = o.noise_kernel_from_operators(values, full_ops)
+    w2, ops2 = o.noise_operators_eigenvalue(kernel)
+    np.testing.assert_allclose(o.noise_kernel_from_operators(w2, ops2), kernel, atol=1e-11)
+    # a kernel built from ONE operator has one non-zero eigenvalue = lambda ||L||^2, operator parallel to L
+    single = o.noise_kernel_from_operators(np.array([2.0]), full_ops[:1])
+    w3, ops3 = o.noise_operators_eigenvalue(single)
+    np.testing.assert_allclose(w3[-1], 2.0 * np.linalg.norm(full_ops[0]) ** 2, rtol=1e-12)
+    overlap = abs(np.vdot(ops3[-1], full_ops[0])) / np.linalg.norm(full_ops[0])
+    np.testing.assert_allclose(overlap, 1.0, atol=1e-12)

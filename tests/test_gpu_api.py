@@ -986,3 +986,81 @@ def test_dense_single_cell_eigenstates_above_512_states(cuda):
     t_values = np.asarray(times.metadata().values)
     want = np.array([v_ref @ (c * np.exp(-1j * w_ref * t / hbar)) for t in t_values])
     np.testing.assert_allclose(got, want, atol=1e-9)
+
+
+def test_noise_kernel_eigenvalue_diagonalisation(cuda):
+    """noise._kernel on the GPU (K7 contractions + K2 eigensolve) against the oracle restatement of
+    noise/_kernel.py:38-177 and noise/diagonalize/_eigenvalue.py:22-131: kernels at 1e-12, eigenvalues at rel
+    1e-10, and the returned operators rebuild the kernel (gauge-free comparison of the eigenvectors)."""
+    _, _, operator, _, TupleBasis, basis, metadata = _api()
+    from slate_quantum_b200 import noise
+    from slate_quantum_b200.core.basis import DiagonalBasis
+    from slate_quantum_b200.metadata import eigenvalue_basis
+    from slate_quantum_b200.operator import OperatorList
+
+    rng = np.random.default_rng(12)
+    n, n_ops = 12, 4
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x((np.array([2 * np.pi]),), (n,))
+    values = np.array([0.4, 0.9, 1.6, 2.5])
+    state_basis = basis.from_metadata(meta)
+    # diagonal operators
+    diag = rng.normal(size=(n_ops, n)) + 1j * rng.normal(size=(n_ops, n))
+    diag_basis = DiagonalBasis(TupleBasis((state_basis, state_basis.dual_basis())))
+    ops = OperatorList(TupleBasis((eigenvalue_basis(values), diag_basis)).upcast(), diag.ravel())
+    kernel = noise.diagonal_kernel_from_operators(ops)
+    want = o.diagonal_noise_kernel_from_operators(values, diag)
+    np.testing.assert_allclose(kernel.raw_data.reshape(n, n), want, atol=1e-12)
+    found = noise.get_periodic_noise_operators_diagonal_eigenvalue(kernel)
+    w_ref, _ = o.noise_operators_diagonal_eigenvalue(want)
+    w = np.asarray(found.basis.metadata().children[0].values)
+    np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-10 * np.abs(w_ref).max())
+    rebuilt = o.diagonal_noise_kernel_from_operators(w, found.raw_data.reshape(n, n))
+    np.testing.assert_allclose(rebuilt, want, atol=1e-10)
+    np.testing.assert_allclose(noise.diagonal_kernel_from_operators(found).raw_data.reshape(n, n), want, atol=1e-10)
+    # full operators: n^2 = 144 x 144 kernel matrix
+    full = rng.normal(size=(n_ops, n, n)) + 1j * rng.normal(size=(n_ops, n, n))
+    dense_basis = basis.from_metadata(ops.basis.metadata().children[1], is_dual=(False, True))
+    ops_full = OperatorList(TupleBasis((eigenvalue_basis(values), dense_basis)).upcast(), full.ravel())
+    kernel_full = noise.noise_kernel_from_operators(ops_full)
+    want_full = o.noise_kernel_from_operators(values, full)
+    np.testing.assert_allclose(kernel_full.raw_data.reshape(n, n, n, n), want_full, atol=1e-12)
+    found_full = noise.get_periodic_noise_operators_eigenvalue(kernel_full)
+    w_full = np.asarray(found_full.basis.metadata().children[0].values)
+    w_full_ref, _ = o.noise_operators_eigenvalue(want_full)
+    np.testing.assert_allclose(w_full, w_full_ref, rtol=0, atol=1e-10 * np.abs(w_full_ref).max())
+    rebuilt_full = o.noise_kernel_from_operators(w_full, found_full.raw_data.reshape(n * n, n, n))
+    np.testing.assert_allclose(rebuilt_full, want_full, atol=1e-9)
+    del operator
+
+
+def test_measure_on_a_non_orthogonal_cell(cuda):
+    """operator.measure.{all_x, all_periodic_x, all_variance_x, all_coherent_width} on the hexagonal cell of
+    reference tests/test_operator.py:324-330 (cfg4's lattice): the Cartesian x mixes both lattice axes; against the
+    oracle restatement of operator/_measure.py:105-305 with slate_core's stacked x points."""
+    _, _, operator, state, _, basis, metadata = _api()
+    from slate_quantum_b200.state import StateList
+
+    vectors = 2 * np.pi * np.array([[np.sin(np.pi / 3), np.cos(np.pi / 3)], [0.0, 1.0]])
+    shape = (12, 10)
+    meta = metadata.volume.spaced_volume_metadata_from_stacked_delta_x((vectors[0], vectors[1]), shape)
+    rng = np.random.default_rng(4)
+    states_np = rng.normal(size=(6, 120)) + 1j * rng.normal(size=(6, 120))
+    states_np[0] = o.coherent_state(vectors, shape, (2.0, 3.5), (0.0, 0.0), (0.8, 0.8))
+    list_basis = basis.from_metadata(metadata.SimpleMetadata(6)) if hasattr(metadata, "SimpleMetadata") else None
+    from slate_quantum_b200.core import FundamentalBasis, TupleBasis
+    from slate_quantum_b200.core.metadata import SimpleMetadata
+
+    del list_basis
+    states = StateList(TupleBasis((FundamentalBasis(SimpleMetadata(6)), basis.from_metadata(meta))).upcast(), states_np.ravel())
+    for axis in (0, 1):
+        np.testing.assert_allclose(operator.measure.all_x(states, axis=axis).raw_data,
+                                   o.measure_all_x(states_np, vectors, shape, axis), atol=1e-10)
+        np.testing.assert_allclose(operator.measure.all_x(states, axis=axis, offset=0.7, wrapped=True).raw_data,
+                                   o.measure_all_x(states_np, vectors, shape, axis, 0.7, True), atol=1e-10)
+        np.testing.assert_allclose(operator.measure.all_periodic_x(states, axis=axis).raw_data,
+                                   o.measure_all_periodic_x(states_np, vectors, shape, axis), atol=1e-10)
+        np.testing.assert_allclose(operator.measure.all_variance_x(states, axis=axis).raw_data,
+                                   o.measure_all_variance_x(states_np, vectors, shape, axis), atol=1e-9)
+        np.testing.assert_allclose(operator.measure.all_coherent_width(states, axis=axis).raw_data,
+                                   o.measure_all_coherent_width(states_np, vectors, shape, axis), atol=1e-9)
+    del state
