@@ -1026,11 +1026,12 @@ extern "C" int sqb_eigh_batched(int n, int64_t batch, sqb_c128* A_inout, double*
     c128* Ab = A + b0 * (int64_t)n * n;
     int rc;
     const int pnb = eigh_panel_nb(n);
-    if (pnb == 4 && n <= 256) rc = launch_tridiag_panel<4, 1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
-    else if (pnb == 8 && n <= 256) rc = launch_tridiag_panel<8, 1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
-    else if (pnb == 16 && n <= 256) rc = launch_tridiag_panel<16, 1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
-    else if (pnb == 4) rc = launch_tridiag_panel<4, 2>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
-    else if (pnb != 0) rc = launch_tridiag_panel<8, 2>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    constexpr int kR1 = 256 / kPnThreads, kR2 = 512 / kPnThreads;  // rows per thread for n <= 256 / n <= 512
+    if (pnb == 4 && n <= 256) rc = launch_tridiag_panel<4, kR1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb == 8 && n <= 256) rc = launch_tridiag_panel<8, kR1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb == 16 && n <= 256) rc = launch_tridiag_panel<16, kR1>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb == 4) rc = launch_tridiag_panel<4, kR2>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
+    else if (pnb != 0) rc = launch_tridiag_panel<8, kR2>(n, cnt, Ab, ws.d, ws.e, ws.tau, ws.y, ls);
     else if (n <= 32) rc = launch_tridiag<1, 1>(n, cnt, Ab, ws, ls);
     else if (n <= 64) rc = launch_tridiag<2, 1>(n, cnt, Ab, ws, ls);
     else if (n <= 128) rc = launch_tridiag<2, 2>(n, cnt, Ab, ws, ls);

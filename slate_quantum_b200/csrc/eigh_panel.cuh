@@ -47,7 +47,11 @@ __device__ unsigned long long pn_prof[16];
   } while (0)
 #endif
 
-constexpr int kPnThreads = 256;
+#ifndef SQB_PN_THREADS
+#define SQB_PN_THREADS 256
+#endif
+constexpr int kPnThreads = SQB_PN_THREADS;          // 256: one CTA per SM (255 registers); 128: two CTAs per SM
+constexpr int kPnCtasPerSm = 256 / kPnThreads;
 constexpr int kPnWarps = kPnThreads / 32;
 constexpr unsigned kPnFull = 0xffffffffu;
 constexpr int kPnMaxN = 512;
@@ -217,7 +221,7 @@ __device__ __forceinline__ c128 pn_unit(int n, int lo, int r0, int c0, int lane,
 }
 
 template <int NB, int NR>
-__global__ void __launch_bounds__(kPnThreads, 1)
+__global__ void __launch_bounds__(kPnThreads, kPnCtasPerSm)
 tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restrict__ d_all, double* __restrict__ e_all,
                      c128* __restrict__ tau_all, c128* __restrict__ Y_all) {
   extern __shared__ __align__(128) unsigned char pn_smem[];
@@ -325,8 +329,8 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
         tau_r = (beta - ar) / beta;
         tau_i = -ai / beta;
         const double pr = ar - beta, pi = ai;
-        const double den = pr * pr + pi * pi;
-        scal = make_double2(pr / den, -pi / den);
+        const double rden = 1.0 / (pr * pr + pi * pi);
+        scal = make_double2(pr * rden, -pi * rden);
       }
       const c128 tau = make_double2(tau_r, tau_i);
       c128 myv[NR];
@@ -579,7 +583,7 @@ inline int panel_jres(int n, int nb, size_t budget, size_t* smem_out) {
 template <int NB, int NR>
 int launch_tridiag_panel(int n, int64_t count, c128* A, double* d, double* e, c128* tau, c128* y, cudaStream_t st) {
   size_t smem = 0;
-  const int jres = panel_jres(n, NB, 232448 - 1024, &smem);
+  const int jres = panel_jres(n, NB, (size_t)(233472 / kPnCtasPerSm) - 1024 - (kPnCtasPerSm > 1 ? 1024 : 0), &smem);
   cudaError_t err =
       cudaFuncSetAttribute(tridiag_panel_kernel<NB, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;

@@ -115,6 +115,32 @@ def _all_variance_x(pos: torch.Tensor, space: TupleMetadata, axis: int) -> torch
     return mom[:, 2] / mom[:, 0]
 
 
+def _position_bundle(states: StateList, space: TupleMetadata) -> dict[str, list[torch.Tensor]]:
+    """<x>, periodic <x> and the variance around it for EVERY axis, from ONE walk over the position-basis tiles.
+
+    The reference computes each observable from the materialised list; here a lazy evolved list would be re-evolved
+    per observable, so the first request reduces everything while each tile is resident (two K6 passes per axis and
+    tile) and caches the [T] results on the list object."""
+    cached = states.__dict__.get("_sqb_measure_cache")
+    if cached is not None:
+        return cached
+    nd = len(space.children)
+    position = _basis.from_metadata(space).upcast()
+    parts: dict[str, list[list[torch.Tensor]]] = {k: [[] for _ in range(nd)] for k in ("x", "periodic", "variance")}
+    for tile in _tiles_in(states, position):
+        for axis in range(nd):
+            length = float(np.linalg.norm(_cell(space)[0][axis]))
+            mom = _moments(tile, space, axis, None, False)
+            centre = torch.remainder(torch.atan2(mom[:, 4], mom[:, 3]), 2 * np.pi) * (length / (2 * np.pi))
+            mom2 = _moments(tile, space, axis, (-centre).contiguous(), True)
+            parts["x"][axis].append(mom[:, 1] / mom[:, 0])
+            parts["periodic"][axis].append(centre)
+            parts["variance"][axis].append(mom2[:, 2] / mom2[:, 0])
+    bundle = {k: [torch.cat(v[axis]) for axis in range(nd)] for k, v in parts.items()}
+    states.__dict__["_sqb_measure_cache"] = bundle
+    return bundle
+
+
 def _momentum_data(states: Array, space: TupleMetadata) -> torch.Tensor:
     """[lead, M] device tensor of the states in the transformed (momentum) basis of ``space`` (K4 on the GPU)."""
     return torch.cat(list(_tiles_in(states, _basis.transformed_from_metadata(space).upcast())))
@@ -180,26 +206,27 @@ def uncertainty(state: State, *, axis: int) -> float:
 def all_x(states: StateList, *, axis: int, offset: float = 0, wrapped: bool = False) -> Array:
     """Position of all states (reference operator/_measure.py:191-210)."""
     space = states.basis.metadata().children[1]
+    if not offset and not wrapped:
+        return _list_array(states, _position_bundle(states, space)["x"][axis])
     return _list_array(states, _reduce_position(states, space, lambda pos: _all_x(pos, space, axis, offset, wrapped)))
 
 
 def all_periodic_x(states: StateList, *, axis: int) -> Array:
     """Periodic position coordinate of all states (reference operator/_measure.py:242-268)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _reduce_position(states, space, lambda pos: _all_periodic_x(pos, space, axis)))
+    return _list_array(states, _position_bundle(states, space)["periodic"][axis])
 
 
 def all_variance_x(states: StateList, *, axis: int) -> Array:
     """<x^2> around each state's periodic position (reference operator/_measure.py:271-292)."""
     space = states.basis.metadata().children[1]
-    return _list_array(states, _reduce_position(states, space, lambda pos: _all_variance_x(pos, space, axis)))
+    return _list_array(states, _position_bundle(states, space)["variance"][axis])
 
 
 def all_coherent_width(states: StateList, *, axis: int) -> Array:
     """Width of a Gaussian wavepacket, sqrt(2 variance) (reference operator/_measure.py:295-305)."""
     space = states.basis.metadata().children[1]
-    variance = _reduce_position(states, space, lambda pos: _all_variance_x(pos, space, axis))
-    return _list_array(states, torch.sqrt(2.0 * variance))
+    return _list_array(states, torch.sqrt(2.0 * _position_bundle(states, space)["variance"][axis]))
 
 
 def x(state: State, *, axis: int, offset: float = 0, wrapped: bool = False) -> float:
