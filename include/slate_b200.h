@@ -16,7 +16,10 @@
  *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_FFT_INPLACE=0 uses the two-buffer FFT pass for 256/512-point strided lines; SQB_EVOLVE_TILES_PER_CTA=<k> sets how
  *    many 64-row time tiles a CTA of the uniform-grid evolve kernel walks (default 8); SQB_BACKTRANSFORM=reflector
  *    selects the reflector-by-reflector back-transformation for every n (default: blocked compact-WY DMMA
- *    kernel for 64 < n <= 512).
+ *    kernel for 64 < n <= 512); SQB_WY_VARIANT=<1|2> picks the blocked back-transformation's tile shape (1: 16-reflector
+ *    blocks, two CTAs per SM, default; 2: 32-reflector blocks); SQB_TRIDIAG=column selects the column-by-column
+ *    tridiagonalisation instead of the blocked panel kernel (default for 64 < n <= 512), SQB_TRIDIAG_NB=<4|8|16> its
+ *    panel width (default 8).
  *
  * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
  * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency
@@ -163,7 +166,10 @@ int sqb_bloch_cell_vectors(int nd, const int* shape_host, const int* repeat_host
  * w        [batch, n] eigenvalues, ascending within each matrix (quirk Q3: not globally sorted)
  * info     [batch] 0 = converged; k > 0 = the implicit-QL iteration failed on k eigenvalues or ran
  *          out of rotation storage (results for that matrix are undefined)
- * n <= 512 (SQB_E_UNSUPPORTED above).  Algorithm: Householder tridiagonalisation; divide and conquer on the
+ * n <= 512 (SQB_E_UNSUPPORTED above: one SM holds a matrix; the Python layer reduces larger matrices to batches of
+ * 512 x 512 sub-problems of this call, slate_quantum_b200/core/jacobi.py).  Algorithm: Householder
+ * tridiagonalisation (64 < n <= 512: blocked LAPACK-zlatrd panels - read-only matrix-vector products inside a panel
+ * and ONE rank-2NB trailing update per panel on the FP64 tensor cores; n <= 64: column by column); divide and conquer on the
  * real tridiagonal (QL leaves of <= 32 rows, dlaed2-style deflation, secular equation per root, Gu/Eisenstat
  * vectors, merge products on the FP64 tensor cores); Householder back-transformation (blocked compact WY on the
  * FP64 tensor cores for 64 < n <= 512, reflector by reflector otherwise).  With the environment
