@@ -131,6 +131,22 @@ int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, const sqb_c128
 size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host);
 int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
                  sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes, void* stream);
+/* sqb_cell_fft_moments: sqb_cell_fft (direction 1) with K6 FUSED into its last pass - every position-basis value
+ * is reduced into the observable sums of sqb_measure_moments for EVERY axis instead of being stored, so the
+ * position-basis state list (68.7 GB at cfg3) is never written (the consumers are
+ * operator/_measure.py:191-305 on the lists of state/_state.py:153-165).  Orthogonal axes.
+ *   stage 0: run the in-place passes of axes 0..nd-2 on `in_scratch` first (clobbers it);
+ *   stage 1: `in_scratch` already holds them (a second reduction of the SAME tile, e.g. the variance around the
+ *            periodic position obtained from the stage-0 sums).
+ *   spacing_host / length_host [nd]: grid spacing and supercell length per axis;  offsets [nd][lead] (device) or
+ *   NULL: per-state shifts added to x;  wrapped: fold x into [-length/2, length/2).
+ *   out [lead][nd][5] = {sum |psi|^2, sum x |psi|^2, sum x^2 |psi|^2, sum cos(2 pi n/N) |psi|^2, sum sin |psi|^2}.
+ * Deterministic (per-CTA partial sums, reduced in a fixed order). */
+size_t sqb_cell_fft_moments_workspace_bytes(int nd, const int* shape_host, const int* repeat_host, int64_t lead);
+int sqb_cell_fft_moments(int nd, const int* shape_host, const int* repeat_host, int64_t lead, int stage,
+                         sqb_c128* in_scratch, const double* spacing_host, const double* length_host,
+                         const double* offsets, int wrapped, double* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 /* sqb_cell_fft_sharded: direction 1 (cell -> position) reading the RECEIVE BUFFER of the k-shard -> time-shard
  * all-to-all directly: in_scratch is [ranks][lead][n_k/ranks][N] (rank r contributed blocks
  * [r n_k/ranks, (r+1) n_k/ranks), i.e. block axis 0 split in `ranks` contiguous pieces; repeat[0] % ranks == 0).

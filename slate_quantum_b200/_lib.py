@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = (
     "sqb_cell_fft_workspace_bytes",
     "sqb_cell_fft",
     "sqb_cell_fft_sharded",
+    "sqb_cell_fft_moments_workspace_bytes",
+    "sqb_cell_fft_moments",
     "sqb_fold_transform",
     "sqb_bloch_cell_vectors",
     "sqb_eigh_workspace_bytes",
@@ -97,6 +99,12 @@ def load() -> ctypes.CDLL:
     lib.sqb_cell_fft.argtypes = [c_int, ip, ip, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_cell_fft_sharded.restype = c_int
     lib.sqb_cell_fft_sharded.argtypes = [c_int, ip, ip, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sqb_cell_fft_moments_workspace_bytes.restype = c_size_t
+    lib.sqb_cell_fft_moments_workspace_bytes.argtypes = [c_int, ip, ip, c_int64]
+    lib.sqb_cell_fft_moments.restype = c_int
+    lib.sqb_cell_fft_moments.argtypes = [
+        c_int, ip, ip, c_int64, c_int, c_void_p, dp, dp, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
     lib.sqb_bloch_cell_vectors.restype = c_int
     lib.sqb_bloch_cell_vectors.argtypes = [c_int, ip, ip, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sqb_fold_transform.restype = c_int

@@ -70,7 +70,49 @@ struct FftPass {
   int64_t tw_len;          // 0 = none; else multiply output (pos k, inner i) by exp(sign*2*pi*i*k*(i/tw_div)/tw_len)
   int64_t tw_div;          // divisor applied to the inner index before the twiddle (>= 1)
   int inplace_mid;         // 1 = the middle stages run in place (one shared buffer; needs work <= threads, see launch_pass)
+  // K6 epilogue (kMom kernels only; mom_nd == 0: off).  Instead of being stored, every output element v at output
+  // offset e adds |v|^2 {1, x_a, x_a^2, cos_a, sin_a} for every axis a of the position grid into per-CTA partial
+  // sums; x_a = idx_a * spacing_a + offset_a(state), folded into [-length_a / 2, length_a / 2) when wrapped.
+  int mom_nd;
+  int mom_wrapped;
+  int mom_grid[SQB_MAX_DIMS];
+  double mom_spacing[SQB_MAX_DIMS], mom_length[SQB_MAX_DIMS];
+  int64_t mom_m;                 // elements per state (all lines of a CTA belong to one state)
+  int64_t mom_lead;              // number of states
+  const double* mom_offsets;     // [nd][lead] or nullptr
+  const c128* mom_cs;            // [sum_a L_a] (cos, sin)(2 pi idx / L_a), axis a at mom_cs_off[a]
+  int mom_cs_off[SQB_MAX_DIMS];
+  double* mom_partials;          // [n_ctas][1 + 4 nd]
 };
+
+constexpr int kMomMax = 1 + 4 * SQB_MAX_DIMS;
+struct MomAcc {
+  double v[kMomMax];
+  double off[SQB_MAX_DIMS];
+  int64_t e0;  // output offset of the CTA's state
+};
+
+__device__ __forceinline__ void mom_add(const FftPass& P, MomAcc& acc, int64_t e, c128 v) {
+  const double w = fma(v.x, v.x, v.y * v.y);
+  uint32_t m = (uint32_t)(e - acc.e0);
+  acc.v[0] += w;
+#pragma unroll
+  for (int a = SQB_MAX_DIMS - 1; a >= 0; --a) {
+    if (a < P.mom_nd) {
+      const uint32_t L = (uint32_t)P.mom_grid[a];
+      const uint32_t q = m / L;
+      const uint32_t idx = m - q * L;
+      m = q;
+      double x = fma((double)idx, P.mom_spacing[a], acc.off[a]);
+      if (P.mom_wrapped) x -= P.mom_length[a] * floor(x / P.mom_length[a] + 0.5);
+      const c128 cs = __ldg(P.mom_cs + P.mom_cs_off[a] + idx);
+      acc.v[1 + 4 * a] = fma(w, x, acc.v[1 + 4 * a]);
+      acc.v[2 + 4 * a] = fma(w * x, x, acc.v[2 + 4 * a]);
+      acc.v[3 + 4 * a] = fma(w, cs.x, acc.v[3 + 4 * a]);
+      acc.v[4 + 4 * a] = fma(w, cs.y, acc.v[4 + 4 * a]);
+    }
+  }
+}
 
 __device__ __forceinline__ c128 tw_lookup(const c128* tab, int idx, int sign) {
   c128 w = tab[idx];
@@ -207,11 +249,34 @@ struct StageIo {
   bool line_major;          // shared layout: true = [pos][line] (line fastest), false = [line][pos]
 };
 
+// block reduction of the K6 accumulators -> mom_partials[blockIdx.x][1 + 4 nd]  (every thread of the CTA calls it)
+template <int kThreads>
+__device__ __forceinline__ void mom_flush(const FftPass& P, const MomAcc& acc) {
+  __shared__ double s_red[kMomMax][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k_count = 1 + 4 * P.mom_nd;
+#pragma unroll
+  for (int k = 0; k < kMomMax; ++k) {
+    if (k < k_count) {
+      const double v = warp_sum(acc.v[k]);
+      if (lane == 0) s_red[k][warp] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < k_count) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += s_red[threadIdx.x][w];
+    P.mom_partials[(int64_t)blockIdx.x * k_count + threadIdx.x] = s;
+  }
+}
+
 // One Stockham stage of radix R over `lines` lines held by the CTA.  The first stage reads its butterfly
 // inputs straight from global memory and the last one writes straight to global memory, so an FFT of S
 // stages makes S-1 round trips through shared memory instead of S+1.
-template <int R, int kThreads>
-__device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io, int ns, int lines, const c128* tab) {
+template <int R, int kThreads, bool kMom = false>
+__device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io, int ns, int lines, const c128* tab,
+                                            MomAcc* acc = nullptr) {
   const int len = P.len, sign = P.sign, lpc = P.lines_per_cta;
   const int per_line = len / R;
   const int tw_step = len / (ns * R);
@@ -259,7 +324,9 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
           sincospi((double)sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
           v = cmul(v, make_double2(cs, sn));
         }
-        io.gout[base + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
+        const int64_t e = base + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl);
+        if constexpr (kMom) mom_add(P, *acc, e, v);
+        else io.gout[e] = v;
       }
     } else {
 #pragma unroll
@@ -330,8 +397,8 @@ __device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 
 // compiled in, which keeps the register count down for 4 CTAs / SM)
 // kVariant 0: radices {2,4,8} only (power-of-two lengths, the hot cell-FFT passes); 1: {2,3,4,5,7,8};
 // 2: any radix <= 31 (local-memory arrays).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
-template <int kVariant, int kThreads>
-__global__ void __launch_bounds__(kThreads, kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2)))
+template <int kVariant, int kThreads, bool kMom = false>
+__global__ void __launch_bounds__(kThreads, kMom ? 2 : (kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))))
 fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
   extern __shared__ c128 smem[];
   __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
@@ -355,6 +422,16 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
   }
   for (int j = threadIdx.x; j < len; j += kThreads) tab[j] = tab_g[j];
   __syncthreads();
+  MomAcc acc;
+  if constexpr (kMom) {
+#pragma unroll
+    for (int k = 0; k < kMomMax; ++k) acc.v[k] = 0.0;
+    const int64_t state = s_out_base[0] / P.mom_m;  // launch_pass guarantees one state per CTA
+    acc.e0 = state * P.mom_m;
+#pragma unroll
+    for (int a = 0; a < SQB_MAX_DIMS; ++a)
+      acc.off[a] = (a < P.mom_nd && P.mom_offsets) ? P.mom_offsets[(int64_t)a * P.mom_lead + state] : 0.0;
+  }
 
   const int lshift = 31 - __clz(lpc);
   // [pos][line] shared layout (and line-fastest work mapping in every stage) whenever the CTA's lines are
@@ -410,17 +487,20 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       continue;
     }
     switch (r) {
-      case 8: stage_fixed<8, kThreads>(P, io, ns, lines, tab); break;
-      case 4: stage_fixed<4, kThreads>(P, io, ns, lines, tab); break;
-      case 2: stage_fixed<2, kThreads>(P, io, ns, lines, tab); break;
-      case 3: if constexpr (kVariant >= 1) stage_fixed<3, kThreads>(P, io, ns, lines, tab); break;
-      case 5: if constexpr (kVariant >= 1) stage_fixed<5, kThreads>(P, io, ns, lines, tab); break;
-      case 7: if constexpr (kVariant >= 1) stage_fixed<7, kThreads>(P, io, ns, lines, tab); break;
+      case 8: stage_fixed<8, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 4: stage_fixed<4, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 2: stage_fixed<2, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 3: if constexpr (kVariant >= 1) stage_fixed<3, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 5: if constexpr (kVariant >= 1) stage_fixed<5, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 7: if constexpr (kVariant >= 1) stage_fixed<7, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
       default:
         if constexpr (kVariant == 2) stage_generic(src, dst, len, ns, r, lines, tab, P.sign);
         break;
     }
-    if (io.last) return;
+    if (io.last) {
+      if constexpr (kMom) mom_flush<kThreads>(P, acc);
+      return;
+    }
     __syncthreads();
     if (io.first) {
       src = buf0;  // first stage wrote buf0
@@ -440,7 +520,9 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
       v = cmul(v, make_double2(cs, sn));
     }
-    out[s_out_base[l] + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
+    const int64_t e = s_out_base[l] + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl);
+    if constexpr (kMom) mom_add(P, acc, e, v);
+    else out[e] = v;
   };
   if (P.out_inner_fastest) {
     const int l = threadIdx.x & (lpc - 1);
@@ -451,6 +533,34 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       const int l = e / len;
       emit(l, e - l * len);
     }
+  }
+  if constexpr (kMom) mom_flush<kThreads>(P, acc);
+}
+
+// per-state sums of the per-CTA partials (fixed order: deterministic); out [lead][nd][5] = {w, wx, wx^2, wcos, wsin}
+__global__ void mom_reduce_kernel(const double* __restrict__ partials, int ctas_per_state, int nd,
+                                  double* __restrict__ out) {
+  const int64_t state = blockIdx.x;
+  const int k_count = 1 + 4 * nd;
+  const int k = threadIdx.x;
+  if (k >= k_count) return;
+  const double* p = partials + state * (int64_t)ctas_per_state * k_count + k;
+  double s = 0.0;
+  for (int c = 0; c < ctas_per_state; ++c) s += p[(int64_t)c * k_count];
+  if (k == 0) {
+    for (int a = 0; a < nd; ++a) out[(state * nd + a) * 5] = s;
+  } else {
+    const int a = (k - 1) / 4, j = (k - 1) % 4;
+    out[(state * nd + a) * 5 + 1 + j] = s;
+  }
+}
+
+// cos / sin tables of the scattering phase, axis a at offset off[a]
+__global__ void mom_table_kernel(c128* tab, int len) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * (double)j / (double)len, &sn, &cs);
+    tab[j] = make_double2(cs, sn);
   }
 }
 
@@ -586,7 +696,7 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   // the lines per CTA in the same shared memory.  SQB_FFT_INPLACE=0 switches it off.
   P.inplace_mid = 0;
   int threads = kFftThreads;
-  if (variant == 0 && P.n_stages == 3 && P.len >= 256 && P.inner_fastest && P.out_inner_fastest && fft_inplace_on()) {
+  if (P.mom_nd == 0 && variant == 0 && P.n_stages == 3 && P.len >= 256 && P.inner_fastest && P.out_inner_fastest && fft_inplace_on()) {
     const int per_line_mid = P.len / P.radix[1];
     int wide = kFftThreadsWide / per_line_mid;  // lines such that the middle stage has one butterfly per thread
     while (wide > 1 && wide / 2 >= n_lines) wide /= 2;
@@ -598,10 +708,18 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
     }
   }
   P.lines_per_cta = lpc;
-  const size_t smem = ((size_t)n_buf_used * lpc * P.len + P.len) * sizeof(c128);
   auto* kern = P.inplace_mid ? fft_pass_kernel<0, kFftThreadsWide>
                              : (variant == 0 ? fft_pass_kernel<0, kFftThreads>
                                              : (variant == 1 ? fft_pass_kernel<1, kFftThreads> : fft_pass_kernel<2, kFftThreads>));
+  if (P.mom_nd > 0) {
+    // K6 epilogue: every CTA must stay inside one state (lines per state divisible by the lines per CTA)
+    const int64_t lines_per_state = n_lines / P.mom_lead;
+    while (lpc > 1 && lines_per_state % lpc) lpc /= 2;
+    P.lines_per_cta = lpc;
+    kern = variant == 0 ? fft_pass_kernel<0, kFftThreads, true>
+                        : (variant == 1 ? fft_pass_kernel<1, kFftThreads, true> : fft_pass_kernel<2, kFftThreads, true>);
+  }
+  const size_t smem = ((size_t)n_buf_used * lpc * P.len + P.len) * sizeof(c128);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   fft_table_kernel<<<(P.len + 255) / 256, 256, 0, st>>>(tab, P.len);
@@ -753,16 +871,28 @@ extern "C" size_t sqb_cell_fft_workspace_bytes(int nd, const int* repeat_host) {
   return align_up((size_t)max_len * sizeof(c128), 256) + 256;
 }
 
+struct MomRequest {  // K6 fused into the last cell-FFT pass (direction 1 only); see sqb_cell_fft_moments
+  int stage;                 // 0: run the in-place axes first; 1: in_scratch already holds them
+  const double* spacing;     // [nd] host
+  const double* length;      // [nd] host
+  const double* offsets;     // [nd][lead] device or nullptr
+  int wrapped;
+  double* out;               // [lead][nd][5] device
+  c128* cs_tab;              // device scratch: cos / sin tables
+  double* partials;          // device scratch
+  size_t partial_doubles;
+};
+
 static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, int direction, int64_t lead,
                          int ranks, sqb_c128* in_scratch, sqb_c128* out, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         void* stream, const MomRequest* mom = nullptr) {
   SqbDims d;
   int64_t n, nk;
   int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
   if (rc) return rc;
-  if (!in_scratch || !out || lead < 0 || (direction != 0 && direction != 1)) return SQB_E_BADARG;
+  if (!in_scratch || (!out && !mom) || lead < 0 || (direction != 0 && direction != 1)) return SQB_E_BADARG;
   if (!workspace || workspace_bytes < sqb_cell_fft_workspace_bytes(nd, repeat_host)) return SQB_E_WORKSPACE;
-  if (nd > 1 && in_scratch == out) return SQB_E_BADARG;  // the scatter / gather pass is out of place
+  if (!mom && nd > 1 && in_scratch == out) return SQB_E_BADARG;  // the scatter / gather pass is out of place
   for (int a = 0; a < nd; ++a)
     if (d.repeat[a] > kMaxSmemLen || !smooth(d.repeat[a])) return SQB_E_UNSUPPORTED;
   if (ranks < 1 || d.repeat[0] % ranks || (ranks > 1 && direction != 1)) return SQB_E_BADARG;
@@ -847,6 +977,32 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
     P.scale = scale;
     P.tw_len = 0;
     P.tw_div = 1;
+    if (mom && cell_is_input) {
+      if (m >= (1LL << 31)) return SQB_E_UNSUPPORTED;
+      P.mom_nd = nd;
+      P.mom_wrapped = mom->wrapped;
+      P.mom_m = m;
+      P.mom_lead = lead;
+      P.mom_offsets = mom->offsets;
+      P.mom_cs = mom->cs_tab;
+      P.mom_partials = mom->partials;
+      int off = 0;
+      for (int q = 0; q < nd; ++q) {
+        P.mom_grid[q] = d.shape[q] * d.repeat[q];
+        P.mom_spacing[q] = mom->spacing[q];
+        P.mom_length[q] = mom->length[q];
+        P.mom_cs_off[q] = off;
+        mom_table_kernel<<<(P.mom_grid[q] + 255) / 256, 256, 0, st>>>(mom->cs_tab + off, P.mom_grid[q]);
+        off += P.mom_grid[q];
+      }
+      int rc2 = launch_pass(P, pin, pout, tab, st);
+      if (rc2) return rc2;
+      const int64_t n_ctas = (P.n_outer * P.n_inner + P.lines_per_cta - 1) / P.lines_per_cta;
+      if ((size_t)n_ctas * (1 + 4 * nd) > mom->partial_doubles || n_ctas % lead) return SQB_E_WORKSPACE;
+      mom_reduce_kernel<<<(unsigned)lead, 32, 0, st>>>(mom->partials, (int)(n_ctas / lead), nd, mom->out);
+      SQB_LAUNCH_CHECK();
+      return SQB_OK;
+    }
     return launch_pass(P, pin, pout, tab, st);
   };
   auto inplace_axis = [&](int a, c128* p, int sign) -> int {
@@ -877,7 +1033,7 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
   };
 
   if (direction == 1) {
-    for (int a = 0; a < nd - 1; ++a) {
+    for (int a = 0; a < nd - 1 && !(mom && mom->stage == 1); ++a) {
       rc = inplace_axis(a, src, +1);
       if (rc) return rc;
     }
@@ -897,6 +1053,49 @@ extern "C" int sqb_cell_fft(int nd, const int* shape_host, const int* repeat_hos
                             void* stream) {
   return cell_fft_impl(nd, shape_host, repeat_host, direction, lead, 1, in_scratch, out, workspace, workspace_bytes,
                        stream);
+}
+
+// K6 fused into the last pass of the cell FFT: the position-basis states are never written.
+extern "C" size_t sqb_cell_fft_moments_workspace_bytes(int nd, const int* shape_host, const int* repeat_host,
+                                                       int64_t lead) {
+  if (nd < 1 || nd > SQB_MAX_DIMS || !shape_host || !repeat_host || lead < 0) return 0;
+  size_t grid_sum = 0;
+  int64_t n = 1, nk = 1;
+  for (int a = 0; a < nd; ++a) {
+    grid_sum += (size_t)shape_host[a] * repeat_host[a];
+    n *= shape_host[a];
+    nk *= repeat_host[a];
+  }
+  const int64_t lines = lead * (nk / repeat_host[nd - 1]) * n;  // one partial row per CTA, at worst one line per CTA
+  return align_up(sqb_cell_fft_workspace_bytes(nd, repeat_host), 256) + align_up(grid_sum * sizeof(c128), 256) +
+         align_up((size_t)lines * (1 + 4 * nd) * sizeof(double), 256) + 256;
+}
+
+extern "C" int sqb_cell_fft_moments(int nd, const int* shape_host, const int* repeat_host, int64_t lead, int stage,
+                                    sqb_c128* in_scratch, const double* spacing_host, const double* length_host,
+                                    const double* offsets, int wrapped, double* out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (nd < 1 || nd > SQB_MAX_DIMS || !shape_host || !repeat_host || !spacing_host || !length_host || !out ||
+      (stage != 0 && stage != 1))
+    return SQB_E_BADARG;
+  if (!workspace || workspace_bytes < sqb_cell_fft_moments_workspace_bytes(nd, shape_host, repeat_host, lead))
+    return SQB_E_WORKSPACE;
+  if (lead == 0) return SQB_OK;
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  const size_t fft_ws = align_up(sqb_cell_fft_workspace_bytes(nd, repeat_host), 256);
+  size_t grid_sum = 0;
+  for (int a = 0; a < nd; ++a) grid_sum += (size_t)shape_host[a] * repeat_host[a];
+  MomRequest mom;
+  mom.stage = stage;
+  mom.spacing = spacing_host;
+  mom.length = length_host;
+  mom.offsets = offsets;
+  mom.wrapped = wrapped;
+  mom.out = out;
+  mom.cs_tab = reinterpret_cast<c128*>(base + fft_ws);
+  mom.partials = reinterpret_cast<double*>(base + fft_ws + align_up(grid_sum * sizeof(c128), 256));
+  mom.partial_doubles = (workspace_bytes - (size_t)(reinterpret_cast<char*>(mom.partials) - reinterpret_cast<char*>(workspace))) / sizeof(double);
+  return cell_fft_impl(nd, shape_host, repeat_host, 1, lead, 1, in_scratch, nullptr, base, fft_ws, stream, &mom);
 }
 
 extern "C" int sqb_cell_fft_sharded(int nd, const int* shape_host, const int* repeat_host, int64_t lead, int ranks,

@@ -177,6 +177,24 @@ class TiledEvolvedStates(StateList):
             tt = min(rows, self.n_times - t0)
             yield t0, self._fill(t0, tt, out[:tt], scratch)
 
+    def cell_tiles(self, rows: int | None = None) -> Iterator[tuple[int, torch.Tensor]]:
+        """kind "position" only: yield (t0, tile[tt, M]) in the CELL layout (block, in-cell position) - the evolve
+        output before the across-block FFT.  Consumers that only reduce the position-basis states
+        (kernels.cell_fft_moments: K6 fused into the last FFT pass) never need them written.  The tensor is reused
+        and may be clobbered by the consumer."""
+        if self._kind != "position":
+            msg = "cell_tiles() needs the supercell position basis of a Bloch Hamiltonian"
+            raise ValueError(msg)
+        self._transform()
+        rows = self.tile_rows(1) if rows is None else int(rows)
+        scratch = torch.empty((rows, self.state_size), dtype=torch.complex128, device="cuda")
+        for t0 in range(0, self.n_times, rows):
+            tt = min(rows, self.n_times - t0)
+            yield t0, self._evolve(t0, tt, scratch[:tt])
+
+    def bloch_dims(self) -> tuple[tuple[int, ...], tuple[int, ...]]:
+        return self._inner._dims()  # noqa: SLF001
+
     def host_tiles(
         self, rows: int | None = None, chunk_bytes: int = 1 << 30, n_host_buffers: int = 3,
     ) -> Iterator[tuple[int, torch.Tensor]]:

@@ -234,6 +234,38 @@ def cell_fft(
     return out
 
 
+def cell_fft_moments(
+    shape: Sequence[int], repeat: Sequence[int], x: torch.Tensor, spacing: Sequence[float], length: Sequence[float],
+    stage: int = 0, offsets: torch.Tensor | None = None, wrapped: bool = False,
+) -> torch.Tensor:
+    """K4b + K6 fused: observable sums [lead, nd, 5] of the position-basis states of the cell-layout tile `x`
+    ([lead, n_k, N]) for every axis, WITHOUT writing those states.  stage 0 clobbers `x` (in-place passes of the
+    leading axes); stage 1 reduces the same tile again (`offsets` [nd, lead], `wrapped`)."""
+    _require_cuda()
+    lib = _lib.load()
+    _c128(x, "x")
+    nd = len(shape)
+    m = int(np.prod(shape)) * int(np.prod(repeat))
+    lead = x.numel() // m
+    if offsets is not None:
+        _f64(offsets, "offsets")
+        if tuple(offsets.shape) != (nd, lead):
+            msg = "offsets must be [nd, lead]"
+            raise ValueError(msg)
+    out = torch.empty((lead, nd, 5), dtype=torch.float64, device="cuda")
+    shape_c, rep_c = _lib.int_array(shape), _lib.int_array(repeat)
+    ws_bytes = lib.sqb_cell_fft_moments_workspace_bytes(nd, shape_c, rep_c, lead)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = lib.sqb_cell_fft_moments(
+        nd, shape_c, rep_c, lead, int(stage), _ptr(x), _lib.double_array(np.asarray(spacing, dtype=np.float64)),
+        _lib.double_array(np.asarray(length, dtype=np.float64)), _ptr(offsets) if offsets is not None else None,
+        int(bool(wrapped)), _ptr(out), _ptr(ws), ws_bytes, _stream(),
+    )
+    _lib.check(rc, "sqb_cell_fft_moments")
+    _count((2 * (nd - 1) if stage == 0 else 0) + nd + 3)
+    return out
+
+
 def fold_transform(
     shape: Sequence[int], repeat: Sequence[int], transform: torch.Tensor, block_begin: int = 0,
     out: torch.Tensor | None = None,

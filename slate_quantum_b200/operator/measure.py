@@ -126,6 +126,10 @@ def _position_bundle(states: StateList, space: TupleMetadata) -> dict[str, list[
         return cached
     nd = len(space.children)
     position = _basis.from_metadata(space).upcast()
+    fused = _fused_bundle(states, space, position)
+    if fused is not None:
+        states.__dict__["_sqb_measure_cache"] = fused
+        return fused
     parts: dict[str, list[list[torch.Tensor]]] = {k: [[] for _ in range(nd)] for k in ("x", "periodic", "variance")}
     for tile in _tiles_in(states, position):
         for axis in range(nd):
@@ -139,6 +143,36 @@ def _position_bundle(states: StateList, space: TupleMetadata) -> dict[str, list[
     bundle = {k: [torch.cat(v[axis]) for axis in range(nd)] for k, v in parts.items()}
     states.__dict__["_sqb_measure_cache"] = bundle
     return bundle
+
+
+def _fused_bundle(states: StateList, space: TupleMetadata, position: Any) -> dict[str, list[torch.Tensor]] | None:
+    """The bundle for a LAZY evolved list of a Bloch Hamiltonian on an orthogonal cell: K6 is fused into the last
+    pass of the cell FFT (sqb_cell_fft_moments), twice per tile (sums, then the variance around the periodic
+    position), so the position-basis states are never written - neither the 68.7 GB list nor a tile of it."""
+    converted = states.with_state_basis(position) if isinstance(states, StateList) else None
+    if converted is None or not hasattr(converted, "cell_tiles") or getattr(converted, "_kind", "") != "position":
+        return None
+    if getattr(converted, "_device", None) is not None:
+        return None  # already materialised: plain read passes
+    nd = len(space.children)
+    if not all(_is_orthogonal_axis(space, a) for a in range(nd)):
+        return None
+    shape, repeat = converted.bloch_dims()
+    geom = [_axis_geometry(space, a) for a in range(nd)]
+    spacing = [g[1] for g in geom]
+    length = [g[2] for g in geom]
+    parts: dict[str, list[list[torch.Tensor]]] = {k: [[] for _ in range(nd)] for k in ("x", "periodic", "variance")}
+    scale = torch.tensor([ln / (2 * np.pi) for ln in length], dtype=torch.float64, device="cuda")
+    for _, tile in converted.cell_tiles():
+        mom = kernels.cell_fft_moments(shape, repeat, tile, spacing, length, stage=0)          # [rows, nd, 5]
+        centre = torch.remainder(torch.atan2(mom[:, :, 4], mom[:, :, 3]), 2 * np.pi) * scale[None, :]
+        mom2 = kernels.cell_fft_moments(shape, repeat, tile, spacing, length, stage=1,
+                                        offsets=(-centre).T.contiguous(), wrapped=True)
+        for axis in range(nd):
+            parts["x"][axis].append(mom[:, axis, 1] / mom[:, axis, 0])
+            parts["periodic"][axis].append(centre[:, axis])
+            parts["variance"][axis].append(mom2[:, axis, 2] / mom2[:, axis, 0])
+    return {k: [torch.cat(v[axis]) for axis in range(nd)] for k, v in parts.items()}
 
 
 def _momentum_data(states: Array, space: TupleMetadata) -> torch.Tensor:

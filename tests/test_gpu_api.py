@@ -867,8 +867,14 @@ def test_lazy_tiled_evolution_access_paths(cuda):
     super_dx = vectors * np.array(repeat)[:, None]
     np.testing.assert_allclose(x_lazy, o.measure_all_x(want["position"], super_dx, big, 0), atol=1e-9)
     np.testing.assert_allclose(w_lazy, o.measure_all_coherent_width(want["position"], super_dx, big, 1), atol=1e-8)
+    np.testing.assert_allclose(operator.measure.all_variance_x(evolution, axis=0).raw_data,
+                               o.measure_all_variance_x(want["position"], super_dx, big, 0), atol=1e-8)
+    np.testing.assert_allclose(operator.measure.all_periodic_x(evolution, axis=1).raw_data,
+                               o.measure_all_periodic_x(want["position"], super_dx, big, 1), atol=1e-9)
     np.testing.assert_allclose(lazy.raw_data.reshape(n_t, -1), want["position"], atol=1e-9)  # materialises
-    np.testing.assert_allclose(operator.measure.all_x(lazy, axis=0).raw_data, x_lazy, atol=1e-12)
+    # a materialised list takes the plain read passes: same numbers as the fused (never written) route above
+    np.testing.assert_allclose(operator.measure.all_x(lazy, axis=0).raw_data, x_lazy, atol=1e-10)
+    np.testing.assert_allclose(operator.measure.all_coherent_width(lazy, axis=1).raw_data, w_lazy, atol=1e-9)
     # momentum and Bloch bases
     momentum_basis = basis.transformed_from_metadata(position_basis.metadata()).upcast()
     in_k = evolution.with_state_basis(momentum_basis)

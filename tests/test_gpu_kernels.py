@@ -932,3 +932,37 @@ def test_round_robin_pairs_cover_every_pair_once():
         for r in rounds:  # disjoint within a round
             flat = [x for p in r for x in p]
             assert sorted(flat) == list(range(nb))
+
+
+@pytest.mark.parametrize(("shape", "repeat"), [((6,), (10,)), ((4, 3), (4, 6)), ((4, 4), (8, 8)), ((3, 2, 2), (2, 3, 4)),
+                                                ((7, 7, 7), (2, 2, 2))])
+def test_cell_fft_moments_fused_equals_cell_fft_then_measure(cuda, shape, repeat):
+    """sqb_cell_fft_moments (K6 fused into the last cell-FFT pass, the position-basis states are never written)
+    against sqb_cell_fft + sqb_measure_moments and against the oracle, for every axis, with and without per-state
+    offsets and wrapping (the variance pass re-reduces the SAME tile: stage 1)."""
+    torch, kernels = _gpu()
+    nd = len(shape)
+    rng = np.random.default_rng(77)
+    big = tuple(n * r for n, r in zip(shape, repeat))
+    m = int(np.prod(big))
+    lead = 5
+    cell_np = rng.normal(size=(lead, m)) + 1j * rng.normal(size=(lead, m))
+    lengths = [2 * np.pi * r * (1.0 + 0.25 * a) for a, r in enumerate(repeat)]
+    spacing = [ln / g for ln, g in zip(lengths, big)]
+    pos = kernels.cell_fft(shape, repeat, kernels.to_device(cell_np, torch.complex128), 1)
+    offsets_np = rng.uniform(-3, 3, size=(nd, lead))
+    offsets = kernels.to_device(offsets_np, torch.float64)
+    tile = kernels.to_device(cell_np, torch.complex128)
+    fused0 = kernels.cell_fft_moments(shape, repeat, tile, spacing, lengths, stage=0).cpu().numpy()
+    fused1 = kernels.cell_fft_moments(shape, repeat, tile, spacing, lengths, stage=1, offsets=offsets, wrapped=True).cpu().numpy()
+    for axis in range(nd):
+        want0 = kernels.measure_moments(pos, big, axis, spacing[axis], lengths[axis]).cpu().numpy()
+        want1 = kernels.measure_moments(pos, big, axis, spacing[axis], lengths[axis], offsets[axis].contiguous(), True).cpu().numpy()
+        scale = np.abs(want0).max()
+        np.testing.assert_allclose(fused0[:, axis, :], want0, atol=1e-11 * scale)
+        np.testing.assert_allclose(fused1[:, axis, :3], want1[:, :3], atol=1e-11 * np.abs(want1).max())
+    # and the oracle: <x> along every axis of the position-basis states
+    pos_np = pos.cpu().numpy()
+    dx = np.diag(lengths)
+    for axis in range(nd):
+        np.testing.assert_allclose(fused0[:, axis, 1] / fused0[:, axis, 0], o.measure_all_x(pos_np, dx, big, axis), atol=1e-10)
