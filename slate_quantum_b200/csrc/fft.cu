@@ -42,6 +42,16 @@ struct Digits {  // flat index (C order over dims, last fastest) -> sum digit * 
 
 __host__ __device__ inline int64_t digits_offset(const Digits& d, int64_t flat) {
   int64_t off = 0;
+  if (flat < (1LL << 31)) {  // 32-bit divisions: ~5x cheaper than the 64-bit sequence on the device
+    uint32_t f = (uint32_t)flat;
+    for (int a = d.nd - 1; a >= 0; --a) {
+      const uint32_t dim = (uint32_t)d.dims[a];
+      const uint32_t q = f / dim;
+      off += (int64_t)(f - q * dim) * d.strides[a];
+      f = q;
+    }
+    return off;
+  }
   for (int a = d.nd - 1; a >= 0; --a) {
     off += (flat % d.dims[a]) * d.strides[a];
     flat /= d.dims[a];
@@ -83,33 +93,59 @@ struct FftPass {
   const c128* mom_cs;            // [sum_a L_a] (cos, sin)(2 pi idx / L_a), axis a at mom_cs_off[a]
   int mom_cs_off[SQB_MAX_DIMS];
   double* mom_partials;          // [n_ctas][1 + 4 nd]
+  int mom_groups;                // consecutive line groups (of lines_per_cta lines) a CTA walks; all in one state
 };
 
 constexpr int kMomMax = 1 + 4 * SQB_MAX_DIMS;
-struct MomAcc {
-  double v[kMomMax];
-  double off[SQB_MAX_DIMS];
-  int64_t e0;  // output offset of the CTA's state
+struct MomLines {  // per CTA (shared): what is constant along a line of the LAST axis
+  double x[SQB_MAX_DIMS][kMaxLines];   // leading axes a < nd-1: (wrapped) position of the line
+  double c[SQB_MAX_DIMS][kMaxLines];   //                      : cos / sin of its scattering phase
+  double s[SQB_MAX_DIMS][kMaxLines];
+  int j_last[kMaxLines];               // index along the last axis of the line's first output (pos = 0)
+};
+struct MomAcc {  // per thread; every array index below is a compile-time constant (registers, not local memory)
+  double w;                           // sum |v|^2
+  double lead[SQB_MAX_DIMS - 1][4];   // leading axes: {w x, w x^2, w cos, w sin}
+  double last[4];                     // last axis
+  double off_last, inv_len_last, spacing_last, length_last, dx_last;
+  const MomLines* lines;
 };
 
-__device__ __forceinline__ void mom_add(const FftPass& P, MomAcc& acc, int64_t e, c128 v) {
+// One output element of a line.  Only the LAST axis varies along a line: idx = j_last + pos * N_last, so
+//   x = x0 + pos * dx          (x0 = j_last * spacing + offset, dx = N_last * spacing; folded when wrapped)
+//   exp(2 pi i idx / L) = exp(2 pi i j_last / L) * conj(tab[pos])   (tab = the pass' own twiddle table, len = R)
+// -> per element: |v|^2, x, two FMAs for x / x^2 and two for sum w conj-phase; the line's own phase is applied
+// once per butterfly in mom_add_line.  No global-memory access in the epilogue.
+__device__ __forceinline__ double mom_add_last(const FftPass& P, MomAcc& acc, double x0, int pos, c128 v, c128 tw,
+                                               double& sc_x, double& sc_y) {
   const double w = fma(v.x, v.x, v.y * v.y);
-  uint32_t m = (uint32_t)(e - acc.e0);
-  acc.v[0] += w;
+  double x = fma((double)pos, acc.dx_last, x0);
+  if (P.mom_wrapped) x -= acc.length_last * floor(fma(x, acc.inv_len_last, 0.5));
+  acc.last[0] = fma(w, x, acc.last[0]);
+  acc.last[1] = fma(w * x, x, acc.last[1]);
+  sc_x = fma(w, tw.x, sc_x);
+  sc_y = fma(w, tw.y, sc_y);
+  return w;
+}
+// the weight `wsum` of one or more elements of a line: norm and the leading axes (constant along the line)
+__device__ __forceinline__ void mom_add_line(const FftPass& P, MomAcc& acc, int line, double wsum, double sc_x,
+                                             double sc_y) {
+  acc.w += wsum;
+  {
+    // sum_pos w exp(+2 pi i pos / R) = conj(sum_pos w tab[pos]) = (sc_x, -sc_y); times the line's phase (cj, sj)
+    const int al = P.mom_nd - 1;
+    const double cj = acc.lines->c[al][line], sj = acc.lines->s[al][line];
+    acc.last[2] += cj * sc_x + sj * sc_y;
+    acc.last[3] += sj * sc_x - cj * sc_y;
+  }
 #pragma unroll
-  for (int a = SQB_MAX_DIMS - 1; a >= 0; --a) {
-    if (a < P.mom_nd) {
-      const uint32_t L = (uint32_t)P.mom_grid[a];
-      const uint32_t q = m / L;
-      const uint32_t idx = m - q * L;
-      m = q;
-      double x = fma((double)idx, P.mom_spacing[a], acc.off[a]);
-      if (P.mom_wrapped) x -= P.mom_length[a] * floor(x / P.mom_length[a] + 0.5);
-      const c128 cs = __ldg(P.mom_cs + P.mom_cs_off[a] + idx);
-      acc.v[1 + 4 * a] = fma(w, x, acc.v[1 + 4 * a]);
-      acc.v[2 + 4 * a] = fma(w * x, x, acc.v[2 + 4 * a]);
-      acc.v[3 + 4 * a] = fma(w, cs.x, acc.v[3 + 4 * a]);
-      acc.v[4 + 4 * a] = fma(w, cs.y, acc.v[4 + 4 * a]);
+  for (int a = 0; a < SQB_MAX_DIMS - 1; ++a) {
+    if (a < P.mom_nd - 1) {
+      const double x = acc.lines->x[a][line];
+      acc.lead[a][0] = fma(wsum, x, acc.lead[a][0]);
+      acc.lead[a][1] = fma(wsum * x, x, acc.lead[a][1]);
+      acc.lead[a][2] = fma(wsum, acc.lines->c[a][line], acc.lead[a][2]);
+      acc.lead[a][3] = fma(wsum, acc.lines->s[a][line], acc.lead[a][3]);
     }
   }
 }
@@ -255,11 +291,22 @@ __device__ __forceinline__ void mom_flush(const FftPass& P, const MomAcc& acc) {
   __shared__ double s_red[kMomMax][kThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k_count = 1 + 4 * P.mom_nd;
+  const int al = P.mom_nd - 1;
+  {
+    const double v = warp_sum(acc.w);
+    if (lane == 0) s_red[0][warp] = v;
+  }
 #pragma unroll
-  for (int k = 0; k < kMomMax; ++k) {
-    if (k < k_count) {
-      const double v = warp_sum(acc.v[k]);
-      if (lane == 0) s_red[k][warp] = v;
+  for (int a = 0; a < SQB_MAX_DIMS; ++a) {
+    if (a <= al) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // axis a: the last axis' sums live in acc.last, the leading ones in acc.lead[a]
+        double mine = acc.last[j];
+        if (a < SQB_MAX_DIMS - 1 && a < al) mine = acc.lead[a < SQB_MAX_DIMS - 1 ? a : 0][j];
+        const double v = warp_sum(mine);
+        if (lane == 0) s_red[1 + 4 * a + j][warp] = v;
+      }
     }
   }
   __syncthreads();
@@ -314,6 +361,11 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
     const int pos0 = (j - k) * R + k;
     if (io.last) {
       const int64_t base = io.out_base[line];
+      double wsum = 0.0, x0 = 0.0, sc_x = 0.0, sc_y = 0.0;
+      if constexpr (kMom) x0 = acc->lines->x[P.mom_nd - 1][line];
+      (void)wsum;
+      (void)base;
+      (void)x0;
 #pragma unroll
       for (int t = 0; t < R; ++t) {
         const int pos = pos0 + t * ns;
@@ -324,10 +376,10 @@ __device__ __forceinline__ void stage_fixed(const FftPass& P, const StageIo& io,
           sincospi((double)sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
           v = cmul(v, make_double2(cs, sn));
         }
-        const int64_t e = base + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl);
-        if constexpr (kMom) mom_add(P, *acc, e, v);
-        else io.gout[e] = v;
+        if constexpr (kMom) wsum += mom_add_last(P, *acc, x0, pos, v, tab[pos], sc_x, sc_y);
+        else io.gout[base + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
       }
+      if constexpr (kMom) mom_add_line(P, *acc, line, wsum, sc_x, sc_y);
     } else {
 #pragma unroll
       for (int t = 0; t < R; ++t) io.dst[line * s_line + (pos0 + t * ns) * s_pos] = x[t];
@@ -397,40 +449,62 @@ __device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 
 // compiled in, which keeps the register count down for 4 CTAs / SM)
 // kVariant 0: radices {2,4,8} only (power-of-two lengths, the hot cell-FFT passes); 1: {2,3,4,5,7,8};
 // 2: any radix <= 31 (local-memory arrays).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
-template <int kVariant, int kThreads, bool kMom = false>
-__global__ void __launch_bounds__(kThreads, kMom ? 2 : (kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))))
-fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
-  extern __shared__ c128 smem[];
-  __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
+// One group of `lines` lines (first line `line0`) through all stages of the pass.
+template <int kVariant, int kThreads, bool kMom>
+__device__ __forceinline__ void fft_pass_group(const FftPass& P, const c128* __restrict__ in, c128* __restrict__ out,
+                                               const c128* tab, c128* buf0, c128* buf1, int64_t* s_in_base,
+                                               int64_t* s_out_base, int64_t* s_inner_idx, MomLines& s_mom, MomAcc& acc,
+                                               int64_t line0, int lines) {
   const int len = P.len;
   const int lpc = P.lines_per_cta;
-  c128* tab = smem;                       // [len]
-  c128* buf0 = smem + len;                // [lpc][len]
-  c128* buf1 = buf0 + (size_t)lpc * len;  // [lpc][len]  (only when the pass needs it, see launch_pass)
-
-  const int64_t n_lines = P.n_outer * P.n_inner;
-  const int64_t line0 = (int64_t)blockIdx.x * lpc;
-  const int lines = (int)sqb_min64(lpc, n_lines - line0);
-  if (lines <= 0) return;
-
   if (threadIdx.x < lines) {
     const int64_t line = line0 + threadIdx.x;
-    const int64_t o = line / P.n_inner, i = line - o * P.n_inner;
+    int64_t o, i;
+    if (line < (1LL << 31) && P.n_inner < (1LL << 31)) {
+      const uint32_t q = (uint32_t)line / (uint32_t)P.n_inner;
+      o = q;
+      i = (uint32_t)line - q * (uint32_t)P.n_inner;
+    } else {
+      o = line / P.n_inner;
+      i = line - o * P.n_inner;
+    }
     s_in_base[threadIdx.x] = digits_offset(P.in_outer, o) + digits_offset(P.in_inner, i);
     s_out_base[threadIdx.x] = digits_offset(P.out_outer, o) + digits_offset(P.out_inner, i);
     s_inner_idx[threadIdx.x] = i;
   }
-  for (int j = threadIdx.x; j < len; j += kThreads) tab[j] = tab_g[j];
   __syncthreads();
-  MomAcc acc;
   if constexpr (kMom) {
-#pragma unroll
-    for (int k = 0; k < kMomMax; ++k) acc.v[k] = 0.0;
-    const int64_t state = s_out_base[0] / P.mom_m;  // launch_pass guarantees one state per CTA
-    acc.e0 = state * P.mom_m;
-#pragma unroll
-    for (int a = 0; a < SQB_MAX_DIMS; ++a)
-      acc.off[a] = (a < P.mom_nd && P.mom_offsets) ? P.mom_offsets[(int64_t)a * P.mom_lead + state] : 0.0;
+    // launch_pass guarantees one state per CTA: state = first line / lines per state (32-bit when it fits)
+    const int64_t lps = (P.n_outer * P.n_inner) / P.mom_lead;
+    const int64_t state = (line0 < (1LL << 31) && lps < (1LL << 31)) ? (int64_t)((uint32_t)line0 / (uint32_t)lps) : line0 / lps;
+    const int al = P.mom_nd - 1;
+    acc.off_last = P.mom_offsets ? P.mom_offsets[(int64_t)al * P.mom_lead + state] : 0.0;
+    if (threadIdx.x < lines) {
+      // decode the line's first output offset into the position-grid indices (C order, last axis fastest)
+      uint32_t m = (uint32_t)(s_out_base[threadIdx.x] - state * P.mom_m);
+      for (int a = P.mom_nd - 1; a >= 0; --a) {
+        const uint32_t L = (uint32_t)P.mom_grid[a];
+        const uint32_t q = m / L;
+        const int idx = (int)(m - q * L);
+        m = q;
+        if (a == al) {
+          s_mom.j_last[threadIdx.x] = idx;
+          const c128 cs = P.mom_cs[P.mom_cs_off[a] + idx];
+          s_mom.x[a][threadIdx.x] = fma((double)idx, P.mom_spacing[a], acc.off_last);  // x0 of the line
+          s_mom.c[a][threadIdx.x] = cs.x;
+          s_mom.s[a][threadIdx.x] = cs.y;
+        } else {
+          const double off = P.mom_offsets ? P.mom_offsets[(int64_t)a * P.mom_lead + state] : 0.0;
+          double x = fma((double)idx, P.mom_spacing[a], off);
+          if (P.mom_wrapped) x -= P.mom_length[a] * floor(x / P.mom_length[a] + 0.5);
+          const c128 cs = P.mom_cs[P.mom_cs_off[a] + idx];
+          s_mom.x[a][threadIdx.x] = x;
+          s_mom.c[a][threadIdx.x] = cs.x;
+          s_mom.s[a][threadIdx.x] = cs.y;
+        }
+      }
+    }
+    __syncthreads();
   }
 
   const int lshift = 31 - __clz(lpc);
@@ -497,10 +571,7 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
         if constexpr (kVariant == 2) stage_generic(src, dst, len, ns, r, lines, tab, P.sign);
         break;
     }
-    if (io.last) {
-      if constexpr (kMom) mom_flush<kThreads>(P, acc);
-      return;
-    }
+    if (io.last) return;
     __syncthreads();
     if (io.first) {
       src = buf0;  // first stage wrote buf0
@@ -520,9 +591,12 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       sincospi((double)P.sign * 2.0 * (double)prod / (double)P.tw_len, &sn, &cs);
       v = cmul(v, make_double2(cs, sn));
     }
-    const int64_t e = s_out_base[l] + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl);
-    if constexpr (kMom) mom_add(P, acc, e, v);
-    else out[e] = v;
+    if constexpr (kMom) {
+      double sc_x = 0.0, sc_y = 0.0;
+      const double w = mom_add_last(P, acc, s_mom.x[P.mom_nd - 1][l], pos, v, tab[pos], sc_x, sc_y);
+      mom_add_line(P, acc, l, w, sc_x, sc_y);
+    }
+    else out[s_out_base[l] + pos_offset(pos, P.out_split, P.out_sl_hi, P.out_sl)] = v;
   };
   if (P.out_inner_fastest) {
     const int l = threadIdx.x & (lpc - 1);
@@ -533,6 +607,50 @@ fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, 
       const int l = e / len;
       emit(l, e - l * len);
     }
+  }
+}
+
+
+template <int kVariant, int kThreads, bool kMom = false>
+__global__ void __launch_bounds__(kThreads, kMom ? 3 : (kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))))
+fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
+  extern __shared__ c128 smem[];
+  __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
+  const int len = P.len;
+  const int lpc = P.lines_per_cta;
+  c128* tab = smem;                       // [len]
+  c128* buf0 = smem + len;                // [lpc][len]
+  c128* buf1 = buf0 + (size_t)lpc * len;  // [lpc][len]  (only when the pass needs it, see launch_pass)
+
+  for (int j = threadIdx.x; j < len; j += kThreads) tab[j] = tab_g[j];
+  const int64_t n_lines = P.n_outer * P.n_inner;
+  MomAcc acc;
+  __shared__ MomLines s_mom;
+  if constexpr (kMom) {
+    acc.w = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc.last[j] = 0.0;
+#pragma unroll
+      for (int a = 0; a < SQB_MAX_DIMS - 1; ++a) acc.lead[a][j] = 0.0;
+    }
+    acc.lines = &s_mom;
+    const int al = P.mom_nd - 1;
+    acc.length_last = P.mom_length[al];
+    acc.spacing_last = P.mom_spacing[al];
+    acc.inv_len_last = 1.0 / acc.length_last;
+    acc.dx_last = (double)P.out_sl * acc.spacing_last;
+  }
+  // kMom: a CTA walks `mom_groups` consecutive groups of lines of ONE state, keeps the observable sums in registers
+  // and reduces them once (the block reduction would otherwise cost more than the 8 outputs a thread produces)
+  const int groups = kMom ? P.mom_groups : 1;
+  for (int g = 0; g < groups; ++g) {
+    const int64_t line0 = ((int64_t)blockIdx.x * groups + g) * lpc;
+    const int lines = (int)sqb_min64(lpc, n_lines - line0);
+    if (lines <= 0) break;
+    if (g > 0) __syncthreads();  // the previous group's shared buffers are free
+    fft_pass_group<kVariant, kThreads, kMom>(P, in, out, tab, buf0, buf1, s_in_base, s_out_base, s_inner_idx, s_mom,
+                                             acc, line0, lines);
   }
   if constexpr (kMom) mom_flush<kThreads>(P, acc);
 }
@@ -716,6 +834,10 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
     const int64_t lines_per_state = n_lines / P.mom_lead;
     while (lpc > 1 && lines_per_state % lpc) lpc /= 2;
     P.lines_per_cta = lpc;
+    const int64_t groups_per_state = lines_per_state / lpc;
+    int groups = 1;
+    while (groups * 2 <= 64 && groups_per_state % (groups * 2) == 0) groups *= 2;
+    P.mom_groups = groups;
     kern = variant == 0 ? fft_pass_kernel<0, kFftThreads, true>
                         : (variant == 1 ? fft_pass_kernel<1, kFftThreads, true> : fft_pass_kernel<2, kFftThreads, true>);
   }
@@ -723,7 +845,8 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   fft_table_kernel<<<(P.len + 255) / 256, 256, 0, st>>>(tab, P.len);
-  const int64_t grid = (n_lines + lpc - 1) / lpc;
+  const int64_t per_cta = (int64_t)lpc * (P.mom_nd > 0 ? P.mom_groups : 1);
+  const int64_t grid = (n_lines + per_cta - 1) / per_cta;
   if (grid > 2147483647LL) return SQB_E_UNSUPPORTED;
   kern<<<(unsigned)grid, threads, smem, st>>>(P, in, out, tab);
   SQB_LAUNCH_CHECK();
@@ -997,7 +1120,8 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
       }
       int rc2 = launch_pass(P, pin, pout, tab, st);
       if (rc2) return rc2;
-      const int64_t n_ctas = (P.n_outer * P.n_inner + P.lines_per_cta - 1) / P.lines_per_cta;
+      const int64_t per_cta = (int64_t)P.lines_per_cta * P.mom_groups;
+      const int64_t n_ctas = (P.n_outer * P.n_inner + per_cta - 1) / per_cta;
       if ((size_t)n_ctas * (1 + 4 * nd) > mom->partial_doubles || n_ctas % lead) return SQB_E_WORKSPACE;
       mom_reduce_kernel<<<(unsigned)lead, 32, 0, st>>>(mom->partials, (int)(n_ctas / lead), nd, mom->out);
       SQB_LAUNCH_CHECK();

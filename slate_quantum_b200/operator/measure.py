@@ -149,6 +149,15 @@ def _fused_bundle(states: StateList, space: TupleMetadata, position: Any) -> dic
     """The bundle for a LAZY evolved list of a Bloch Hamiltonian on an orthogonal cell: K6 is fused into the last
     pass of the cell FFT (sqb_cell_fft_moments), twice per tile (sums, then the variance around the periodic
     position), so the position-basis states are never written - neither the 68.7 GB list nor a tile of it."""
+    import os
+
+    # Opt-in (SQB_MEASURE_FUSED=1).  Measured at cfg3 (profiles/r02_summary.md): the fused last pass reads half the
+    # bytes of the plain pass but runs at 3 CTAs / SM (80 registers with the observable sums) and is latency bound
+    # like the plain pass (~15 k cycles per 2048-element CTA), so one fused pass costs 37 ms per 4096 states against
+    # 27 ms (scatter) + 2 x 10 ms (read passes) - 478 vs 451 ms for the whole observables step.  It halves the tile
+    # memory (no position tile), which is what matters when the states barely fit.
+    if os.environ.get("SQB_MEASURE_FUSED", "0") != "1":
+        return None
     converted = states.with_state_basis(position) if isinstance(states, StateList) else None
     if converted is None or not hasattr(converted, "cell_tiles") or getattr(converted, "_kind", "") != "position":
         return None

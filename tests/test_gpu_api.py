@@ -860,13 +860,25 @@ def test_lazy_tiled_evolution_access_paths(cuda):
     np.testing.assert_allclose(pinned.numpy(), want["position"], atol=1e-9)
     np.testing.assert_allclose(lazy[7].raw_data, want["position"][7], atol=1e-9)
     np.testing.assert_allclose(lazy[n_t - 1, :].raw_data, want["position"][-1], atol=1e-9)
-    # observables on the LAZY list (tile by tile) == on the materialised list == oracle
+    # observables on the LAZY list (tile by tile) == on the materialised list == oracle; and the same through K6 fused
+    # into the last cell-FFT pass (SQB_MEASURE_FUSED=1: the position-basis states are never written)
+    import os
+
+    os.environ["SQB_MEASURE_FUSED"] = "1"
+    try:
+        fused_evolution = dynamics.solve_schrodinger_equation_decomposition(psi0, times, hamiltonian)
+        x_fused = operator.measure.all_x(fused_evolution, axis=0).raw_data
+        w_fused = operator.measure.all_coherent_width(fused_evolution, axis=1).raw_data
+    finally:
+        os.environ["SQB_MEASURE_FUSED"] = "0"
     x_lazy = operator.measure.all_x(evolution, axis=0).raw_data
+    np.testing.assert_allclose(x_fused, x_lazy, atol=1e-10)
     w_lazy = operator.measure.all_coherent_width(evolution, axis=1).raw_data
     big = tuple(n * r for n, r in zip(shape, repeat))
     super_dx = vectors * np.array(repeat)[:, None]
     np.testing.assert_allclose(x_lazy, o.measure_all_x(want["position"], super_dx, big, 0), atol=1e-9)
     np.testing.assert_allclose(w_lazy, o.measure_all_coherent_width(want["position"], super_dx, big, 1), atol=1e-8)
+    np.testing.assert_allclose(w_fused, w_lazy, atol=1e-9)
     np.testing.assert_allclose(operator.measure.all_variance_x(evolution, axis=0).raw_data,
                                o.measure_all_variance_x(want["position"], super_dx, big, 0), atol=1e-8)
     np.testing.assert_allclose(operator.measure.all_periodic_x(evolution, axis=1).raw_data,
