@@ -33,6 +33,8 @@ namespace {
 #ifdef SQB_PANEL_PROFILE
 // developer build only (nvcc -DSQB_PANEL_PROFILE): cycles of block 0 per phase, printed by the launcher
 __device__ unsigned long long pn_prof[16];
+__device__ unsigned long long pn_prof2[4];
+__device__ unsigned long long pn_prof3[32];  // per warp: cycles inside the units / whole of phase (b)
 #define PN_TICK(slot)                                          \
   do {                                                         \
     if (blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -55,6 +57,17 @@ constexpr int kPnCtasPerSm = 256 / kPnThreads;
 constexpr int kPnWarps = kPnThreads / 32;
 constexpr unsigned kPnFull = 0xffffffffu;
 constexpr int kPnMaxN = 512;
+// cost model of the matrix-vector product's work list, in quarter-kilocycles (see phase (b))
+#ifndef SQB_PN_W_SF
+#define SQB_PN_W_SF 4   // streamed full unit
+#define SQB_PN_W_SD 4   // streamed diagonal unit
+#define SQB_PN_W_RF 4   // resident full unit
+#define SQB_PN_W_RD 4   // resident diagonal unit
+#define SQB_PN_W_DOT 1  // one correction dot product
+#endif
+constexpr int kPnWDot = SQB_PN_W_DOT;
+__device__ __forceinline__ int pn_wfull(bool resident) { return resident ? SQB_PN_W_RF : SQB_PN_W_SF; }
+__device__ __forceinline__ int pn_wdiag(bool resident) { return resident ? SQB_PN_W_RD : SQB_PN_W_SD; }
 
 __device__ __forceinline__ void pn_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -220,6 +233,61 @@ __device__ __forceinline__ c128 pn_unit(int n, int lo, int r0, int c0, int lane,
   return y[0];
 }
 
+// Off-diagonal unit (all rows > all columns): NO per-element predicates.  Addresses are clamped into the live part
+// of the matrix (columns to [lo, n), rows to < n; a clamped lane re-reads an element another lane needs, so no extra
+// traffic) and the masking rides on v: vn[c] is zero for c < lo and for the padding rows >= n (index clamped to n8,
+// a padding entry), so dead columns add nothing to y, dead rows nothing to z, and the sums a dead lane accumulates
+// are never stored.  Unconditional volatile loads: no destination zeroing, no predicate set-up (~half the
+// instructions of the predicated unit, which matters with two warps per scheduler).
+__device__ __forceinline__ c128 pn_ldg_u(const c128* p) {
+  c128 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ c128 pn_lds_u(const c128* p) {
+  c128 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+template <bool RES>
+__device__ __forceinline__ c128 pn_unit_full(int n, int n8, int lo, int r0, int c0, int lane,
+                                             const c128* __restrict__ vn, const c128* res, const int* cbase,
+                                             const c128* A, c128 (&z)[8]) {
+  const int li = lane & 7, lj = lane >> 3;
+  const int rb = r0 + li;
+  int roff[4];
+#pragma unroll
+  for (int rho = 0; rho < 4; ++rho) roff[rho] = min(rb + 8 * rho, n - 1);
+  c128 a[8][4];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int cc = min(max(c0 + lj + 4 * q, lo), n - 1);
+    const c128* colp = RES ? res + cbase[cc] : A + (int64_t)cc * n;
+#pragma unroll
+    for (int rho = 0; rho < 4; ++rho) a[q][rho] = RES ? pn_lds_u(colp + roff[rho]) : pn_ldg_u(colp + roff[rho]);
+  }
+  c128 vr[4], y[4];
+#pragma unroll
+  for (int rho = 0; rho < 4; ++rho) {
+    vr[rho] = vn[min(rb + 8 * rho, n8)];
+    y[rho] = make_double2(0.0, 0.0);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const c128 vc = vn[min(c0 + lj + 4 * q, n8)];
+#pragma unroll
+    for (int rho = 0; rho < 4; ++rho) {
+      cfma(y[rho], a[q][rho], vc);
+      cfmac(z[q], a[q][rho], vr[rho]);
+    }
+  }
+  const bool b3 = (lane >> 3) & 1, b4 = (lane >> 4) & 1;
+  pn_xchg(y[0], y[2], b3, 8);
+  pn_xchg(y[1], y[3], b3, 8);
+  pn_xchg(y[0], y[1], b4, 16);
+  return y[0];
+}
+
 template <int NB, int NR>
 __global__ void __launch_bounds__(kPnThreads, kPnCtasPerSm)
 tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restrict__ d_all, double* __restrict__ e_all,
@@ -268,6 +336,14 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
   long long pn_t0__ = clock64();
 #endif
   PN_TICK(0);
+#if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
+  long long pb_setup = 0, pb_flush = 0, pb_dots = 0, pb_units = 0, pb_t = 0, pb_count = 0;
+#define PB_START() pb_t = clock64()
+#define PB_ADD(var) do { const long long n__ = clock64(); var += n__ - pb_t; pb_t = n__; } while (0)
+#else
+#define PB_START() do {} while (0)
+#define PB_ADD(var) do {} while (0)
+#endif
   // column phases: thread t owns rows t + kPnThreads * s, s < NR  (n <= NR * kPnThreads)
   c128 a_pref[NR];
 #pragma unroll
@@ -354,6 +430,7 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
 
       // ---------------- (b) p = A22 v from the panel-start matrix (read only) + the correction dot products
       {
+        PB_START();
         // next column of the panel for phase (a) of the next step (rows >= lo; hidden behind the units below)
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
@@ -366,13 +443,20 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
         for (int x = (lo & ~31) + lane; x < n8; x += 32) part_w[x] = make_double2(0.0, 0.0);
         __syncwarp();
         const int X0 = lo >> 5;
-        const int T = RC - X0;
-        const int total = T * T;  // half-units: diagonal unit = 1, full unit = 2
-        // this warp's contiguous range of the column-major unit list, in half-units
-        const int w_lo = (warp * total + kPnWarps - 1) / kPnWarps, w_hi = ((warp + 1) * total + kPnWarps - 1) / kPnWarps;
+        // Units are dealt to the warps as contiguous ranges of the column-major unit list, by COST: a unit is
+        // latency bound, not flop bound, so a diagonal unit costs as much as a full one (clock64, N = 256: streamed
+        // full 2.5 k cycles, streamed diagonal 2.8 k, resident full 1.5 k, resident diagonal 1.9 k, one correction
+        // dot product ~0.5 k); the 2 jj correction dot products are the tail of the same list.
+        int W = 0;
+        for (int Cb = X0; Cb < RC; ++Cb) W += pn_wdiag(Cb * 32 >= jres) + (RC - Cb - 1) * pn_wfull(Cb * 32 >= jres);
+        const int W_units = W;
+        W += 2 * jj * kPnWDot;
+        const int w_lo = (warp * W + kPnWarps - 1) / kPnWarps, w_hi = ((warp + 1) * W + kPnWarps - 1) / kPnWarps;
         int pos = 0;
+        PB_ADD(pb_setup);
         for (int Cb = X0; Cb < RC && pos < w_hi; ++Cb) {
-          const int strip = 2 * (RC - Cb) - 1;
+          const int wd = pn_wdiag(Cb * 32 >= jres), wf = pn_wfull(Cb * 32 >= jres);
+          const int strip = wd + (RC - Cb - 1) * wf;
           if (pos + strip <= w_lo) {
             pos += strip;
             continue;
@@ -382,38 +466,35 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
           c128 z[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) z[q] = make_double2(0.0, 0.0);
-          // first unit of the strip whose start position is >= w_lo: position of unit Rc = pos + (Rc == Cb ? 0 : 2 (Rc - Cb) - 1)
-          int Rc = Cb;
+          // first unit of the strip whose start position is >= w_lo: unit Rc starts at pos (Rc == Cb) or at
+          // pos + wd + (Rc - Cb - 1) wf
+          int Rc = Cb, start = pos;
           if (pos < w_lo) {
-            Rc = Cb + (w_lo - pos + 2) / 2;  // smallest Rc > Cb with pos + 2 (Rc - Cb) - 1 >= w_lo
-            pos += 2 * (Rc - Cb) - 1;
+            const int k = max(0, (w_lo - pos - wd + wf - 1) / wf);
+            Rc = Cb + 1 + k;
+            start = pos + wd + k * wf;
           }
-          for (; Rc < RC && pos < w_hi; ++Rc) {
-            pos += (Rc == Cb) ? 1 : 2;
+          pos += strip;
+          for (; Rc < RC && start < w_hi; ++Rc) {
+            start += (Rc == Cb) ? wd : wf;
             open = true;
-            c128 y;
 #if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
-            const long long u0__ = clock64();
+            ++pb_count;
 #endif
+            c128 y;
             const int r0 = Rc * 32;
             if (c0 >= jres) {
               if (Rc == Cb) y = pn_unit<true, true>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
-              else y = pn_unit<true, false>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
+              else y = pn_unit_full<true>(n, n8, lo, r0, c0, lane, vn, res, cbase, A, z);
             } else {
               if (Rc == Cb) y = pn_unit<false, true>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
-              else y = pn_unit<false, false>(n, lo, r0, c0, lane, vn, res, cbase, A, z);
+              else y = pn_unit_full<false>(n, n8, lo, r0, c0, lane, vn, res, cbase, A, z);
             }
-#if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-              const int slot = (c0 >= jres ? 8 : 6) + (Rc == Cb ? 1 : 0);
-              pn_prof[slot] += (unsigned long long)(clock64() - u0__);
-              pn_prof[slot + 4] += 1;
-            }
-#endif
             const int rr = Rc * 32 + (lane & 7) + 8 * (((lane >> 3) & 1) * 2 + ((lane >> 4) & 1));
             if (rr < n) part_w[rr] = cadd(part_w[rr], y);
             __syncwarp();
           }
+          PB_ADD(pb_units);
           if (open) {
             // z: 8 values per lane, summed over the 8 row lanes li (lane bits 0, 1, 2) -> one column per lane
             const bool b0 = lane & 1, b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1;
@@ -428,9 +509,13 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
             if (c < n) part_w[c] = cadd(part_w[c], z[0]);
             __syncwarp();
           }
+          PB_ADD(pb_flush);
         }
+        PB_ADD(pb_units);
         // correction dot products: tmp1[k] = W_k^H v, tmp2[k] = V_k^H v over rows >= lo
-        for (int q = kPnWarps - 1 - warp; q < 2 * jj; q += kPnWarps) {
+        for (int q = 0; q < 2 * jj; ++q) {
+          const int start = W_units + q * kPnWDot;
+          if (start < w_lo || start >= w_hi) continue;
           const int k = q >> 1;
           const c128* P = (q & 1) ? Vp + k * ldp : Wp + k * ldp;
           c128 acc = make_double2(0.0, 0.0);
@@ -439,6 +524,7 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
           acc.y = warp_sum(acc.y);
           if (lane == 0) ((q & 1) ? tmp2 : tmp1)[k] = acc;
         }
+        PB_ADD(pb_dots);
       }
       PN_TICK(2);
       __syncthreads();
@@ -501,6 +587,26 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
               cre[s2][t4][0] = cre[s2][t4][1] = 0.0;
               cim[s2][t4][0] = cim[s2][t4][1] = 0.0;
             }
+          // the C tile is fetched BEFORE the MMA loop (predicated volatile loads keep their place in the instruction
+          // stream), so its L2 / shared-memory latency hides behind the 128 DMMAs instead of following them
+          c128 cpre[2][4][2];
+          c128* ccol[2];
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int c = c0 + 8 * s2 + g;
+            const bool cok = c >= t0 && c < n;
+            const bool resident = c0 + 8 * s2 >= jres;
+            const int cc = min(c, n - 1);
+            ccol[s2] = resident ? res + cbase[cc] : A + (int64_t)cc * n;
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int rr = r0 + 8 * t4 + 2 * q + e;
+                const bool ok = cok && rr >= c && rr < n;
+                cpre[s2][t4][e] = resident ? pn_lds(ccol[s2] + rr, ok) : pn_ldg(ccol[s2] + rr, ok);
+              }
+          }
 #pragma unroll
           for (int kc = 0; kc < (2 * NB) / 4; ++kc) {
             // L = [V W] (row side), R = [W V] (column side)
@@ -534,17 +640,16 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
           for (int s2 = 0; s2 < 2; ++s2) {
             const int c = c0 + 8 * s2 + g;
             if (c < t0 || c >= n) continue;
-            c128* colp = (c0 + 8 * s2 >= jres) ? res + cbase[c] : A + (int64_t)c * n;
 #pragma unroll
             for (int t4 = 0; t4 < 4; ++t4) {
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int rr = r0 + 8 * t4 + 2 * q + e;
                 if (rr >= c && rr < n) {
-                  c128 a = colp[rr];
+                  c128 a = cpre[s2][t4][e];
                   a.x -= cre[s2][t4][e];
                   a.y -= cim[s2][t4][e];
-                  colp[rr] = a;
+                  ccol[s2][rr] = a;
                 }
               }
             }
@@ -555,6 +660,21 @@ tridiag_panel_kernel(int n, int jres, c128* __restrict__ A_all, double* __restri
     __syncthreads();
     PN_TICK(5);
   }
+#if defined(SQB_PANEL_PROFILE) && SQB_PANEL_PROFILE > 1
+  if (blockIdx.x == 0 && tid == 0) {
+    pn_prof[14] += (unsigned long long)pb_setup;
+    pn_prof[15] += (unsigned long long)pb_flush;
+    pn_prof[4 + 8] += 0;
+    pn_prof[3] += 0;
+    atomicAdd(&pn_prof2[0], (unsigned long long)pb_units);
+    atomicAdd(&pn_prof2[1], (unsigned long long)pb_dots);
+  }
+  if (blockIdx.x == 0 && lane == 0) {
+    pn_prof3[warp] += (unsigned long long)pb_units;
+    pn_prof3[8 + warp] += (unsigned long long)(pb_setup + pb_flush + pb_dots);
+    pn_prof3[16 + warp] += (unsigned long long)pb_count;
+  }
+#endif
   if (tid == 0) {
     const int l = n - 1;
     const c128 a = l >= jres ? res[cbase[l] + l] : A[(int64_t)l * n + l];
@@ -598,6 +718,19 @@ int launch_tridiag_panel(int n, int64_t count, c128* A, double* d, double* e, c1
             NB, n, jres, smem, h[0], h[1], h[2], h[3], h[4], h[5]);
     fprintf(stderr, "   warp 0 units: streamed full %llu x %llu cyc, streamed diag %llu x %llu, resident full %llu x %llu, resident diag %llu x %llu\n",
             h[10], h[10] ? h[6] / h[10] : 0, h[11], h[11] ? h[7] / h[11] : 0, h[12], h[12] ? h[8] / h[12] : 0, h[13], h[13] ? h[9] / h[13] : 0);
+#if SQB_PANEL_PROFILE > 1
+    unsigned long long h2[4];
+    cudaMemcpyFromSymbol(h2, pn_prof2, sizeof(h2));
+    fprintf(stderr, "   warp 0 inside (b): setup %llu | units %llu | strip flush %llu | dots %llu\n", h[14], h2[0], h[15], h2[1]);
+    memset(h2, 0, sizeof(h2));
+    cudaMemcpyToSymbol(pn_prof2, h2, sizeof(h2));
+    unsigned long long h3[32];
+    cudaMemcpyFromSymbol(h3, pn_prof3, sizeof(h3));
+    for (int w = 0; w < kPnWarps; ++w)
+      fprintf(stderr, "   warp %d: %llu units, %llu cycles in units, %llu in set-up / flush / dots\n", w, h3[16 + w], h3[w], h3[8 + w]);
+    memset(h3, 0, sizeof(h3));
+    cudaMemcpyToSymbol(pn_prof3, h3, sizeof(h3));
+#endif
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(pn_prof, h, sizeof(h));
   }
