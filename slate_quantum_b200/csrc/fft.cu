@@ -232,6 +232,41 @@ __device__ __forceinline__ void dft_small<8>(c128* x, int sign, const c128*, int
   }
 }
 
+// 16 = 4 x 4 Cooley-Tukey in registers (t = 4 t1 + t2, k = k1 + 4 k2): four 4-point DFTs over t1, the twiddles
+// W16^(t2 k1), four 4-point DFTs over t2.  Lets 128- and 256-point lines run in TWO Stockham stages (one shared
+// round trip) instead of three.
+template <>
+__device__ __forceinline__ void dft_small<16>(c128* x, int sign, const c128*, int) {
+  const double c1 = 0.92387953251128674, s1 = 0.38268343236508977, h = 0.70710678118654752440;
+  const double sg = sign > 0 ? 1.0 : -1.0;
+  c128 y[4][4];  // y[t2][k1]
+#pragma unroll
+  for (int t2 = 0; t2 < 4; ++t2) {
+    c128 v[4] = {x[t2], x[4 + t2], x[8 + t2], x[12 + t2]};
+    dft_small<4>(v, sign, nullptr, 0);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) y[t2][k1] = v[k1];
+  }
+  const c128 w1 = make_double2(c1, sg * s1), w2 = make_double2(h, sg * h), w3 = make_double2(s1, sg * c1);
+  const c128 w6 = make_double2(-h, sg * h), w9 = make_double2(-c1, -sg * s1);
+  y[1][1] = cmul(y[1][1], w1);
+  y[1][2] = cmul(y[1][2], w2);
+  y[1][3] = cmul(y[1][3], w3);
+  y[2][1] = cmul(y[2][1], w2);
+  y[2][2] = mul_i_sign(y[2][2], sign);
+  y[2][3] = cmul(y[2][3], w6);
+  y[3][1] = cmul(y[3][1], w3);
+  y[3][2] = cmul(y[3][2], w6);
+  y[3][3] = cmul(y[3][3], w9);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    c128 v[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+    dft_small<4>(v, sign, nullptr, 0);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) x[k1 + 4 * k2] = v[k2];
+  }
+}
+
 // Generic small DFT of any radix r using the root table: roots[j] = exp(-2 pi i j / r).
 __device__ __forceinline__ void dft_generic(c128* x, int r, const c128* tab, int tab_stride, int sign) {
   c128 y[kMaxRadix];
@@ -443,12 +478,13 @@ __device__ __forceinline__ void stage_generic(const c128* src, c128* dst, int le
   }
 }
 
-__device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; }
+__device__ __forceinline__ bool radix_is_fixed(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16; }
 
 // kGeneric = false: every radix is one of {2,3,4,5,7,8} (the common case; no local-memory radix arrays are
 // compiled in, which keeps the register count down for 4 CTAs / SM)
 // kVariant 0: radices {2,4,8} only (power-of-two lengths, the hot cell-FFT passes); 1: {2,3,4,5,7,8};
-// 2: any radix <= 31 (local-memory arrays).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
+// 2: any radix <= 31 (local-memory arrays); 3: {2,4,8,16} (power-of-two lengths of 128 points and more: the radix-16
+// butterfly needs ~128 registers, two CTAs / SM).  Fewer compiled-in radices = fewer registers = more CTAs / SM.
 // One group of `lines` lines (first line `line0`) through all stages of the pass.
 template <int kVariant, int kThreads, bool kMom>
 __device__ __forceinline__ void fft_pass_group(const FftPass& P, const c128* __restrict__ in, c128* __restrict__ out,
@@ -561,12 +597,13 @@ __device__ __forceinline__ void fft_pass_group(const FftPass& P, const c128* __r
       continue;
     }
     switch (r) {
+      case 16: if constexpr (kVariant == 3) stage_fixed<16, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
       case 8: stage_fixed<8, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
       case 4: stage_fixed<4, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
       case 2: stage_fixed<2, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
-      case 3: if constexpr (kVariant >= 1) stage_fixed<3, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
-      case 5: if constexpr (kVariant >= 1) stage_fixed<5, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
-      case 7: if constexpr (kVariant >= 1) stage_fixed<7, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 3: if constexpr (kVariant == 1 || kVariant == 2) stage_fixed<3, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 5: if constexpr (kVariant == 1 || kVariant == 2) stage_fixed<5, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
+      case 7: if constexpr (kVariant == 1 || kVariant == 2) stage_fixed<7, kThreads, kMom>(P, io, ns, lines, tab, &acc); break;
       default:
         if constexpr (kVariant == 2) stage_generic(src, dst, len, ns, r, lines, tab, P.sign);
         break;
@@ -612,7 +649,7 @@ __device__ __forceinline__ void fft_pass_group(const FftPass& P, const c128* __r
 
 
 template <int kVariant, int kThreads, bool kMom = false>
-__global__ void __launch_bounds__(kThreads, kMom ? 3 : (kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2))))
+__global__ void __launch_bounds__(kThreads, kVariant == 3 ? 2 : (kMom ? 3 : (kThreads == kFftThreadsWide ? 2 : (kVariant == 0 ? 4 : (kVariant == 1 ? 3 : 2)))))
 fft_pass_kernel(FftPass P, const c128* __restrict__ in, c128* __restrict__ out, const c128* __restrict__ tab_g) {
   extern __shared__ c128 smem[];
   __shared__ int64_t s_in_base[kMaxLines], s_out_base[kMaxLines], s_inner_idx[kMaxLines];
@@ -728,8 +765,35 @@ fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int si
 }
 
 // ------------------------------------------------------------------------------------------ host side
-bool factorize(int len, int* radix, int* n_stages) {
+bool fft_radix16_on() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* v = getenv("SQB_FFT_RADIX16");
+    cached = (v && v[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+// allow16: power-of-two lengths may use radix-16 stages when that saves a stage (2^7, 2^8: two stages instead of
+// three; 2^10 .. 2^12: three instead of four); the fewest 16s that reach the minimum, 16s first.
+bool factorize(int len, int* radix, int* n_stages, bool allow16 = false) {
   int n = 0, rem = len;
+  if (allow16 && len >= 128 && (len & (len - 1)) == 0 && fft_radix16_on()) {
+    int k = 0;
+    while ((1 << k) < len) ++k;
+    int best16 = 0, best = (k + 2) / 3;
+    for (int n16 = 1; 4 * n16 <= k; ++n16) {
+      const int st = n16 + (k - 4 * n16 + 2) / 3;
+      if (st < best) {
+        best = st;
+        best16 = n16;
+      }
+    }
+    for (int q = 0; q < best16; ++q) {
+      radix[n++] = 16;
+      rem /= 16;
+    }
+  }
   while (rem % 8 == 0) { radix[n++] = 8; rem /= 8; if (n >= kMaxStages) return false; }
   while (rem % 4 == 0) { radix[n++] = 4; rem /= 4; if (n >= kMaxStages) return false; }
   while (rem % 2 == 0) { radix[n++] = 2; rem /= 2; if (n >= kMaxStages) return false; }
@@ -780,10 +844,10 @@ bool fft_inplace_on() {
 }
 
 int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t st) {
-  if (!factorize(P.len, P.radix, &P.n_stages)) return SQB_E_UNSUPPORTED;
+  if (!factorize(P.len, P.radix, &P.n_stages, P.mom_nd == 0)) return SQB_E_UNSUPPORTED;
   if (P.len > kMaxSmemLen) return SQB_E_UNSUPPORTED;
   // buffers: first fixed-radix stage reads global, last writes global -> S-1 shared round trips
-  auto fixed = [](int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8; };
+  auto fixed = [](int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16; };
   const bool copy_in = P.n_stages == 0 || !fixed(P.radix[0]);
   const bool copy_out = P.n_stages == 0 || !fixed(P.radix[P.n_stages - 1]);
   const int smem_writes = P.n_stages - 1 + (copy_in ? 1 : 0) + (copy_out ? 1 : 0);  // stages writing shared
@@ -808,6 +872,22 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
     if (!fixed(r)) variant = 2;
     else if ((r == 3 || r == 5 || r == 7) && variant < 1) variant = 1;
   }
+  if (P.radix[0] == 16) {
+    variant = 3;  // pure power of two (factorize): {16, 8, 4, 2} only
+    // two CTAs / SM (128 registers): up to 32 lines per CTA (64 KB) keep ~128 KB in flight per SM; measured on the
+    // position stage of the weak-scaling k-grids: 128 x 64 blocks 71.2 -> 63.5 ms, 256 x 64 69.7 -> 64.5 ms per rank step
+    static int lines16 = -1;
+    if (lines16 < 0) {
+      const char* v = getenv("SQB_FFT_LINES16");
+      lines16 = v ? atoi(v) : 32;
+    }
+    int want16 = lines16;
+    while (want16 > 1 && (size_t)want16 * P.len * n_buf * sizeof(c128) > 100 * 1024) want16 /= 2;
+    if ((P.inner_fastest || P.out_inner_fastest) && lpc < want16) {
+      lpc = want16;
+      while (lpc > 1 && lpc / 2 >= n_lines) lpc /= 2;
+    }
+  }
   // Long strided power-of-two lines with three stages (256, 512 points: the across-block cell FFT of an enlarged
   // k-grid): the two-buffer version can only take 8 / 4 adjacent lines (128 / 64 B runs).  Running the middle stage
   // in place on ONE buffer, with 512 threads so that every thread owns exactly one butterfly per stage, doubles
@@ -828,7 +908,8 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   P.lines_per_cta = lpc;
   auto* kern = P.inplace_mid ? fft_pass_kernel<0, kFftThreadsWide>
                              : (variant == 0 ? fft_pass_kernel<0, kFftThreads>
-                                             : (variant == 1 ? fft_pass_kernel<1, kFftThreads> : fft_pass_kernel<2, kFftThreads>));
+                                             : (variant == 1 ? fft_pass_kernel<1, kFftThreads>
+                                                             : (variant == 2 ? fft_pass_kernel<2, kFftThreads> : fft_pass_kernel<3, kFftThreads>)));
   if (P.mom_nd > 0) {
     // K6 epilogue: every CTA must stay inside one state (lines per state divisible by the lines per CTA)
     const int64_t lines_per_state = n_lines / P.mom_lead;

@@ -10,9 +10,19 @@ from __future__ import annotations
 import numpy as np
 
 
-def factorize(length: int) -> list[int]:
-    """launch_pass / factorize: 8s, then 4s, then 2s, then odd primes."""
+def factorize(length: int, allow16: bool = False) -> list[int]:
+    """launch_pass / factorize: 8s, then 4s, then 2s, then odd primes; with `allow16`, power-of-two lengths of 128
+    points and more lead with the fewest radix-16 stages that reach the minimum stage count."""
     out, rem = [], length
+    if allow16 and length >= 128 and length & (length - 1) == 0:
+        k = length.bit_length() - 1
+        best16, best = 0, (k + 2) // 3
+        for n16 in range(1, k // 4 + 1):
+            st = n16 + (k - 4 * n16 + 2) // 3
+            if st < best:
+                best, best16 = st, n16
+        out += [16] * best16
+        rem //= 16**best16
     for r in (8, 4, 2):
         while rem % r == 0:
             out.append(r)

@@ -770,7 +770,22 @@ def test_fft_axis_long_strided_lines(cuda, length, outer, inner, sign):
     np.testing.assert_allclose(got.reshape(x.shape), want, rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize(("shape", "repeat"), [((2, 2), (512, 3)), ((3,), (256,)), ((2, 2), (4, 512))])
+@pytest.mark.parametrize("length", [128, 256, 1024, 2048, 4096])
+@pytest.mark.parametrize(("outer", "inner"), [(2, 1), (1, 40), (3, 33)])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_fft_axis_radix16_lengths(cuda, length, outer, inner, sign):
+    """Power-of-two lines of 128 points and more lead with radix-16 stages (dft_small<16>: 128 = 16*8 and
+    256 = 16*16 in two stages, 1024 .. 4096 in three), contiguous lines and adjacent strided lines (up to 32 per CTA,
+    ragged counts included)."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(length + 5 * outer + inner)
+    x = _rand_c(rng, outer, length, inner)
+    got = kernels.fft_axis(kernels.to_device(x, torch.complex128), outer, length, inner, sign).cpu().numpy()
+    want = (np.fft.fft if sign < 0 else np.fft.ifft)(x, axis=1, norm="ortho")
+    np.testing.assert_allclose(got.reshape(x.shape), want, rtol=0, atol=2e-13)
+
+
+@pytest.mark.parametrize(("shape", "repeat"), [((2, 2), (512, 3)), ((3,), (256,)), ((2, 2), (4, 512)), ((2, 2), (128, 4))])
 def test_cell_fft_long_block_axis(cuda, shape, repeat):
     """cell FFT across 256 / 512 blocks (8-GPU weak-scaling k-grids) against the literal supercell chain."""
     torch, kernels = _gpu()
