@@ -764,6 +764,119 @@ fold_twiddle_kernel(SqbDims d, int n, int64_t block_begin, int64_t batch, int si
   }
 }
 
+// Fused fold (sqb_fold_transform) for small cells whose axes are single fixed radices (16 x 16, 8 x 8, 7 x 7 x 7, ...):
+// one pass over the eigenvectors instead of one FFT pass per axis plus the twiddle pass.  A CTA stages `rows`
+// eigenvector rows of one block in shared memory (the last axis padded by one element when its length is even, so
+// the register butterflies of that axis are bank-conflict free), transforms every axis in place - one thread per
+// line, the whole line in registers - and the pass of axis 0 multiplies by the ortho scale and the block's Bloch
+// twiddle and stores straight to global memory (runs of n / shape[0] contiguous elements).
+__device__ __forceinline__ void fold_dft(c128* x, int len, int sign, const c128* roots) {
+  switch (len) {
+    case 16: dft_small<16>(x, sign, roots, 1); break;
+    case 8: dft_small<8>(x, sign, roots, 1); break;
+    case 7: dft_small<7>(x, sign, roots, 1); break;
+    case 5: dft_small<5>(x, sign, roots, 1); break;
+    case 4: dft_small<4>(x, sign, roots, 1); break;
+    case 3: dft_small<3>(x, sign, roots, 1); break;
+    case 2: dft_small<2>(x, sign, roots, 1); break;
+    default: break;  // length 1
+  }
+}
+__global__ void __launch_bounds__(256, 2)
+fold_fused_kernel(SqbDims d, int n, int rows_per_cta, int64_t block_begin, const c128* __restrict__ in,
+                  c128* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char fold_smem[];
+  const int n_last = d.shape[d.nd - 1];
+  const int pad = (n_last & 1) ? 0 : 1;
+  const int row_stride = (n / n_last) * (n_last + pad);
+  c128* tw = reinterpret_cast<c128*>(fold_smem);  // [n] scale * Bloch twiddle
+  c128* roots = tw + n;                            // [nd][16] exp(-2 pi i j / shape[a])
+  c128* buf = roots + 16 * SQB_MAX_DIMS;           // [rows][row_stride]
+  const int64_t bl = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, n - r0);
+  const double scale = rsqrt((double)n);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int64_t b = block_begin + bl;
+    int jj = j;
+    double phase = 0.0;  // in turns
+    for (int a = d.nd - 1; a >= 0; --a) {
+      const int ja = jj % d.shape[a];
+      jj /= d.shape[a];
+      const int ba = (int)(b % d.repeat[a]);
+      b /= d.repeat[a];
+      const int qa = ba < (d.repeat[a] + 1) / 2 ? ba : ba - d.repeat[a];
+      const int64_t big = (int64_t)d.shape[a] * d.repeat[a];
+      phase += (double)(((int64_t)qa * ja) % big) / (double)big;
+    }
+    double sn, cs;
+    sincospi(2.0 * phase, &sn, &cs);
+    tw[j] = make_double2(cs * scale, sn * scale);
+  }
+  if (threadIdx.x < 16 * d.nd) {
+    const int a = threadIdx.x >> 4, j = threadIdx.x & 15;
+    double sn, cs;
+    sincospi(-2.0 * (double)j / (double)d.shape[a], &sn, &cs);
+    roots[threadIdx.x] = make_double2(cs, sn);
+  }
+  const c128* src = in + (bl * n + r0) * (int64_t)n;
+  c128* dst = out + (bl * n + r0) * (int64_t)n;
+  const int n_shift = pow2_shift(n), nl_shift = pow2_shift(n_last);
+  const int total = rows * n;
+  for (int base = 0; base < total; base += 8 * 256) {  // 8 independent 16-byte loads per thread in flight
+    c128 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + threadIdx.x;
+      v[u] = idx < total ? src[idx] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + threadIdx.x;
+      if (idx < total) {
+        int r, e, hi, lo;
+        fast_divmod(idx, n, n_shift, r, e);
+        fast_divmod(e, n_last, nl_shift, hi, lo);
+        buf[r * row_stride + hi * (n_last + pad) + lo] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  int s_a = 1;  // element stride of axis a inside a row (unpadded index)
+  for (int a = d.nd - 1; a >= 0; --a) {
+    const int len = d.shape[a];
+    const int lines = n / len;
+    const int ln_shift = pow2_shift(lines), sa_shift = pow2_shift(s_a);
+    // padded offset of element e0 + t s_a: axis nd-1 walks inside a padded run, the others jump whole runs
+    const int pstride = a == d.nd - 1 ? 1 : (s_a / n_last) * (n_last + pad);
+    for (int w = threadIdx.x; w < rows * lines; w += blockDim.x) {
+      int r, line, outer, inner, hi, lo;
+      fast_divmod(w, lines, ln_shift, r, line);
+      fast_divmod(line, s_a, sa_shift, outer, inner);
+      const int e0 = outer * len * s_a + inner;
+      fast_divmod(e0, n_last, nl_shift, hi, lo);
+      c128* p0 = buf + r * row_stride + hi * (n_last + pad) + lo;
+      c128 x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < len) x[t] = p0[t * pstride];
+      fold_dft(x, len, +1, roots + 16 * a);
+      if (a == 0) {
+        c128* g0 = dst + (int64_t)r * n + e0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < len) g0[t * s_a] = cmul(x[t], tw[e0 + t * s_a]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < len) p0[t * pstride] = x[t];
+      }
+    }
+    s_a *= len;
+    if (a > 0) __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 bool fft_radix16_on() {
   static int cached = -1;
@@ -1319,6 +1432,38 @@ extern "C" int sqb_fold_transform(int nd, const int* shape_host, const int* repe
   if (rc) return rc;
   if (!transform || !folded || batch < 0 || block_begin < 0 || block_begin + batch > nk) return SQB_E_BADARG;
   if (batch == 0) return SQB_OK;
+  // fused single pass when every cell axis is one fixed radix (SQB_FOLD_FUSED=0: the per-axis passes below)
+  {
+    static int fused_on = -1;
+    if (fused_on < 0) {
+      const char* v = getenv("SQB_FOLD_FUSED");
+      fused_on = (v && v[0] == '0') ? 0 : 1;
+    }
+    bool ok = fused_on && n <= 2048 && transform != folded;
+    for (int a = 0; a < nd; ++a) {
+      const int l = d.shape[a];
+      ok = ok && (l == 1 || l == 2 || l == 3 || l == 4 || l == 5 || l == 7 || l == 8 || l == 16);
+    }
+    if (ok) {
+      const int n_last = d.shape[nd - 1];
+      const int row_stride = (int)(n / n_last) * (n_last + ((n_last & 1) ? 0 : 1));
+      int rows = (int)((64 * 1024) / ((size_t)row_stride * sizeof(c128)));
+      if (rows < 1) rows = 1;
+      if (rows > n) rows = (int)n;
+      const size_t smem = ((size_t)n + 16 * SQB_MAX_DIMS + (size_t)rows * row_stride) * sizeof(c128);
+      cudaError_t e = cudaFuncSetAttribute(fold_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int64_t cnt = sqb_min64(65535, batch - b0);
+        const dim3 grid((unsigned)((n + rows - 1) / rows), (unsigned)cnt);
+        fold_fused_kernel<<<grid, 256, smem, sqb_stream(stream)>>>(
+            d, (int)n, rows, block_begin + b0, reinterpret_cast<const c128*>(transform) + b0 * n * n,
+            reinterpret_cast<c128*>(folded) + b0 * n * n);
+        SQB_LAUNCH_CHECK();
+      }
+      return SQB_OK;
+    }
+  }
   // (1) in-cell inverse FFT of every eigenvector: [batch*n, shape...] ortho, momentum -> position
   rc = sqb_fft_c2c(nd, shape_host, batch * n, +1, transform, folded, workspace, workspace_bytes, stream);
   if (rc) return rc;

@@ -287,6 +287,30 @@ def test_cell_fft_and_fold_equal_permute_plus_supercell_fft(cuda, shape, repeat)
     np.testing.assert_allclose(back.cpu().numpy(), cell_ref.cpu().numpy(), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize(
+    ("shape", "repeat"),
+    [((16, 16), (3, 2)), ((8, 8), (2, 5)), ((7, 7, 7), (2, 1, 3)), ((5, 4), (4, 3)), ((16,), (6,)), ((3, 2, 8), (2, 2, 2)),
+     ((32, 16), (2, 2)), ((12,), (5,))],
+)
+def test_fold_transform_against_numpy(cuda, shape, repeat):
+    """sqb_fold_transform = in-cell ifftn(ortho) of every eigenvector x the block's Bloch twiddle
+    exp(2 pi i sum_a q_a j_a / (N_a R_a)); cells whose axes are single radices take the fused one-pass kernel
+    (fold_fused_kernel), the rest ((32, 16), (12,)) the per-axis passes - both against the same numpy expression."""
+    torch, kernels = _gpu()
+    n, n_k = int(np.prod(shape)), int(np.prod(repeat))
+    rng = np.random.default_rng(n + n_k)
+    v = _rand_c(rng, n_k, n, n)
+    got = kernels.fold_transform(shape, repeat, kernels.to_device(v, torch.complex128)).cpu().numpy()
+    nd = len(shape)
+    cell = np.fft.ifftn(v.reshape(n_k, n, *shape), axes=tuple(range(2, 2 + nd)), norm="ortho").reshape(n_k, n, n)
+    blocks = np.stack(np.unravel_index(np.arange(n_k), repeat), axis=-1)          # [n_k, nd]
+    q = np.where(blocks < (np.asarray(repeat) + 1) // 2, blocks, blocks - np.asarray(repeat))
+    j = np.stack(np.unravel_index(np.arange(n), shape), axis=-1)                  # [n, nd]
+    phase = np.einsum("ba,ja->bj", q / (np.asarray(shape) * np.asarray(repeat)), j)
+    want = cell * np.exp(2j * np.pi * phase)[:, None, :]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+
+
 def test_fold_transform_block_range(cuda):
     torch, kernels = _gpu()
     shape, repeat = (4, 3), (3, 4)
