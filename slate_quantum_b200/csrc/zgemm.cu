@@ -10,23 +10,36 @@
 //
 //   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   A(i, k) = a[b*stride_a + i*a_rs + k*a_cs] (conjugated if asked)
 //
-// Tensor roofline: 8 m n k real flop per batch entry.  64x64 output tile per CTA, 4 warps of 32x32, K chunks of 8
-// staged through registers into split re / im planes in shared memory (fragment loads conflict free, row stride
-// == 8 mod 16 doubles), 4 real DMMA.8x8x4 products per complex MAC.
+// Tensor roofline: 8 m n k real flop per batch entry.  64x64 output tile per CTA, 4 warps of 32x32, K chunks of 16
+// through a 3-stage cp.async ring of interleaved (re, im) tiles (16-byte fragment loads, conflict free with a row
+// stride == 2 mod 8 elements), 4 real DMMA.8x8x4 products per complex MAC.
 #include "sqb_common.cuh"
 
 namespace {
 
 constexpr int kZgTile = 64;
-constexpr int kZgKc = 8;
-constexpr int kZgLd = kZgTile + 8;
+constexpr int kZgKc = 16;
+constexpr int kZgStages = 3;
+constexpr int kZgLd = kZgTile + 2;  // row stride == 2 (mod 8) complex elements: conflict-free 16-byte fragment loads
 constexpr int kZgThreads = 128;
 constexpr int kZgGroup = 8;  // tile rows per L2 group
+constexpr int kZgStageElems = 2 * kZgKc * kZgLd;  // A chunk [kk][m] + B chunk [kk][n], interleaved (re, im)
+constexpr size_t kZgSmem = (size_t)kZgStages * kZgStageElems * sizeof(c128);
 
 __device__ __forceinline__ void zg_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes == 0 writes zeros (edge tiles)
+__device__ __forceinline__ void zg_cp_async(c128* dst, const c128* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+// sign flip on the integer pipe (the FP64 pipe belongs to the DMMAs)
+__device__ __forceinline__ double zg_flip(double v, int mask) {
+  return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v));
 }
 
 struct ZgOperand {
@@ -39,19 +52,21 @@ struct ZgOperand {
 // mapping whose consecutive threads walk the unit-stride direction of the operand
 __device__ __forceinline__ void zg_map(int idx, bool kfast, int& o, int& kk) {
   if (kfast) {
-    o = idx >> 3;
-    kk = idx & 7;
+    o = idx >> 4;
+    kk = idx & (kZgKc - 1);
   } else {
     kk = idx >> 6;
     o = idx & 63;
   }
 }
 
-__global__ void __launch_bounds__(kZgThreads)
+// K chunks of 16 travel global -> shared as 16-byte cp.async copies through a 3-stage ring (one block barrier per
+// chunk; nothing is staged in registers), operands stay interleaved (re, im) in shared memory so that a fragment is
+// ONE 16-byte load, and conjugation is a sign flip of the imaginary fragment on the integer pipe.
+__global__ void __launch_bounds__(kZgThreads, 2)
 zgemm_kernel(int m, int n, int k, ZgOperand A, ZgOperand B, c128* __restrict__ c, int64_t ldc, int64_t c_bs,
              c128 alpha, c128 beta, int64_t batch0) {
-  __shared__ double Ar[2][kZgKc * kZgLd], Ai[2][kZgKc * kZgLd];
-  __shared__ double Br[2][kZgKc * kZgLd], Bi[2][kZgKc * kZgLd];
+  extern __shared__ __align__(16) c128 zg_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = batch0 + blockIdx.z;
   // grouped tile order: consecutive CTAs walk kZgGroup tile rows column by column, so the CTAs resident at the same
@@ -65,7 +80,7 @@ zgemm_kernel(int m, int n, int k, ZgOperand A, ZgOperand B, c128* __restrict__ c
   const c128* a = A.p + b * A.bs;
   const c128* bb = B.p + b * B.bs;
   const bool a_kfast = A.cs == 1, b_kfast = B.rs == 1 && B.cs != 1;
-  const double a_sign = A.conj ? -1.0 : 1.0, b_sign = B.conj ? -1.0 : 1.0;
+  const int a_mask = A.conj ? (int)0x80000000 : 0, b_mask = B.conj ? (int)0x80000000 : 0;
 
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
   const int frow = lane >> 2, fcol = lane & 3;
@@ -75,58 +90,49 @@ zgemm_kernel(int m, int n, int k, ZgOperand A, ZgOperand B, c128* __restrict__ c
 #pragma unroll
     for (int y = 0; y < 4; ++y) cr[x][y][0] = cr[x][y][1] = ci[x][y][0] = ci[x][y][1] = 0.0;
 
-  c128 ra[4], rb[4];
-  auto fetch = [&](int kc) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + kZgThreads * q;
-      int o, kk;
-      zg_map(idx, a_kfast, o, kk);
-      c128 v = make_double2(0.0, 0.0);
-      if (i0 + o < m && kc + kk < k) v = a[(int64_t)(i0 + o) * A.rs + (int64_t)(kc + kk) * A.cs];
-      ra[q] = v;
-      zg_map(idx, b_kfast, o, kk);
-      v = make_double2(0.0, 0.0);
-      if (j0 + o < n && kc + kk < k) v = bb[(int64_t)(kc + kk) * B.rs + (int64_t)(j0 + o) * B.cs];
-      rb[q] = v;
-    }
-  };
-  auto stash = [&](int s) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + kZgThreads * q;
-      int o, kk;
-      zg_map(idx, a_kfast, o, kk);
-      Ar[s][kk * kZgLd + o] = ra[q].x;
-      Ai[s][kk * kZgLd + o] = a_sign * ra[q].y;
-      zg_map(idx, b_kfast, o, kk);
-      Br[s][kk * kZgLd + o] = rb[q].x;
-      Bi[s][kk * kZgLd + o] = b_sign * rb[q].y;
-    }
-  };
-
   const int nchunks = (k + kZgKc - 1) / kZgKc;
-  if (nchunks > 0) {
-    fetch(0);
-    stash(0);
-  }
-  __syncthreads();
+  auto issue = [&](int ch) {  // every thread; always closes a commit group (empty past the last chunk)
+    if (ch < nchunks) {
+      const int kc = ch * kZgKc;
+      c128* As = zg_smem + (size_t)(ch % kZgStages) * kZgStageElems;
+      c128* Bs = As + kZgKc * kZgLd;
+#pragma unroll
+      for (int q = 0; q < (kZgTile * kZgKc) / kZgThreads; ++q) {
+        const int idx = tid + kZgThreads * q;
+        int o, kk;
+        zg_map(idx, a_kfast, o, kk);
+        bool ok = i0 + o < m && kc + kk < k;
+        zg_cp_async(As + kk * kZgLd + o, ok ? a + (int64_t)(i0 + o) * A.rs + (int64_t)(kc + kk) * A.cs : a, ok ? 16 : 0);
+        zg_map(idx, b_kfast, o, kk);
+        ok = j0 + o < n && kc + kk < k;
+        zg_cp_async(Bs + kk * kZgLd + o, ok ? bb + (int64_t)(kc + kk) * B.rs + (int64_t)(j0 + o) * B.cs : bb, ok ? 16 : 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  issue(1);
   for (int ch = 0; ch < nchunks; ++ch) {
-    const int s = ch & 1;
-    if (ch + 1 < nchunks) fetch((ch + 1) * kZgKc);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk ch has landed (only the newest group may be pending)
+    __syncthreads();                                      // ... for every thread, and stage (ch - 1) % 3 is free
+    issue(ch + 2);
+    const c128* As = zg_smem + (size_t)(ch % kZgStages) * kZgStageElems;
+    const c128* Bs = As + kZgKc * kZgLd;
 #pragma unroll
     for (int k4 = 0; k4 < kZgKc; k4 += 4) {
       double ar[4], ai[4], nai[4], br[4], bi[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        ar[x] = Ar[s][(k4 + fcol) * kZgLd + wm + x * 8 + frow];
-        ai[x] = Ai[s][(k4 + fcol) * kZgLd + wm + x * 8 + frow];
-        nai[x] = -ai[x];
+        const c128 v = As[(k4 + fcol) * kZgLd + wm + x * 8 + frow];
+        ar[x] = v.x;
+        ai[x] = zg_flip(v.y, a_mask);
+        nai[x] = zg_flip(v.y, a_mask ^ (int)0x80000000);
       }
 #pragma unroll
       for (int y = 0; y < 4; ++y) {
-        br[y] = Br[s][(k4 + fcol) * kZgLd + wn + y * 8 + frow];
-        bi[y] = Bi[s][(k4 + fcol) * kZgLd + wn + y * 8 + frow];
+        const c128 v = Bs[(k4 + fcol) * kZgLd + wn + y * 8 + frow];
+        br[y] = v.x;
+        bi[y] = zg_flip(v.y, b_mask);
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x)
@@ -138,8 +144,6 @@ zgemm_kernel(int m, int n, int k, ZgOperand A, ZgOperand B, c128* __restrict__ c
           zg_dmma(ci[x][y][0], ci[x][y][1], ai[x], br[y]);
         }
     }
-    if (ch + 1 < nchunks) stash(s ^ 1);
-    __syncthreads();
   }
 
   c128* cb = c + b * c_bs;
@@ -269,9 +273,11 @@ extern "C" int sqb_zgemm_batched(int m, int n, int k, int64_t batch, const sqb_c
   const c128 al = make_double2(alpha[0], alpha[1]), be = make_double2(beta[0], beta[1]);
   const int64_t tiles = (int64_t)((n + kZgTile - 1) / kZgTile) * ((m + kZgTile - 1) / kZgTile);
   if (tiles > 0x7fffffff) return SQB_E_UNSUPPORTED;
+  cudaError_t attr = cudaFuncSetAttribute(zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgSmem);
+  if (attr != cudaSuccess) return (int)attr;
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const unsigned gz = (unsigned)sqb_min64(65535, batch - b0);
-    zgemm_kernel<<<dim3((unsigned)tiles, 1, gz), kZgThreads, 0, sqb_stream(stream)>>>(
+    zgemm_kernel<<<dim3((unsigned)tiles, 1, gz), kZgThreads, kZgSmem, sqb_stream(stream)>>>(
         m, n, k, A, B, reinterpret_cast<c128*>(c), ldc, c_batch_stride, al, be, b0);
     SQB_LAUNCH_CHECK();
   }
