@@ -19,7 +19,10 @@
  *    kernel for 64 < n <= 512); SQB_WY_VARIANT=<1|2> picks the blocked back-transformation's tile shape (1: 16-reflector
  *    blocks, two CTAs per SM, default; 2: 32-reflector blocks); SQB_TRIDIAG=column selects the column-by-column
  *    tridiagonalisation instead of the blocked panel kernel (default for 64 < n <= 512), SQB_TRIDIAG_NB=<4|8|16> its
- *    panel width (default 8).
+ *    panel width (default 8); SQB_FFT_RADIX16=0 keeps power-of-two FFT lines on radix 8 / 4 / 2 stages (default:
+ *    lines of 128 points and more lead with radix-16 stages), SQB_FFT_LINES16=<k> caps the adjacent lines a CTA of
+ *    that variant takes (default 32); SQB_FOLD_FUSED=0 runs sqb_fold_transform as per-axis FFT passes plus the
+ *    twiddle pass instead of the fused single pass.
  *
  * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
  * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency
