@@ -877,6 +877,226 @@ fold_fused_kernel(SqbDims d, int n, int rows_per_cta, int64_t block_begin, const
   }
 }
 
+// ------------------------------------------------------------------------------------ 2-D cell FFT in one pass (clusters)
+// Both across-block axes of a 64 x 64 block grid in ONE kernel: HBM traffic is one read + one write of the state
+// list instead of two of each.  A thread-block CLUSTER of 8 CTAs owns one (state, group of 8 adjacent cell
+// columns): 64 x 64 x 8 elements = 512 KB, 64 KB of shared memory per CTA.
+//   phase 1  CTA r loads the block rows b_0 in [8r, 8r + 8) (128-byte runs) and transforms axis 1 (64 points, two
+//            radix-8 stages; the second in place: a butterfly reads and writes the same eight positions);
+//   exchange the first radix-8 stage of axis 0 reads its eight inputs b_0 = jj + 8 t straight out of the eight CTAs'
+//            shared memories (DSMEM: input t lives in CTA t) into registers - the whole axis-0 working set of a
+//            CTA (4096 elements) is 16 registers' worth per thread - bracketed by two cluster barriers (slabs
+//            complete / slabs no longer read), after which the slab is overwritten with the stage's outputs;
+//   phase 2  second radix-8 stage of axis 0 for the block columns c_1 in [8r, 8r + 8), scaled, scattered into the
+//            supercell position layout x_a = c_a N_a + j_a in 128-byte runs.
+#ifndef SQB_C2_CTAS
+#define SQB_C2_CTAS 2
+#endif
+constexpr int kC2Cluster = 8, kC2Threads = 256;
+constexpr size_t kC2Smem = (size_t)8 * 64 * 8 * sizeof(c128);
+
+__device__ __forceinline__ void c2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ c128 c2_ld_remote(const c128* local, uint32_t rank) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  c128 v;
+  asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void __cluster_dims__(kC2Cluster, 1, 1) __launch_bounds__(kC2Threads, SQB_C2_CTAS)
+cell_fft2_cluster_kernel(int n, int n1, int64_t item0, const c128* __restrict__ in, c128* __restrict__ out,
+                         const c128* __restrict__ tab_g, double scale) {
+  extern __shared__ __align__(16) c128 c2_S[];  // [8 rows][64 positions][8 columns]
+  __shared__ c128 tab[64];
+  const int tid = threadIdx.x;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int64_t item = item0 + (blockIdx.x >> 3);
+  const int groups = n >> 3;  // groups of 8 adjacent cell columns
+  const int64_t t = item / groups;
+  const int jg = (int)(item - t * groups);
+  if (tid < 64) tab[tid] = tab_g[tid];
+  const int jl = tid & 7, a = (tid >> 3) & 7, hi = tid >> 6;
+  const int64_t m = (int64_t)4096 * n;
+  const c128* src = in + t * m + (8 * jg + jl);
+  // ---- phase 1, stage 1: rows b_0l = hi, hi + 4; butterfly jj = a: positions b_1 = jj + 8 tt from global memory
+  c128 x[2][8];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int b0 = 8 * (int)rank + hi + 4 * pass;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) x[pass][tt] = src[(int64_t)(b0 * 64 + a + 8 * tt) * n];
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    dft_small<8>(x[pass], +1, nullptr, 0);
+    const int b0l = hi + 4 * pass;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) c2_S[(b0l * 64 + a * 8 + tt) * 8 + jl] = x[pass][tt];
+  }
+  __syncthreads();
+  // ---- phase 1, stage 2 (in place): butterfly jj2 = a reads and writes positions jj2 + 8 tt
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int b0l = hi + 4 * pass;
+    c128 v[8];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      v[tt] = c2_S[(b0l * 64 + a + 8 * tt) * 8 + jl];
+      if (tt) v[tt] = cmul(v[tt], tw_lookup(tab, tt * a, +1));
+    }
+    dft_small<8>(v, +1, nullptr, 0);
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) c2_S[(b0l * 64 + a + 8 * tt) * 8 + jl] = v[tt];
+  }
+  c2_cluster_sync();  // every CTA's slab holds the axis-1 transform of its block rows
+  // ---- axis 0, stage 1: column c_1 = 8 rank + a, butterfly jj = hi, hi + 4: input tt = row b_0 = jj + 8 tt = row jj
+  //      of CTA tt
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int jj = hi + 4 * pass;
+    const c128* local = c2_S + (jj * 64 + 8 * (int)rank + a) * 8 + jl;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) x[pass][tt] = c2_ld_remote(local, (uint32_t)tt);
+  }
+  c2_cluster_sync();  // nobody reads a slab any more: it becomes the axis-0 work buffer [c_1l][position][column]
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    dft_small<8>(x[pass], +1, nullptr, 0);
+    const int jj = hi + 4 * pass;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) c2_S[(a * 64 + jj * 8 + tt) * 8 + jl] = x[pass][tt];
+  }
+  __syncthreads();
+  // ---- axis 0, stage 2: butterfly jj2 = hi, hi + 4; outputs c_0 = jj2 + 8 tt scattered into the position layout
+  const int j = 8 * jg + jl;
+  const int j0 = j / n1, j1 = j - j0 * n1;
+  const int n0 = n / n1;
+  const int64_t l1 = (int64_t)64 * n1;
+  c128* dst = out + t * m + (int64_t)j0 * l1 + (int64_t)(8 * (int)rank + a) * n1 + j1;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int jj2 = hi + 4 * pass;
+    c128 v[8];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      v[tt] = c2_S[(a * 64 + jj2 + 8 * tt) * 8 + jl];
+      if (tt) v[tt] = cmul(v[tt], tw_lookup(tab, tt * jj2, +1));
+    }
+    dft_small<8>(v, +1, nullptr, 0);
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) dst[(int64_t)(jj2 + 8 * tt) * n0 * l1] = cscale(v[tt], scale);
+  }
+}
+
+// Push variant: the second axis-1 stage sends every output straight into the shared memory of the CTA that owns
+// its block column (remote stores are fire and forget; the pull variant stalls on 16 remote loads per thread), so a
+// single cluster barrier separates the two axes.  Shared memory: a 32 KB scratch for axis 1 (two halves of four
+// block rows) + the 64 KB axis-0 buffer [c_1l][b_0][column] the peers write into.  (Measured and dropped: the same
+// kernel made persistent - no gain, cluster launches are not the cost - and a 512-thread one-CTA-per-SM version
+// that prefetches the next item's rows into registers: 52.6 instead of 43.3 ms per 4096 cfg3 states.)
+constexpr size_t kC2PushSmem = (size_t)(4 * 64 * 8 + 8 * 64 * 8) * sizeof(c128);
+__device__ __forceinline__ void c2_st_remote(c128* local, uint32_t rank, c128 v) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__global__ void __cluster_dims__(kC2Cluster, 1, 1) __launch_bounds__(kC2Threads, 2)
+cell_fft2_cluster_push_kernel(int n, int n1, int64_t item0, const c128* __restrict__ in, c128* __restrict__ out,
+                              const c128* __restrict__ tab_g, double scale) {
+  extern __shared__ __align__(16) c128 c2_S[];
+  c128* Sx = c2_S;                 // [4 rows][64 positions][8 columns]   axis-1 scratch (one half at a time)
+  c128* P2 = c2_S + 4 * 64 * 8;    // [8 c_1l][64 b_0][8 columns]         axis-0 buffer, written by the peers
+  __shared__ c128 tab[64];
+  const int tid = threadIdx.x;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int64_t item = item0 + (blockIdx.x >> 3);
+  const int groups = n >> 3;
+  const int64_t t = item / groups;
+  const int jg = (int)(item - t * groups);
+  if (tid < 64) tab[tid] = tab_g[tid];
+  const int jl = tid & 7, a = (tid >> 3) & 7, hi = tid >> 6;
+  const int64_t m = (int64_t)4096 * n;
+  const c128* src = in + t * m + (8 * jg + jl);
+  c128 x[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int b0 = 8 * (int)rank + 4 * h + hi;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) x[h][tt] = src[(int64_t)(b0 * 64 + a + 8 * tt) * n];
+  }
+  // every CTA of the cluster must be running before its shared memory is written remotely
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    dft_small<8>(x[h], +1, nullptr, 0);
+    if (h) __syncthreads();  // the first half's scratch reads are over
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) Sx[(hi * 64 + a * 8 + tt) * 8 + jl] = x[h][tt];
+    __syncthreads();
+    c128 v[8];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      v[tt] = Sx[(hi * 64 + a + 8 * tt) * 8 + jl];
+      if (tt) v[tt] = cmul(v[tt], tw_lookup(tab, tt * a, +1));
+    }
+    dft_small<8>(v, +1, nullptr, 0);
+    if (h == 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    // output tt is block column c_1 = a + 8 tt: column a of CTA tt, row b_0 = 8 rank + 4 h + hi
+    c128* slot = P2 + (a * 64 + 8 * (int)rank + 4 * h + hi) * 8 + jl;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) c2_st_remote(slot, (uint32_t)tt, v[tt]);
+  }
+  c2_cluster_sync();  // all eight CTAs have delivered: P2 holds the axis-1 transform of EVERY block row for my columns
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int jj = hi + 4 * pass;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) x[pass][tt] = P2[(a * 64 + jj + 8 * tt) * 8 + jl];
+    dft_small<8>(x[pass], +1, nullptr, 0);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int jj = hi + 4 * pass;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) P2[(a * 64 + jj * 8 + tt) * 8 + jl] = x[pass][tt];
+  }
+  __syncthreads();
+  const int j = 8 * jg + jl;
+  const int j0 = j / n1, j1 = j - j0 * n1;
+  const int n0 = n / n1;
+  const int64_t l1 = (int64_t)64 * n1;
+  c128* dst = out + t * m + (int64_t)j0 * l1 + (int64_t)(8 * (int)rank + a) * n1 + j1;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int jj2 = hi + 4 * pass;
+    c128 v[8];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      v[tt] = P2[(a * 64 + jj2 + 8 * tt) * 8 + jl];
+      if (tt) v[tt] = cmul(v[tt], tw_lookup(tab, tt * jj2, +1));
+    }
+    dft_small<8>(v, +1, nullptr, 0);
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) dst[(int64_t)(jj2 + 8 * tt) * n0 * l1] = cscale(v[tt], scale);
+  }
+}
+
+int cell_fft_cluster_mode() {
+  static int cached = -1;  // 0: off (two passes), 1: pull variant, 2: push variant
+  if (cached < 0) {
+    const char* v = getenv("SQB_CELL_FFT_CLUSTER");
+    cached = v ? atoi(v) : 2;
+  }
+  return cached;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 bool fft_radix16_on() {
   static int cached = -1;
@@ -1350,6 +1570,28 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
     return fft_one_axis(outer, d.repeat[a], inner, sign, 1.0, p, p, tab, nullptr, st);
   };
 
+  if (direction == 1 && nd == 2 && ranks == 1 && !mom && d.repeat[0] == 64 && d.repeat[1] == 64 && d.shape[1] % 8 == 0 &&
+      in_scratch != out && cell_fft_cluster_mode() > 0) {
+    // one pass over the state list: both block axes inside a cluster of 8 CTAs (cell_fft2_cluster_*_kernel)
+    const bool push = cell_fft_cluster_mode() == 2;
+    cudaError_t e = push ? cudaFuncSetAttribute(cell_fft2_cluster_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2PushSmem)
+                         : cudaFuncSetAttribute(cell_fft2_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2Smem);
+    if (e != cudaSuccess) return (int)e;
+    fft_table_kernel<<<1, 256, 0, st>>>(tab, 64);
+    const int64_t items = lead * (n / 8);
+    const int64_t per_launch = (int64_t)1 << 26;  // clusters per launch (grid.x = 8 x clusters < 2^31)
+    for (int64_t i0 = 0; i0 < items; i0 += per_launch) {
+      const int64_t cnt = sqb_min64(per_launch, items - i0);
+      if (push)
+        cell_fft2_cluster_push_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2PushSmem, st>>>((int)n, d.shape[1], i0, src,
+                                                                                                  dst, tab, scale);
+      else
+        cell_fft2_cluster_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2Smem, st>>>((int)n, d.shape[1], i0, src, dst,
+                                                                                          tab, scale);
+      SQB_LAUNCH_CHECK();
+    }
+    return SQB_OK;
+  }
   if (direction == 1) {
     for (int a = 0; a < nd - 1 && !(mom && mom->stage == 1); ++a) {
       rc = inplace_axis(a, src, +1);

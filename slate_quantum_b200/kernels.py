@@ -6,6 +6,8 @@ computes on the CPU.  Calling without a CUDA device raises.
 
 from __future__ import annotations
 
+import os
+
 import ctypes
 from typing import Sequence
 
@@ -230,7 +232,11 @@ def cell_fft(
             _stream(),
         )
     _lib.check(rc, "sqb_cell_fft")
-    _count(2 * len(shape))
+    one_pass = (  # the cluster kernel of csrc/fft.cu (cell_fft_impl): table + one launch instead of a pass per axis
+        direction == 1 and ranks == 1 and len(shape) == 2 and tuple(repeat) == (64, 64) and shape[1] % 8 == 0
+        and x.data_ptr() != out.data_ptr() and os.environ.get("SQB_CELL_FFT_CLUSTER", "2") != "0"
+    )
+    _count(2 if one_pass else 2 * len(shape))
     return out
 
 

@@ -809,6 +809,24 @@ def test_fft_axis_radix16_lengths(cuda, length, outer, inner, sign):
     np.testing.assert_allclose(got.reshape(x.shape), want, rtol=0, atol=2e-13)
 
 
+@pytest.mark.parametrize("shape", [(16, 16), (2, 8), (3, 24)])
+def test_cell_fft_64x64_block_grid_cluster_kernel(cuda, shape):
+    """64 x 64 block grids (cfg3) take the one-pass cluster kernel (cell_fft2_cluster_kernel: axis 1 per CTA, axis 0
+    across the 8 CTAs of a cluster through distributed shared memory).  Against numpy: ifft2(ortho) over the two block
+    axes of the cell layout [t, b0, b1, j0, j1], scattered to x_a = c_a N_a + j_a; 3 states (ragged against nothing:
+    every (state, column group) is one cluster)."""
+    torch, kernels = _gpu()
+    repeat = (64, 64)
+    n = shape[0] * shape[1]
+    rng = np.random.default_rng(shape[0])
+    x = _rand_c(rng, 3, 64, 64, shape[0], shape[1])
+    want = np.fft.ifft2(x, axes=(1, 2), norm="ortho").transpose(0, 1, 3, 2, 4).reshape(3, -1)
+    xd = kernels.to_device(x.reshape(3, -1), torch.complex128)
+    got = kernels.cell_fft(shape, repeat, xd, 1).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+    assert got.shape == (3, 4096 * n)
+
+
 @pytest.mark.parametrize(("shape", "repeat"), [((2, 2), (512, 3)), ((3,), (256,)), ((2, 2), (4, 512)), ((2, 2), (128, 4))])
 def test_cell_fft_long_block_axis(cuda, shape, repeat):
     """cell FFT across 256 / 512 blocks (8-GPU weak-scaling k-grids) against the literal supercell chain."""
