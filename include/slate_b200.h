@@ -22,7 +22,8 @@
  *    panel width (default 8); SQB_FFT_RADIX16=0 keeps power-of-two FFT lines on radix 8 / 4 / 2 stages (default:
  *    lines of 128 points and more lead with radix-16 stages), SQB_FFT_LINES16=<k> caps the adjacent lines a CTA of
  *    that variant takes (default 32); SQB_FOLD_FUSED=0 runs sqb_fold_transform as per-axis FFT passes plus the
- *    twiddle pass instead of the fused single pass.
+ *    twiddle pass instead of the fused single pass; SQB_CELL_FFT_CLUSTER=0 runs the cell FFT of 64 x 64 block grids as
+ *    one pass per axis instead of the one-pass cluster kernel (=1: its pull variant).
  *
  * Each entry point cites the reference interface (Matt-Ord/slate_quantum, paths relative to the
  * reference root) whose arithmetic it replaces.  That arithmetic lives in the un-vendored dependency
