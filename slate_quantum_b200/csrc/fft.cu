@@ -1572,25 +1572,36 @@ static int cell_fft_impl(int nd, const int* shape_host, const int* repeat_host, 
 
   if (direction == 1 && nd == 2 && ranks == 1 && !mom && d.repeat[0] == 64 && d.repeat[1] == 64 && d.shape[1] % 8 == 0 &&
       in_scratch != out && cell_fft_cluster_mode() > 0) {
-    // one pass over the state list: both block axes inside a cluster of 8 CTAs (cell_fft2_cluster_*_kernel)
+    // one pass over the state list: both block axes inside a cluster of 8 CTAs (cell_fft2_cluster_*_kernel).  A
+    // device that refuses the cluster launch (e.g. a partitioned GPU without 8 co-schedulable SMs) falls through to
+    // the pass per axis below: nothing has been written yet when the first launch fails.
     const bool push = cell_fft_cluster_mode() == 2;
     cudaError_t e = push ? cudaFuncSetAttribute(cell_fft2_cluster_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2PushSmem)
                          : cudaFuncSetAttribute(cell_fft2_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2Smem);
-    if (e != cudaSuccess) return (int)e;
-    fft_table_kernel<<<1, 256, 0, st>>>(tab, 64);
-    const int64_t items = lead * (n / 8);
-    const int64_t per_launch = (int64_t)1 << 26;  // clusters per launch (grid.x = 8 x clusters < 2^31)
-    for (int64_t i0 = 0; i0 < items; i0 += per_launch) {
-      const int64_t cnt = sqb_min64(per_launch, items - i0);
-      if (push)
-        cell_fft2_cluster_push_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2PushSmem, st>>>((int)n, d.shape[1], i0, src,
-                                                                                                  dst, tab, scale);
-      else
-        cell_fft2_cluster_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2Smem, st>>>((int)n, d.shape[1], i0, src, dst,
-                                                                                          tab, scale);
-      SQB_LAUNCH_CHECK();
+    bool launched = false;
+    if (e == cudaSuccess) {
+      fft_table_kernel<<<1, 256, 0, st>>>(tab, 64);
+      const int64_t items = lead * (n / 8);
+      const int64_t per_launch = (int64_t)1 << 26;  // clusters per launch (grid.x = 8 x clusters < 2^31)
+      for (int64_t i0 = 0; i0 < items; i0 += per_launch) {
+        const int64_t cnt = sqb_min64(per_launch, items - i0);
+        if (push)
+          cell_fft2_cluster_push_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2PushSmem, st>>>((int)n, d.shape[1], i0,
+                                                                                                    src, dst, tab, scale);
+        else
+          cell_fft2_cluster_kernel<<<(unsigned)(cnt * kC2Cluster), kC2Threads, kC2Smem, st>>>((int)n, d.shape[1], i0, src, dst,
+                                                                                            tab, scale);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+          if (i0 == 0) break;  // refused outright: use the passes below
+          return (int)e;
+        }
+        launched = true;
+      }
+    } else {
+      (void)cudaGetLastError();
     }
-    return SQB_OK;
+    if (launched) return SQB_OK;
   }
   if (direction == 1) {
     for (int a = 0; a < nd - 1 && !(mom && mom->stage == 1); ++a) {

@@ -22,7 +22,10 @@ constexpr int kZgKc = 16;
 constexpr int kZgStages = 3;
 constexpr int kZgLd = kZgTile + 2;  // row stride == 2 (mod 8) complex elements: conflict-free 16-byte fragment loads
 constexpr int kZgThreads = 128;
-constexpr int kZgGroup = 8;  // tile rows per L2 group
+#ifndef SQB_ZG_GROUP
+#define SQB_ZG_GROUP 16
+#endif
+constexpr int kZgGroup = SQB_ZG_GROUP;  // tile rows per L2 group
 constexpr int kZgStageElems = 2 * kZgKc * kZgLd;  // A chunk [kk][m] + B chunk [kk][n], interleaved (re, im)
 constexpr size_t kZgSmem = (size_t)kZgStages * kZgStageElems * sizeof(c128);
 
