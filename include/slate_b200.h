@@ -105,7 +105,8 @@ int sqb_bloch_permute(int nd, const int* shape_host, const int* repeat_host, int
  * (operator/_operator.py:70-74, state/_state.py:37-43).
  *   sign = -1 : forward  (np.fft.fftn,  position -> momentum on a ket index)
  *   sign = +1 : backward (np.fft.ifftn, momentum -> position on a ket index)
- * Every axis length must factor into primes <= 31.  in == out allowed.
+ * Any axis length: lengths that factor into primes <= 31 run on the shared-memory passes, the others as a chirp-z
+ * (Bluestein) convolution on the power-of-two passes (workspace sized by sqb_fft_workspace_bytes).  in == out allowed.
  * ---------------------------------------------------------------------------------------------- */
 size_t sqb_fft_workspace_bytes(int nd, const int* dims_host, int64_t batch);
 int sqb_fft_c2c(int nd, const int* dims_host, int64_t batch, int sign, const sqb_c128* in,

@@ -1267,10 +1267,101 @@ int launch_pass(FftPass& P, const c128* in, c128* out, c128* tab, cudaStream_t s
   return SQB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ Bluestein (any length)
+// Axis lengths with a prime factor above kMaxRadix (the shared-memory passes stop at 31) run as a chirp-z
+// convolution on the power-of-two passes: with w[n] = exp(sign i pi n^2 / L),
+//   y[k] = w[k] * sum_n (x[n] w[n]) * conj(w[k - n])
+// i.e. three M-point FFTs (M = 2^p >= 2 L - 1), one of them of the filter only.  The reference takes any length
+// through numpy's FFT; this keeps the mirror from refusing e.g. 37- or 101-point axes.
+__global__ void bluestein_chirp_kernel(c128* __restrict__ w, int len, int sign) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < len; n += gridDim.x * blockDim.x) {
+    const int64_t q = ((int64_t)n * n) % (2 * (int64_t)len);  // exact reduction of the phase n^2 pi / L
+    double sn, cs;
+    sincospi((double)sign * (double)q / (double)len, &sn, &cs);
+    w[n] = make_double2(cs, sn);
+  }
+}
+__global__ void bluestein_filter_kernel(c128* __restrict__ f, const c128* __restrict__ w, int len, int m) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    c128 v = make_double2(0.0, 0.0);
+    if (j < len) v = cconj(w[j]);
+    else if (m - j < len) v = cconj(w[m - j]);
+    f[j] = v;
+  }
+}
+// mode 0: a[o][j][i] = j < len ? in[o][j][i] * w[j] : 0      (pad to m)
+// mode 1: a[o][j][i] *= f[j]
+// mode 2: out[o][k][i] = a[o][k][i] * w[k] * scale            (k < len)
+__global__ void bluestein_pointwise_kernel(int mode, int64_t outer, int len, int m, int64_t inner,
+                                           const c128* __restrict__ in, c128* __restrict__ a,
+                                           const c128* __restrict__ tabv, c128* __restrict__ out, double scale) {
+  const int64_t rows = mode == 2 ? len : m;
+  const int64_t total = outer * rows * inner;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = g % inner;
+    const int64_t j = (g / inner) % rows;
+    const int64_t o = g / (inner * rows);
+    if (mode == 0) {
+      a[g] = j < len ? cmul(in[(o * len + j) * inner + i], tabv[j]) : make_double2(0.0, 0.0);
+    } else if (mode == 1) {
+      a[g] = cmul(a[g], tabv[j]);
+    } else {
+      out[g] = cscale(cmul(a[(o * m + j) * inner + i], tabv[j]), scale);
+    }
+  }
+}
+
+int bluestein_m(int len) {
+  int m = 1;
+  while (m < 2 * len - 1) m *= 2;
+  return m;
+}
+// elements of scratch a Bluestein axis needs behind the chirp table: filter + padded array (+ the four-step scratch
+// of the M-point passes when M does not fit shared memory)
+size_t bluestein_scratch_elems(int len, int64_t lines) {
+  const size_t m = (size_t)bluestein_m(len);
+  size_t e = align_up((size_t)len, 16) + align_up(m, 16) + align_up((size_t)lines * m, 16);
+  if (m > (size_t)kMaxSmemLen) e += align_up((size_t)lines * m, 16);
+  return e;
+}
+
+int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, const c128* in, c128* out, c128* tab,
+                 c128* scratch, cudaStream_t st);
+
+int bluestein_axis(int64_t outer, int len, int64_t inner, int sign, double scale, const c128* in, c128* out, c128* tab,
+                   c128* scratch, cudaStream_t st) {
+  if (!scratch) return SQB_E_WORKSPACE;
+  const int m = bluestein_m(len);
+  const int64_t lines = outer * inner;
+  c128* w = scratch;
+  c128* f = w + align_up((size_t)len, 16);
+  c128* a = f + align_up((size_t)m, 16);
+  c128* scratch2 = m > kMaxSmemLen ? a + align_up((size_t)lines * m, 16) : nullptr;
+  const int64_t total = lines * m;
+  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
+  bluestein_chirp_kernel<<<(len + 255) / 256, 256, 0, st>>>(w, len, sign);
+  bluestein_filter_kernel<<<(m + 255) / 256, 256, 0, st>>>(f, w, len, m);
+  SQB_LAUNCH_CHECK();
+  int rc = fft_one_axis(1, m, 1, -1, 1.0, f, f, tab, scratch2, st);
+  if (rc) return rc;
+  bluestein_pointwise_kernel<<<grid, 256, 0, st>>>(0, outer, len, m, inner, in, a, w, nullptr, 1.0);
+  SQB_LAUNCH_CHECK();
+  rc = fft_one_axis(outer, m, inner, -1, 1.0, a, a, tab, scratch2, st);
+  if (rc) return rc;
+  bluestein_pointwise_kernel<<<grid, 256, 0, st>>>(1, outer, len, m, inner, nullptr, a, f, nullptr, 1.0);
+  SQB_LAUNCH_CHECK();
+  rc = fft_one_axis(outer, m, inner, +1, 1.0 / (double)m, a, a, tab, scratch2, st);
+  if (rc) return rc;
+  bluestein_pointwise_kernel<<<grid, 256, 0, st>>>(2, outer, len, m, inner, nullptr, a, w, out, scale);
+  SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
 // One axis of a [outer, len, inner] array, in -> out (in == out allowed when the line fits shared memory).
 int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, const c128* in, c128* out,
                  c128* tab, c128* scratch, cudaStream_t st) {
   if (outer >= (1LL << 31) || inner >= (1LL << 31)) return SQB_E_UNSUPPORTED;
+  if (!smooth(len)) return bluestein_axis(outer, len, inner, sign, scale, in, out, tab, scratch, st);
   if (len <= kMaxSmemLen) {
     FftPass P{};
     P.len = len;
@@ -1338,18 +1429,33 @@ int fft_one_axis(int64_t outer, int len, int64_t inner, int sign, double scale, 
 
 }  // namespace
 
+// table area: the longest table any pass of this transform builds (a Bluestein axis runs M-point passes)
+static int fft_table_len(int nd, const int* dims_host) {
+  int max_len = 1;
+  for (int a = 0; a < nd; ++a) {
+    const int l = smooth(dims_host[a]) ? dims_host[a] : bluestein_m(dims_host[a]);
+    if (l > max_len) max_len = l;
+  }
+  return max_len;
+}
+
 extern "C" size_t sqb_fft_workspace_bytes(int nd, const int* dims_host, int64_t batch) {
   if (nd < 1 || nd > SQB_MAX_DIMS || !dims_host || batch < 0) return 0;
   int64_t total = batch;
-  int max_len = 1;
   bool any_long = false;
   for (int a = 0; a < nd; ++a) {
+    if (dims_host[a] < 1) return 0;
     total *= dims_host[a];
-    if (dims_host[a] > max_len) max_len = dims_host[a];
     if (dims_host[a] > kMaxSmemLen) any_long = true;
   }
-  size_t bytes = align_up((size_t)max_len * sizeof(c128), 256);
-  if (any_long) bytes += align_up((size_t)total * sizeof(c128), 256);
+  size_t bytes = align_up((size_t)fft_table_len(nd, dims_host) * sizeof(c128), 256);
+  size_t scratch = any_long ? (size_t)total : 0;  // four-step split of long smooth axes
+  for (int a = 0; a < nd; ++a)
+    if (!smooth(dims_host[a])) {
+      const size_t need = bluestein_scratch_elems(dims_host[a], total / dims_host[a]);
+      if (need > scratch) scratch = need;
+    }
+  if (scratch) bytes += align_up(scratch * sizeof(c128), 256);
   return bytes + 256;
 }
 
@@ -1368,7 +1474,7 @@ extern "C" int sqb_fft_c2c(int nd, const int* dims_host, int64_t batch, int sign
   }
   c128* tab = reinterpret_cast<c128*>(workspace);
   c128* scratch = reinterpret_cast<c128*>(reinterpret_cast<char*>(workspace) +
-                                          align_up((size_t)max_len * sizeof(c128), 256));
+                                          align_up((size_t)fft_table_len(nd, dims_host) * sizeof(c128), 256));
   const double scale = 1.0 / sqrt((double)total);
   cudaStream_t st = sqb_stream(stream);
   const c128* src = reinterpret_cast<const c128*>(in);
@@ -1395,7 +1501,7 @@ extern "C" int sqb_fft_axis(int64_t outer, int len, int64_t inner, int sign, con
   if (outer == 0) return SQB_OK;
   c128* tab = reinterpret_cast<c128*>(workspace);
   c128* scratch = reinterpret_cast<c128*>(reinterpret_cast<char*>(workspace) +
-                                          align_up((size_t)len * sizeof(c128), 256));
+                                          align_up((size_t)fft_table_len(1, dims) * sizeof(c128), 256));
   return fft_one_axis(outer, len, inner, sign, 1.0 / sqrt((double)len), reinterpret_cast<const c128*>(in),
                       reinterpret_cast<c128*>(out), tab, scratch, sqb_stream(stream));
 }

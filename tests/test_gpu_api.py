@@ -298,7 +298,7 @@ def test_measure_api_coherent_states(cuda):
         np.testing.assert_allclose(wrapped, 0, atol=1e-7 * dx)
 
 
-@pytest.mark.parametrize("shape", [(24,), (6, 5)])
+@pytest.mark.parametrize("shape", [(24,), (6, 5), (37,), (3, 41)])
 def test_dense_hamiltonian_schrodinger_evolution_and_observables(cuda, shape):
     """the reference's examples/schrodinger.py on ONE cell (no Bloch decomposition):
     operator.build.kinetic_hamiltonian -> into_diagonal_hermitian (batch of one matrix) -> decomposition

@@ -423,6 +423,33 @@ def test_fft_generic_primes_and_unit_axes(cuda, dims):
     np.testing.assert_allclose(got, np.fft.fftn(x, axes=axes, norm="ortho"), rtol=0, atol=1e-13)
 
 
+@pytest.mark.parametrize("dims", [(37,), (101,), (74, 3), (2, 41, 4), (6, 43), (4099,), (2 * 2053,)])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_fft_lengths_with_large_prime_factors(cuda, dims, sign):
+    """Axis lengths with a prime factor above 31 run as a chirp-z (Bluestein) convolution on the power-of-two passes
+    (the reference takes any length through numpy): strided and contiguous axes, in place, and M = 8192 > the
+    shared-memory line limit (4099, 4106 points: four-step passes inside the convolution)."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(sum(dims))
+    x = rng.normal(size=(2, *dims)) + 1j * rng.normal(size=(2, *dims))
+    axes = tuple(range(1, 1 + len(dims)))
+    want = (np.fft.fftn if sign < 0 else np.fft.ifftn)(x, axes=axes, norm="ortho")
+    xd = kernels.to_device(x, torch.complex128)
+    got = kernels.fft_c2c(xd, dims, sign).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-12)
+    kernels.fft_c2c(xd, dims, sign, out=xd)
+    np.testing.assert_allclose(xd.cpu().numpy(), want, rtol=0, atol=2e-12)
+
+
+def test_operator_basis_change_on_a_37_point_axis(cuda):
+    """The momentum <-> position conversion of the mirror on a prime axis (slate_core goes through numpy there)."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(37)
+    x = _rand_c(rng, 3, 37)
+    got = kernels.fft_axis(kernels.to_device(x, torch.complex128), 3, 37, 1, +1).cpu().numpy()
+    np.testing.assert_allclose(got.reshape(3, 37), np.fft.ifft(x, axis=1, norm="ortho"), rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize(("shape", "repeat"), [((4,), (1,)), ((3, 4), (1, 5)), ((3, 4), (5, 1)), ((2, 3, 4), (3, 1, 2))])
 def test_unit_repeats(cuda, shape, repeat):
     """repeat = 1 along an axis: permutation, cell FFT and build must degrade gracefully."""
