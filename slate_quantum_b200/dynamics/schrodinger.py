@@ -216,8 +216,15 @@ class TiledEvolvedStates(StateList):
         tile_free = [None, None]
         pending: deque = deque()  # (event, t0, host view) in time order
         k = 0
-        for i_tile, t0 in enumerate(range(0, self.n_times, rows)):
-            tt = min(rows, self.n_times - t0)
+        # tile boundaries: the first tiles ramp up (64 rows = one time tile of the evolve kernel, then x 2) so that the
+        # device -> host stream - the bottleneck of the whole call at config sizes - starts as soon as a few rows exist
+        bounds, t_next, ramp = [], 0, min(rows, 64)
+        while t_next < self.n_times:
+            tt = min(ramp, self.n_times - t_next)
+            bounds.append((t_next, tt))
+            t_next += tt
+            ramp = min(rows, ramp * 2)
+        for i_tile, (t0, tt) in enumerate(bounds):
             buf = dev[i_tile & 1]
             if tile_free[i_tile & 1] is not None:
                 cur.wait_event(tile_free[i_tile & 1])  # the D2H of the tile that used this buffer is done
