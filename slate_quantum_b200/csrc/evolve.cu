@@ -632,7 +632,7 @@ int launch_evolve_bloch(int n, int64_t batch, const sqb_c128* transform, const d
   if (e != cudaSuccess) return (int)e;
   int64_t t_tiles = (t_count + TM - 1) / TM;
   static const int tiles_env = getenv("SQB_EVOLVE_TILES_PER_CTA") ? atoi(getenv("SQB_EVOLVE_TILES_PER_CTA")) : 0;
-  const int tiles_per_cta = tiles_env > 0 ? tiles_env : 8;
+  const int tiles_per_cta = tiles_env > 0 ? tiles_env : 16;  // measured at cfg3: 4 -> 224.0, 8 -> 221.6, 16 -> 220.4, 32 -> 220.5 ms
   if (use_3m) t_tiles = (t_tiles + tiles_per_cta - 1) / tiles_per_cta;  // CTAs walk several time tiles
   if (t_tiles > 65535) return SQB_E_UNSUPPORTED;
   const int tn = use_3m ? TN3 : TN;
