@@ -233,7 +233,19 @@ int sqb_tridiag_eigh_batched(int n, int64_t batch, const double* d, const double
  * instead of 4).  Accuracy: <= ~10 extra roundings per element, normwise 1e-15.
  * The workspace also holds the plane Re+Im of `transform` (the third operand of 3M).  It only depends on
  * `transform`: pass reuse_transform_plane = 1 on later calls with the SAME transform, n, batch and workspace
- * (e.g. the next time tile) to skip recomputing it. */
+ * (e.g. the next time tile) to skip recomputing it.
+ *
+ * Two routes, same result to ~1e-13 of sum_e |c_e V[e, j]| (sqb_evolve_uniform_route tells which one a call takes:
+ * 1 = NUFFT, 0 = GEMM; SQB_EVOLVE = gemm | nufft overrides the heuristic n <= 256, t_count >= 192):
+ *   GEMM  - the 3M tensor-core product above, 6 N flop per output element;
+ *   NUFFT - the sum over eigenstates is a sum of N complex exponentials in the row index whose angles
+ *           (w dt / hbar) mod 2 pi are shared by every column of a block: per tile of 512 rows the sources are
+ *           gathered onto a 1024-point grid with a 14-point "exponential of semicircle" window, one 1024-point FFT
+ *           per column in shared memory, scale by the inverse window transform (csrc/evolve_nufft.cuh;
+ *           ~130 flop per output element whatever N).
+ * The workspace covers both routes and records whether its Re+Im plane matches the transform, so calls with
+ * different t_count (different routes) may share it under the reuse_transform_plane protocol. */
+int sqb_evolve_uniform_route(int n, int64_t batch, int64_t t_count);
 size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count);
 int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
                              const sqb_c128* c, const double* times, int64_t t_count, double dt, double hbar,

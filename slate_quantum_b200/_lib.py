@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "sqb_apply_transform",
     "sqb_evolve_eigen",
     "sqb_evolve_bloch",
+    "sqb_evolve_uniform_route",
     "sqb_evolve_uniform_workspace_bytes",
     "sqb_evolve_bloch_uniform",
     "sqb_measure_moments",
@@ -152,6 +153,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_evolve_bloch.argtypes = [
         c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_int64, c_void_p,
     ]
+    lib.sqb_evolve_uniform_route.restype = c_int
+    lib.sqb_evolve_uniform_route.argtypes = [c_int, c_int64, c_int64]
     lib.sqb_evolve_uniform_workspace_bytes.restype = c_size_t
     lib.sqb_evolve_uniform_workspace_bytes.argtypes = [c_int, c_int64, c_int64]
     lib.sqb_evolve_bloch_uniform.restype = c_int

@@ -97,7 +97,8 @@ constexpr int TM = 64;    // times per CTA tile (both GEMM variants)
 __global__ void __launch_bounds__(256)
 phase_tables_kernel(int64_t m, const double* __restrict__ w, const double* __restrict__ times, int64_t t_count,
                     double dt, double hbar, c128* __restrict__ step8, c128* __restrict__ pow8,
-                    c128* __restrict__ tilebase) {
+                    c128* __restrict__ tilebase, int* __restrict__ plane_valid_flag) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *plane_valid_flag = 1;  // ordered after bsum_kernel on the stream
   const int64_t n_tiles = (t_count + TM - 1) / TM;
   const int64_t total = m * (9 + n_tiles);
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -351,7 +352,10 @@ evolve_bloch_kernel(int n, const c128* __restrict__ V, const double* __restrict_
 // stride padded to an even number of doubles so that its rows can be bulk-copied) - a DADD in the consumer
 // warps would queue behind their own DMMAs on the shared FP64 pipe.
 __global__ void __launch_bounds__(256)
-bsum_kernel(int n, int n_pad, int64_t rows, const c128* __restrict__ V, double* __restrict__ bsum) {
+bsum_kernel(int n, int n_pad, int64_t rows, const c128* __restrict__ V, double* __restrict__ bsum,
+            const int* __restrict__ valid_flag, int force) {
+  // reuse requested by the caller: skip unless the NUFFT route ran on a new transform since the plane was built
+  if (!force && *valid_flag == 1) return;
   const int64_t total = rows * n_pad;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = g / n_pad;
@@ -574,6 +578,8 @@ evolve_bloch_3m_kernel(int n, const c128* __restrict__ V, const c128* __restrict
 
 }  // namespace
 
+#include "evolve_nufft.cuh"
+
 extern "C" int sqb_project(int n, int64_t batch, const sqb_c128* transform, const sqb_c128* psi, sqb_c128* c,
                            void* stream) {
   if (n < 1 || batch < 0 || !transform || !psi || !c) return SQB_E_BADARG;
@@ -663,11 +669,30 @@ extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform,
                              nullptr, nullptr, 0, stream);
 }
 
+namespace {
+// uniform grids: 1 = NUFFT route (evolve_nufft.cuh), 0 = 3M GEMM.  SQB_EVOLVE = gemm | nufft overrides the
+// heuristic (the NUFFT kernel holds <= 256 sources; a tile of 512 rows costs the same whatever t_count, so short
+// row counts stay on the GEMM)
+int evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
+  static const char* env = getenv("SQB_EVOLVE");
+  if (n > kNuMaxN || batch < 1 || t_count < 1) return 0;
+  if (env && env[0] == 'g') return 0;
+  if (env && env[0] == 'n') return 1;
+  return (t_count >= 192 && n >= 32) ? 1 : 0;
+}
+inline size_t round_up_256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+extern "C" int sqb_evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
+  return evolve_uniform_route(n, batch, t_count);
+}
+
 extern "C" size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count) {
   if (n < 1 || batch < 0 || t_count < 0) return 0;
   const int64_t tiles = (t_count + TM - 1) / TM;
   const int64_t n_pad = n + (n & 1);
-  return (size_t)(batch * n) * (size_t)(9 + tiles) * sizeof(c128) + (size_t)(batch * n) * n_pad * sizeof(double) + 512;
+  return round_up_256((size_t)(batch * n) * n_pad * sizeof(double)) + 256 + round_up_256(nufft_plan_bytes(n, batch)) +
+         (size_t)(batch * n) * (size_t)(9 + tiles) * sizeof(c128) + 512;
 }
 
 extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
@@ -679,22 +704,36 @@ extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* tr
   if (!workspace || workspace_bytes < sqb_evolve_uniform_workspace_bytes(n, batch, t_count)) return SQB_E_WORKSPACE;
   const int64_t m = batch * n;
   const int64_t tiles = (t_count + TM - 1) / TM;
-  // workspace layout: [bsum: m * n_pad doubles][step8: m][pow8: 8 m][tilebase: tiles * m]; bsum first so that
-  // its position does not depend on t_count and it can be reused across calls on the same transform
+  // workspace layout: [bsum: m * n_pad doubles][flag: "bsum matches the transform"][NUFFT plan][step8: m][pow8: 8 m]
+  // [tilebase: tiles * m]; everything before the phase tables has a position that does not depend on t_count, so
+  // the plane can be reused across calls on the same transform
   const int n_pad = n + (n & 1);
-  double* bsum = reinterpret_cast<double*>(workspace);  // [batch*n][n_pad] plane Re + Im of `transform`
-  c128* step8 = reinterpret_cast<c128*>(bsum + (m * n_pad + (m * n_pad & 1)));
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  double* bsum = reinterpret_cast<double*>(base);  // [batch*n][n_pad] plane Re + Im of `transform`
+  base += round_up_256((size_t)m * n_pad * sizeof(double));
+  int* plane_flag = reinterpret_cast<int*>(base);
+  base += 256;
+  void* plan_base = base;
+  base += round_up_256(nufft_plan_bytes(n, batch));
+  if (evolve_uniform_route(n, batch, t_count)) {
+    if (!transform || !c || !out || out_row_stride < batch * n) return SQB_E_BADARG;
+    return launch_evolve_nufft(n, batch, transform, w, c, times, t_count, dt, hbar, out, out_row_stride, plan_base,
+                               plane_flag, reuse_transform_plane ? 0 : 1, sqb_stream(stream));
+  }
+  c128* step8 = reinterpret_cast<c128*>(base);
   c128* pow8 = step8 + m;
   c128* tilebase = pow8 + 8 * m;
-  const int64_t total = m * (9 + tiles);
-  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
-  phase_tables_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, times, t_count, dt, hbar, step8, pow8, tilebase);
-  SQB_LAUNCH_CHECK();
-  if (!reuse_transform_plane) {
+  {
     const int grid2 = (int)sqb_min64((m * n_pad + 255) / 256, 148 * 32);
-    bsum_kernel<<<grid2, 256, 0, sqb_stream(stream)>>>(n, n_pad, m, reinterpret_cast<const c128*>(transform), bsum);
+    bsum_kernel<<<grid2, 256, 0, sqb_stream(stream)>>>(n, n_pad, m, reinterpret_cast<const c128*>(transform), bsum,
+                                                       plane_flag, reuse_transform_plane ? 0 : 1);
     SQB_LAUNCH_CHECK();
   }
+  const int64_t total = m * (9 + tiles);
+  const int grid = (int)sqb_min64((total + 255) / 256, 148 * 16);
+  phase_tables_kernel<<<grid, 256, 0, sqb_stream(stream)>>>(m, w, times, t_count, dt, hbar, step8, pow8, tilebase,
+                                                            plane_flag);
+  SQB_LAUNCH_CHECK();
   return launch_evolve_bloch(n, batch, transform, w, c, times, t_count, hbar, out, out_row_stride, step8, pow8, tilebase,
                              bsum, n_pad, stream);
 }

@@ -476,6 +476,11 @@ def evolve_uniform_workspace_bytes(n: int, batch: int, t_count: int) -> int:
     return int(_lib.load().sqb_evolve_uniform_workspace_bytes(n, batch, t_count))
 
 
+def evolve_uniform_route(n: int, batch: int, t_count: int) -> str:
+    """Which kernel `evolve_bloch(..., uniform_dt=dt)` runs for this shape: "nufft" or "gemm" (SQB_EVOLVE overrides)."""
+    return "nufft" if _lib.load().sqb_evolve_uniform_route(n, batch, t_count) else "gemm"
+
+
 def evolve_bloch(
     transform: torch.Tensor, w: torch.Tensor, c: torch.Tensor, times: torch.Tensor, hbar: float,
     out: torch.Tensor | None = None, uniform_dt: float | None = None,
@@ -483,8 +488,9 @@ def evolve_bloch(
 ) -> torch.Tensor:
     """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM).
 
-    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`) to use the 3M kernel with
-    table-driven phases.  workspace / reuse_plane: a caller-owned workspace (>= evolve_uniform_workspace_bytes)
+    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`): blocks of <= 256 states and >= 192
+    rows then take the NUFFT route (gather + 1024-point FFT per 512-row tile, csrc/evolve_nufft.cuh), the rest the 3M
+    tensor-core GEMM with table-driven phases (`evolve_uniform_route`).  workspace / reuse_plane: a caller-owned workspace (>= evolve_uniform_workspace_bytes)
     lets consecutive calls on the SAME transform (time tiles) skip recomputing the Re+Im plane."""
     _require_cuda()
     lib = _lib.load()
@@ -524,7 +530,9 @@ def evolve_bloch(
             _ptr(out), row_stride, _ptr(workspace), workspace.numel(), int(bool(reuse_plane)), _stream(),
         )
         _lib.check(rc, "sqb_evolve_bloch_uniform")
-        _count((1 if reuse_plane else 2) - (-batch // 65535))  # phase tables (+ Re+Im plane) + GEMM
+        # GEMM route: Re+Im plane (returns at once when reused) + phase tables + GEMM; NUFFT route: window transform +
+        # plan + one transform kernel per 65535 blocks
+        _count(2 - (-batch // 65535))
     return out
 
 

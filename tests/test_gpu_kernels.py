@@ -413,6 +413,66 @@ def test_evolve_ragged_sizes(cuda, n, n_t):
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize(
+    ("n", "n_t", "spread"),
+    [(32, 192, 1.0), (100, 512, 30.0), (256, 513, 3.0), (255, 1500, 500.0), (64, 2048, 0.0)],
+)
+def test_evolve_uniform_nufft_route(cuda, n, n_t, spread):
+    """Uniform grids with <= 256 states per block and >= 192 rows take the NUFFT route (csrc/evolve_nufft.cuh): against
+    the oracle's direct sum for ragged tiles, clustered / fully degenerate spectra (spread = 0: every source in ONE
+    window), phases of hundreds of radians per step, and a column-slice output."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(n + n_t)
+    batch = 3
+    assert kernels.evolve_uniform_route(n, batch, n_t) == "nufft"
+    assert kernels.evolve_uniform_route(n, batch, 64) == "gemm"
+    assert kernels.evolve_uniform_route(343, batch, n_t) == "gemm"
+    g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+    _, t_ref = o.eigh_blocks(g + np.swapaxes(g.conj(), 1, 2))
+    w_ref = np.sort(rng.uniform(-0.2, 1.0, size=(batch, n)) * spread, axis=1) + 0.7
+    w_ref[0, : n // 2] = w_ref[0, 0]  # a degenerate band
+    c = (rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n))) / np.sqrt(n)
+    times = 0.3 * HBAR + np.arange(n_t) * 0.37 * HBAR
+    want = o.back_transform(t_ref, o.evolve_eigenbasis(c, w_ref, times, HBAR)).reshape(n_t, batch * n)
+    args = (kernels.to_device(t_ref, torch.complex128), kernels.to_device(w_ref, torch.float64),
+            kernels.to_device(c, torch.complex128), kernels.to_device(times, torch.float64), HBAR)
+    dt = kernels.uniform_step(times)
+    got = kernels.evolve_bloch(*args, uniform_dt=dt).cpu().numpy()
+    # the oracle's own phases carry |w t / hbar| * 1e-16 of rounding (up to ~3e-11 at spread = 500)
+    tol = 1e-11 * max(1.0, spread / 10.0)
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+    # output as a column slice of a wider buffer (the multi-GPU segment layout)
+    wide = torch.zeros((n_t, batch * n + 40), dtype=torch.complex128, device="cuda")
+    kernels.evolve_bloch(*args, uniform_dt=dt, out=wide[:, 24 : 24 + batch * n])
+    np.testing.assert_allclose(wide[:, 24 : 24 + batch * n].cpu().numpy(), want, rtol=0, atol=tol)
+    assert float(wide[:, :24].abs().max()) == 0.0 and float(wide[:, 24 + batch * n :].abs().max()) == 0.0
+
+
+def test_evolve_uniform_routes_share_one_workspace(cuda):
+    """Time tiles of different length take different routes (host_tiles ramps 64, 128, ... rows): the GEMM route's
+    Re+Im plane must be rebuilt when the NUFFT route served the first call on a new transform."""
+    torch, kernels = _gpu()
+    rng = np.random.default_rng(99)
+    n, batch = 96, 4
+    times = 0.1 * HBAR + np.arange(600) * 0.21 * HBAR
+    dt = kernels.uniform_step(times)
+    ws = torch.empty(kernels.evolve_uniform_workspace_bytes(n, batch, 600), dtype=torch.uint8, device="cuda")
+    ws.fill_(0xFF)
+    for trial in range(2):  # second trial: a NEW transform in the same workspace, first served by the NUFFT route
+        g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
+        w_ref, t_ref = o.eigh_blocks(g + np.swapaxes(g.conj(), 1, 2))
+        c = (rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n))) / np.sqrt(n)
+        want = o.back_transform(t_ref, o.evolve_eigenbasis(c, w_ref, times, HBAR)).reshape(600, batch * n)
+        td, wd, cd = (kernels.to_device(t_ref, torch.complex128), kernels.to_device(w_ref, torch.float64),
+                      kernels.to_device(c, torch.complex128))
+        reuse = False
+        for t0, t1 in ((0, 500), (500, 564), (564, 600)) if trial else ((0, 64), (64, 564), (564, 600)):
+            tt = kernels.to_device(times[t0:t1], torch.float64)
+            got = kernels.evolve_bloch(td, wd, cd, tt, HBAR, uniform_dt=dt, workspace=ws, reuse_plane=reuse)
+            np.testing.assert_allclose(got.cpu().numpy(), want[t0:t1], rtol=0, atol=1e-10)
+            reuse = True
+
+
 @pytest.mark.parametrize("dims", [(11,), (13 * 17,), (19 * 2,), (23, 4), (29,), (31, 3), (1,), (2, 1, 3)])
 def test_fft_generic_primes_and_unit_axes(cuda, dims):
     torch, kernels = _gpu()
