@@ -204,11 +204,20 @@ __device__ __forceinline__ void nu_dft16(c128* x) {
 constexpr size_t kNuSmemG = (size_t)kNuNG * kNuJ * sizeof(c128);        // 131072
 constexpr size_t kNuSmemA = (size_t)kNuMaxN * kNuJ * sizeof(c128);      // 32768
 constexpr size_t kNuSmemWt = (size_t)kNuMaxN * kNuRow * sizeof(double);  // 40960
-constexpr size_t kNuSmemTw = (size_t)kNuNG * sizeof(c128);              // 16384
+constexpr size_t kNuSmemTw = (size_t)(kNuNG / 2) * sizeof(c128);        // 8192: w^k, k < NG/2 (w^(k + NG/2) = -w^k)
+constexpr size_t kNuSmemDec = (size_t)kNuTT * sizeof(double);           // 4096
 constexpr size_t kNuSmemPh = (size_t)kNuMaxN * sizeof(c128);            // 4096
 constexpr size_t kNuSmemPc = (size_t)kNuPcStride * 2;                   // 2064
 constexpr size_t kNuSmemIdx = (size_t)kNuMaxN * 2;                      // 512 (x 2: src, l0s)
-constexpr size_t kNuSmem = kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw + kNuSmemPh + kNuSmemPc + 2 * kNuSmemIdx;
+constexpr size_t kNuSmem =
+    kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw + kNuSmemDec + kNuSmemPh + kNuSmemPc + 2 * kNuSmemIdx;
+constexpr int kNuVreg = kNuMaxN * kNuJ / kNuThreads;  // eigenvector elements a thread keeps across the row tiles
+
+// w_1024^k for k < NG from the half table
+__device__ __forceinline__ c128 nu_tw(const c128* tw, int k) {
+  const c128 t = tw[k & (kNuNG / 2 - 1)];
+  return (k & (kNuNG / 2)) ? make_double2(-t.x, -t.y) : t;
+}
 
 __global__ void __launch_bounds__(kNuThreads, 1)
 evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict__ wv, const c128* __restrict__ cv,
@@ -219,8 +228,10 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   c128* A = reinterpret_cast<c128*>(nu_smem + kNuSmemG);
   double* wt = reinterpret_cast<double*>(nu_smem + kNuSmemG + kNuSmemA);
   c128* tw = reinterpret_cast<c128*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt);
-  c128* ph = reinterpret_cast<c128*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw);
-  unsigned short* pcs = reinterpret_cast<unsigned short*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw + kNuSmemPh);
+  double* decs = reinterpret_cast<double*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw);
+  c128* ph = reinterpret_cast<c128*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw + kNuSmemDec);
+  unsigned short* pcs = reinterpret_cast<unsigned short*>(nu_smem + kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw +
+                                                         kNuSmemDec + kNuSmemPh);
   unsigned short* srcs = pcs + kNuPcStride;
   unsigned short* l0ss = srcs + kNuMaxN;
 
@@ -239,13 +250,22 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       srcs[i] = p.src[b * n + i];
       l0ss[i] = p.l0s[b * n + i];
     }
-    for (int i = tid; i < kNuNG; i += kNuThreads) {
+    for (int i = tid; i < kNuNG / 2; i += kNuThreads) {
       double s, c;
       sincospi(-(double)i / (kNuNG / 2), &s, &c);
       tw[i] = make_double2(c, s);
     }
+    for (int i = tid; i < kNuTT; i += kNuThreads) decs[i] = p.dec[i];
   }
   __syncthreads();
+  // the block's eigenvector elements of this CTA's columns stay in registers for every row tile
+  c128 vreg[kNuVreg];
+#pragma unroll
+  for (int i = 0; i < kNuVreg; ++i) {
+    const int idx = tid + i * kNuThreads;
+    vreg[i] = make_double2(0.0, 0.0);
+    if (idx < n * kNuJ && col_ok) vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + j0 + j);
+  }
   // source s = tid keeps its eigenvalue and coefficient
   double we = 0.0;
   c128 ce = make_double2(0.0, 0.0);
@@ -264,11 +284,10 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       ph[tid] = cmul(ce, make_double2(c, s));
     }
     __syncthreads();
-    for (int idx = tid; idx < n * kNuJ; idx += kNuThreads) {
-      const int s = idx >> 3;
-      c128 v = make_double2(0.0, 0.0);
-      if (col_ok) v = __ldg(V + (b * n + srcs[s]) * (int64_t)n + j0 + j);
-      A[idx] = cmul(ph[s], v);
+#pragma unroll
+    for (int i = 0; i < kNuVreg; ++i) {
+      const int idx = tid + i * kNuThreads;
+      if (idx < n * kNuJ) A[idx] = cmul(ph[idx >> 3], vreg[i]);
     }
     __syncthreads();
 
@@ -308,7 +327,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       for (int i = 0; i < 16; ++i) x[i] = G[(64 * i + n2) * kNuJ + j];
       nu_dft16(x);
 #pragma unroll
-      for (int i = 1; i < 16; ++i) x[i] = cmul(x[i], tw[(n2 * i) & (kNuNG - 1)]);
+      for (int i = 1; i < 16; ++i) x[i] = cmul(x[i], nu_tw(tw, n2 * i));
 #pragma unroll
       for (int i = 0; i < 16; ++i) G[(64 * i + n2) * kNuJ + j] = x[i];
     }
@@ -322,7 +341,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       for (int i = 0; i < 8; ++i) x[i] = g[8 * i * kNuJ];
       nu_dft8(x);
 #pragma unroll
-      for (int i = 1; i < 8; ++i) x[i] = cmul(x[i], tw[16 * n2b * i]);
+      for (int i = 1; i < 8; ++i) x[i] = cmul(x[i], nu_tw(tw, 16 * n2b * i));
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[8 * i * kNuJ] = x[i];
     }
@@ -341,7 +360,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       for (int q = 0; q < 4; ++q) {
         // q = 0, 1: k3 = 6, 7 -> rows mlow, mlow + 128;  q = 2, 3: k3 = 0, 1 -> rows mlow + 256, mlow + 384
         const int m = mlow + 128 * q;
-        const c128 val = cscale(x[q < 2 ? 6 + q : q - 2], __ldg(p.dec + m));
+        const c128 val = cscale(x[q < 2 ? 6 + q : q - 2], decs[m]);
         const int64_t r = r0 + m;
         if (r < t_count && col_ok) __stcs(out + r * out_row_stride + b * (int64_t)n + j0 + j, val);
       }
