@@ -500,6 +500,35 @@ class PositionRun:
             "clocks": sampler.summary() if sampler else None,
         }
 
+    def evolve_route_ms(self, route: str, reps: int = 2) -> float:
+        """K3c alone over all T rows through one route of the uniform-grid evolve (SQB_EVOLVE = gemm | nufft), on the
+        eigensystem the last step left in the solver; N = 1 only.  Overwrites `states` (not `pos_out`)."""
+        ctx, solver = self.ctx, self.solver
+        T, t_tile = self.T, self.t_tile
+        os.environ["SQB_EVOLVE"] = route
+        try:
+            c = solver.project(self.psi0)
+
+            def once():
+                for t0 in range(0, T, t_tile):
+                    tt = min(t_tile, T - t0)
+                    if self.with_position:
+                        solver.evolve_cell(c, self.times[t0 : t0 + tt], out=self.states[:tt], uniform_dt=self.dt_uniform)
+                    else:
+                        solver.evolve_bloch(c, self.times[t0 : t0 + tt], out=self.states[:tt], uniform_dt=self.dt_uniform)
+
+            once()
+            ctx.sync_all()
+            a, b = ctx.ev(), ctx.ev()
+            a.record()
+            for _ in range(reps):
+                once()
+            b.record()
+            ctx.sync_all()
+            return a.elapsed_time(b) / reps
+        finally:
+            os.environ.pop("SQB_EVOLVE", None)
+
     def parity_check(self) -> dict:
         """Sampled blocks of the FIRST and LAST time row this rank holds (the last tile of the last step), against
         the CPU oracle; max over ranks.  At N > 1 the sampled blocks lie in several ranks' k-ranges and every rank
@@ -918,10 +947,17 @@ def run_ours(args) -> None:
     dmma_peak = max(dmma_variants)
     dfma_peak = peak(lib.sqb_peak_dfma)
     parity = run.parity_check()
+    # the tensor-core GEMM route of the same stage (north_star kernel 3), timed on the same eigensystem: what the NUFFT
+    # route replaced on uniform grids, and what still runs for general grids, N > 256 and short tiles
+    gemm_route_ms = None
+    if world == 1 and run.dt_uniform is not None and not os.environ.get("SQB_EVOLVE"):
+        if kernels.evolve_uniform_route(n, run.n_k_local, min(run.t_tile, T)) == "nufft":
+            gemm_route_ms = run.evolve_route_ms("gemm")
     stage_ms, ms_per_step, value = main["stage_ms"], main["ms_per_step"], main["value"]
     t_tile, n_k_local, n_k_global = run.t_tile, run.n_k_local, run.n_k_global
     repeat_global = run.repeat_global
     exchange_mode = run.sharded.exchange_mode if run.sharded is not None else None
+    time_sharded = run.sharded is not None
 
     # ---- K6 (SURVEY 8f "next" row, outside the step): observables of the position-basis states of the last time
     # tile, one pass over the tile; reported beside the step, extrapolated to all T samples
@@ -1002,8 +1038,113 @@ def run_ours(args) -> None:
         flops_eigh = (68.0 / 3.0) * n**3 * n_k_local
         ach = flops_evolve / (stage_ms["evolve"] * 1e-3) / 1e12
         uniform = kernels.uniform_step(cfg.times()) is not None
-        kernel_name = "evolve_bloch_3m_kernel" if uniform else "evolve_bloch_kernel"
-        traffic, traffic_src = ncu_traffic(kernel_name, cfg.name, min(t_tile, T)) if world == 1 else (None, None)
+        rows_launch = min(t_tile, T)
+        nufft = uniform and kernels.evolve_uniform_route(n, n_k_local, rows_launch) == "nufft"
+        kernel_name = "evolve_nufft_kernel" if nufft else ("evolve_bloch_3m_kernel" if uniform else "evolve_bloch_kernel")
+        traffic, traffic_src = ncu_traffic(kernel_name, cfg.name, rows_launch) if world == 1 else (None, None)
+        # time rows one rank evolves per step (time-sharded over the ranks when the position stage follows)
+        rows_step = T // world if (world > 1 and time_sharded) else T
+        n_k_evolved = n_k_global if (world > 1 and time_sharded) else n_k_local
+        rows_launch = min(rows_launch, rows_step)
+        launches_per_step = -(-rows_step // rows_launch)
+        launch_ms = stage_ms["evolve"] / launches_per_step
+        if nufft:
+            # executed flop of the NUFFT route per output element, counted from csrc/evolve_nufft.cuh at N = 256: gather
+            # 1088 (quad, source) pairs x 16 + phases 1536 + radix-16 stage 64 x 258 + radix-8 stage 128 x 98 + pruned
+            # last stage 128 x 56 = 55 k flop per column and tile of 512 rows
+            flop_per_output = (n * 4.25 * 16 + n * 6 + 64 * 258 + 128 * 98 + 128 * 56) / 512.0
+            exec_flops = flop_per_output * n * n_k_evolved * 512.0 * -(-rows_launch // 512)
+            out_bytes = 16.0 * n * rows_launch * n_k_evolved
+            roofline_kernel = {
+                "kernel": "evolve_nufft_kernel (K3c on a uniform time grid as a type-1 non-uniform FFT: window gather of "
+                "the N eigenstates onto 1024 grid points + one shared-memory FFT per column and 512-row tile; "
+                "csrc/evolve_nufft.cuh)",
+                "bound": "tensor",
+                "achieved": ach,
+                "peak": dmma_peak,
+                "unit": "TFLOP/s",
+                "frac": ach / dmma_peak,
+                "normalisation": "SURVEY 8d useful-work figure 8 N^2 T flop per block (the complex GEMM [T x N] . [N x N] the "
+                "reference evaluates) over the measured launch time: the NUFFT route executes ~110 flop per output "
+                "element instead of 8 N = 2048, which is why `frac` exceeds 1 - the resources this kernel actually "
+                "loads are in `executed` (FP64 pipe) and `hbm` (its remaining bound: the states it must write)",
+                "executed": {
+                    "flops_per_launch": exec_flops,
+                    "flop_per_output_element": flop_per_output,
+                    "achieved": exec_flops / (launch_ms * 1e-3) / 1e12,
+                    "peak": dfma_peak,
+                    "frac": exec_flops / (launch_ms * 1e-3) / 1e12 / dfma_peak,
+                    "note": "plain FP64 adds / multiplies / FMAs of the gather and the radix-16/8/8 butterflies (no tensor "
+                    "cores: B200's DMMA and DFMA peaks are equal); ncu: shared-memory wavefronts ~55-60 % of peak, FP64 "
+                    "pipe ~28 %",
+                },
+                "hbm": {
+                    "bound": "hbm",
+                    "achieved": (out_bytes + 16.0 * n * n * n_k_evolved) / (launch_ms * 1e-3) / 1e9,
+                    "peak": _hbm_peak(),
+                    "unit": "GB/s",
+                    "frac": (out_bytes + 16.0 * n * n * n_k_evolved) / (launch_ms * 1e-3) / 1e9 / _hbm_peak(),
+                    "note": "algorithmic bytes of SURVEY 8d: 16 N T written per block + the eigenvectors read once",
+                },
+                "traffic": traffic,
+                "traffic_source": traffic_src,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed "
+                "--set full capture of this kernel at this config and time tile; null when no capture matches)",
+                "algorithmic_bytes_per_launch": out_bytes + 16.0 * n * n * n_k_evolved,
+                "launch_ms": launch_ms,
+                "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
+                f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
+                "the timed steps; MEASURED_PEAKS.json carries only bf16 and HBM - the FP64 tensor peak it lacks is "
+                "ncu's sm__ops_path_tensor_src_fp64.sum.peak_sustained (18 944 op/cycle x 1.965 GHz = 37.2 TFLOP/s, "
+                f"profiles/r01_s2_evolve3m_cfg3_raw.csv), which this micro-benchmark reproduces; plain DFMA {dfma_peak:.1f}; "
+                "HBM: MEASURED_PEAKS.json copy figure",
+                "algorithmic_flops_per_launch": flops_evolve * rows_launch / T,
+            }
+            if gemm_route_ms is not None:
+                g_ach = flops_evolve / (gemm_route_ms * 1e-3) / 1e12
+                roofline_kernel["gemm_route"] = {
+                    "kernel": "evolve_bloch_3m_kernel (SQB_EVOLVE=gemm: fused phase x eigenvector complex GEMM, 3M product, "
+                    "DMMA.8x8x4; also the route of general grids, N > 256 and tiles under 192 rows)",
+                    "stage_ms": gemm_route_ms,
+                    "bound": "tensor",
+                    "achieved": g_ach,
+                    "peak": dmma_peak,
+                    "unit": "TFLOP/s",
+                    "frac": g_ach / dmma_peak,
+                    "executed_frac": 0.75 * g_ach / dmma_peak,
+                    "note": "same eigensystem, same run, timed after the steps; the default route is "
+                    f"{gemm_route_ms / stage_ms['evolve']:.2f}x faster",
+                }
+        else:
+            roofline_kernel = {
+                "kernel": f"{kernel_name} (K3c fused phase x eigenvector complex GEMM"
+                + (", 3M product" if uniform else "") + ", DMMA.8x8x4)",
+                "bound": "tensor",
+                "achieved": ach,
+                "peak": dmma_peak,
+                "unit": "TFLOP/s",
+                "frac": ach / dmma_peak,
+                # the 3M complex product executes 6 N^2 T real flop for the 8 N^2 T algorithmic flop of the
+                # normalisation, so `frac` (algorithmic / peak) can exceed 1; the tensor-pipe utilisation is this:
+                "executed": {
+                    "flops_per_launch": (0.75 if uniform else 1.0) * flops_evolve * rows_launch / T,
+                    "achieved": (0.75 if uniform else 1.0) * ach,
+                    "frac": (0.75 if uniform else 1.0) * ach / dmma_peak,
+                    "note": "3 real DMMA products per complex MAC (3M) instead of 4: executed = 0.75 x algorithmic flop",
+                },
+                "traffic": traffic,
+                "traffic_source": traffic_src,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed "
+                "--set full capture of this kernel at this config and time tile; null when no capture matches)",
+                # states written + eigenvectors read once (+ their Re+Im plane for the 3M kernel)
+                "algorithmic_bytes_per_launch": (16.0 * n * rows_launch + (24.0 if uniform else 16.0) * n * n) * n_k_local,
+                "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
+                f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
+                "the timed steps; MEASURED_PEAKS.json carries only bf16 and HBM - the FP64 tensor peak it lacks is "
+                "ncu's sm__ops_path_tensor_src_fp64.sum.peak_sustained (18 944 op/cycle x 1.965 GHz = 37.2 TFLOP/s, "
+                f"profiles/r01_s2_evolve3m_cfg3_raw.csv), which this micro-benchmark reproduces; plain DFMA {dfma_peak:.1f}",
+                "algorithmic_flops_per_launch": flops_evolve * rows_launch / T,
+            }
         line = {
             "metric": METRIC,
             "value": value,
@@ -1033,35 +1174,7 @@ def run_ours(args) -> None:
             / ((stage_ms["fold"] + stage_ms["project"] + stage_ms["evolve"] + stage_ms["exchange"] + stage_ms["position"]) * 1e-3),
             "stage_ms": stage_ms,
             "parity_check": parity,
-            "roofline": {
-                "kernel": f"{kernel_name} (K3c fused phase x eigenvector complex GEMM"
-                + (", 3M product" if uniform else "") + ", DMMA.8x8x4)",
-                "bound": "tensor",
-                "achieved": ach,
-                "peak": dmma_peak,
-                "unit": "TFLOP/s",
-                "frac": ach / dmma_peak,
-                # the 3M complex product executes 6 N^2 T real flop for the 8 N^2 T algorithmic flop of the
-                # normalisation, so `frac` (algorithmic / peak) can exceed 1; the tensor-pipe utilisation is this:
-                "executed": {
-                    "flops_per_launch": (0.75 if uniform else 1.0) * flops_evolve * min(t_tile, T) / T,
-                    "achieved": (0.75 if uniform else 1.0) * ach,
-                    "frac": (0.75 if uniform else 1.0) * ach / dmma_peak,
-                    "note": "3 real DMMA products per complex MAC (3M) instead of 4: executed = 0.75 x algorithmic flop",
-                },
-                "traffic": traffic,
-                "traffic_source": traffic_src,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the committed "
-                "--set full capture of this kernel at this config and time tile; null when no capture matches)",
-                # states written + eigenvectors read once (+ their Re+Im plane for the 3M kernel)
-                "algorithmic_bytes_per_launch": (16.0 * n * min(t_tile, T) + (24.0 if uniform else 16.0) * n * n) * n_k_local,
-                "peak_source": "best of the FP64 DMMA issue-rate micro-benchmark variants (sqb_peak_dmma, "
-                f"4/8/16 chains per warp: {[round(v, 1) for v in dmma_variants]} TFLOP/s) measured in this run after "
-                "the timed steps; MEASURED_PEAKS.json carries only bf16 and HBM - the FP64 tensor peak it lacks is "
-                "ncu's sm__ops_path_tensor_src_fp64.sum.peak_sustained (18 944 op/cycle x 1.965 GHz = 37.2 TFLOP/s, "
-                f"profiles/r01_s2_evolve3m_cfg3_raw.csv), which this micro-benchmark reproduces; plain DFMA {dfma_peak:.1f}",
-                "algorithmic_flops_per_launch": flops_evolve * min(t_tile, T) / T,
-            },
+            "roofline": roofline_kernel,
             "roofline_stages": {
                 "eigh": {
                     "bound": "tensor (FP64)",

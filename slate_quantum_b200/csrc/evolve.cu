@@ -674,7 +674,7 @@ namespace {
 // heuristic (the NUFFT kernel holds <= 256 sources; a tile of 512 rows costs the same whatever t_count, so short
 // row counts stay on the GEMM)
 int evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
-  static const char* env = getenv("SQB_EVOLVE");
+  const char* env = getenv("SQB_EVOLVE");  // read per call: bench.py times both routes in one process
   if (n > kNuMaxN || batch < 1 || t_count < 1) return 0;
   if (env && env[0] == 'g') return 0;
   if (env && env[0] == 'n') return 1;
