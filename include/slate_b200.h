@@ -236,7 +236,7 @@ int sqb_tridiag_eigh_batched(int n, int64_t batch, const double* d, const double
  * (e.g. the next time tile) to skip recomputing it.
  *
  * Two routes, same result to ~1e-13 of sum_e |c_e V[e, j]| (sqb_evolve_uniform_route tells which one a call takes:
- * 1 = NUFFT, 0 = GEMM; SQB_EVOLVE = gemm | nufft overrides the heuristic n <= 256, t_count >= 192):
+ * 1 = NUFFT, 0 = GEMM; SQB_EVOLVE = gemm | nufft overrides the heuristic n <= 512, t_count >= 192):
  *   GEMM  - the 3M tensor-core product above, 6 N flop per output element;
  *   NUFFT - the sum over eigenstates is a sum of N complex exponentials in the row index whose angles
  *           (w dt / hbar) mod 2 pi are shared by every column of a block: per tile of 512 rows the sources are

@@ -671,7 +671,7 @@ extern "C" int sqb_evolve_bloch(int n, int64_t batch, const sqb_c128* transform,
 
 namespace {
 // uniform grids: 1 = NUFFT route (evolve_nufft.cuh), 0 = 3M GEMM.  SQB_EVOLVE = gemm | nufft overrides the
-// heuristic (the NUFFT kernel holds <= 256 sources; a tile of 512 rows costs the same whatever t_count, so short
+// heuristic (the NUFFT kernel takes <= 512 sources; a tile of 512 rows costs the same whatever t_count, so short
 // row counts stay on the GEMM)
 int evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
   const char* env = getenv("SQB_EVOLVE");  // read per call: bench.py times both routes in one process

@@ -7,7 +7,7 @@
 //
 // is a sum of N complex exponentials in r whose angles theta_e = (w_e dt / hbar) mod 2 pi are the SAME for every
 // column j of the block.  The GEMM form (evolve_bloch_3m_kernel) costs N multiply-adds per output element; here a tile
-// of TT = 512 rows costs a gather of the N sources onto an oversampled grid of NG = 1024 points (W = 14 window weights
+// of TT = 512 rows costs a gather of the N <= 512 sources onto an oversampled grid of NG = 1024 points (W = 14 window weights
 // per source, shared by all columns of the block), one 1024-point FFT per column and a scale:
 //
 //     out[r0 + m, j] = dec[m] * FFT_NG( g_j )[(m - TT/2) mod NG],
@@ -34,7 +34,8 @@ constexpr int kNuW = 14;                      // window width in grid points
 constexpr int kNuPad = 3;                     // zero weights either side (a thread gathers 4 consecutive grid points)
 constexpr int kNuRow = kNuW + 2 * kNuPad;     // padded weight row
 constexpr double kNuBeta = 2.3 * kNuW;
-constexpr int kNuMaxN = 256;                  // sources (eigenstates) per block
+constexpr int kNuMaxN = 512;                  // sources (eigenstates) per block
+constexpr int kNuChunk = 256;                 // sources resident in shared memory per gather pass
 constexpr int kNuJ = 8;                       // columns per CTA
 constexpr int kNuPcStride = kNuNG + 8;        // pc[x + 1] = #sources with first grid point <= x, x = -1 .. NG-1
 constexpr int kNuThreads = 512;
@@ -202,16 +203,16 @@ __device__ __forceinline__ void nu_dft16(c128* x) {
 }
 
 constexpr size_t kNuSmemG = (size_t)kNuNG * kNuJ * sizeof(c128);        // 131072
-constexpr size_t kNuSmemA = (size_t)kNuMaxN * kNuJ * sizeof(c128);      // 32768
-constexpr size_t kNuSmemWt = (size_t)kNuMaxN * kNuRow * sizeof(double);  // 40960
+constexpr size_t kNuSmemA = (size_t)kNuChunk * kNuJ * sizeof(c128);     // 32768
+constexpr size_t kNuSmemWt = (size_t)kNuChunk * kNuRow * sizeof(double);  // 40960
 constexpr size_t kNuSmemTw = (size_t)(kNuNG / 2) * sizeof(c128);        // 8192: w^k, k < NG/2 (w^(k + NG/2) = -w^k)
 constexpr size_t kNuSmemDec = (size_t)kNuTT * sizeof(double);           // 4096
-constexpr size_t kNuSmemPh = (size_t)kNuMaxN * sizeof(c128);            // 4096
+constexpr size_t kNuSmemPh = (size_t)kNuChunk * sizeof(c128);           // 4096
 constexpr size_t kNuSmemPc = (size_t)kNuPcStride * 2;                   // 2064
-constexpr size_t kNuSmemIdx = (size_t)kNuMaxN * 2;                      // 512 (x 2: src, l0s)
+constexpr size_t kNuSmemIdx = (size_t)kNuMaxN * 2;                      // 1024 (x 2: src, l0s)
 constexpr size_t kNuSmem =
     kNuSmemG + kNuSmemA + kNuSmemWt + kNuSmemTw + kNuSmemDec + kNuSmemPh + kNuSmemPc + 2 * kNuSmemIdx;
-constexpr int kNuVreg = kNuMaxN * kNuJ / kNuThreads;  // eigenvector elements a thread keeps across the row tiles
+constexpr int kNuVreg = kNuChunk * kNuJ / kNuThreads;  // eigenvector elements a thread keeps across the row tiles
 
 // w_1024^k for k < NG from the half table
 __device__ __forceinline__ c128 nu_tw(const c128* tw, int k) {
@@ -241,10 +242,14 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   const int j0 = blockIdx.x * kNuJ;
   const bool col_ok = j0 + j < n;
 
+  // blocks of more than kNuChunk eigenstates are gathered in passes of kNuChunk SORTED sources (the window weights
+  // and the phase x eigenvector products of one pass fill the shared memory left beside the grid lines)
+  const int n_chunks = (n + kNuChunk - 1) / kNuChunk;
+  const double* wsrc = p.wts + b * (int64_t)n * kNuRow;
   // ---- per-block plan and twiddles -> shared memory
   {
-    const double* wsrc = p.wts + b * (int64_t)n * kNuRow;
-    for (int i = tid; i < n * kNuRow; i += kNuThreads) wt[i] = wsrc[i];
+    if (n_chunks == 1)
+      for (int i = tid; i < n * kNuRow; i += kNuThreads) wt[i] = wsrc[i];
     for (int i = tid; i < kNuNG + 1; i += kNuThreads) pcs[i] = p.pc[b * kNuPcStride + i];
     for (int i = tid; i < n; i += kNuThreads) {
       srcs[i] = p.src[b * n + i];
@@ -264,7 +269,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   for (int i = 0; i < kNuVreg; ++i) {
     const int idx = tid + i * kNuThreads;
     vreg[i] = make_double2(0.0, 0.0);
-    if (idx < n * kNuJ && col_ok) vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + j0 + j);
+    if (n_chunks == 1 && idx < n * kNuJ && col_ok) vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + j0 + j);
   }
   // source s = tid keeps its eigenvalue and coefficient
   double we = 0.0;
@@ -276,47 +281,62 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   }
 
   for (int64_t r0 = 0; r0 < t_count; r0 += kNuTT) {
-    // ---- tile-centre phases, then A[s][j] = c_e exp(-1j w_e t_c / hbar) V[e][j0 + j]
-    if (tid < n) {
-      const double tc = times[r0] + (double)(kNuTT / 2) * dt;
-      double s, c;
-      sincos(-(we * tc) / hbar, &s, &c);
-      ph[tid] = cmul(ce, make_double2(c, s));
-    }
-    __syncthreads();
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int cs = chunk * kNuChunk, cnt = min(kNuChunk, n - cs);
+      if (n_chunks > 1) {
+        if (chunk > 0) __syncthreads();  // the previous pass has finished reading wt / A
+        for (int i = tid; i < cnt * kNuRow; i += kNuThreads) wt[i] = wsrc[cs * kNuRow + i];
+      }
+      // ---- tile-centre phases, then A[s][j] = c_e exp(-1j w_e t_c / hbar) V[e][j0 + j]
+      if (tid >= cs && tid < cs + cnt) {
+        const double tc = times[r0] + (double)(kNuTT / 2) * dt;
+        double s, c;
+        sincos(-(we * tc) / hbar, &s, &c);
+        ph[tid - cs] = cmul(ce, make_double2(c, s));
+      }
+      __syncthreads();
+      if (n_chunks == 1) {
 #pragma unroll
-    for (int i = 0; i < kNuVreg; ++i) {
-      const int idx = tid + i * kNuThreads;
-      if (idx < n * kNuJ) A[idx] = cmul(ph[idx >> 3], vreg[i]);
-    }
-    __syncthreads();
-
-    // ---- gather: a thread owns 4 consecutive grid points of column j
-    for (int quad = slot; quad < kNuNG / 4; quad += kNuSlots) {
-      const int l = 4 * quad;
-      c128 acc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = make_double2(0.0, 0.0);
-#pragma unroll 1
-      for (int wrap = 0; wrap < 2; ++wrap) {
-        if (wrap == 1 && l >= kNuW + kNuPad) break;
-        const int base = l + wrap * kNuNG;
-        const int lo = base - kNuW, hi = base + 3;
-        const int s0 = pcs[(lo < -1 ? -1 : (lo > kNuNG - 1 ? kNuNG - 1 : lo)) + 1];
-        const int s1 = pcs[(hi > kNuNG - 1 ? kNuNG - 1 : hi) + 1];
-        for (int s = s0; s < s1; ++s) {
-          const double* wr = wt + s * kNuRow + kNuPad + (base - (int)l0ss[s]);
-          const c128 a = A[s * kNuJ + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double wgt = wr[i];
-            acc[i].x = fma(wgt, a.x, acc[i].x);
-            acc[i].y = fma(wgt, a.y, acc[i].y);
-          }
+        for (int i = 0; i < kNuVreg; ++i) {
+          const int idx = tid + i * kNuThreads;
+          if (idx < n * kNuJ) A[idx] = cmul(ph[idx >> 3], vreg[i]);
+        }
+      } else {
+        for (int idx = tid; idx < cnt * kNuJ; idx += kNuThreads) {
+          c128 v = make_double2(0.0, 0.0);
+          if (col_ok) v = __ldg(V + (b * n + srcs[cs + (idx >> 3)]) * (int64_t)n + j0 + j);
+          A[idx] = cmul(ph[idx >> 3], v);
         }
       }
+      __syncthreads();
+
+      // ---- gather: a thread owns 4 consecutive grid points of column j
+      for (int quad = slot; quad < kNuNG / 4; quad += kNuSlots) {
+        const int l = 4 * quad;
+        c128 acc[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) G[(l + i) * kNuJ + j] = acc[i];
+        for (int i = 0; i < 4; ++i) acc[i] = chunk == 0 ? make_double2(0.0, 0.0) : G[(l + i) * kNuJ + j];
+#pragma unroll 1
+        for (int wrap = 0; wrap < 2; ++wrap) {
+          if (wrap == 1 && l >= kNuW + kNuPad) break;
+          const int base = l + wrap * kNuNG;
+          const int lo = base - kNuW, hi = base + 3;
+          const int s0 = max(cs, (int)pcs[(lo < -1 ? -1 : (lo > kNuNG - 1 ? kNuNG - 1 : lo)) + 1]);
+          const int s1 = min(cs + cnt, (int)pcs[(hi > kNuNG - 1 ? kNuNG - 1 : hi) + 1]);
+          for (int s = s0; s < s1; ++s) {
+            const double* wr = wt + (s - cs) * kNuRow + kNuPad + (base - (int)l0ss[s]);
+            const c128 a = A[(s - cs) * kNuJ + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double wgt = wr[i];
+              acc[i].x = fma(wgt, a.x, acc[i].x);
+              acc[i].y = fma(wgt, a.y, acc[i].y);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G[(l + i) * kNuJ + j] = acc[i];
+      }
     }
     __syncthreads();
 
@@ -378,7 +398,7 @@ int launch_evolve_nufft(int n, int64_t batch, const sqb_c128* transform, const d
   const NuPlan p = nufft_plan_at(plan_base, n, batch);
   nufft_deconv_kernel<<<kNuTT / 8, 256, 0, st>>>(p.dec);
   SQB_LAUNCH_CHECK();
-  nufft_plan_kernel<<<(unsigned)batch, kNuMaxN, 0, st>>>(n, w, dt, hbar, p, bsum_flag, clear_flag);
+  nufft_plan_kernel<<<(unsigned)batch, n <= 256 ? 256 : kNuMaxN, 0, st>>>(n, w, dt, hbar, p, bsum_flag, clear_flag);
   SQB_LAUNCH_CHECK();
   const unsigned jg = (unsigned)((n + kNuJ - 1) / kNuJ);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {

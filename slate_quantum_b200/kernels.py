@@ -488,7 +488,7 @@ def evolve_bloch(
 ) -> torch.Tensor:
     """K3c: out[t, b, k] for every time in `times` (fused phase x eigenvector DMMA GEMM).
 
-    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`): blocks of <= 256 states and >= 192
+    uniform_dt: pass the grid spacing when `times` is uniform (see `uniform_step`): blocks of <= 512 states and >= 192
     rows then take the NUFFT route (gather + 1024-point FFT per 512-row tile, csrc/evolve_nufft.cuh), the rest the 3M
     tensor-core GEMM with table-driven phases (`evolve_uniform_route`).  workspace / reuse_plane: a caller-owned workspace (>= evolve_uniform_workspace_bytes)
     lets consecutive calls on the SAME transform (time tiles) skip recomputing the Re+Im plane."""

@@ -415,18 +415,20 @@ def test_evolve_ragged_sizes(cuda, n, n_t):
 
 @pytest.mark.parametrize(
     ("n", "n_t", "spread"),
-    [(32, 192, 1.0), (100, 512, 30.0), (256, 513, 3.0), (255, 1500, 500.0), (64, 2048, 0.0)],
+    [(32, 192, 1.0), (100, 512, 30.0), (256, 513, 3.0), (255, 1500, 500.0), (64, 2048, 0.0), (343, 512, 8.0),
+     (512, 600, 2.0), (300, 1100, 0.0)],
 )
 def test_evolve_uniform_nufft_route(cuda, n, n_t, spread):
-    """Uniform grids with <= 256 states per block and >= 192 rows take the NUFFT route (csrc/evolve_nufft.cuh): against
+    """Uniform grids with <= 512 states per block and >= 192 rows take the NUFFT route (csrc/evolve_nufft.cuh): against
     the oracle's direct sum for ragged tiles, clustered / fully degenerate spectra (spread = 0: every source in ONE
-    window), phases of hundreds of radians per step, and a column-slice output."""
+    window), phases of hundreds of radians per step, blocks of more than 256 states (gathered in two passes of sorted sources), and
+    a column-slice output."""
     torch, kernels = _gpu()
     rng = np.random.default_rng(n + n_t)
     batch = 3
     assert kernels.evolve_uniform_route(n, batch, n_t) == "nufft"
     assert kernels.evolve_uniform_route(n, batch, 64) == "gemm"
-    assert kernels.evolve_uniform_route(343, batch, n_t) == "gemm"
+    assert kernels.evolve_uniform_route(513, batch, n_t) == "gemm"
     g = rng.normal(size=(batch, n, n)) + 1j * rng.normal(size=(batch, n, n))
     _, t_ref = o.eigh_blocks(g + np.swapaxes(g.conj(), 1, 2))
     w_ref = np.sort(rng.uniform(-0.2, 1.0, size=(batch, n)) * spread, axis=1) + 0.7
