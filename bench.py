@@ -2,13 +2,15 @@
 """bench.py -- one "step" = one pass of the hot path over one synthetic Bloch workload:
 
     K1 build every k-block  ->  K2 eigh of every block  ->  K4+K5+K3a project psi0  ->
-    K3c evolve over T times (fused phase x eigenvector DMMA GEMM)  ->  K4b cell FFT to the position basis
+    K3c evolve over T times (NUFFT on uniform grids, else the fused phase x eigenvector DMMA GEMM)  ->  K4b cell FFT to
+    the position basis
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), k-blocks sharded in contiguous ranges.
-`value` is the weak-scaling figure (each rank owns the config's k-grid, enlarged along axis 0); the same line carries
-`strong_scaling` (the config's own k-grid split over the ranks), `parity_check` (sampled blocks of the LAST time rows
+`value` is the STRONG-scaling figure by default - the config's own k-grid split over the ranks, the north_star's "cfg3
+... scales >= 7x at 8 GPUs" - and the same line carries `weak_scaling` (each rank owns the config's k-grid, enlarged
+along axis 0; `--scaling weak` swaps the two), `parity_check` (sampled blocks of the LAST time rows
 against the CPU oracle, every N), `e2e` (through the reference-shaped API at N=1; position-basis, time-sharded states
 to host at N>1), and short runs of the other BASELINE.json configs (`other_configs`).  See DESIGN.md "Measurement".
 """
@@ -397,12 +399,25 @@ class PositionRun:
         if self.gathered:
             row_bytes = self.n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
             t_tile = T // world
-        budget = int(free * 0.8 / (2 if with_position else 1))
-        while t_tile * row_bytes > budget and t_tile > 64:
-            t_tile //= 2
-        self.t_tile, self.row_bytes = t_tile, row_bytes
+        # the evolve tile (`states`) and the position tile (`pos_out`) need not be equal: the NUFFT evolve works in
+        # tiles of 512 rows whatever the call asks for, so `states` keeps as many rows as fit and the cell FFT runs
+        # in chunks of `o_tile` rows when two full tiles do not fit
+        o_tile = t_tile
+        if with_position:
+            fits = lambda t, o: (t + o) * row_bytes <= int(free * 0.85)  # noqa: E731
+            while not fits(t_tile, o_tile) and o_tile > 64:
+                if self.gathered and o_tile * 4 > t_tile:
+                    o_tile //= 2  # first shrink the position tile (down to a quarter of the evolve tile)
+                else:
+                    t_tile //= 2
+                    o_tile = min(o_tile, t_tile)
+        else:
+            while t_tile * row_bytes > int(free * 0.8) and t_tile > 64:
+                t_tile //= 2
+            o_tile = t_tile
+        self.t_tile, self.o_tile, self.row_bytes = t_tile, o_tile, row_bytes
         self.states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
-        self.pos_out = torch.empty_like(self.states) if with_position else None
+        self.pos_out = torch.empty((o_tile, row_bytes // 16), dtype=torch.complex128, device="cuda") if with_position else None
         self.eig_all = (
             torch.empty((world, self.n_k_local * n), dtype=torch.float64, device="cuda")
             if world > 1 and not self.gathered else None
@@ -445,7 +460,9 @@ class PositionRun:
             t_lo = sharded.time_begin
             sharded.evolve_position(self.times[t_lo : t_lo + sharded.rows], self.states, self.pos_out,
                                     self.dt_uniform, wrap=timed)
-            last0 = (sharded.rows - 1) // t_tile * t_tile
+            last_t = (sharded.rows - 1) // t_tile * t_tile          # first row of the last evolve tile
+            o_tile = min(self.o_tile, sharded.rows - last_t)
+            last0 = last_t + (sharded.rows - last_t - 1) // o_tile * o_tile  # ... of its last position chunk
             self.last_tile = (t_lo + last0, sharded.rows - last0)
             return
         for t0 in range(0, T, t_tile):
@@ -955,6 +972,7 @@ def run_ours(args) -> None:
             gemm_route_ms = run.evolve_route_ms("gemm")
     stage_ms, ms_per_step, value = main["stage_ms"], main["ms_per_step"], main["value"]
     t_tile, n_k_local, n_k_global = run.t_tile, run.n_k_local, run.n_k_global
+    run_o_tile = run.o_tile
     repeat_global = run.repeat_global
     exchange_mode = run.sharded.exchange_mode if run.sharded is not None else None
     time_sharded = run.sharded is not None
@@ -999,13 +1017,14 @@ def run_ours(args) -> None:
             e2e = e2e_sharded(ctx, run, args.steps)
     run.close()
 
-    # ---- strong scaling of the SAME config in the same line (north_star: "cfg3 ... scales >= 7x at 8 GPUs")
-    strong_line = None
-    if world > 1 and not strong and not args.no_strong and cfg.n_k % world == 0 and T % world == 0:
-        srun = PositionRun(ctx, cfg, True, with_position)
+    # ---- the OTHER scaling mode in the same line.  Default: `value` is strong scaling of the config itself
+    # (north_star: "cfg3 ... scales >= 7x at 8 GPUs") and `weak_scaling` the k-grid enlarged to N x the blocks.
+    second_line = None
+    if world > 1 and not (args.no_strong or args.no_weak) and cfg.n_k % world == 0 and T % world == 0:
+        srun = PositionRun(ctx, cfg, not strong, with_position)
         sm = srun.measure(args.steps, args.warmup, clocks=False)
         sp = srun.parity_check()
-        strong_line = {
+        second_line = {
             "value": sm["value"],
             "unit": UNIT,
             "ms_per_step": sm["ms_per_step"],
@@ -1014,9 +1033,17 @@ def run_ours(args) -> None:
             "k_blocks_total": srun.n_k_global,
             "k_blocks_per_gpu": srun.n_k_local,
             "time_rows_per_gpu": T // world,
+            "time_tile": srun.t_tile,
+            "position_tile": srun.o_tile,
             "parity_check": sp,
-            "note": f"{cfg.name}'s own k-grid split over {world} GPUs (same kernels and exchange as the weak run); "
-            "speed-up = this value / the 1-GPU value of the same bench",
+            "note": (
+                f"{cfg.name}'s own k-grid split over {world} GPUs (same kernels and exchange as the weak run); "
+                "speed-up = this value / the 1-GPU value of the same bench"
+                if not strong else
+                f"every GPU owns {cfg.name}'s k-grid (k-grid enlarged along axis 0 to {world} x the blocks; same kernels "
+                "and exchange as the strong run); efficiency = this value / (N x the 1-GPU value); the cell FFT of the "
+                "enlarged block grid takes one pass per axis instead of the one-pass cluster kernel of 64 x 64 grids"
+            ),
         }
         srun.close()
 
@@ -1162,6 +1189,7 @@ def run_ours(args) -> None:
             "config": config_dict(cfg, world, strong, with_position),
             "execution": {
                 "time_tile": t_tile,
+                "position_tile": run_o_tile,
                 "collectives": ("NCCL all-gather of eigenvalues and coefficients" if world > 1 else "none")
                 + (f"; eigenvector exchange ({exchange_mode}: "
                    + ("peer copies over NVLink from symmetric memory" if exchange_mode == "p2p"
@@ -1201,8 +1229,8 @@ def run_ours(args) -> None:
             "gpu_launches": main["gpu_launches"],
             "clocks": main["clocks"],
         }
-        if strong_line is not None:
-            line["strong_scaling"] = strong_line
+        if second_line is not None:
+            line["weak_scaling" if strong else "strong_scaling"] = second_line
         if observables is not None:
             line["observables"] = observables
         if e2e is not None:
@@ -1226,12 +1254,14 @@ def main() -> None:
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--position", type=int, default=1, help="include the cell FFT to the position basis")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="what `value` is.  weak (default): every GPU owns the config's k-grid; strong: the config is "
-                    "split over the GPUs.  The weak line also carries the strong figure (`strong_scaling`)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="what `value` is at N > 1.  strong (default): the config's own k-grid split over the GPUs; weak: "
+                    "every GPU owns the config's k-grid.  The line also carries the other figure (`weak_scaling` / "
+                    "`strong_scaling`)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the second scaling mode (same as --no-weak)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the second scaling mode")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

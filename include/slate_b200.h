@@ -13,8 +13,10 @@
  *    Numerical failures of the eigensolver are reported per matrix in `info[]`, not in the return value.
  *  - Re-entrant / thread-safe: no global mutable state.  A few environment variables are read once per process
  *    (tuning / fallback switches, never needed for correctness): SQB_EIGH_TRIDIAG_SOLVER=ql selects the
- *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_FFT_INPLACE=0 uses the two-buffer FFT pass for 256/512-point strided lines; SQB_EVOLVE_TILES_PER_CTA=<k> sets how
- *    many 64-row time tiles a CTA of the uniform-grid evolve kernel walks (default 16); SQB_BACKTRANSFORM=reflector
+ *    QL + rotation-replay tridiagonal stage instead of divide and conquer; SQB_FFT_INPLACE=0 uses the two-buffer FFT pass for 256/512-point strided lines; SQB_EVOLVE=gemm|nufft forces the route of
+ *    sqb_evolve_bloch_uniform (default: NUFFT for n <= 512 and t_count >= 192; this one is read at EVERY call);
+ *    SQB_EVOLVE_TILES_PER_CTA=<k> sets how
+ *    many 64-row time tiles a CTA of the uniform-grid GEMM evolve kernel walks (default 16); SQB_BACKTRANSFORM=reflector
  *    selects the reflector-by-reflector back-transformation for every n (default: blocked compact-WY DMMA
  *    kernel for 64 < n <= 512); SQB_WY_VARIANT=<1|2> picks the blocked back-transformation's tile shape (1: 16-reflector
  *    blocks, two CTAs per SM, default; 2: 32-reflector blocks); SQB_TRIDIAG=column selects the column-by-column

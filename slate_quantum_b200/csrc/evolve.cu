@@ -675,7 +675,7 @@ namespace {
 // row counts stay on the GEMM)
 int evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
   const char* env = getenv("SQB_EVOLVE");  // read per call: bench.py times both routes in one process
-  if (n > kNuMaxN || batch < 1 || t_count < 1) return 0;
+  if (n > kNuMaxN || n > kNuThreads || batch < 1 || t_count < 1) return 0;  // one thread per source holds (w, c)
   if (env && env[0] == 'g') return 0;
   if (env && env[0] == 'n') return 1;
   return (t_count >= 192 && n >= 32) ? 1 : 0;
@@ -689,9 +689,13 @@ extern "C" int sqb_evolve_uniform_route(int n, int64_t batch, int64_t t_count) {
 
 extern "C" size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count) {
   if (n < 1 || batch < 0 || t_count < 0) return 0;
+  // [flag][NUFFT plan] serve the NUFFT route; the GEMM route adds [Re+Im plane][phase tables] behind them (2 GB at
+  // cfg3), so a workspace sized for a NUFFT call is small and a GEMM call on it reports SQB_E_WORKSPACE
+  const size_t head = 256 + round_up_256(nufft_plan_bytes(n, batch));
+  if (evolve_uniform_route(n, batch, t_count)) return head + 256;
   const int64_t tiles = (t_count + TM - 1) / TM;
   const int64_t n_pad = n + (n & 1);
-  return round_up_256((size_t)(batch * n) * n_pad * sizeof(double)) + 256 + round_up_256(nufft_plan_bytes(n, batch)) +
+  return head + round_up_256((size_t)(batch * n) * n_pad * sizeof(double)) +
          (size_t)(batch * n) * (size_t)(9 + tiles) * sizeof(c128) + 512;
 }
 
@@ -704,13 +708,12 @@ extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* tr
   if (!workspace || workspace_bytes < sqb_evolve_uniform_workspace_bytes(n, batch, t_count)) return SQB_E_WORKSPACE;
   const int64_t m = batch * n;
   const int64_t tiles = (t_count + TM - 1) / TM;
-  // workspace layout: [bsum: m * n_pad doubles][flag: "bsum matches the transform"][NUFFT plan][step8: m][pow8: 8 m]
-  // [tilebase: tiles * m]; everything before the phase tables has a position that does not depend on t_count, so
-  // the plane can be reused across calls on the same transform
+  // workspace layout: [flag: "the Re+Im plane matches the transform"][NUFFT plan][bsum: m * n_pad doubles][step8: m]
+  // [pow8: 8 m][tilebase: tiles * m]; everything before the phase tables has a position that does not depend on
+  // t_count, so the plane can be reused across calls on the same transform.  A workspace that is too small for the
+  // GEMM part never held a valid plane: the flag is only trusted when the plane fits.
   const int n_pad = n + (n & 1);
   unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
-  double* bsum = reinterpret_cast<double*>(base);  // [batch*n][n_pad] plane Re + Im of `transform`
-  base += round_up_256((size_t)m * n_pad * sizeof(double));
   int* plane_flag = reinterpret_cast<int*>(base);
   base += 256;
   void* plan_base = base;
@@ -720,6 +723,8 @@ extern "C" int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* tr
     return launch_evolve_nufft(n, batch, transform, w, c, times, t_count, dt, hbar, out, out_row_stride, plan_base,
                                plane_flag, reuse_transform_plane ? 0 : 1, sqb_stream(stream));
   }
+  double* bsum = reinterpret_cast<double*>(base);  // [batch*n][n_pad] plane Re + Im of `transform`
+  base += round_up_256((size_t)m * n_pad * sizeof(double));
   c128* step8 = reinterpret_cast<c128*>(base);
   c128* pow8 = step8 + m;
   c128* tilebase = pow8 + 8 * m;

@@ -38,11 +38,15 @@ constexpr int kNuMaxN = 512;                  // sources (eigenstates) per block
 constexpr int kNuChunk = 256;                 // sources resident in shared memory per gather pass
 constexpr int kNuJ = 8;                       // columns per CTA
 constexpr int kNuPcStride = kNuNG + 8;        // pc[x + 1] = #sources with first grid point <= x, x = -1 .. NG-1
-constexpr int kNuThreads = 512;
+#ifndef SQB_NU_THREADS
+#define SQB_NU_THREADS 512  // developer switch (tools/build_variant.sh): 256 threads x 255 registers measured slower
+#endif
+constexpr int kNuThreads = SQB_NU_THREADS;
 constexpr int kNuSlots = kNuThreads / kNuJ;   // threads along the grid axis
 
 struct NuPlan {
   double* dec;          // [TT]      1 / window transform at m' = m - TT/2
+  c128* tw;             // [NG/2]    exp(-2 pi i k / NG)
   double* wts;          // [batch][n][kNuRow]  window weights of the SORTED sources, zero padded
   unsigned short* src;  // [batch][n]  sorted position -> eigenstate
   unsigned short* l0s;  // [batch][n]  first grid point of the window (mod NG), ascending
@@ -51,7 +55,8 @@ struct NuPlan {
 
 __host__ __device__ inline size_t nufft_plan_bytes(int n, int64_t batch) {
   if (n > kNuMaxN) return 0;
-  return (size_t)kNuTT * 8 + (size_t)batch * ((size_t)n * kNuRow * 8 + (size_t)n * 4 + (size_t)kNuPcStride * 2) + 1024;
+  return (size_t)kNuTT * 8 + (size_t)(kNuNG / 2) * 16 +
+         (size_t)batch * ((size_t)n * kNuRow * 8 + (size_t)n * 4 + (size_t)kNuPcStride * 2) + 1024;
 }
 
 inline NuPlan nufft_plan_at(void* base, int n, int64_t batch) {
@@ -59,6 +64,8 @@ inline NuPlan nufft_plan_at(void* base, int n, int64_t batch) {
   unsigned char* q = reinterpret_cast<unsigned char*>(base);
   p.dec = reinterpret_cast<double*>(q);
   q += (size_t)kNuTT * 8;
+  p.tw = reinterpret_cast<c128*>(q);
+  q += (size_t)(kNuNG / 2) * 16;
   p.wts = reinterpret_cast<double*>(q);
   q += (size_t)batch * n * kNuRow * 8;
   p.src = reinterpret_cast<unsigned short*>(q);
@@ -72,7 +79,16 @@ inline NuPlan nufft_plan_at(void* base, int n, int64_t batch) {
 // dec[m] = 1 / ((W/2) int_{-1}^{1} phi(z) cos(alpha_m z) dz), alpha_m = (m - TT/2) (2 pi / NG) (W/2); with z = sin t
 // the integrand is smooth and (up to exp(-beta)) periodic, so the midpoint rule converges geometrically.  One warp
 // per m, 256 nodes.
-__global__ void __launch_bounds__(256) nufft_deconv_kernel(double* __restrict__ dec) {
+__global__ void __launch_bounds__(256) nufft_deconv_kernel(double* __restrict__ dec, c128* __restrict__ tw) {
+  {
+    // the FFT's half twiddle table, one entry per thread of the grid (64 CTAs x 256 >= NG / 2)
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < kNuNG / 2) {
+      double s, c;
+      sincospi(-(double)i / (kNuNG / 2), &s, &c);
+      tw[i] = make_double2(c, s);
+    }
+  }
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= kNuTT) return;
   const double alpha = (double)(m - kNuTT / 2) * (6.283185307179586 / kNuNG) * (0.5 * kNuW);
@@ -246,39 +262,40 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   // and the phase x eigenvector products of one pass fill the shared memory left beside the grid lines)
   const int n_chunks = (n + kNuChunk - 1) / kNuChunk;
   const double* wsrc = p.wts + b * (int64_t)n * kNuRow;
-  // ---- per-block plan and twiddles -> shared memory
-  {
-    if (n_chunks == 1)
-      for (int i = tid; i < n * kNuRow; i += kNuThreads) wt[i] = wsrc[i];
-    for (int i = tid; i < kNuNG + 1; i += kNuThreads) pcs[i] = p.pc[b * kNuPcStride + i];
-    for (int i = tid; i < n; i += kNuThreads) {
-      srcs[i] = p.src[b * n + i];
-      l0ss[i] = p.l0s[b * n + i];
-    }
-    for (int i = tid; i < kNuNG / 2; i += kNuThreads) {
-      double s, c;
-      sincospi(-(double)i / (kNuNG / 2), &s, &c);
-      tw[i] = make_double2(c, s);
-    }
-    for (int i = tid; i < kNuTT; i += kNuThreads) decs[i] = p.dec[i];
+  // ---- global loads that feed registers first (they depend on the plan in GLOBAL memory only, so their latency
+  // overlaps the shared-memory fills below): the source's eigenvalue and coefficient, and - for blocks of one pass -
+  // the block's eigenvector elements of this CTA's columns, which stay in registers for every row tile
+  double we = 0.0;
+  c128 ce = make_double2(0.0, 0.0);
+  if (tid < n) {
+    const int e = p.src[b * n + tid];
+    we = wv[b * n + e];
+    ce = cv[b * n + e];
   }
-  __syncthreads();
-  // the block's eigenvector elements of this CTA's columns stay in registers for every row tile
   c128 vreg[kNuVreg];
 #pragma unroll
   for (int i = 0; i < kNuVreg; ++i) {
     const int idx = tid + i * kNuThreads;
     vreg[i] = make_double2(0.0, 0.0);
-    if (n_chunks == 1 && idx < n * kNuJ && col_ok) vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + j0 + j);
+    if (n_chunks == 1 && idx < n * kNuJ && col_ok)
+      vreg[i] = __ldg(V + (b * n + p.src[b * n + (idx >> 3)]) * (int64_t)n + j0 + j);
   }
-  // source s = tid keeps its eigenvalue and coefficient
-  double we = 0.0;
-  c128 ce = make_double2(0.0, 0.0);
-  if (tid < n) {
-    const int e = srcs[tid];
-    we = wv[b * n + e];
-    ce = cv[b * n + e];
+  // ---- per-block plan and tables -> shared memory
+  {
+    if (n_chunks == 1) {
+      const double2* w2 = reinterpret_cast<const double2*>(wsrc);  // rows of kNuRow = 20 doubles: 16-byte aligned
+      double2* d2 = reinterpret_cast<double2*>(wt);
+      for (int i = tid; i < n * kNuRow / 2; i += kNuThreads) d2[i] = w2[i];
+    }
+    for (int i = tid; i < kNuNG + 1; i += kNuThreads) pcs[i] = p.pc[b * kNuPcStride + i];
+    for (int i = tid; i < n; i += kNuThreads) {
+      srcs[i] = p.src[b * n + i];
+      l0ss[i] = p.l0s[b * n + i];
+    }
+    for (int i = tid; i < kNuNG / 2; i += kNuThreads) tw[i] = p.tw[i];
+    for (int i = tid; i < kNuTT; i += kNuThreads) decs[i] = p.dec[i];
   }
+  __syncthreads();
 
   for (int64_t r0 = 0; r0 < t_count; r0 += kNuTT) {
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
@@ -396,7 +413,7 @@ int launch_evolve_nufft(int n, int64_t batch, const sqb_c128* transform, const d
       cudaFuncSetAttribute(evolve_nufft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNuSmem);
   if (e != cudaSuccess) return (int)e;
   const NuPlan p = nufft_plan_at(plan_base, n, batch);
-  nufft_deconv_kernel<<<kNuTT / 8, 256, 0, st>>>(p.dec);
+  nufft_deconv_kernel<<<kNuTT / 8, 256, 0, st>>>(p.dec, p.tw);
   SQB_LAUNCH_CHECK();
   nufft_plan_kernel<<<(unsigned)batch, n <= 256 ? 256 : kNuMaxN, 0, st>>>(n, w, dt, hbar, p, bsum_flag, clear_flag);
   SQB_LAUNCH_CHECK();

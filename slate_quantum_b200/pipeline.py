@@ -460,8 +460,9 @@ class TimeShardedEvolver:
         on_tile=None, wrap=None,
     ) -> None:
         """Evolve this rank's time samples `times_local` ([rows], = times[time_begin : time_begin + rows]) for all
-        blocks, tile by tile: `states` / `out` are [t_tile, M] buffers (states in the cell layout is scratch);
-        on_tile(t0, tt, out[:tt]) is called after each tile's position-basis states have been enqueued.
+        blocks, tile by tile: `states` is a [t_tile, M] scratch buffer (cell layout), `out` a [o_tile <= t_tile, M]
+        buffer; on_tile(t0, tt, out[:tt]) is called after each (chunk of a) tile's position-basis states have been
+        enqueued.
 
         `out` may be a LIST of buffers used round-robin (a consumer that drains a tile asynchronously, e.g. a
         device -> host copy on another stream): when on_tile returns a CUDA event, the buffer it was given is not
@@ -477,6 +478,7 @@ class TimeShardedEvolver:
         outs = list(out) if isinstance(out, (list, tuple)) else [out]
         busy: list = [None] * len(outs)
         t_tile = states.shape[0]
+        i_out = 0
         for i_tile, t0 in enumerate(range(0, times_local.numel(), t_tile)):
             tt = min(t_tile, times_local.numel() - t0)
             tsl = times_local[t0 : t0 + tt]
@@ -491,14 +493,28 @@ class TimeShardedEvolver:
                     call("evolve", lambda: kernels.evolve_bloch(
                         tr, ww, cc, tsl, s.hbar, out=states[:tt, b0 * n : (b0 + cnt) * n]))
                 else:
+                    # the workspace size depends on the route the call takes (a short ragged tile runs the GEMM,
+                    # whose Re+Im plane needs far more than the NUFFT plan): grow on demand
+                    need = kernels.evolve_uniform_workspace_bytes(n, cnt, tt)
+                    reuse = i_tile > 0
+                    if self._ws[i_seg].numel() < need:
+                        self._ws[i_seg] = torch.empty(need, dtype=torch.uint8, device="cuda")
+                        reuse = False
+                    ws = self._ws[i_seg]
                     call("evolve", lambda: kernels.evolve_bloch(
                         tr, ww, cc, tsl, s.hbar, out=states[:tt, b0 * n : (b0 + cnt) * n], uniform_dt=uniform_dt,
-                        workspace=self._ws[i_seg], reuse_plane=i_tile > 0))
-            slot = i_tile % len(outs)
-            if busy[slot] is not None:
-                cur.wait_event(busy[slot])
-                busy[slot] = None
-            dst = outs[slot]
-            call("position", lambda: s.cell_to_position(states[:tt], out=dst[:tt]))
-            if on_tile is not None:
-                busy[slot] = on_tile(t0, tt, dst[:tt])
+                        workspace=ws, reuse_plane=reuse))
+            # the position-basis buffers may hold fewer rows than the evolve tile (two full tiles of a 512 x 64 block
+            # grid do not fit beside the exchanged eigenvectors): the cell FFT then runs chunk by chunk
+            o_tile = min(tt, outs[0].shape[0])
+            for p0 in range(0, tt, o_tile):
+                pt = min(o_tile, tt - p0)
+                slot = i_out % len(outs)
+                i_out += 1
+                if busy[slot] is not None:
+                    cur.wait_event(busy[slot])
+                    busy[slot] = None
+                dst = outs[slot]
+                call("position", lambda: s.cell_to_position(states[p0 : p0 + pt], out=dst[:pt]))
+                if on_tile is not None:
+                    busy[slot] = on_tile(t0 + p0, pt, dst[:pt])

@@ -45,7 +45,9 @@ def test_reference_arm_prints_the_contract_line():
     assert len(out) == 1
     line = json.loads(out[0])
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
-    assert line["config"] == bench.config_dict(bench.CONFIGS["cfg1"], 2, False, True)
+    # default scaling mode = strong: the config's own k-grid split over the GPUs, same dict as the GPU arm
+    assert line["scaling"] == "strong"
+    assert line["config"] == bench.config_dict(bench.CONFIGS["cfg1"], 2, True, True)
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["sample_wall_s"] > 0
     assert line["cpu_baseline"]["blas_threads"] >= 1 and line["n_gpus"] == 2
