@@ -289,17 +289,21 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
 
   // A CTA takes `groups_per_cta` adjacent groups of 8 columns one after the other, so that the 55 KB of per-block
   // tables above are fetched once per ~4 tile-sized work items even when a call has a single row tile
+  c128 vreg[kNuVreg];
+  auto load_vreg = [&](int jbase) {
+#pragma unroll
+    for (int i = 0; i < kNuVreg; ++i) {
+      const int idx = tid + i * kNuThreads;
+      vreg[i] = make_double2(0.0, 0.0);
+      if (n_chunks == 1 && idx < n * kNuJ && jbase + j < n)
+        vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + jbase + j);
+    }
+  };
+  load_vreg(blockIdx.x * groups_per_cta * kNuJ);
   for (int gi = 0; gi < groups_per_cta; ++gi) {
   const int j0 = (blockIdx.x * groups_per_cta + gi) * kNuJ;
   if (j0 >= n) break;
   const bool col_ok = j0 + j < n;
-  c128 vreg[kNuVreg];
-#pragma unroll
-  for (int i = 0; i < kNuVreg; ++i) {
-    const int idx = tid + i * kNuThreads;
-    vreg[i] = make_double2(0.0, 0.0);
-    if (n_chunks == 1 && idx < n * kNuJ && col_ok) vreg[i] = __ldg(V + (b * n + srcs[idx >> 3]) * (int64_t)n + j0 + j);
-  }
   for (int64_t r0 = 0; r0 < t_count; r0 += kNuTT) {
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int cs = chunk * kNuChunk, cnt = min(kNuChunk, n - cs);
@@ -321,6 +325,9 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
           const int idx = tid + i * kNuThreads;
           if (idx < n * kNuJ) A[idx] = cmul(ph[idx >> 3], vreg[i]);
         }
+        // last row tile of this column group: the registers are free, fetch the next group's eigenvector elements
+        // now so that their latency hides behind this tile's gather and FFT
+        if (r0 + kNuTT >= t_count && gi + 1 < groups_per_cta) load_vreg(j0 + kNuJ);
       } else {
         for (int idx = tid; idx < cnt * kNuJ; idx += kNuThreads) {
           c128 v = make_double2(0.0, 0.0);
