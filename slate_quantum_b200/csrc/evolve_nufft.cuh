@@ -10,9 +10,9 @@
 // of TT = 512 rows costs a gather of the N <= 512 sources onto an oversampled grid of NG = 1024 points (W = 14 window weights
 // per source, shared by all columns of the block), one 1024-point FFT per column and a scale:
 //
-//     out[r0 + m, j] = dec[m] * FFT_NG( g_j )[(m - TT/2) mod NG],
-//     g_j[l]  = sum_e a_e[j] phi((l - u_e) / (W/2)),   u_e = theta_e NG / 2 pi,
-//     a_e[j]  = c_e exp(-1j w_e t_{r0 + TT/2} / hbar) V[e, j]         (the tile-centre phase is evaluated directly),
+//     out[r0 + K m, j] = dec[m] * FFT_NG( g_j )[(m - TT/2) mod NG],                  (K = 1, 2, 4 ...: nu_interleave)
+//     g_j[l]  = sum_e a_e[j] phi((l - u_e) / (W/2)),   u_e = (K theta_e mod 2 pi) NG / 2 pi,
+//     a_e[j]  = c_e exp(-1j w_e t_{r0 + K TT/2} / hbar) V[e, j]       (the tile-centre phase is evaluated directly),
 //
 // phi(z) = exp(beta (sqrt(1 - z^2) - 1)) the "exponential of semicircle" window (Barnett, Magland, af Klinteberg,
 // SIAM J. Sci. Comput. 41 (2019)), beta = 2.3 W, dec = 1 / (window transform).  Aliasing error ~1e-13 of sum_e |a_e|
@@ -47,6 +47,7 @@ constexpr int kNuSlots = kNuThreads / kNuJ;   // threads along the grid axis
 struct NuPlan {
   double* dec;          // [TT]      1 / window transform at m' = m - TT/2
   c128* tw;             // [NG/2]    exp(-2 pi i k / NG)
+  unsigned long long* band;  // [2]  order-preserving keys of min / max of w dt / hbar over the call (nu_interleave)
   double* wts;          // [batch][n][kNuRow]  window weights of the SORTED sources, zero padded
   unsigned short* src;  // [batch][n]  sorted position -> eigenstate
   unsigned short* l0s;  // [batch][n]  first grid point of the window (mod NG), ascending
@@ -55,7 +56,7 @@ struct NuPlan {
 
 __host__ __device__ inline size_t nufft_plan_bytes(int n, int64_t batch) {
   if (n > kNuMaxN) return 0;
-  return (size_t)kNuTT * 8 + (size_t)(kNuNG / 2) * 16 +
+  return (size_t)kNuTT * 8 + (size_t)(kNuNG / 2) * 16 + 256 +
          (size_t)batch * ((size_t)n * kNuRow * 8 + (size_t)n * 4 + (size_t)kNuPcStride * 2) + 1024;
 }
 
@@ -66,6 +67,8 @@ inline NuPlan nufft_plan_at(void* base, int n, int64_t batch) {
   q += (size_t)kNuTT * 8;
   p.tw = reinterpret_cast<c128*>(q);
   q += (size_t)(kNuNG / 2) * 16;
+  p.band = reinterpret_cast<unsigned long long*>(q);
+  q += 256;
   p.wts = reinterpret_cast<double*>(q);
   q += (size_t)batch * n * kNuRow * 8;
   p.src = reinterpret_cast<unsigned short*>(q);
@@ -76,10 +79,69 @@ inline NuPlan nufft_plan_at(void* base, int n, int64_t batch) {
   return p;
 }
 
+// ---- interleaved row tiles.  Physical time steps resolve the dynamics, so the angles theta_e = w_e dt / hbar of a
+// call usually fill a small part of the circle (cfg3: 0.45 rad) and every source would fall on the same few grid
+// points - a few threads of the gather would do all the work.  A tile therefore takes every K-th row of a super-tile
+// of K * 512 rows, rows r0 + K m + m0 (m0 = the tile's index in the super-tile): its angles are K theta_e, K times
+// further apart, at the same cost per tile.  K = the largest power of two that divides the call's tile count and keeps
+// K * (max - min of w dt / hbar) below 0.8 * 2 pi; it is computed on the device (no host synchronisation) by every
+// kernel from the min / max the band kernel leaves in the workspace.
+__device__ __forceinline__ unsigned long long nu_key(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double nu_unkey(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ int nu_interleave(const unsigned long long* band, int64_t tiles) {
+  const double span = nu_unkey(band[1]) - nu_unkey(band[0]);
+  int64_t k_max = tiles & (-tiles);  // largest power of two dividing the tile count: super-tiles are complete
+  if (k_max > 64) k_max = 64;
+  int k = 1;
+  while (2 * k <= k_max && 2.0 * k * span < 0.8 * 6.283185307179586) k *= 2;
+  return k;
+}
+
+__global__ void __launch_bounds__(256)
+nufft_band_kernel(int64_t m, const double* __restrict__ w, double dt, double hbar, unsigned long long* band) {
+  __shared__ double lo_s[8], hi_s[8];
+  double lo = 1.0e300, hi = -1.0e300;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < m; g += (int64_t)gridDim.x * blockDim.x) {
+    const double x = (w[g] * dt) / hbar;
+    lo = fmin(lo, x);
+    hi = fmax(hi, x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    lo_s[threadIdx.x >> 5] = lo;
+    hi_s[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      lo = fmin(lo, lo_s[i]);
+      hi = fmax(hi, hi_s[i]);
+    }
+    if (lo <= hi) {
+      atomicMin(band, nu_key(lo));
+      atomicMax(band + 1, nu_key(hi));
+    }
+  }
+}
+
 // dec[m] = 1 / ((W/2) int_{-1}^{1} phi(z) cos(alpha_m z) dz), alpha_m = (m - TT/2) (2 pi / NG) (W/2); with z = sin t
 // the integrand is smooth and (up to exp(-beta)) periodic, so the midpoint rule converges geometrically.  One warp
 // per m, 256 nodes.
-__global__ void __launch_bounds__(256) nufft_deconv_kernel(double* __restrict__ dec, c128* __restrict__ tw) {
+__global__ void __launch_bounds__(256)
+nufft_deconv_kernel(double* __restrict__ dec, c128* __restrict__ tw, unsigned long long* __restrict__ band) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    band[0] = ~0ull;  // min key
+    band[1] = 0ull;   // max key
+  }
   {
     // the FFT's half twiddle table, one entry per thread of the grid (64 CTAs x 256 >= NG / 2)
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -105,7 +167,8 @@ __global__ void __launch_bounds__(256) nufft_deconv_kernel(double* __restrict__ 
 
 // One CTA per k-block: angles, windows, sources sorted by the first grid point of their window.
 __global__ void __launch_bounds__(kNuMaxN)
-nufft_plan_kernel(int n, const double* __restrict__ w, double dt, double hbar, NuPlan p, int* bsum_flag, int clear_flag) {
+nufft_plan_kernel(int n, const double* __restrict__ w, double dt, double hbar, int64_t tiles, NuPlan p, int* bsum_flag,
+                  int clear_flag) {
   __shared__ int key_s[kNuMaxN];
   __shared__ unsigned short l0_sorted[kNuMaxN];
   const int64_t b = blockIdx.x;
@@ -114,7 +177,7 @@ nufft_plan_kernel(int n, const double* __restrict__ w, double dt, double hbar, N
   double u = 0.0;
   int l0 = 0, key = 0x7fffffff;
   if (tid < n) {
-    const double x = (w[b * n + tid] * dt) / hbar;
+    const double x = (double)nu_interleave(p.band, tiles) * ((w[b * n + tid] * dt) / hbar);  // angle per row of a tile
     const double q = rint(x / 6.283185307179586);
     double th = fma(-q, 6.283185307179586, x);
     th = fma(-q, 2.4492935982947064e-16, th);
@@ -289,6 +352,8 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
 
   // A CTA takes `groups_per_cta` adjacent groups of 8 columns one after the other, so that the 55 KB of per-block
   // tables above are fetched once per ~4 tile-sized work items even when a call has a single row tile
+  const int64_t tiles = (t_count + kNuTT - 1) / kNuTT;
+  const int kint = nu_interleave(p.band, tiles);
   c128 vreg[kNuVreg];
   auto load_vreg = [&](int jbase) {
 #pragma unroll
@@ -304,7 +369,9 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   const int j0 = (blockIdx.x * groups_per_cta + gi) * kNuJ;
   if (j0 >= n) break;
   const bool col_ok = j0 + j < n;
-  for (int64_t r0 = 0; r0 < t_count; r0 += kNuTT) {
+  for (int64_t ti = 0; ti < tiles; ++ti) {
+    // interleaved tile: rows r0 + kint m, m = 0 .. 511 (see nu_interleave)
+    const int64_t r0 = (ti / kint) * kint * kNuTT + (ti % kint);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int cs = chunk * kNuChunk, cnt = min(kNuChunk, n - cs);
       if (n_chunks > 1) {
@@ -313,7 +380,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
       }
       // ---- tile-centre phases, then A[s][j] = c_e exp(-1j w_e t_c / hbar) V[e][j0 + j]
       if (tid >= cs && tid < cs + cnt) {
-        const double tc = times[r0] + (double)(kNuTT / 2) * dt;
+        const double tc = times[r0] + (double)(kint * (kNuTT / 2)) * dt;
         double s, c;
         sincos(-(we * tc) / hbar, &s, &c);
         ph[tid - cs] = cmul(ce, make_double2(c, s));
@@ -327,7 +394,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
         }
         // last row tile of this column group: the registers are free, fetch the next group's eigenvector elements
         // now so that their latency hides behind this tile's gather and FFT
-        if (r0 + kNuTT >= t_count && gi + 1 < groups_per_cta) load_vreg(j0 + kNuJ);
+        if (ti + 1 == tiles && gi + 1 < groups_per_cta) load_vreg(j0 + kNuJ);
       } else {
         for (int idx = tid; idx < cnt * kNuJ; idx += kNuThreads) {
           c128 v = make_double2(0.0, 0.0);
@@ -408,7 +475,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
         // q = 0, 1: k3 = 6, 7 -> rows mlow, mlow + 128;  q = 2, 3: k3 = 0, 1 -> rows mlow + 256, mlow + 384
         const int m = mlow + 128 * q;
         const c128 val = cscale(x[q < 2 ? 6 + q : q - 2], decs[m]);
-        const int64_t r = r0 + m;
+        const int64_t r = r0 + (int64_t)kint * m;
         if (r < t_count && col_ok) __stcs(out + r * out_row_stride + b * (int64_t)n + j0 + j, val);
       }
     }
@@ -424,12 +491,15 @@ int launch_evolve_nufft(int n, int64_t batch, const sqb_c128* transform, const d
       cudaFuncSetAttribute(evolve_nufft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNuSmem);
   if (e != cudaSuccess) return (int)e;
   const NuPlan p = nufft_plan_at(plan_base, n, batch);
-  nufft_deconv_kernel<<<kNuTT / 8, 256, 0, st>>>(p.dec, p.tw);
+  const int64_t tiles = (t_count + kNuTT - 1) / kNuTT;
+  nufft_deconv_kernel<<<kNuTT / 8, 256, 0, st>>>(p.dec, p.tw, p.band);
   SQB_LAUNCH_CHECK();
-  nufft_plan_kernel<<<(unsigned)batch, n <= 256 ? 256 : kNuMaxN, 0, st>>>(n, w, dt, hbar, p, bsum_flag, clear_flag);
+  nufft_band_kernel<<<(unsigned)sqb_min64((batch * n + 255) / 256, 148 * 4), 256, 0, st>>>(batch * n, w, dt, hbar, p.band);
+  SQB_LAUNCH_CHECK();
+  nufft_plan_kernel<<<(unsigned)batch, n <= 256 ? 256 : kNuMaxN, 0, st>>>(n, w, dt, hbar, tiles, p, bsum_flag,
+                                                                         clear_flag);
   SQB_LAUNCH_CHECK();
   const int groups = (n + kNuJ - 1) / kNuJ;
-  const int64_t tiles = (t_count + kNuTT - 1) / kNuTT;
   // ~8 tile-sized work items per CTA, as long as the grid keeps >= 8 CTAs per SM (measured at cfg3's block shape, 512
   // rows per call: 11.6 ms with one group per CTA, 9.9 with four)
   int groups_per_cta = tiles >= 8 ? 1 : (tiles >= 4 ? 2 : (tiles >= 2 ? 4 : 8));

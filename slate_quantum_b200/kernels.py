@@ -531,8 +531,8 @@ def evolve_bloch(
         )
         _lib.check(rc, "sqb_evolve_bloch_uniform")
         # GEMM route: Re+Im plane (returns at once when reused) + phase tables + GEMM; NUFFT route: window transform +
-        # plan + one transform kernel per 65535 blocks
-        _count(2 - (-batch // 65535))
+        # band + plan + one transform kernel per 65535 blocks
+        _count((3 if lib.sqb_evolve_uniform_route(n, batch, t_count) else 2) - (-batch // 65535))
     return out
 
 

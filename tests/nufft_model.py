@@ -11,6 +11,8 @@ shared by every column j of the block:
 
     out[r0 + m, j] = sum_e a_e[j] exp(-1j (m - TT/2) theta_e),   a_e[j] = c_e exp(-1j w_e t_{r0 + TT/2} / hbar) V[e, j]
 
+(interleaved tiles: rows r0 + K m with the angles K theta_e, see `interleave`)
+
 evaluated as (1) a gather of the sources onto an oversampled grid of NG = 2 TT points with the "exponential of
 semicircle" window of width W (Barnett, Magland, af Klinteberg 2019), (2) an in-place decimation-in-frequency FFT of
 NG points (radix 16, 8, 8) and (3) a division by the window's Fourier transform on the TT wanted frequencies.
@@ -37,10 +39,22 @@ def reduce_angle(x: np.ndarray) -> np.ndarray:
     return np.where(th < 0.0, th + two_pi_hi, th)
 
 
-def plan(w: np.ndarray, dt: float, hbar: float, width: int, beta: float):
+def interleave(w_all: np.ndarray, dt: float, hbar: float, tiles: int) -> int:
+    """K of the kernel's nu_interleave: a tile takes every K-th row of a super-tile of K * TT rows, so that its angles
+    K w dt / hbar spread over the circle even when the time step is small against the bandwidth of the spectrum."""
+    x = w_all * dt / hbar
+    span = float(x.max() - x.min())
+    k_max = min(tiles & (-tiles), 64)
+    k = 1
+    while 2 * k <= k_max and 2.0 * k * span < 0.8 * 2 * np.pi:
+        k *= 2
+    return k
+
+
+def plan(w: np.ndarray, dt: float, hbar: float, width: int, beta: float, k: int = 1):
     """Per block: sources sorted by the first grid point of their window.  Returns (src, l0s, wts, pc)."""
     n = len(w)
-    u = reduce_angle(w * dt / hbar) * (NG / (2 * np.pi))
+    u = reduce_angle(k * (w * dt / hbar)) * (NG / (2 * np.pi))
     l0 = np.ceil(u - width / 2).astype(np.int64)
     l0w = np.mod(l0, NG)
     order = np.lexsort((np.arange(n), l0w))
@@ -48,8 +62,8 @@ def plan(w: np.ndarray, dt: float, hbar: float, width: int, beta: float):
     l0s = l0w[order]
     wts = np.zeros((n, width + 2 * PAD))
     for s, e in enumerate(order):
-        k = np.arange(width)
-        wts[s, PAD : PAD + width] = es_window((l0[e] + k - u[e]) / (width / 2), beta)
+        kk = np.arange(width)
+        wts[s, PAD : PAD + width] = es_window((l0[e] + kk - u[e]) / (width / 2), beta)
     # pc[x + 1] = number of sources with l0s <= x for x in [-1, NG + width + 3): pc[0] = 0
     xs = np.arange(-1, NG + width + 3)
     pc = np.searchsorted(l0s, xs, side="right")
@@ -115,16 +129,21 @@ def fft_dif(g: np.ndarray) -> np.ndarray:
     return out
 
 
-def evolve_uniform(w, c, v, t0: float, dt: float, t_count: int, hbar: float, width: int = 14, beta_per_w: float = 2.3):
-    """out[r, j] for r < t_count from eigenvalues w [N], coefficients c [N], eigenvector rows v [N, NJ]."""
+def evolve_uniform(w, c, v, t0: float, dt: float, t_count: int, hbar: float, width: int = 14, beta_per_w: float = 2.3,
+                   w_all=None):
+    """out[r, j] for r < t_count from eigenvalues w [N], coefficients c [N], eigenvector rows v [N, NJ]; `w_all` =
+    the eigenvalues of every block of the call (they fix the interleave factor; default: this block's)."""
     beta = beta_per_w * width
-    src, l0s, wts, pc = plan(w, dt, hbar, width, beta)
+    tiles = -(-t_count // TT)
+    k = interleave(w if w_all is None else w_all, dt, hbar, tiles)
+    src, l0s, wts, pc = plan(w, dt, hbar, width, beta, k)
     dec = deconvolution(width, beta)
     out = np.zeros((t_count, v.shape[1]), dtype=np.complex128)
-    for r0 in range(0, t_count, TT):
-        tc = (t0 + r0 * dt) + (TT // 2) * dt
+    for ti in range(tiles):
+        r0 = (ti // k) * k * TT + ti % k  # rows r0 + k m
+        tc = (t0 + r0 * dt) + (k * (TT // 2)) * dt
         a = (c * np.exp(-1j * w * tc / hbar))[:, None] * v
         f = fft_dif(gather(src, l0s, wts, pc, a, width)) * dec[:, None]
-        rows = min(TT, t_count - r0)
-        out[r0 : r0 + rows] = f[:rows]
+        rows = np.arange(r0, t_count, k)[:TT]
+        out[rows] = f[: len(rows)]
     return out

@@ -416,13 +416,13 @@ def test_evolve_ragged_sizes(cuda, n, n_t):
 @pytest.mark.parametrize(
     ("n", "n_t", "spread"),
     [(32, 192, 1.0), (100, 512, 30.0), (256, 513, 3.0), (255, 1500, 500.0), (64, 2048, 0.0), (343, 512, 8.0),
-     (512, 600, 2.0), (300, 1100, 0.0)],
+     (512, 600, 2.0), (300, 1100, 0.0), (256, 2048, 1.0), (128, 1324, 0.5), (100, 4096, 0.3), (72, 1024, 1.2)],
 )
 def test_evolve_uniform_nufft_route(cuda, n, n_t, spread):
     """Uniform grids with <= 512 states per block and >= 192 rows take the NUFFT route (csrc/evolve_nufft.cuh): against
     the oracle's direct sum for ragged tiles, clustered / fully degenerate spectra (spread = 0: every source in ONE
-    window), phases of hundreds of radians per step, blocks of more than 256 states (gathered in two passes of sorted sources), and
-    a column-slice output."""
+    window), phases of hundreds of radians per step, blocks of more than 256 states (gathered in two passes of sorted sources),
+    narrow bands (small spread: the kernel interleaves the rows of 2 / 4 / 8 tiles) and a column-slice output."""
     torch, kernels = _gpu()
     rng = np.random.default_rng(n + n_t)
     batch = 3

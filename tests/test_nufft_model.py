@@ -30,6 +30,22 @@ def test_model_matches_direct_sum(n, t_count, scale):
     assert np.abs(got - want).max() < 3e-12 * amp * max(1.0, scale / 40.0)
 
 
+@pytest.mark.parametrize(("t_count", "want_k"), [(2048, 4), (1024, 2), (1536, 1), (4096 + 100, 1), (4096, 8)])
+def test_interleaved_tiles_spread_a_narrow_band(t_count, want_k):
+    """A time step that is small against the spectrum's bandwidth (the physical case): every source falls on a few grid
+    points unless a tile takes every K-th row of a super-tile.  Ragged and odd tile counts fall back to smaller K."""
+    rng = np.random.default_rng(t_count)
+    n = 24
+    dt = 1e-12
+    w = rng.uniform(-0.05, 0.4, n) * HBAR / dt  # angles within 0.45 rad, as at cfg3
+    c = (rng.normal(size=n) + 1j * rng.normal(size=n)) / np.sqrt(n)
+    v = (rng.normal(size=(n, 3)) + 1j * rng.normal(size=(n, 3))) / np.sqrt(n)
+    assert nm.interleave(w, dt, HBAR, -(-t_count // nm.TT)) == want_k
+    got = nm.evolve_uniform(w, c, v, 0.2e-12, dt, t_count, HBAR)
+    amp = (np.abs(c)[:, None] * np.abs(v)).sum(axis=0).max()
+    assert np.abs(got - _direct(w, c, v, 0.2e-12, dt, t_count)).max() < 3e-12 * amp
+
+
 def test_sources_at_the_grid_seam_wrap_around():
     n = 6
     theta = np.array([1e-9, 2 * np.pi - 1e-9, 0.0, np.pi, 2 * np.pi * 3.5 / nm.NG, 2 * np.pi * (nm.NG - 6.5) / nm.NG])
