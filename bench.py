@@ -392,6 +392,15 @@ class PositionRun:
         self.solver._eigh_ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")  # noqa: SLF001
         self.gathered = world > 1 and with_position  # time-sharded evolve over exchanged eigenvectors
         self.sharded = TimeShardedEvolver(self.solver, T) if self.gathered else None
+        # time sharding at N > 1: on a uniform grid rank r evolves rows r, r + N, r + 2N ... (again a uniform grid, step
+        # N dt: the wider step spreads the NUFFT evolve's angles when a rank's share is a single tile), else a
+        # contiguous range
+        self.interleaved = self.gathered and self.dt_uniform is not None
+        if self.gathered:
+            rows_sl = self.sharded.time_rows(self.interleaved)
+            self.time_index = np.arange(T)[rows_sl]                      # global time index of every local row
+            self.times_local = self.times[rows_sl].contiguous()
+            self.dt_local = self.dt_uniform * world if self.interleaved else self.dt_uniform
         self.folded_buf = torch.empty_like(self.h_buf) if with_position and not self.gathered else None
         free = kernels.free_bytes()
         row_bytes = self.n_k_local * n * 16
@@ -457,13 +466,11 @@ class PositionRun:
             # Position output at N > 1 (pipeline.TimeShardedEvolver): the ranks exchange the folded eigenvectors on a
             # side stream and each evolves its own T/G time samples of EVERY block, then runs the local cell FFT.
             sharded.start_exchange(c, wrap=timed)
-            t_lo = sharded.time_begin
-            sharded.evolve_position(self.times[t_lo : t_lo + sharded.rows], self.states, self.pos_out,
-                                    self.dt_uniform, wrap=timed)
+            sharded.evolve_position(self.times_local, self.states, self.pos_out, self.dt_local, wrap=timed)
             last_t = (sharded.rows - 1) // t_tile * t_tile          # first row of the last evolve tile
             o_tile = min(self.o_tile, sharded.rows - last_t)
             last0 = last_t + (sharded.rows - last_t - 1) // o_tile * o_tile  # ... of its last position chunk
-            self.last_tile = (t_lo + last0, sharded.rows - last0)
+            self.last_tile = (last0, sharded.rows - last0)  # LOCAL row range; global indices through time_index
             return
         for t0 in range(0, T, t_tile):
             tt = min(t_tile, T - t0)
@@ -555,7 +562,7 @@ class PositionRun:
         buf = self.pos_out if self.with_position else self.states
         pick = sorted({0, tt - 1})
         rows = buf[pick].cpu().numpy()
-        t_idx = [t0 + r for r in pick]
+        t_idx = [int(self.time_index[t0 + r]) for r in pick] if self.gathered else [t0 + r for r in pick]
         if self.with_position:
             err, blocks = oracle_gate(self.cfg, self.repeat_global, self.psi_np, self.times_np[t_idx], rows, "position")
         else:
@@ -782,11 +789,11 @@ def e2e_sharded(ctx: Ctx, run: PositionRun, steps: int) -> dict:
                 done.synchronize()
                 last = (k[0] - 1) % n_stage
                 rr = tt - (tt - 1) // host_rows * host_rows
-                kept[sharded.time_begin + rows_local - 1] = stage[last][rr - 1].numpy().copy()
+                kept[int(run.time_index[rows_local - 1])] = stage[last][rr - 1].numpy().copy()
             return done
 
-        t_lo = sharded.time_begin
-        sharded.evolve_position(tm[t_lo : t_lo + rows_local], states, outs, run.dt_uniform, on_tile=drain)
+        sharded.evolve_position(tm[sharded.time_rows(run.interleaved)].contiguous(), states, outs, run.dt_local,
+                                on_tile=drain)
         cur.wait_stream(copy_stream)
 
     result = {}
@@ -813,8 +820,8 @@ def e2e_sharded(ctx: Ctx, run: PositionRun, steps: int) -> dict:
         "h2d_bytes_per_step": int(h2d),
         "d2h_bytes_per_step": int(eig_host.numel() * 8 + rows_local * row_bytes),
         "ms_per_step": result["states"],
-        "basis": "position (supercell), time-sharded: rank r returns time rows [r T/G, (r+1) T/G) - the deliverable "
-        "`value` measures",
+        "basis": "position (supercell), time-sharded: rank r returns time rows "
+        + ("r, r + G, r + 2G, ..." if run.interleaved else "[r T/G, (r+1) T/G)") + " - the deliverable `value` measures",
         "numa_node_rank0": ctx.numa_node,
         "note": "pinned host inputs -> C ABI (pipeline.TimeShardedEvolver) -> eigenvalues and this rank's evolved "
         f"position-basis states copied back through {n_stage} x {host_rows * row_bytes / 2**30:.2f} GiB pinned staging "
@@ -973,6 +980,7 @@ def run_ours(args) -> None:
     stage_ms, ms_per_step, value = main["stage_ms"], main["ms_per_step"], main["value"]
     t_tile, n_k_local, n_k_global = run.t_tile, run.n_k_local, run.n_k_global
     run_o_tile = run.o_tile
+    run_interleaved = bool(getattr(run, "interleaved", False))
     repeat_global = run.repeat_global
     exchange_mode = run.sharded.exchange_mode if run.sharded is not None else None
     time_sharded = run.sharded is not None
@@ -1190,6 +1198,9 @@ def run_ours(args) -> None:
             "execution": {
                 "time_tile": t_tile,
                 "position_tile": run_o_tile,
+                "time_sharding": (("interleaved: rank r evolves time rows r, r + N, ..." if run_interleaved else
+                                   "contiguous: rank r evolves time rows [r T/N, (r+1) T/N)") if world > 1 and time_sharded
+                                  else "none"),
                 "collectives": ("NCCL all-gather of eigenvalues and coefficients" if world > 1 else "none")
                 + (f"; eigenvector exchange ({exchange_mode}: "
                    + ("peer copies over NVLink from symmetric memory" if exchange_mode == "p2p"

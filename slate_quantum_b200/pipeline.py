@@ -351,6 +351,7 @@ class TimeShardedEvolver:
             raise ValueError(msg)
         self.rows = n_times // self.world
         self.time_begin = self.rank * self.rows
+        self.n_times = n_times
         self.segments = ring_segments(self.rank, self.world, c)
         self.transforms = torch.empty((self.world, c, n, n), dtype=torch.complex128, device="cuda")
         self.coefficients = torch.empty((self.world, c, n), dtype=torch.complex128, device="cuda")
@@ -401,6 +402,15 @@ class TimeShardedEvolver:
             self._fold_buffers = [both[0], both[1]]
         else:
             self._fold_buffers = [torch.empty((c, n, n), dtype=torch.complex128, device="cuda")]
+
+    def time_rows(self, interleaved: bool = False) -> slice:
+        """Which rows of the global time grid this rank evolves: the contiguous range [time_begin, time_begin + rows),
+        or - `interleaved` - every world-th row starting at `rank`.  On a uniform grid the interleaved rows are again a
+        uniform grid (step world * dt, pass that as `uniform_dt`); the wider step spreads the angles w dt / hbar of the
+        NUFFT evolve over its gather grid when a rank's share is a single 512-row tile (csrc/evolve_nufft.cuh)."""
+        if interleaved:
+            return slice(self.rank, self.n_times, self.world)
+        return slice(self.time_begin, self.time_begin + self.rows)
 
     def gather_eigenvalues(self) -> torch.Tensor:
         """All-gather of the eigenvalues ([n_k, N], global block order); part of the eigensolve stage."""
@@ -459,7 +469,7 @@ class TimeShardedEvolver:
         self, times_local: torch.Tensor, states: torch.Tensor, out, uniform_dt: float | None,
         on_tile=None, wrap=None,
     ) -> None:
-        """Evolve this rank's time samples `times_local` ([rows], = times[time_begin : time_begin + rows]) for all
+        """Evolve this rank's time samples `times_local` ([rows], = times[self.time_rows(...)], contiguous) for all
         blocks, tile by tile: `states` is a [t_tile, M] scratch buffer (cell layout), `out` a [o_tile <= t_tile, M]
         buffer; on_tile(t0, tt, out[:tt]) is called after each (chunk of a) tile's position-basis states have been
         enqueued.

@@ -71,6 +71,31 @@ for mode in ("p2p", "nccl"):
             torch.cuda.synchronize()
             err = np.abs(got - want[lo:lo + sharded.rows]).max()
             assert err < 1e-9, (rank, mode, uniform, t_tile, err)
+    # interleaved time ownership (rank r evolves rows r, r + G, ...: what bench.py uses on uniform grids) with enough rows
+    # per rank for the NUFFT route of the uniform-grid evolve (n = 64 states, 600 rows: one full tile + a ragged one)
+    T2 = 600 * world
+    times = np.linspace(0, 40 * HBAR, T2)
+    dt = kernels.uniform_step(times)
+    assert kernels.evolve_uniform_route(solver.n, cnt, 600) == "nufft"
+    sharded2 = TimeShardedEvolver(solver, T2, exchange=mode)
+    sharded2.gather_eigenvalues()
+    rows_sl = sharded2.time_rows(interleaved=True)
+    assert np.arange(T2)[rows_sl].tolist() == list(range(rank, T2, world))
+    sel = [0, 1, 255, 511, 512, 599]  # local rows checked against the oracle (the oracle evolves only those times)
+    want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times[rows_sl][sel], HBAR)["position"]
+    for t_tile, o_tile in ((600, 600), (600, 150), (256, 256)):
+        sharded2.fold()
+        sharded2.start_exchange(c)
+        states = torch.empty((t_tile, solver.m), dtype=torch.complex128, device="cuda")
+        out = torch.empty((o_tile, solver.m), dtype=torch.complex128, device="cuda")
+        got = np.empty((600, solver.m), dtype=np.complex128)
+        def keep2(t0, tt, tile):
+            got[t0:t0 + tt] = tile.cpu().numpy()
+        sharded2.evolve_position(kernels.to_device(times[rows_sl], torch.float64), states, out, dt * world, on_tile=keep2)
+        torch.cuda.synchronize()
+        err = np.abs(got[sel] - want).max()
+        assert err < 1e-9, (rank, mode, "interleaved", t_tile, o_tile, err)
+    del sharded2
     dist.barrier()
 dist.barrier()
 dist.destroy_process_group()
