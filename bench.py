@@ -977,6 +977,30 @@ def run_ours(args) -> None:
     if world == 1 and run.dt_uniform is not None and not os.environ.get("SQB_EVOLVE"):
         if kernels.evolve_uniform_route(n, run.n_k_local, min(run.t_tile, T)) == "nufft":
             gemm_route_ms = run.evolve_route_ms("gemm")
+    # opt-in time-reversal eigensolve (pipeline.BlochSolver.time_reversal: blocks of half the k-grid are diagonalised,
+    # the rest mirrored from their partners), timed beside the default on the same run; N = 1 only - at N > 1 a rank's
+    # contiguous block range does not contain its partners
+    time_reversal = None
+    if world == 1 and not args.no_time_reversal:
+        run.solver.time_reversal = True
+        try:
+            m2 = run.measure(min(args.steps, 3), 1, clocks=False)
+            if run.solver._time_reversal_applies():  # noqa: SLF001
+                time_reversal = {
+                    "value": m2["value"],
+                    "unit": UNIT,
+                    "ms_per_step": m2["ms_per_step"],
+                    "stage_ms": m2["stage_ms"],
+                    "gpu_launches": m2["gpu_launches"],
+                    "parity_check": run.parity_check(),
+                    "blocks_diagonalised": (cfg.repeat[0] // 2 + 1) * (cfg.n_k // cfg.repeat[0]),
+                    "note": "SQB_TIME_REVERSAL=1 / BlochSolver.time_reversal (off by default): orthogonal lattice + "
+                    "Hermitian-symmetric potential table => H_{-k}[pi g, pi g'] = conj(H_k[g, g']); only the blocks of "
+                    "half the k-grid go through the eigensolver, the others take eigenvalues and permuted, conjugated "
+                    "eigenvectors from their partners (sqb_bloch_time_reversal_mirror)",
+                }
+        finally:
+            run.solver.time_reversal = False
     stage_ms, ms_per_step, value = main["stage_ms"], main["ms_per_step"], main["value"]
     t_tile, n_k_local, n_k_global = run.t_tile, run.n_k_local, run.n_k_global
     run_o_tile = run.o_tile
@@ -1242,6 +1266,8 @@ def run_ours(args) -> None:
         }
         if second_line is not None:
             line["weak_scaling" if strong else "strong_scaling"] = second_line
+        if time_reversal is not None:
+            line["time_reversal_eigensolve"] = time_reversal
         if observables is not None:
             line["observables"] = observables
         if e2e is not None:
@@ -1270,6 +1296,7 @@ def main() -> None:
                     "every GPU owns the config's k-grid.  The line also carries the other figure (`weak_scaling` / "
                     "`strong_scaling`)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-time-reversal", action="store_true", help="skip the extra run with the time-reversal eigensolve")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the second scaling mode (same as --no-weak)")
     ap.add_argument("--no-weak", action="store_true", help="skip the second scaling mode")

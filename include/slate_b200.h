@@ -101,6 +101,19 @@ int sqb_bloch_permute(int nd, const int* shape_host, const int* repeat_host, int
                       int64_t lead, const sqb_c128* in, sqb_c128* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Time-reversal pairing of Bloch blocks (no counterpart in the reference, which diagonalises every block:
+ * bloch/_linalg.py:72-84 -> operator/_linalg.py:45-83).  On an ORTHOGONAL lattice with a Hermitian-symmetric potential
+ * table (a real V(x): every physical potential) the blocks of k and -k satisfy H_{-k}[pi g, pi g'] = conj(H_k[g, g'])
+ * with s = q + R g -> -s (mod R N per axis) on the supercell momentum index, so only the blocks of half the k-grid
+ * need the eigensolver.  sqb_bloch_time_reversal_mirror fills the eigensystems of blocks [first, first + count) of the
+ * FULL [n_k, n, n] transform / [n_k, n] eigenvalue arrays from their partners (which must lie outside that range and
+ * hold rows = eigenvectors): V[b'][e][pi g] = conj(V[b][e][g]), w[b'] = w[b].  The caller is responsible for the two
+ * preconditions (pipeline.BlochSolver.diagonalise(time_reversal=True) checks the lattice and verifies the table).
+ * ---------------------------------------------------------------------------------------------- */
+int sqb_bloch_time_reversal_mirror(int nd, const int* shape_host, const int* repeat_host, int64_t first, int64_t count,
+                                   sqb_c128* transform, double* w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K4  complex128 FFT, norm="ortho", over the trailing `nd` axes of a [batch, dims...] C-order array.
  * Replaces: slate_core TransformedBasis conversions (np.fft.fft / ifft(norm="ortho") per axis;
  * convention pinned by tests/test_operator.py:197-204) reached from Array.with_basis

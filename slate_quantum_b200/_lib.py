@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "sqb_cell_fft_moments",
     "sqb_fold_transform",
     "sqb_bloch_cell_vectors",
+    "sqb_bloch_time_reversal_mirror",
     "sqb_eigh_workspace_bytes",
     "sqb_eigh_batched",
     "sqb_tridiag_eigh_workspace_bytes",
@@ -153,6 +154,8 @@ def load() -> ctypes.CDLL:
     lib.sqb_evolve_bloch.argtypes = [
         c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_int64, c_void_p,
     ]
+    lib.sqb_bloch_time_reversal_mirror.restype = c_int
+    lib.sqb_bloch_time_reversal_mirror.argtypes = [c_int, ip, ip, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.sqb_evolve_uniform_route.restype = c_int
     lib.sqb_evolve_uniform_route.argtypes = [c_int, c_int64, c_int64]
     lib.sqb_evolve_uniform_workspace_bytes.restype = c_size_t

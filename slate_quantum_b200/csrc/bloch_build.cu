@@ -195,6 +195,57 @@ int fill_params(BuildParams& P, int nd, const int* shape, const int* repeat, con
   return SQB_OK;
 }
 
+// Time-reversal partner of (block multi-index, in-block multi-index): on an orthogonal lattice with a potential table
+// that is Hermitian-symmetric (a real V(x)) the blocks of k and -k satisfy
+//     H_{-k}[pi g, pi g'] = conj(H_k[g, g'])
+// where the supercell momentum index s = q + R g (signed FFT-order values, mod M = R N per axis) maps to -s.  The
+// eigenvalues of the two blocks are equal and the eigenvectors are V_{-k}[e, pi g] = conj(V_k[e, g]).
+// (operator/_build/_hamiltonian.py:121-146: the kinetic diagonal is even in the wrapped k-point;
+//  bloch/build.py:123-128: the potential part is the convolution matrix of the table.)
+__device__ __forceinline__ void time_reversal_partner(const SqbDims& d, int64_t blk, int k, int64_t* blk_out, int* k_out) {
+  int64_t b_out = 0, b_mul = 1;
+  int g_out = 0, g_mul = 1;
+  for (int a = d.nd - 1; a >= 0; --a) {
+    const int r = d.repeat[a], na = d.shape[a];
+    const int iq = (int)(blk % r), ig = k % na;
+    blk /= r;
+    k /= na;
+    const int64_t m = (int64_t)r * na;
+    int64_t s = ((int64_t)fft_int(iq, r) + (int64_t)r * fft_int(ig, na)) % m;
+    if (s < 0) s += m;
+    const int64_t sp = (m - s) % m;
+    const int qi = (int)(sp % r);
+    int64_t gi = ((sp - fft_int(qi, r)) / r) % na;
+    if (gi < 0) gi += na;
+    b_out += b_mul * qi;
+    b_mul *= r;
+    g_out += g_mul * (int)gi;
+    g_mul *= na;
+  }
+  *blk_out = b_out;
+  *k_out = g_out;
+}
+
+// one CTA per (target block, 8 eigenvector rows): the partner block and the in-block permutation are computed once per
+// thread column; writes are contiguous, reads run through the permutation (mostly reversed runs)
+__global__ void __launch_bounds__(256)
+time_reversal_mirror_kernel(SqbDims d, int n, int64_t first, int64_t count, c128* __restrict__ v, double* __restrict__ w) {
+  const int64_t bt = first + blockIdx.y;  // target block (global index)
+  if (bt >= first + count) return;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    int64_t bs;
+    int ks;
+    time_reversal_partner(d, bt, k, &bs, &ks);
+    const c128* src = v + bs * (int64_t)n * n;
+    c128* dst = v + bt * (int64_t)n * n;
+    for (int e = blockIdx.x * 8; e < min(n, blockIdx.x * 8 + 8); ++e) {
+      const c128 z = src[(int64_t)e * n + ks];
+      dst[(int64_t)e * n + k] = make_double2(z.x, -z.y);
+    }
+    if (blockIdx.x == 0) w[bt * n + k] = w[bs * n + k];  // eigenvalue e = k here: same spectrum, same order
+  }
+}
+
 }  // namespace
 
 extern "C" int sqb_bloch_build(int nd, const int* shape_host, const int* repeat_host, const double* dk_host,
@@ -272,5 +323,22 @@ extern "C" int sqb_bloch_permute(int nd, const int* shape_host, const int* repea
                                                              reinterpret_cast<const c128*>(in),
                                                              reinterpret_cast<c128*>(out));
   SQB_LAUNCH_CHECK();
+  return SQB_OK;
+}
+
+extern "C" int sqb_bloch_time_reversal_mirror(int nd, const int* shape_host, const int* repeat_host, int64_t first,
+                                              int64_t count, sqb_c128* transform, double* w, void* stream) {
+  SqbDims d;
+  int64_t n, nk;
+  int rc = sqb_fill_dims(d, nd, shape_host, repeat_host, &n, &nk);
+  if (rc) return rc;
+  if (!transform || !w || first < 0 || count < 0 || first + count > nk || n > (1 << 20)) return SQB_E_BADARG;
+  if (count == 0) return SQB_OK;
+  for (int64_t b0 = 0; b0 < count; b0 += 65535) {
+    const int64_t cnt = sqb_min64(65535, count - b0);
+    time_reversal_mirror_kernel<<<dim3((unsigned)((n + 7) / 8), (unsigned)cnt), 256, 0, sqb_stream(stream)>>>(
+        d, (int)n, first + b0, cnt, reinterpret_cast<c128*>(transform), w);
+    SQB_LAUNCH_CHECK();
+  }
   return SQB_OK;
 }

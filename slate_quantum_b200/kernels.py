@@ -377,6 +377,22 @@ def eigh_batched(a: torch.Tensor, workspace: torch.Tensor | None = None) -> tupl
     return w, a, info
 
 
+def time_reversal_mirror(
+    shape: Sequence[int], repeat: Sequence[int], first: int, count: int, transform: torch.Tensor, w: torch.Tensor
+) -> None:
+    """Fill the eigensystems of blocks [first, first + count) of the FULL [n_k, n, n] / [n_k, n] arrays from their
+    time-reversal partners: V[b'][e][pi g] = conj(V[b][e][g]), w[b'] = w[b] (orthogonal lattice, real V(x))."""
+    _require_cuda()
+    _c128(transform, "transform")
+    _f64(w, "w")
+    nd = len(shape)
+    sh = (ctypes.c_int * nd)(*[int(x) for x in shape])
+    rp = (ctypes.c_int * nd)(*[int(x) for x in repeat])
+    rc = _lib.load().sqb_bloch_time_reversal_mirror(nd, sh, rp, int(first), int(count), _ptr(transform), _ptr(w), _stream())
+    _lib.check(rc, "sqb_bloch_time_reversal_mirror")
+    _count(-(-int(count) // 65535))
+
+
 def _dc_depth(n: int) -> int:
     depth = 0
     while ((n + (1 << depth) - 1) >> depth) > 32:

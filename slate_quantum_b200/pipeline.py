@@ -52,9 +52,44 @@ class BlochSolver:
         self.transform_folded: torch.Tensor | None = None
         self._evolve_ws: torch.Tensor | None = None
         self._evolve_ws_for: tuple | None = None  # (data_ptr of the transform whose Re+Im plane the workspace holds)
+        # Opt-in (SQB_TIME_REVERSAL=1 or .time_reversal = True): diagonalise only the blocks of half the k-grid and
+        # mirror the rest, see diagonalise().  Needs an orthogonal lattice, the whole k-grid on this solver and a
+        # Hermitian-symmetric potential table (checked on the table build() receives).
+        import os
+
+        self.time_reversal = os.environ.get("SQB_TIME_REVERSAL", "0") == "1"
+        self._table_symmetric: tuple | None = None  # (data_ptr, version, verdict) of the last table checked
 
     # ------------------------------------------------------------------ K1
+    def _time_reversal_applies(self) -> bool:
+        off_diagonal = self.dk - np.diag(np.diag(self.dk))
+        return (
+            self.time_reversal
+            and self.block_begin == 0
+            and self.block_count == self.n_k
+            and self.repeat[0] > 2
+            and self.n <= kernels.EIGH_KERNEL_MAX_N
+            and float(np.abs(off_diagonal).max()) <= 1e-14 * float(np.abs(self.dk).max())
+            and self._table_symmetric is not None
+            and self._table_symmetric[2]
+        )
+
+    def _check_table(self, table: torch.Tensor) -> None:
+        """Is the potential table Hermitian-symmetric, Vt[-q] = conj(Vt[q]) (a real V(x))?  One small device reduction
+        and a host read per NEW table; the verdict is cached on (data_ptr, version)."""
+        key = (table.data_ptr(), table._version)  # noqa: SLF001
+        if self._table_symmetric is not None and self._table_symmetric[:2] == key:
+            return
+        t = table.reshape(self.shape)
+        axes = tuple(range(t.dim()))
+        mirrored = torch.roll(torch.flip(t, axes), shifts=(1,) * t.dim(), dims=axes)
+        scale = float(t.abs().max().item())
+        ok = float((torch.conj_physical(mirrored) - t).abs().max().item()) <= 1e-14 * max(scale, 1e-300)
+        self._table_symmetric = (*key, ok)
+
     def build(self, potential_table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if self.time_reversal:
+            self._check_table(potential_table)
         self.hamiltonian = kernels.bloch_build(
             self.shape, self.repeat, self.dk, potential_table, self.mass, self.hbar,
             self.block_begin, self.block_count, out=out,
@@ -75,7 +110,20 @@ class BlochSolver:
             free = kernels.free_bytes()
             floor = _lib.load().sqb_eigh_workspace_bytes(self.n, 1)
             self._eigh_ws = torch.empty(max(min(want, int(free * 0.5)), floor), dtype=torch.uint8, device="cuda")
-        w, v, info = kernels.eigh_batched(h, workspace=self._eigh_ws)
+        n_rep = (self.repeat[0] // 2 + 1) * (self.n_k // self.repeat[0])
+        if hamiltonian is None and self._time_reversal_applies() and n_rep < self.n_k:
+            # time reversal: H_{-k}[pi g, pi g'] = conj(H_k[g, g']) (csrc/bloch_build.cu), so the blocks whose first
+            # k-index lies in the upper half of its FFT-ordered range take eigenvalues and (permuted, conjugated)
+            # eigenvectors from their partners; the partners are the contiguous prefix of the block array
+            w_rep, _, info_rep = kernels.eigh_batched(h[:n_rep], workspace=self._eigh_ws)
+            w = torch.empty((self.n_k, self.n), dtype=torch.float64, device="cuda")
+            w[:n_rep] = w_rep
+            info = torch.zeros((self.n_k,), dtype=torch.int32, device="cuda")
+            info[:n_rep] = info_rep
+            kernels.time_reversal_mirror(self.shape, self.repeat, n_rep, self.n_k - n_rep, h, w)
+            v = h
+        else:
+            w, v, info = kernels.eigh_batched(h, workspace=self._eigh_ws)
         self.eigenvalues, self.transform, self.info = w, v, info
         self.hamiltonian = None
         self.transform_folded = None

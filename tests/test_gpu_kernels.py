@@ -263,6 +263,58 @@ def test_full_pipeline_vs_expm(cuda):
     np.testing.assert_allclose(outx, ref, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize(
+    ("shape", "repeat", "kind"),
+    [((8,), (6,), "sin"), ((7,), (5,), "sin"), ((6, 4), (4, 3), "cos"), ((5, 4), (3, 4), "sin"), ((3, 4, 2), (4, 3, 2), "cos"),
+     ((8, 8), (8, 4), "cos"), ((6, 4), (4, 3), "complex"), ((4, 4), (4, 2), "hex")],
+)
+def test_time_reversal_eigensolve(cuda, shape, repeat, kind):
+    """BlochSolver.diagonalise with time_reversal = True: the blocks of half the k-grid are diagonalised, the rest take
+    eigenvalues and permuted, conjugated eigenvectors from their partners (H_{-k}[pi g, pi g'] = conj(H_k[g, g'])).
+    Against the oracle on EVERY block (eigenvalues, residual, orthogonality) and through the evolution; a table that is
+    not Hermitian-symmetric and a non-orthogonal lattice must fall back to the full eigensolve."""
+    torch, kernels = _gpu()
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    nd = len(shape)
+    dx = 2 * np.pi * np.eye(nd)
+    if kind == "hex":
+        dx = 2 * np.pi * np.array([[1.0, 0.0], [0.5, np.sqrt(3) / 2]])
+        comps = o.fcc_potential_components(shape, 5.0)
+    elif kind == "sin":
+        comps = o.sin_potential_components(shape, 4.0, 0.2)
+    else:
+        comps = o.cos_potential_components(shape, 6.0)
+    table = o.pad_components(shape, comps).astype(np.complex128)
+    rng = np.random.default_rng(3)
+    if kind == "complex":  # V(x) not real: the k / -k pairing does not hold (the blocks are not even Hermitian pairs)
+        table = table + 0.3j * np.roll(table, 1, axis=0)
+    solver = BlochSolver(shape, repeat, o.stacked_dk(dx), HBAR**2, HBAR)
+    solver.time_reversal = True
+    h = solver.build(kernels.to_device(table.ravel(), torch.complex128)).clone()
+    blocks = h.cpu().numpy()
+    applies = solver._time_reversal_applies()  # noqa: SLF001
+    assert applies == (kind in ("sin", "cos"))
+    if kind == "complex":
+        return  # such blocks are not Hermitian: nothing to diagonalise, only the fallback decision is checked
+    launches = kernels.LAUNCHES
+    w, v = solver.diagonalise()
+    assert int(solver.info.abs().sum()) == 0
+    w_ref, t_ref = o.eigh_blocks(blocks)
+    assert np.abs(w.cpu().numpy() - w_ref).max() < 1e-10 * np.abs(w_ref).max()
+    res, orth = o.eigh_residuals(blocks, w.cpu().numpy(), v.cpu().numpy())
+    assert res < 1e-10 and orth < 1e-10, (res, orth)
+    del launches
+    # ... and through the evolution to the position basis
+    psi = rng.normal(size=solver.m) + 1j * rng.normal(size=solver.m)
+    psi /= np.linalg.norm(psi)
+    times = np.linspace(0, 3 * HBAR, 7)
+    c = solver.project(kernels.to_device(psi, torch.complex128))
+    pos = solver.evolve_position(c, kernels.to_device(times, torch.float64)).cpu().numpy()
+    want = o.evolve_pipeline(psi, shape, repeat, w_ref, t_ref, times, HBAR)["position"]
+    np.testing.assert_allclose(pos, want, rtol=0, atol=1e-9)
+
+
 # ---------------------------------------------------------------------------------------- K4b cell FFT
 @pytest.mark.parametrize(("shape", "repeat"), [((5,), (4,)), ((8,), (6,)), ((4, 3), (3, 4)), ((4, 4), (8, 2)),
                                                 ((3, 4, 5), (2, 3, 4)), ((7, 7, 7), (2, 4, 2))])
