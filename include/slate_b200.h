@@ -257,9 +257,14 @@ int sqb_tridiag_eigh_batched(int n, int64_t batch, const double* d, const double
  *           (w dt / hbar) mod 2 pi are shared by every column of a block: per tile of 512 rows the sources are
  *           gathered onto a 1024-point grid with a 14-point "exponential of semicircle" window, one 1024-point FFT
  *           per column in shared memory, scale by the inverse window transform (csrc/evolve_nufft.cuh;
- *           ~130 flop per output element whatever N).
- * The workspace covers both routes and records whether its Re+Im plane matches the transform, so calls with
- * different t_count (different routes) may share it under the reuse_transform_plane protocol. */
+ *           ~110 flop per output element whatever N).  A tile takes every K-th row of a super-tile of K x 512 rows
+ *           (K a power of two chosen on the device from the spread of w dt / hbar), so that narrow-band spectra
+ *           spread over the gather grid.
+ * sqb_evolve_uniform_workspace_bytes is the size THIS call needs: the NUFFT route needs its plan only (~37 KB per
+ * block at n = 256), the GEMM route adds the Re+Im plane and the phase tables (8 n^2 + 16 n (9 + t_count / 64) bytes
+ * per block).  A workspace sized for the larger of the calls it will see can be shared by both routes: it records
+ * whether its Re+Im plane matches the transform, so calls with different t_count (different routes) follow the same
+ * reuse_transform_plane protocol; a call whose workspace is too small returns SQB_E_WORKSPACE. */
 int sqb_evolve_uniform_route(int n, int64_t batch, int64_t t_count);
 size_t sqb_evolve_uniform_workspace_bytes(int n, int64_t batch, int64_t t_count);
 int sqb_evolve_bloch_uniform(int n, int64_t batch, const sqb_c128* transform, const double* w,
