@@ -351,7 +351,7 @@ evolve_nufft_kernel(int n, const c128* __restrict__ V, const double* __restrict_
   __syncthreads();
 
   // A CTA takes `groups_per_cta` adjacent groups of 8 columns one after the other, so that the 55 KB of per-block
-  // tables above are fetched once per ~4 tile-sized work items even when a call has a single row tile
+  // tables above are fetched once per ~8 tile-sized work items even when a call has a single row tile
   const int64_t tiles = (t_count + kNuTT - 1) / kNuTT;
   const int kint = nu_interleave(p.band, tiles);
   c128 vreg[kNuVreg];
