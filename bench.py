@@ -98,6 +98,27 @@ class ClockSampler:
         }
 
 
+def choose_tiles(rows: int, row_bytes: int, free_bytes: int, with_position: bool, gathered: bool) -> tuple[int, int]:
+    """(evolve tile, position tile) in time rows for `rows` rows of `row_bytes` each and `free_bytes` of HBM.
+
+    The two tiles need not be equal: the NUFFT evolve works in tiles of 512 rows whatever the call asks for, so the
+    evolve tile (`states`) keeps as many rows as fit and - in the time-sharded multi-GPU layout, where two full tiles of
+    the enlarged block grid do not fit beside the exchanged eigenvectors - the cell FFT runs in chunks of a smaller
+    position tile (`pos_out`, down to a quarter of the evolve tile) before the evolve tile itself is halved."""
+    t_tile = o_tile = int(rows)
+    if not with_position:
+        while t_tile * row_bytes > int(free_bytes * 0.8) and t_tile > 64:
+            t_tile //= 2
+        return t_tile, t_tile
+    while (t_tile + o_tile) * row_bytes > int(free_bytes * 0.85) and o_tile > 64:
+        if gathered and o_tile * 4 > t_tile:
+            o_tile //= 2
+        else:
+            t_tile //= 2
+            o_tile = min(o_tile, t_tile)
+    return t_tile, o_tile
+
+
 def config_dict(cfg: BlochWorkload, world: int, strong: bool, with_position: bool, **extra) -> dict:
     """The `config` object of the JSON line; the reference arm prints the SAME dict (same keys and values)."""
     repeat_global = tuple(cfg.repeat) if strong else (cfg.repeat[0] * world, *cfg.repeat[1:])
@@ -408,22 +429,7 @@ class PositionRun:
         if self.gathered:
             row_bytes = self.n_k_global * n * 16  # a rank evolves T / world time samples of EVERY block
             t_tile = T // world
-        # the evolve tile (`states`) and the position tile (`pos_out`) need not be equal: the NUFFT evolve works in
-        # tiles of 512 rows whatever the call asks for, so `states` keeps as many rows as fit and the cell FFT runs
-        # in chunks of `o_tile` rows when two full tiles do not fit
-        o_tile = t_tile
-        if with_position:
-            fits = lambda t, o: (t + o) * row_bytes <= int(free * 0.85)  # noqa: E731
-            while not fits(t_tile, o_tile) and o_tile > 64:
-                if self.gathered and o_tile * 4 > t_tile:
-                    o_tile //= 2  # first shrink the position tile (down to a quarter of the evolve tile)
-                else:
-                    t_tile //= 2
-                    o_tile = min(o_tile, t_tile)
-        else:
-            while t_tile * row_bytes > int(free * 0.8) and t_tile > 64:
-                t_tile //= 2
-            o_tile = t_tile
+        t_tile, o_tile = choose_tiles(t_tile, row_bytes, free, with_position, self.gathered)
         self.t_tile, self.o_tile, self.row_bytes = t_tile, o_tile, row_bytes
         self.states = torch.empty((t_tile, row_bytes // 16), dtype=torch.complex128, device="cuda")
         self.pos_out = torch.empty((o_tile, row_bytes // 16), dtype=torch.complex128, device="cuda") if with_position else None

@@ -114,3 +114,24 @@ def test_is_smooth():
 
     assert all(kernels.is_smooth(n) for n in (1, 2, 64, 100, 343, 1024, 31 * 29, 4096))
     assert not any(kernels.is_smooth(n) for n in (0, 37, 2 * 37, 1009))
+
+
+def test_tile_sizing_keeps_whole_evolve_tiles_where_two_position_tiles_do_not_fit():
+    """bench.choose_tiles: one GPU takes the whole time grid when two tiles fit, else equal halves; the time-sharded
+    multi-GPU layout first shrinks the POSITION tile (down to a quarter of the evolve tile) so that a rank's share stays
+    one whole 512-row NUFFT tile; without the position stage a single buffer may use 80 % of the memory."""
+    bench = _bench()
+    gb = 1 << 30
+    row = 4096 * 256 * 16  # cfg3 on one GPU: 16.8 MB per time row
+    assert bench.choose_tiles(4096, row, 165 * gb, True, False) == (4096, 4096)
+    assert bench.choose_tiles(4096, row, 150 * gb, True, False) == (2048, 2048)
+    assert bench.choose_tiles(4096, row, 60 * gb, True, False) == (1024, 1024)
+    # 8 GPUs, weak scaling: 512 rows of a 512 x 64 block grid = 68.7 GB per tile
+    assert bench.choose_tiles(512, 8 * row, 135 * gb, True, True) == (512, 256)
+    assert bench.choose_tiles(512, 8 * row, 100 * gb, True, True) == (512, 128)
+    assert bench.choose_tiles(512, 8 * row, 70 * gb, True, True) == (256, 128)
+    # strong scaling: everything fits
+    assert bench.choose_tiles(512, row, 150 * gb, True, True) == (512, 512)
+    assert bench.choose_tiles(4096, row, 60 * gb, False, False) == (2048, 2048)
+    t, o_ = bench.choose_tiles(4096, row, 1 * gb, True, False)
+    assert t == o_ and t <= 64
