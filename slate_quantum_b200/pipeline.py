@@ -371,6 +371,17 @@ def ring_exchange(local: torch.Tensor, gathered: torch.Tensor, group=None, on_ar
             on_arrival(k)
 
 
+def shard_time_rows(rank: int, world: int, n_times: int, interleaved: bool = False) -> slice:
+    """Rows of the global time grid that `rank` of `world` evolves (n_times divisible by world): the contiguous range
+    [rank T/G, (rank + 1) T/G), or - `interleaved` - rows rank, rank + G, ... (on a uniform grid again a uniform grid,
+    step G dt)."""
+    if n_times % world:
+        msg = f"the number of time samples ({n_times}) must be divisible by the number of ranks ({world})"
+        raise ValueError(msg)
+    rows = n_times // world
+    return slice(rank, n_times, world) if interleaved else slice(rank * rows, (rank + 1) * rows)
+
+
 class TimeShardedEvolver:
     """Position-basis states at G > 1: every rank evolves T/G time samples of EVERY k-block.
 
@@ -456,9 +467,7 @@ class TimeShardedEvolver:
         or - `interleaved` - every world-th row starting at `rank`.  On a uniform grid the interleaved rows are again a
         uniform grid (step world * dt, pass that as `uniform_dt`); the wider step spreads the angles w dt / hbar of the
         NUFFT evolve over its gather grid when a rank's share is a single 512-row tile (csrc/evolve_nufft.cuh)."""
-        if interleaved:
-            return slice(self.rank, self.n_times, self.world)
-        return slice(self.time_begin, self.time_begin + self.rows)
+        return shard_time_rows(self.rank, self.world, self.n_times, interleaved)
 
     def gather_eigenvalues(self) -> torch.Tensor:
         """All-gather of the eigenvalues ([n_k, N], global block order); part of the eigensolve stage."""

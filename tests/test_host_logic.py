@@ -262,3 +262,27 @@ def test_x_k_p_builders_bookkeeping_on_cpu():
     assert len(cl) == 1
     np.testing.assert_allclose(cl.raw_data.ravel(), x.raw_data)
     np.testing.assert_array_equal(cl.basis.metadata().children[0].values, [1])
+
+
+def test_time_rows_of_a_rank_partition_the_grid_and_stay_uniform():
+    """pipeline.shard_time_rows: contiguous or interleaved ownership of the time rows; every row has exactly one owner,
+    and the interleaved rows of a uniform grid are a uniform grid with step G dt (what the NUFFT evolve is given)."""
+    import numpy as np
+    import pytest
+
+    from slate_quantum_b200 import kernels
+    from slate_quantum_b200.pipeline import shard_time_rows
+
+    times = 0.25 + 0.125 * np.arange(48)
+    for world in (1, 2, 3, 8):
+        for interleaved in (False, True):
+            owned = np.concatenate([np.arange(48)[shard_time_rows(r, world, 48, interleaved)] for r in range(world)])
+            assert sorted(owned.tolist()) == list(range(48))
+            for r in range(world):
+                local = times[shard_time_rows(r, world, 48, interleaved)]
+                assert len(local) == 48 // world
+                step = kernels.uniform_step(local) if len(local) > 1 else None
+                if len(local) > 1:
+                    assert step == pytest.approx(0.125 * (world if interleaved else 1))
+    with pytest.raises(ValueError, match="divisible"):
+        shard_time_rows(0, 5, 48)
