@@ -295,6 +295,24 @@ def ncu_traffic(kernel: str, cfg_name: str, t_tile: int) -> tuple[float | None, 
     return None, None
 
 
+def ncu_metric(kernel: str, cfg_name: str, t_tile: int, metric: str) -> float | None:
+    """One metric of `kernel`'s row in the committed ncu `--set full` raw page named in profiles/traffic_index.json for
+    exactly this (config, time tile); None when there is no matching capture (never a guess)."""
+    try:
+        entry = json.loads((ROOT / "profiles" / "traffic_index.json").read_text()).get(kernel)
+        if not entry or not cfg_name.startswith(entry["config"]) or int(entry["t_tile"]) != int(t_tile):
+            return None
+        rows = list(csv.reader((ROOT / "profiles" / entry["csv"]).open()))
+        head = rows[0]
+        k_col, m_col = head.index("Kernel Name"), head.index(metric)
+        for row in rows[2:]:
+            if kernel in row[k_col]:
+                return float(row[m_col].replace(",", ""))
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
 def bind_to_gpu_numa_node(local_rank: int) -> int | None:
     """Pin this process (and so its first-touch pinned allocations) to the NUMA node of its GPU."""
     try:
@@ -1150,6 +1168,14 @@ def run_ours(args) -> None:
                     "unit": "GB/s",
                     "frac": (out_bytes + 16.0 * n * n * n_k_evolved) / (launch_ms * 1e-3) / 1e9 / _hbm_peak(),
                     "note": "algorithmic bytes of SURVEY 8d: 16 N T written per block + the eigenvectors read once",
+                },
+                "limiter": {
+                    "resource": "shared-memory pipe (the grid lines of the gather and of the in-place FFT live in shared "
+                    "memory: neither the FP64 pipes nor HBM bound this kernel)",
+                    "pct_of_peak": (ncu_metric(kernel_name, cfg.name, rows_launch,
+                                               "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
+                                    if world == 1 else None),
+                    "source": "same committed ncu capture as `traffic` (null when no capture matches this launch shape)",
                 },
                 "traffic": traffic,
                 "traffic_source": traffic_src,
