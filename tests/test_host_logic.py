@@ -286,3 +286,45 @@ def test_time_rows_of_a_rank_partition_the_grid_and_stay_uniform():
                     assert step == pytest.approx(0.125 * (world if interleaved else 1))
     with pytest.raises(ValueError, match="divisible"):
         shard_time_rows(0, 5, 48)
+
+
+def test_time_reversal_eligibility_decisions_on_the_host():
+    """BlochSolver._time_reversal_applies: the pairing of the blocks of k and -k is used only when it provably holds -
+    orthogonal lattice, the whole k-grid on this solver, a Hermitian-symmetric potential table (a real V(x))."""
+    import numpy as np
+    import torch
+
+    from oracle import bloch_oracle as o
+    from slate_quantum_b200.pipeline import BlochSolver
+
+    hbar = o.HBAR_SI
+    shape, repeat = (6, 4), (4, 3)
+    dk = o.stacked_dk(2 * np.pi * np.eye(2))
+
+    def solver(**kw):
+        s = BlochSolver(shape, repeat, kw.pop("dk", dk), hbar**2, hbar, **kw)
+        s.time_reversal = True
+        return s
+
+    cos = torch.from_numpy(o.pad_components(shape, o.cos_potential_components(shape, 6.0)).astype(np.complex128).ravel())
+    sin = torch.from_numpy(o.pad_components(shape, o.sin_potential_components(shape, 4.0, 0.2)).astype(np.complex128).ravel())
+    s = solver()
+    assert not s._time_reversal_applies()  # noqa: SLF001  (no table seen yet)
+    for table in (cos, sin):  # sin: an asymmetric but still Hermitian-symmetric table, Vt[-q] = conj(Vt[q])
+        s._check_table(table)  # noqa: SLF001
+        assert s._time_reversal_applies()  # noqa: SLF001
+    bad = cos.clone()
+    bad[1] += 0.25j  # V(x) no longer real
+    s._check_table(bad)  # noqa: SLF001
+    assert not s._time_reversal_applies()  # noqa: SLF001
+    s._check_table(cos)  # noqa: SLF001
+    s.time_reversal = False
+    assert not s._time_reversal_applies()  # noqa: SLF001
+    # a rank's share of the k-grid does not contain its partners
+    part = solver(block_begin=0, block_count=6)
+    part._check_table(cos)  # noqa: SLF001
+    assert not part._time_reversal_applies()  # noqa: SLF001
+    # the hexagonal lattice (quirk Q1) breaks the pairing
+    hexa = solver(dk=o.stacked_dk(2 * np.pi * np.array([[1.0, 0.0], [0.5, np.sqrt(3) / 2]])))
+    hexa._check_table(cos)  # noqa: SLF001
+    assert not hexa._time_reversal_applies()  # noqa: SLF001
